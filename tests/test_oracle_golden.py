@@ -1,0 +1,119 @@
+"""Pins the CPU oracle against outputs of the unmodified reference (tests/golden, made by oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+from multi_view_active_learning_b200 import synthetic as S
+from oracle import coreset_oracle as C
+from oracle import scores_oracle as SC
+from oracle import triangulation_oracle as O
+
+POOLS = ["pool_v5_j19", "pool_v8_j19", "pool_v20_j42", "pool_v31_j19", "pool_v2_j3"]
+
+
+def test_reference_unit_test_known_answer(golden):
+    g = golden("ref_unit_triangulation")
+    hm = np.zeros((8, 19, 64, 64), dtype=np.float32)
+    for r, c, v in g["bump_rc"]:
+        hm[:, :, int(r), int(c)] = v
+    out = O.triangulate_pool(hm[None], g["P"][None].astype(np.float64), int(g["stride"]), g["valid"][None])
+    assert np.array_equal(out["keypoints_2d"][0], g["keypoints_2d"])
+    assert (out["keypoints_2d"] == 88).all()
+    assert int(out["inlier_count"][0]) == int(g["inlier_count"]) == 3
+    # values the survey recorded from the reference
+    np.testing.assert_allclose(out["keypoints_3d"][0, 0], [-37.2230772535, -125.6428366493, -23.8942096679], rtol=1e-10)
+    np.testing.assert_allclose(out["metric"][0], 3.1619149383944163, rtol=1e-13)
+    np.testing.assert_allclose(out["keypoints_3d"][0], g["keypoints_3d"], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(out["metric"][0], g["metric"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("name", POOLS)
+def test_ransac_pool_matches_reference(golden, name):
+    g = golden(name)
+    kp = g["keypoints_2d"]
+    V = kp.shape[1]
+    out = O.triangulate_pool(None, g["P"], int(g["stride"]), g["valid"], pair_seed=int(g["pair_seed"]), keypoints_2d=kp)
+    assert np.array_equal(out["inlier_count"], g["inlier_count"])
+    np.testing.assert_allclose(out["keypoints_3d"], g["keypoints_3d"], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(out["metric"], g["metric"], rtol=1e-12)
+    # invalid joints stay exactly zero (reference :206-211)
+    assert (out["keypoints_3d"][~g["valid"]] == 0).all()
+    # decode of the rebuilt one-hot heatmaps reproduces the reference's keypoints_2d (incl. invalid -> [0,0])
+    hm = S.onehot_heatmaps(g["keypoints_2d_unmasked"][:2], int(g["stride"]))
+    assert np.array_equal(O.decode_argmax(hm, int(g["stride"]), g["valid"][:2]), kp[:2])
+    assert V == g["P"].shape[1]
+
+
+def test_pair_tables():
+    assert O.pair_table(8, 64).tolist() == [list(p) for p in __import__("itertools").combinations(range(8), 2)]
+    t = O.pair_table(20, 64, seed=5, frame_index=3, joint=2)
+    assert t.shape == (64, 2) and len({tuple(p) for p in t.tolist()}) == 64 and (t[:, 0] < t[:, 1]).all()
+    assert not np.array_equal(t, O.pair_table(20, 64, seed=5, frame_index=3, joint=3))
+    # the shim hands the reference the same subset, in the same order
+    lst = list(__import__("itertools").combinations(range(20), 2))
+    O.DeterministicShuffle(5, [(3, 2)]).shuffle(lst)
+    assert [list(p) for p in lst[:64]] == t.tolist() and len(set(lst)) == 190
+
+
+def test_decode_edge_cases(golden):
+    g = golden("decode_edge_cases")
+    hm, stride = g["heatmaps"], int(g["stride"])
+    assert np.array_equal(O.decode_argmax(hm, stride, g["valid"]), g["scaled"])
+    assert np.array_equal(O.decode_argmax(hm, stride), g["scaled_all_valid"])
+    # get_pred_coordinates (utils/evaluation.py:46-57): same argmax scaled by bbox extent / map size
+    flat = O.decode_argmax(hm, 1)
+    boxes = g["boxes"].astype(np.float64)
+    sx = (boxes[:, 3] - boxes[:, 1]) / 64.0
+    sy = (boxes[:, 2] - boxes[:, 0]) / 64.0
+    exp = np.stack([flat[..., 0] * sx[:, None], flat[..., 1] * sy[:, None]], axis=-1)
+    np.testing.assert_allclose(exp, g["pred_coordinates"], rtol=1e-6)
+
+
+def test_hp_scores(golden):
+    g = golden("hp_scores")
+    s = SC.hp_scores(g["heatmaps"])
+    np.testing.assert_allclose(s, g["hp_per_map"], atol=2e-6)
+    np.testing.assert_allclose(SC.hp_metric(g["heatmaps"], g["valid"], "AVG"), float(g["hp_avg"]), atol=2e-6)
+    np.testing.assert_allclose(SC.hp_metric(g["heatmaps"], g["valid"], "STD"), float(g["hp_std"]), atol=2e-6)
+
+
+def test_coreset_matches_reference(golden):
+    g = golden("coreset_random")
+    F = C.stacked_features(g["sal_poses"], g["al_poses"], int(g["root"]))
+    assert np.array_equal(F, g["features"])
+    n = len(g["sal_poses"])
+    picked, min_d = C.kcenter_greedy_f64(F, n, int(g["budget"]))
+    assert picked == g["picked"].tolist()
+    assert np.array_equal(min_d, g["min_distances"])
+    # the float32 canonical-order variant selects the same rows on this well separated pool
+    picked32, min32 = C.kcenter_greedy_f32(F, n, int(g["budget"]))
+    assert picked32 == picked
+    np.testing.assert_allclose(min32, min_d[:, 0], rtol=1e-4, atol=1e-2)
+
+
+def test_coreset_reference_unit_test(golden):
+    g = golden("ref_unit_coreset")
+    pose = [[0, 1, 2] for _ in range(int(g["n_joints"]))]
+    F = C.stacked_features([pose] * int(g["n_sal"]), [pose] * int(g["n_al"]), int(g["root"]))
+    assert F.shape == (25, 57)
+    picked, _ = C.kcenter_greedy_f64(F, 20, 5)
+    assert picked == g["picked"].tolist() == [0] * 5
+    assert C.kcenter_greedy_f32(F, 20, 5)[0] == [0] * 5
+
+
+def test_canonical_dot_is_order_defined():
+    rng = np.random.default_rng(0)
+    for d in (3, 57, 126, 128, 300, 2048):
+        X = rng.normal(size=(5, d)).astype(np.float32)
+        c = rng.normal(size=d).astype(np.float32)
+        got = C.canonical_dot_f32(X, c)
+        np.testing.assert_allclose(got, X.astype(np.float64) @ c.astype(np.float64), rtol=2e-4, atol=1e-4)
+        assert got.dtype == np.float32
+    x = rng.normal(size=(1, 2048)).astype(np.float32)
+    xx = C.canonical_dot_f32(x, x[0])
+    assert C.canonical_dist_f32(x, xx, x[0])[0] == 0.0  # a row is at distance exactly 0 from itself
+
+
+def test_ranking():
+    d = {"a": 1.0, "b": float("nan"), "c": 3.0, "d": 3.0, "e": 2.0}
+    assert SC.rank_nlargest(d, 3) == ["c", "d", "e"]
+    assert SC.rank_nlargest(d, 10) == ["c", "d", "e", "a"]
