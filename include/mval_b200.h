@@ -1,0 +1,177 @@
+/*
+ * mval_b200.h -- C ABI of the B200-native (sm_100a) active-learning scoring-and-selection hot path.
+ *
+ * The upstream reference (facebookresearch/multi_view_active_learning) is pure Python and has no FFI
+ * layer; the functions below are what a ctypes binding of its hot path binds (INTEGRATION.md shows the
+ * stub).  Every entry point cites the reference interface it replaces as  file:line  relative to the
+ * reference tree.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - "device" pointers are caller-owned CUDA device memory on the current device, "host" pointers are
+ *     caller-owned host memory (pinned if the copy is to overlap); nothing is retained after return
+ *     except by the explicit *_create / *_destroy handle pairs;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all device entry points
+ *     are asynchronous with respect to the host and ordered on `stream`;
+ *   - return value: 0 = MVAL_OK, negative = error (see enum); mval_last_error() returns a thread-local
+ *     human readable message for the last failing call.  No exceptions cross the ABI;
+ *   - there is NO CPU fallback: every compute entry point requires a CUDA device.
+ *
+ * Layouts (row-major, innermost last)
+ *   heatmaps  float32 [n_frames][V][J][H][W]          (reference strategy.py:1035  heatmaps.view(B,-1,kp,w,h))
+ *   proj      float64 [n_frames][V][3][4]             (reference dataset/dataset.py:195, strategy.py:1030)
+ *   valid     uint8   [n_frames][J]  (0/1; NULL = all valid)   (strategy.py:1031 joint_valid)
+ *   xy        int32 / float32 [n_frames][V][J][2]     (x, y) in image pixels = heat-map pixel * stride
+ */
+#ifndef MVAL_B200_H_
+#define MVAL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVAL_ABI_VERSION 1
+#define MVAL_MAX_VIEWS 32
+
+enum mval_status {
+  MVAL_OK = 0,
+  MVAL_ERR_INVALID_ARGUMENT = -1, /* reference raises AssertionError / TypeError (utils/triangulation.py:267-268) */
+  MVAL_ERR_UNSUPPORTED = -2,      /* shape outside what the kernels cover (e.g. V > 32)                         */
+  MVAL_ERR_CUDA = -3,             /* a CUDA runtime call or kernel launch failed                                */
+  MVAL_ERR_NO_DEVICE = -4,        /* no CUDA device: there is deliberately no CPU fallback                      */
+  MVAL_ERR_OUT_OF_MEMORY = -5
+};
+
+/* ABI version of the loaded library (== MVAL_ABI_VERSION it was built with). */
+int mval_version(void);
+/* Message of the last error on this thread ("" if none). */
+const char* mval_last_error(void);
+/* Number of kernel launches issued through this library by the calling process so far (bench bookkeeping). */
+uint64_t mval_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (1) heat-map decode
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* Replaces utils/evaluation.py:13-30 get_scaled_pred_corrdinates (one call per frame there, V*J argmax
+ * launches + .item() syncs).  Per map: c = first flat index of the maximum (NaN counts as maximum, as in
+ * torch.argmax); x = (c % H) * stride, y = (c / H) * stride -- the reference divides by shape[2] = H for
+ * both (evaluation.py:25-26) and so do we.  Invalid joints give (0, 0) and their maps are not read.
+ * out_xy   int32   device [n_frames][V][J][2]
+ * out_peak float32 device [n_frames][V][J] value at the arg-max (may be NULL). */
+int mval_decode_argmax(const float* heatmaps, int64_t n_frames, int V, int J, int H, int W, int stride,
+                       const uint8_t* valid, int32_t* out_xy, float* out_peak, void* stream);
+
+/* Replaces the soft-argmax branch utils/triangulation.py:191-200 (kornia.spatial_soft_argmax2d(hm,
+ * normalized_coordinates=False) * stride): softmax over the whole H*W map, expectation of the pixel grid.
+ * All joints are decoded (the reference ignores valid_joints on this branch).
+ * out_xy float32 device [n_frames][V][J][2]. */
+int mval_decode_softargmax(const float* heatmaps, int64_t n_frames, int V, int J, int H, int W, float stride,
+                           float* out_xy, void* stream);
+
+/* Replaces strategy.py:1178-1187 (_compute_hp inner loop): per map 1 - max(softmax over each ROW of the map)
+ * (F.softmax without dim on a 2-D tensor = dim 1).  Maps of invalid joints are skipped and get NaN.
+ * out_hp float32 device [n_frames][V][J]. */
+int mval_score_hp(const float* heatmaps, int64_t n_frames, int V, int J, int H, int W, const uint8_t* valid,
+                  float* out_hp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (2) multi-view RANSAC + DLT triangulation and reprojection uncertainty
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* Pair-subset policy for C(V,2) > n_iters (utils/triangulation.py:279-282 uses random.shuffle there).
+ *   pairs != NULL : uint8 device [n_frames][J][n_iters][2], the pairs to visit, in order, for every
+ *                   (frame, joint)  (the per-frame drop-in wrapper draws them with Python's random.shuffle
+ *                   exactly like the reference and passes them here);
+ *   pairs == NULL : counter-based subset keyed by (pair_seed, frame_offset + frame, joint), see
+ *                   oracle/triangulation_oracle.py:pair_subset_indices for the exact arithmetic.
+ * When C(V,2) <= n_iters both are ignored and all pairs are visited in lexicographic order. */
+typedef struct mval_ransac_params {
+  int32_t n_iters;       /* utils/triangulation.py:176 n_iters=64 */
+  double epsilon;        /* :177 reprojection_error_epsilon=5 (compared with HALF the pixel distance, :377-381) */
+  uint64_t pair_seed;
+  int64_t frame_offset;  /* global index of frame 0 of this call (pool sharding / chunking) */
+  const uint8_t* pairs;  /* optional explicit pair table, see above */
+} mval_ransac_params;
+
+/* Replaces utils/triangulation.py:205-232 for a whole batch of frames: per valid (frame, joint)
+ * _triangulate_ransac (:260-316, direct_optimization=False) = DLT on every view pair (:341-368), inlier vote
+ * with err = 0.5*||kp - proj|| < epsilon over all views (:371-384), first strictly-largest inlier set wins,
+ * final DLT on the sorted inlier views, score = mean error over those views.  Then per frame
+ * metric = mean over valid joints (:226) and inlier_count = min over valid joints (:231).
+ *
+ * xy            device [n_frames][V][J][2], int32 (xy_is_float = 0, from mval_decode_argmax) or float32 (= 1)
+ * out_xyz       float64 device [n_frames][J][3]   (zeros for invalid joints, :206)
+ * out_reproj    float64 device [n_frames][J]      (NaN for invalid joints)                      may be NULL
+ * out_inliers   int32   device [n_frames][J]      (0 for invalid joints)                        may be NULL
+ * out_mask      uint32  device [n_frames][J]      bit v set = view v in the final inlier set    may be NULL
+ * out_metric    float64 device [n_frames]         (NaN when a frame has no valid joint; the reference raises)
+ * out_inlier_count int32 device [n_frames]        (0 when a frame has no valid joint)
+ * workspace: none (out_mask doubles as scratch when given; otherwise an internal per-call buffer is
+ * allocated with cudaMallocAsync on `stream`). */
+int mval_triangulate_ransac(const void* xy, int xy_is_float, const double* proj, const uint8_t* valid,
+                            int64_t n_frames, int V, int J, const mval_ransac_params* params, double* out_xyz,
+                            double* out_reproj, int32_t* out_inliers, uint32_t* out_mask, double* out_metric,
+                            int32_t* out_inlier_count, void* stream);
+
+/* Fused pool scoring = mval_decode_argmax + mval_triangulate_ransac on device-resident heat maps
+ * (what strategy.py:1036-1045 does per frame, for a batch of frames).  out_xy may be NULL. */
+int mval_score_pool(const float* heatmaps, const double* proj, const uint8_t* valid, int64_t n_frames, int V,
+                    int J, int H, int W, int stride, const mval_ransac_params* params, int32_t* out_xy,
+                    double* out_xyz, double* out_reproj, int32_t* out_inliers, double* out_metric,
+                    int32_t* out_inlier_count, void* stream);
+
+/* Same as mval_score_pool but every pointer is HOST memory (pinned recommended): the library streams the
+ * pool through the device in chunks of `chunk_frames` frames (0 = choose), double-buffered on two internal
+ * streams so that host->device copies overlap the kernels, and returns after the last result has landed in
+ * host memory.  This is the end-to-end entry a caller with host-side heat maps uses. */
+int mval_score_pool_host(const float* heatmaps, const double* proj, const uint8_t* valid, int64_t n_frames,
+                         int V, int J, int H, int W, int stride, const mval_ransac_params* params,
+                         int64_t chunk_frames, int32_t* out_xy, double* out_xyz, double* out_reproj,
+                         int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (3) ranking and coreset k-center greedy selection
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* Replaces strategy.py:932-949: drop NaN scores, then heapq.nlargest(k, ...) = descending by score, ties by
+ * ascending pool index.  Writes min(k, #non-NaN) entries; *out_count (device int32) receives that number.
+ * scores float64 device [n]; out_idx int64 device [k] (global index = index_offset + local);
+ * out_val float64 device [k]. */
+int mval_topk_desc(const double* scores, int64_t n, int64_t index_offset, int32_t k, int64_t* out_idx,
+                   double* out_val, int32_t* out_count, void* stream);
+
+/* Coreset (utils/coreset.py:49-95) on float32 features in the canonical summation order documented in
+ * oracle/coreset_oracle.py.  features float32 device [n][d] row-major.
+ *   mval_kcenter_norms       : row_norms[i] = <x_i, x_i>
+ *   mval_kcenter_update      : min_dist[i] = min(min_dist[i], dist(x_i, centre)) for the local rows, and the
+ *                              local arg-max (value, lowest index) of the updated min_dist ->
+ *                              out_best_val float32 device[1], out_best_idx int64 device[1] (index_offset added)
+ *                              (coreset.py:64-69 followed by :90).  `centre` float32 device [d].
+ * The caller seeds min_dist with +inf and calls update once per labeled centre (coreset.py:83-84), then
+ * budget times with the row the (global) arg-max selected. */
+int mval_kcenter_norms(const float* features, int64_t n, int d, float* row_norms, void* stream);
+int mval_kcenter_update(const float* features, const float* row_norms, int64_t n, int d, const float* centre,
+                        float* min_dist, int64_t index_offset, float* out_best_val, int64_t* out_best_idx,
+                        void* stream);
+/* Single-device greedy loop (coreset.py:86-93) run entirely on the device: `budget` dependent steps without
+ * host round trips.  labeled rows are [n_unlabeled, n); out_selected int64 device [budget]. */
+int mval_kcenter_greedy(const float* features, int64_t n, int64_t n_unlabeled, int d, int32_t budget,
+                        float* min_dist, int64_t* out_selected, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * synthetic pools (benchmark / test support)
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* Renders float32 [n_maps][H][W] heat maps: Gaussian bump (sigma) at centres[m] = (x, y) heat-map pixels plus
+ * uniform noise of the given amplitude from a counter-based hash of (seed, element index). */
+int mval_synth_heatmaps(const float* centres, int64_t n_maps, int H, int W, float sigma, float noise,
+                        uint64_t seed, float* out_heatmaps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVAL_B200_H_ */

@@ -1,0 +1,78 @@
+"""ctypes binding of libmval_b200.so (include/mval_b200.h).  No CPU fallback: a missing library or device raises."""
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libmval_b200.so")
+
+MVAL_OK = 0
+MVAL_ERR_INVALID_ARGUMENT = -1
+MVAL_ERR_UNSUPPORTED = -2
+MVAL_ERR_CUDA = -3
+MVAL_ERR_NO_DEVICE = -4
+MVAL_ERR_OUT_OF_MEMORY = -5
+MAX_VIEWS = 32
+
+
+class MvalError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("mval_b200 error %d: %s" % (status, message))
+        self.status = status
+
+
+class RansacParams(C.Structure):
+    _fields_ = [("n_iters", C.c_int32), ("epsilon", C.c_double), ("pair_seed", C.c_uint64),
+                ("frame_offset", C.c_int64), ("pairs", C.c_void_p)]
+
+
+_p, _i, _i64, _f, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
+
+PROTOTYPES = {
+    "mval_version": (C.c_int, []),
+    "mval_last_error": (C.c_char_p, []),
+    "mval_launch_count": (C.c_uint64, []),
+    "mval_decode_argmax": (C.c_int, [_p, _i64, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "mval_decode_softargmax": (C.c_int, [_p, _i64, _i, _i, _i, _i, _f, _p, _p]),
+    "mval_score_hp": (C.c_int, [_p, _i64, _i, _i, _i, _i, _p, _p, _p]),
+    "mval_triangulate_ransac": (C.c_int, [_p, _i, _p, _p, _i64, _i, _i, C.POINTER(RansacParams), _p, _p, _p, _p, _p, _p, _p]),
+    "mval_score_pool": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _p, _p, _p, _p, _p, _p, _p]),
+    "mval_score_pool_host": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _i64, _p, _p, _p, _p, _p, _p]),
+    "mval_topk_desc": (C.c_int, [_p, _i64, _i64, C.c_int32, _p, _p, _p, _p]),
+    "mval_kcenter_norms": (C.c_int, [_p, _i64, _i, _p, _p]),
+    "mval_kcenter_update": (C.c_int, [_p, _p, _i64, _i, _p, _p, _i64, _p, _p, _p]),
+    "mval_kcenter_greedy": (C.c_int, [_p, _i64, _i64, _i, C.c_int32, _p, _p, _p]),
+    "mval_synth_heatmaps": (C.c_int, [_p, _i64, _i, _i, _f, _f, _u64, _p, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads (building first if it is missing and nvcc exists) and returns the ctypes library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH) or os.environ.get("MVAL_REBUILD") == "1":
+        from . import build as _build
+
+        _build.build()
+    if not os.path.isfile(LIB_PATH):
+        raise MvalError(MVAL_ERR_NO_DEVICE, "libmval_b200.so is missing and could not be built; there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mval_version() != 1:
+        raise MvalError(MVAL_ERR_UNSUPPORTED, "ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != MVAL_OK:
+        raise MvalError(status, load().mval_last_error().decode("utf-8", "replace"))
+
+
+def launch_count():
+    return int(load().mval_launch_count())

@@ -1,0 +1,252 @@
+"""Tensor-level wrappers over the C ABI (include/mval_b200.h).
+
+torch is used for device memory and streams only: every function takes CUDA tensors, passes raw
+pointers + the current stream to libmval_b200.so and returns CUDA tensors.  There is no CPU
+implementation here on purpose -- a CPU tensor raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RansacParams, check
+
+DEFAULT_N_ITERS = 64  # utils/triangulation.py:176
+DEFAULT_EPSILON = 5.0  # utils/triangulation.py:177
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _cuda(t, dtype, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s is on %s: mval_b200 has no CPU fallback, move it to the GPU" % (name, t.device))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _valid_u8(valid, n_frames, J, device):
+    """valid: None | [J] | [N, J] of anything truthy -> uint8 CUDA [N, J] (or None)."""
+    if valid is None:
+        return None
+    v = torch.as_tensor(valid)
+    v = (v != 0).to(torch.uint8)
+    if v.dim() == 1:
+        v = v.unsqueeze(0).expand(n_frames, J)
+    if tuple(v.shape) != (n_frames, J):
+        raise ValueError("valid has shape %s, expected [%d, %d]" % (tuple(v.shape), n_frames, J))
+    return v.to(device).contiguous()
+
+
+def ransac_params(n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0, frame_offset=0, pairs=None):
+    p = RansacParams()
+    p.n_iters = int(n_iters)
+    p.epsilon = float(epsilon)
+    p.pair_seed = int(pair_seed) & ((1 << 64) - 1)
+    p.frame_offset = int(frame_offset)
+    p.pairs = None if pairs is None else pairs.data_ptr()
+    return p
+
+
+def decode_argmax(heatmaps, stride, valid=None, return_peak=False):
+    """heatmaps [N, V, J, H, W] float32 CUDA -> int32 [N, V, J, 2] (x, y)*stride  (utils/evaluation.py:13-30)."""
+    hm = _cuda(heatmaps, torch.float32, "heatmaps")
+    N, V, J, H, W = hm.shape
+    v = _valid_u8(valid, N, J, hm.device)
+    out = torch.empty((N, V, J, 2), dtype=torch.int32, device=hm.device)
+    peak = torch.empty((N, V, J), dtype=torch.float32, device=hm.device) if return_peak else None
+    with torch.cuda.device(hm.device):
+        check(_lib.load().mval_decode_argmax(_ptr(hm), N, V, J, H, W, int(stride), _ptr(v), _ptr(out), _ptr(peak), _stream()))
+    return (out, peak) if return_peak else out
+
+
+def decode_softargmax(heatmaps, stride):
+    """heatmaps [N, V, J, H, W] -> float32 [N, V, J, 2]  (utils/triangulation.py:191-197)."""
+    hm = _cuda(heatmaps, torch.float32, "heatmaps")
+    N, V, J, H, W = hm.shape
+    out = torch.empty((N, V, J, 2), dtype=torch.float32, device=hm.device)
+    with torch.cuda.device(hm.device):
+        check(_lib.load().mval_decode_softargmax(_ptr(hm), N, V, J, H, W, float(stride), _ptr(out), _stream()))
+    return out
+
+
+def score_hp(heatmaps, valid=None):
+    """heatmaps [N, V, J, H, W] -> float32 [N, V, J]: 1 - max(row-wise softmax)  (strategy.py:1185-1186)."""
+    hm = _cuda(heatmaps, torch.float32, "heatmaps")
+    N, V, J, H, W = hm.shape
+    v = _valid_u8(valid, N, J, hm.device)
+    out = torch.empty((N, V, J), dtype=torch.float32, device=hm.device)
+    with torch.cuda.device(hm.device):
+        check(_lib.load().mval_score_hp(_ptr(hm), N, V, J, H, W, _ptr(v), _ptr(out), _stream()))
+    return out
+
+
+def _alloc_tri_outputs(N, J, device):
+    return {
+        "keypoints_3d": torch.empty((N, J, 3), dtype=torch.float64, device=device),
+        "reproj_mean": torch.empty((N, J), dtype=torch.float64, device=device),
+        "inliers": torch.empty((N, J), dtype=torch.int32, device=device),
+        "metric": torch.empty((N,), dtype=torch.float64, device=device),
+        "inlier_count": torch.empty((N,), dtype=torch.int32, device=device),
+    }
+
+
+def triangulate_ransac(keypoints_2d, proj, valid=None, n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0,
+                       frame_offset=0, pairs=None):
+    """keypoints_2d [N, V, J, 2] int32/float32 CUDA, proj [N, V, 3, 4] -> dict of CUDA tensors
+    (utils/triangulation.py:205-232 for N frames at once)."""
+    kp = keypoints_2d
+    if not kp.is_cuda:
+        raise RuntimeError("keypoints_2d is on %s: mval_b200 has no CPU fallback" % kp.device)
+    is_float = kp.dtype.is_floating_point
+    kp = kp.to(torch.float32 if is_float else torch.int32).contiguous()
+    N, V, J, _ = kp.shape
+    P = _cuda(proj.to(kp.device) if not proj.is_cuda else proj, torch.float64, "proj")
+    if tuple(P.shape) != (N, V, 3, 4):
+        raise ValueError("proj has shape %s, expected [%d, %d, 3, 4]" % (tuple(P.shape), N, V))
+    v = _valid_u8(valid, N, J, kp.device)
+    if pairs is not None:
+        pairs = _cuda(pairs, torch.uint8, "pairs")
+        if tuple(pairs.shape) != (N, J, int(n_iters), 2):
+            raise ValueError("pairs must be uint8 [N, J, n_iters, 2]")
+    out = _alloc_tri_outputs(N, J, kp.device)
+    out["inlier_mask"] = torch.empty((N, J), dtype=torch.int32, device=kp.device)
+    prm = ransac_params(n_iters, epsilon, pair_seed, frame_offset, pairs)
+    with torch.cuda.device(kp.device):
+        check(_lib.load().mval_triangulate_ransac(_ptr(kp), int(is_float), _ptr(P), _ptr(v), N, V, J, C.byref(prm),
+                                                  _ptr(out["keypoints_3d"]), _ptr(out["reproj_mean"]),
+                                                  _ptr(out["inliers"]), _ptr(out["inlier_mask"]), _ptr(out["metric"]),
+                                                  _ptr(out["inlier_count"]), _stream()))
+    out["keypoints_2d"] = kp
+    return out
+
+
+def score_pool(heatmaps, proj, stride, valid=None, n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0,
+               frame_offset=0, return_keypoints_2d=True):
+    """Device-resident pool scoring: decode (arg-max) + RANSAC triangulation + per-frame uncertainty."""
+    hm = _cuda(heatmaps, torch.float32, "heatmaps")
+    N, V, J, H, W = hm.shape
+    P = _cuda(proj.to(hm.device) if not proj.is_cuda else proj, torch.float64, "proj")
+    if tuple(P.shape) != (N, V, 3, 4):
+        raise ValueError("proj has shape %s, expected [%d, %d, 3, 4]" % (tuple(P.shape), N, V))
+    v = _valid_u8(valid, N, J, hm.device)
+    out = _alloc_tri_outputs(N, J, hm.device)
+    xy = torch.empty((N, V, J, 2), dtype=torch.int32, device=hm.device) if return_keypoints_2d else None
+    prm = ransac_params(n_iters, epsilon, pair_seed, frame_offset)
+    with torch.cuda.device(hm.device):
+        check(_lib.load().mval_score_pool(_ptr(hm), _ptr(P), _ptr(v), N, V, J, H, W, int(stride), C.byref(prm), _ptr(xy),
+                                          _ptr(out["keypoints_3d"]), _ptr(out["reproj_mean"]), _ptr(out["inliers"]),
+                                          _ptr(out["metric"]), _ptr(out["inlier_count"]), _stream()))
+    if xy is not None:
+        out["keypoints_2d"] = xy
+    return out
+
+
+def score_pool_host(heatmaps, proj, stride, valid=None, n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0,
+                    frame_offset=0, chunk_frames=0, out=None, device=None):
+    """End-to-end entry for HOST heat maps (CPU tensors, pinned for overlap): streams the pool through the GPU in
+    chunks (H2D, kernels, D2H all inside the call) and returns CPU tensors."""
+    if heatmaps.is_cuda:
+        raise RuntimeError("score_pool_host takes host tensors; use score_pool for device-resident heat maps")
+    hm = heatmaps.to(torch.float32).contiguous()
+    N, V, J, H, W = hm.shape
+    P = proj.to(torch.float64).contiguous()
+    v = None
+    if valid is not None:
+        v = (torch.as_tensor(valid) != 0).to(torch.uint8)
+        if v.dim() == 1:
+            v = v.unsqueeze(0).expand(N, J)
+        v = v.contiguous()
+    if out is None:
+        pin = hm.is_pinned()
+        out = {
+            "keypoints_2d": torch.empty((N, V, J, 2), dtype=torch.int32, pin_memory=pin),
+            "keypoints_3d": torch.empty((N, J, 3), dtype=torch.float64, pin_memory=pin),
+            "reproj_mean": torch.empty((N, J), dtype=torch.float64, pin_memory=pin),
+            "inliers": torch.empty((N, J), dtype=torch.int32, pin_memory=pin),
+            "metric": torch.empty((N,), dtype=torch.float64, pin_memory=pin),
+            "inlier_count": torch.empty((N,), dtype=torch.int32, pin_memory=pin),
+        }
+    prm = ransac_params(n_iters, epsilon, pair_seed, frame_offset)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        check(_lib.load().mval_score_pool_host(_ptr(hm), _ptr(P), _ptr(v), N, V, J, H, W, int(stride), C.byref(prm),
+                                               int(chunk_frames), _ptr(out.get("keypoints_2d")), _ptr(out["keypoints_3d"]),
+                                               _ptr(out.get("reproj_mean")), _ptr(out.get("inliers")), _ptr(out["metric"]),
+                                               _ptr(out["inlier_count"])))
+    return out
+
+
+def topk_desc(scores, k, index_offset=0):
+    """scores float64 CUDA [n] -> (idx int64 [m], val float64 [m]), m = min(k, #non-NaN): descending score, ties by
+    ascending index, NaN dropped (strategy.py:932-949)."""
+    s = _cuda(scores, torch.float64, "scores").reshape(-1)
+    n = s.numel()
+    k = int(min(k, n))
+    idx = torch.empty((max(k, 1),), dtype=torch.int64, device=s.device)
+    val = torch.empty((max(k, 1),), dtype=torch.float64, device=s.device)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=s.device)
+    with torch.cuda.device(s.device):
+        check(_lib.load().mval_topk_desc(_ptr(s), n, int(index_offset), k, _ptr(idx), _ptr(val), _ptr(cnt), _stream()))
+    m = int(cnt.item())
+    return idx[:m], val[:m]
+
+
+def kcenter_norms(features):
+    f = _cuda(features, torch.float32, "features")
+    n, d = f.shape
+    out = torch.empty((n,), dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        check(_lib.load().mval_kcenter_norms(_ptr(f), n, d, _ptr(out), _stream()))
+    return out
+
+
+def kcenter_update(features, norms, centre, min_dist, index_offset=0, out_best=None):
+    """In-place min_dist = min(min_dist, dist(features, centre)); returns (best_val [1] f32, best_idx [1] i64) CUDA."""
+    f = _cuda(features, torch.float32, "features")
+    n, d = f.shape
+    c = _cuda(centre, torch.float32, "centre").reshape(-1)
+    assert c.numel() == d and min_dist.dtype == torch.float32 and min_dist.is_contiguous() and min_dist.numel() == n
+    if out_best is None:
+        out_best = (torch.empty((1,), dtype=torch.float32, device=f.device),
+                    torch.empty((1,), dtype=torch.int64, device=f.device))
+    with torch.cuda.device(f.device):
+        check(_lib.load().mval_kcenter_update(_ptr(f), _ptr(norms), n, d, _ptr(c), _ptr(min_dist), int(index_offset),
+                                              _ptr(out_best[0]), _ptr(out_best[1]), _stream()))
+    return out_best
+
+
+def kcenter_greedy(features, n_unlabeled, budget):
+    """features float32 CUDA [n, d] (rows >= n_unlabeled are the labeled centres) -> (selected int64 [budget],
+    min_dist float32 [n]); the whole greedy loop of utils/coreset.py:83-93 on the device."""
+    f = _cuda(features, torch.float32, "features")
+    n, d = f.shape
+    min_dist = torch.empty((n,), dtype=torch.float32, device=f.device)
+    sel = torch.empty((max(int(budget), 1),), dtype=torch.int64, device=f.device)
+    with torch.cuda.device(f.device):
+        check(_lib.load().mval_kcenter_greedy(_ptr(f), n, int(n_unlabeled), d, int(budget), _ptr(min_dist), _ptr(sel), _stream()))
+    return sel[: int(budget)], min_dist
+
+
+def synth_heatmaps(centres, H=64, W=64, sigma=1.0, noise=0.05, seed=0, out=None):
+    """centres float32 CUDA [..., 2] heat-map pixel (x, y) -> float32 [..., H, W]."""
+    c = _cuda(centres, torch.float32, "centres")
+    n_maps = c.numel() // 2
+    if out is None:
+        out = torch.empty(tuple(c.shape[:-1]) + (H, W), dtype=torch.float32, device=c.device)
+    with torch.cuda.device(c.device):
+        check(_lib.load().mval_synth_heatmaps(_ptr(c), n_maps, H, W, float(sigma), float(noise), int(seed), _ptr(out), _stream()))
+    return out
+
+
+def to_numpy(d):
+    return {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}

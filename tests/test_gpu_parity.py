@@ -1,0 +1,308 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed golden
+fixtures produced by the unmodified reference.  Run on the B200 box with  pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): arg-max key-points, inlier sets/counts, ranking order and coreset index
+sets bit-exact; 3-D joints within 1e-3 relative / 1e-2 mm; reprojection errors within 1e-4 px.
+"""
+import itertools
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from multi_view_active_learning_b200 import synthetic as S
+from oracle import coreset_oracle as CO
+from oracle import scores_oracle as SO
+from oracle import triangulation_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+POOLS = ["pool_v5_j19", "pool_v8_j19", "pool_v20_j42", "pool_v31_j19", "pool_v2_j3"]
+XYZ_ATOL_MM, XYZ_RTOL, REPROJ_ATOL_PX = 1e-2, 1e-3, 1e-4
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from multi_view_active_learning_b200 import ops as _ops
+
+    return _ops
+
+
+def _cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _check_tri(out, ref, valid):
+    """out: dict of numpy from the CUDA path; ref: oracle / golden dict."""
+    assert np.array_equal(out["inlier_count"], ref["inlier_count"])
+    if "inliers" in ref:
+        assert np.array_equal(out["inliers"], ref["inliers"])
+    if "inlier_mask" in ref and "inlier_mask" in out:
+        assert np.array_equal(out["inlier_mask"].astype(np.uint32), ref["inlier_mask"])
+    np.testing.assert_allclose(out["keypoints_3d"], ref["keypoints_3d"], rtol=XYZ_RTOL, atol=XYZ_ATOL_MM)
+    # in practice the float64 Jacobi solve agrees far better than the contract; keep an eye on it
+    assert np.abs(out["keypoints_3d"] - ref["keypoints_3d"]).max() < 1e-5
+    np.testing.assert_allclose(out["metric"], ref["metric"], rtol=0, atol=REPROJ_ATOL_PX)
+    assert (out["keypoints_3d"][~valid] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------ decode
+def test_decode_edge_cases_golden(ops, golden):
+    g = golden("decode_edge_cases")
+    hm = _cuda(g["heatmaps"])[None]
+    xy = ops.decode_argmax(hm, int(g["stride"]), torch.from_numpy(g["valid"]))
+    assert np.array_equal(xy[0].cpu().numpy(), g["scaled"])
+    xy, peak = ops.decode_argmax(hm, int(g["stride"]), None, return_peak=True)
+    assert np.array_equal(xy[0].cpu().numpy(), g["scaled_all_valid"])
+    flat = g["heatmaps"].reshape(3, 5, -1)
+    exp_peak = np.take_along_axis(flat, np.argmax(flat, -1)[..., None], -1)[..., 0]
+    np.testing.assert_array_equal(peak[0].cpu().numpy(), exp_peak)
+
+
+def test_decode_reference_api(ops, golden):
+    from multi_view_active_learning_b200.utils import evaluation
+
+    g = golden("decode_edge_cases")
+    hm = torch.from_numpy(g["heatmaps"])
+    out = evaluation.get_scaled_pred_corrdinates(hm, int(g["stride"]), 5, torch.from_numpy(g["valid"]))
+    assert out.dtype == np.int64 and np.array_equal(out, g["scaled"])
+    pc = evaluation.get_pred_coordinates(hm.cuda(), torch.from_numpy(g["boxes"]), 5)
+    pc = np.array([[[float(c) for c in k] for k in b] for b in pc])
+    np.testing.assert_allclose(pc, g["pred_coordinates"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(3, 2, 5, 64, 64), (2, 3, 4, 48, 48), (1, 2, 3, 7, 9), (2, 2, 2, 32, 64)])
+def test_decode_argmax_random_vs_oracle(ops, shape):
+    rng = np.random.default_rng(sum(shape))
+    hm = rng.normal(size=shape).astype(np.float32)
+    hm[0, 0, 0].flat[[3, 77 % hm[0, 0, 0].size]] = 11.0  # a tie
+    valid = rng.uniform(size=(shape[0], shape[2])) < 0.7
+    got = ops.decode_argmax(_cuda(hm), 4, torch.from_numpy(valid)).cpu().numpy()
+    assert np.array_equal(got, O.decode_argmax(hm, 4, valid))
+
+
+def test_softargmax_vs_oracle(ops):
+    pool = S.make_pool(3, 4, 6, seed=9)
+    hm = S.render_heatmaps(pool["centres"], noise=0.05, seed=1) * np.float32(8.0)
+    got = ops.decode_softargmax(_cuda(hm), 4).cpu().numpy()
+    exp = O.decode_softargmax(hm, 4)
+    # float32 expectation of a 0..252 px coordinate: a few 1e-5 px of rounding is inherent (kornia's own float32
+    # output has the same spread); 2e-4 px bounds it
+    np.testing.assert_allclose(got, exp, rtol=0, atol=2e-4)
+
+
+def test_hp_scores(ops, golden):
+    g = golden("hp_scores")
+    valid = g["valid"] != 0
+    got = ops.score_hp(_cuda(g["heatmaps"])[None], torch.from_numpy(valid)).cpu().numpy()[0]
+    assert np.isnan(got[:, ~valid]).all()
+    np.testing.assert_allclose(got[:, valid], g["hp_per_map"][:, valid], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(got[:, valid], SO.hp_scores(g["heatmaps"])[:, valid], rtol=0, atol=2e-6)
+    # non-64-wide maps take the generic kernel
+    hm = np.random.default_rng(0).normal(size=(1, 2, 3, 20, 24)).astype(np.float32) * 3
+    np.testing.assert_allclose(ops.score_hp(_cuda(hm)).cpu().numpy(), SO.hp_scores(hm), rtol=0, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------ triangulation
+def test_reference_unit_test_known_answer(ops, golden):
+    from multi_view_active_learning_b200.utils.triangulation import triangulation
+
+    g = golden("ref_unit_triangulation")
+    hm = torch.zeros(8, 19, 64, 64)
+    for r, c, v in g["bump_rc"]:
+        hm[:, :, int(r), int(c)] = float(v)
+    res = triangulation(hm, torch.from_numpy(g["P"]), int(g["stride"]), torch.from_numpy(g["valid"]))
+    assert list(res["keypoints_3d"].shape) == [19, 3] and list(res["keypoints_2d"].shape) == [8, 19, 2]
+    assert res["keypoints_2d"].dtype == np.int64 and (res["keypoints_2d"] == 88).all()
+    assert res["inlier_count"] == 3 and isinstance(res["inlier_count"], np.int64)
+    np.testing.assert_allclose(res["keypoints_3d"], g["keypoints_3d"], rtol=XYZ_RTOL, atol=XYZ_ATOL_MM)
+    np.testing.assert_allclose(res["keypoints_3d"][0], [-37.2230772535, -125.6428366493, -23.8942096679], atol=1e-6)
+    np.testing.assert_allclose(res["metric"], 3.1619149383944163, atol=REPROJ_ATOL_PX)
+
+
+@pytest.mark.parametrize("name", POOLS)
+def test_pool_matches_reference_golden(ops, golden, name):
+    g = golden(name)
+    stride, valid = int(g["stride"]), g["valid"]
+    hm = S.onehot_heatmaps(g["keypoints_2d_unmasked"], stride)
+    out = ops.to_numpy(ops.score_pool(_cuda(hm), _cuda(g["P"]), stride, torch.from_numpy(valid),
+                                      pair_seed=int(g["pair_seed"])))
+    assert np.array_equal(out["keypoints_2d"], g["keypoints_2d"])
+    _check_tri(out, g, valid)
+
+
+@pytest.mark.parametrize("N,V,J,seed,vp", [(48, 8, 19, 1, 1.0), (32, 5, 19, 2, 0.8), (6, 20, 42, 3, 0.8),
+                                           (6, 31, 19, 4, 1.0), (16, 12, 5, 5, 0.9), (16, 3, 4, 6, 1.0)])
+def test_noisy_pool_vs_oracle(ops, N, V, J, seed, vp):
+    pool = S.make_pool(N, V, J, seed=seed, valid_prob=vp, p_outlier=0.15)
+    hm = S.render_heatmaps(pool["centres"], noise=0.05, seed=seed + 100)
+    ref = O.triangulate_pool(hm, pool["P"], 4, pool["valid"], pair_seed=77, frame_offset=1000)
+    out = ops.to_numpy(ops.score_pool(_cuda(hm), _cuda(pool["P"]), 4, torch.from_numpy(pool["valid"]), pair_seed=77,
+                                      frame_offset=1000))
+    assert np.array_equal(out["keypoints_2d"], ref["keypoints_2d"])
+    _check_tri(out, ref, pool["valid"])
+    np.testing.assert_allclose(out["reproj_mean"][pool["valid"]], ref["reproj_mean"][pool["valid"]], atol=REPROJ_ATOL_PX)
+    assert np.isnan(out["reproj_mean"][~pool["valid"]]).all()
+    # ranking order of the uncertainty metric is identical (strategy.py:945-949)
+    assert np.array_equal(np.argsort(-out["metric"], kind="stable"), np.argsort(-ref["metric"], kind="stable"))
+
+
+def test_triangulate_from_float_keypoints_and_explicit_pairs(ops):
+    N, V, J = 5, 14, 6
+    pool = S.make_pool(N, V, J, seed=21, p_outlier=0.1)
+    kp = (pool["centres"] * 4).astype(np.float32)  # sub-pixel float key-points (soft-arg-max path)
+    rng = random.Random(5)
+    allp = list(itertools.combinations(range(V), 2))
+    pairs = np.zeros((N, J, 64, 2), dtype=np.uint8)
+    for n in range(N):
+        for j in range(J):
+            p = list(allp)
+            rng.shuffle(p)
+            pairs[n, j] = p[:64]
+    kp3, rm, inl, mask = O.ransac_pool(pool["P"], kp, np.ones((N, J), bool), pairs.astype(np.int64))
+    out = ops.to_numpy(ops.triangulate_ransac(_cuda(kp), _cuda(pool["P"]), None, pairs=_cuda(pairs)))
+    assert np.array_equal(out["inliers"], inl) and np.array_equal(out["inlier_mask"].astype(np.uint32), mask)
+    np.testing.assert_allclose(out["keypoints_3d"], kp3, rtol=XYZ_RTOL, atol=XYZ_ATOL_MM)
+    np.testing.assert_allclose(out["reproj_mean"], rm, atol=REPROJ_ATOL_PX)
+
+
+def test_per_frame_api_consumes_python_random_like_reference(ops):
+    """V >= 12: the drop-in triangulation() draws its pair subsets with random.shuffle exactly like the reference
+    (utils/triangulation.py:279-282), so seeding ``random`` reproduces the reference's choice."""
+    from multi_view_active_learning_b200.utils.triangulation import triangulation
+
+    V, J = 13, 4
+    pool = S.make_pool(1, V, J, seed=33, p_outlier=0.2)
+    kp = np.round(pool["centres"]).astype(np.int64) * 4
+    hm = S.onehot_heatmaps(kp)
+    valid = np.array([1, 0, 1, 1], dtype=bool)
+    random.seed(1234)
+    res = triangulation(torch.from_numpy(hm[0]), torch.from_numpy(pool["P"][0]), 4, torch.from_numpy(valid))
+    state_after = random.getstate()
+    random.seed(1234)
+    pairs = np.zeros((1, J, 64, 2), dtype=np.int64)
+    for j in range(J):
+        if valid[j]:
+            p = list(itertools.combinations(set(range(V)), 2))
+            random.shuffle(p)
+            pairs[0, j] = p[:64]
+    assert random.getstate() == state_after
+    kp_masked = np.where(valid[None, :, None], kp[0], 0)
+    kp3, rm, inl, _ = O.ransac_pool(pool["P"], kp_masked[None], valid[None], pairs)
+    assert np.array_equal(res["keypoints_2d"], kp_masked)
+    np.testing.assert_allclose(res["keypoints_3d"], kp3[0], rtol=XYZ_RTOL, atol=XYZ_ATOL_MM)
+    assert res["inlier_count"] == inl[0][valid].min()
+    np.testing.assert_allclose(res["metric"], rm[0][valid].mean(), atol=REPROJ_ATOL_PX)
+
+
+def test_error_behaviour(ops):
+    from multi_view_active_learning_b200._lib import MvalError
+    from multi_view_active_learning_b200.utils.triangulation import triangulation
+
+    hm = torch.zeros(1, 3, 64, 64)
+    with pytest.raises(AssertionError):  # reference :268 assert len(points) >= 2
+        triangulation(hm, torch.zeros(1, 3, 4), 4, torch.ones(3).bool())
+    with pytest.raises(ValueError):  # reference :231 np.min([])
+        triangulation(torch.zeros(2, 3, 64, 64), torch.zeros(2, 3, 4), 4, torch.zeros(3).bool())
+    with pytest.raises(MvalError):
+        ops.triangulate_ransac(torch.zeros(1, 40, 2, 2, dtype=torch.int32).cuda(), torch.zeros(1, 40, 3, 4).cuda())
+    # empty pool is fine
+    out = ops.score_pool(torch.zeros(0, 4, 3, 64, 64).cuda(), torch.zeros(0, 4, 3, 4).double().cuda(), 4)
+    assert out["metric"].numel() == 0
+
+
+def test_host_pipeline_matches_device_path(ops):
+    N, V, J = 37, 8, 19
+    pool = S.make_pool(N, V, J, seed=8, valid_prob=0.9)
+    hm = torch.from_numpy(S.render_heatmaps(pool["centres"], noise=0.05, seed=3)).pin_memory()
+    P, valid = torch.from_numpy(pool["P"]), torch.from_numpy(pool["valid"])
+    dev = ops.to_numpy(ops.score_pool(hm.cuda(), P.cuda(), 4, valid, pair_seed=5, frame_offset=10))
+    host = ops.to_numpy(ops.score_pool_host(hm, P, 4, valid, pair_seed=5, frame_offset=10, chunk_frames=8))
+    for k in ("keypoints_2d", "keypoints_3d", "inliers", "inlier_count"):
+        assert np.array_equal(dev[k], host[k]), k
+    np.testing.assert_array_equal(dev["metric"], host["metric"])
+
+
+def test_full_size_properties(ops):
+    """C2-sized chunk (8 views x 19 joints): size-independent properties on 2048 frames -- invariance to the
+    chunking / frame offset, duplicated frames score identically, scores are finite and inlier counts in [2, V]."""
+    N, V, J = 2048, 8, 19
+    pool = S.make_pool(N, V, J, seed=77)
+    hm = ops.synth_heatmaps(_cuda(pool["centres"]), noise=0.05, seed=4)
+    P = _cuda(pool["P"])
+    full = ops.score_pool(hm, P, 4)
+    a = ops.score_pool(hm[:1000], P[:1000], 4)
+    b = ops.score_pool(hm[1000:], P[1000:], 4, frame_offset=1000)
+    assert torch.equal(torch.cat([a["metric"], b["metric"]]), full["metric"])
+    assert torch.equal(torch.cat([a["keypoints_3d"], b["keypoints_3d"]]), full["keypoints_3d"])
+    m = full["metric"].cpu().numpy()
+    ic = full["inlier_count"].cpu().numpy()
+    assert np.isfinite(m).all() and (m >= 0).all() and (ic >= 2).all() and (ic <= V).all()
+    dup = ops.score_pool(torch.cat([hm[:8], hm[:8]]), torch.cat([P[:8], P[:8]]), 4)
+    assert torch.equal(dup["metric"][:8], dup["metric"][8:])
+    # and a sample of it against the oracle
+    sample = slice(500, 532)
+    ref = O.triangulate_pool(hm[sample].cpu().numpy(), pool["P"][sample], 4, pool["valid"][sample])
+    out = ops.to_numpy({k: v[sample] for k, v in full.items()})
+    assert np.array_equal(out["keypoints_2d"], ref["keypoints_2d"])
+    _check_tri(out, ref, pool["valid"][sample])
+
+
+# ------------------------------------------------------------------------------------------------ ranking
+def test_topk_matches_nlargest(ops):
+    rng = np.random.default_rng(0)
+    n = 5000
+    s = rng.normal(size=n).round(2)  # many exact ties
+    s[rng.integers(0, n, 50)] = np.nan
+    s[10], s[20], s[30] = np.inf, -np.inf, -0.0
+    d = {"g%d" % i: float(s[i]) for i in range(n)}
+    for k in (1, 7, 100, 4000, n + 5):
+        exp = SO.rank_nlargest(d, k)
+        idx, val = ops.topk_desc(_cuda(s), k, index_offset=0)
+        assert ["g%d" % i for i in idx.cpu().tolist()] == exp
+        assert np.array_equal(val.cpu().numpy(), np.array([d[g] for g in exp]))
+    idx, _ = ops.topk_desc(_cuda(s), 5, index_offset=1000)
+    assert idx.cpu().tolist() == [1000 + int(g[1:]) for g in SO.rank_nlargest(d, 5)]
+
+
+# ------------------------------------------------------------------------------------------------ coreset
+@pytest.mark.parametrize("n,L,d,budget", [(700, 30, 57, 40), (300, 10, 126, 25), (513, 7, 2048, 30), (200, 5, 130, 20),
+                                          (100, 3, 3, 10)])
+def test_kcenter_bit_exact_vs_f32_oracle(ops, n, L, d, budget):
+    rng = np.random.default_rng(n + d)
+    F = (rng.normal(size=(n + L, d)) * 50).astype(np.float32)
+    F[5] = F[3]  # duplicate rows: exact ties in min-distance
+    exp_sel, exp_min = CO.kcenter_greedy_f32(F, n, budget)
+    sel, min_d = ops.kcenter_greedy(_cuda(F), n, budget)
+    assert sel.cpu().tolist() == exp_sel
+    assert np.array_equal(min_d.cpu().numpy(), exp_min)  # bit-exact float32 distances, not only indices
+    assert np.array_equal(ops.kcenter_norms(_cuda(F)).cpu().numpy(), CO.canonical_dot_f32(F, F))
+
+
+def test_coreset_class_matches_reference_golden(ops, golden):
+    from multi_view_active_learning_b200.utils.coreset import CoreSet
+
+    g = golden("coreset_random")
+    keys = [str(k) for k in g["sal_keys"]]
+    sal = {k: p.tolist() for k, p in zip(keys, g["sal_poses"])}
+    al = {i: p for i, p in enumerate(g["al_poses"])}
+    cs = CoreSet(sal, al, int(g["root"]))
+    assert np.array_equal(cs.features, g["features"])
+    picked = cs.select_batch(int(g["budget"]))
+    assert picked == [keys[i] for i in g["picked"]]
+    np.testing.assert_allclose(cs.min_distances, g["min_distances"], rtol=1e-4, atol=1e-2)
+    assert cs.n_obs == 425 and cs.al_indices == list(range(400, 425))
+    # incremental API (update_distances + repeated select_batch) continues the same greedy sequence
+    cs2 = CoreSet(sal, al, int(g["root"]))
+    first = cs2.select_batch(10)
+    cs2.update_distances([keys.index(k) for k in first])
+    assert first == picked[:10]
+
+    g2 = golden("ref_unit_coreset")
+    pose = [[0, 1, 2] for _ in range(19)]
+    sal2 = {"k%d" % i: pose for i in range(20)}
+    cs3 = CoreSet(sal2, {i: pose for i in range(5)}, 2)
+    assert cs3.select_batch(5) == ["k%d" % i for i in g2["picked"]] == ["k0"] * 5
