@@ -1,0 +1,255 @@
+"""Scoring-and-selection half of the reference's ``ActiveLearningStrategy`` (strategy.py:54-135, 915-1215),
+re-built around batched sm_100a kernels.
+
+``ScoringSelectionMixin`` carries the hot-path methods with the reference's names and signatures so that it can be
+mixed over the reference class and ``workflow.py`` runs unchanged; ``ActiveLearningStrategy`` is the
+stand-alone form used by the tests.  Training, evaluation, checkpoints and TensorBoard (strategy.py:137-914) stay
+with the reference -- they are outside SURVEY.md section 8.
+
+What changes relative to the reference's ``_compute_sal_dict`` (strategy.py:1004-1147):
+  * one batched kernel pass per data-loader batch instead of a Python loop over frames, joints and view pairs;
+  * no per-frame collectives: every rank accumulates its frames on the device and the 8 per-frame all_gathers
+    (:1106-1114) become one all_gather per field at the end;
+  * the guid-keyed OrderedDicts are built once, in the order the reference would have inserted them (for each
+    local position, rank 0..G-1), with the reference's float32 / float64 roundings.
+"""
+import math
+import random
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import ops
+from .utils import coreset, triangulation
+
+
+def _item32(x):
+    return float(np.float32(x))
+
+
+class ScoringSelectionMixin:
+    # ------------------------------------------------------------------------------------------ entry point
+    def sample_next_batch(self, train_dataset, al_num_frames, sal_num_frames, pose_estimator, iteration, rank=-1):
+        """Reference strategy.py:54-135 without the rank-0 JSON / TensorBoard side effects (those stay in the
+        reference class; mixing this class over it keeps them via ``_after_sampling``)."""
+        sal_guids, sal_dict = [], {}
+        if iteration == 0:
+            train_dataset, al_guids = self._random_sample_frames(train_dataset, al_num_frames)
+        else:
+            train_dataset, al_guids, sal_guids, sal_dict = self._sal_pseudo_labeling(
+                train_dataset, al_num_frames, sal_num_frames, pose_estimator)
+        hook = getattr(self, "_after_sampling", None)
+        if hook is not None:
+            hook(iteration, rank, al_guids, sal_guids, sal_dict)
+        self.last_al_guids, self.last_sal_guids, self.last_sal_dict = al_guids, sal_guids, sal_dict
+        return train_dataset
+
+    def _random_sample_frames(self, train_dataset, num_frames, seed=None):
+        """Reference strategy.py:868-878."""
+        if seed is None:
+            seed = self.al_cfg.RANDOM_SEED
+        random.seed(seed)
+        guids = random.sample(list(train_dataset.unlabeled_data.keys()), num_frames)
+        train_dataset.label_by_frame_guids(guids)
+        return train_dataset, guids
+
+    # ------------------------------------------------------------------------------------------ selection
+    def _sal_pseudo_labeling(self, train_dataset, al_num_frames, pseudo_num_frames, pose_estimator):
+        """Reference strategy.py:915-1002."""
+        cfg = self.al_cfg
+        if cfg.AL.STRATEGY == "RANDOM" and cfg.EXPR_TYPE == "AL":
+            train_dataset, al_guids = self._random_sample_frames(train_dataset, al_num_frames, seed=cfg.RANDOM_SEED)
+            return train_dataset, al_guids, [], {}
+        train_dataset.resample_unlabeled_data()
+        data_loader = self._get_dataloader(train_dataset, cfg.AL.INFERENCE.BATCH_SIZE, cfg.AL.INFERENCE.NUM_WORKERS)
+        sal_dict = self._compute_sal_dict(data_loader, pose_estimator)
+        if cfg.AL.STRATEGY == "CORESET":
+            cs = coreset.CoreSet(sal_dict["pred_3d_keypoints"], train_dataset.get_al_dict_for_coreset(),
+                                 self.joint_root_index)
+            al_guids = cs.select_batch(al_num_frames)
+        else:
+            al_guids = self._rank_nlargest(sal_dict["al_metric"], al_num_frames)
+        train_dataset.label_by_frame_guids(al_guids)
+        sal_sampled_guids = []
+        if cfg.EXPR_TYPE == "SAL":
+            # reference :957-1001 -- host-side dict filtering, kept literal (SURVEY.md 8f row 2 moves it on device)
+            chosen = set(al_guids)
+            already = set(train_dataset.pseudo_label_guids)
+            sal_metric_dict = {
+                guid: m for guid, m in sal_dict["sal_metric"].items()
+                if guid not in chosen and not math.isnan(m) and guid not in already
+                and sal_dict["inlier_count"][guid] > cfg.SAL.INLIER_THRESHOLD
+            }
+            sal_guids = sorted(sal_metric_dict, key=sal_metric_dict.get)
+            if cfg.SAL.CLUSTER_FILE_PATH != "":
+                counter = [0 for _ in range(cfg.SAL.NUM_CLUSTERS)]
+                per_cluster_count = pseudo_num_frames // cfg.SAL.NUM_CLUSTERS
+                for guid in sal_guids:
+                    kp = np.array(sal_dict["pred_3d_keypoints"][guid]).T
+                    kp = (kp[0:3, :] - kp[0:3, self.joint_root_index:self.joint_root_index + 1]).flatten()
+                    cluster_id = self.kmeans.predict([kp])[0]
+                    if counter[cluster_id] < per_cluster_count:
+                        counter[cluster_id] += 1
+                        sal_sampled_guids.append(guid)
+            else:
+                sal_sampled_guids = random.sample(sal_guids[:2 * pseudo_num_frames], pseudo_num_frames)
+            train_dataset.pseudo_label_by_frame_guids(sal_sampled_guids, sal_dict["pred_3d_keypoints"])
+        return train_dataset, al_guids, sal_sampled_guids, sal_dict
+
+    @staticmethod
+    def _rank_nlargest(al_metric, n):
+        """strategy.py:932-949 (NaN filter + heapq.nlargest) as a device top-k: descending score, ties by dict
+        insertion order."""
+        keys = list(al_metric.keys())
+        if not keys or n <= 0:
+            return []
+        scores = torch.tensor(list(al_metric.values()), dtype=torch.float64).cuda()
+        idx, _ = ops.topk_desc(scores, n)
+        return [keys[i] for i in idx.cpu().tolist()]
+
+    # ------------------------------------------------------------------------------------------ scoring
+    def _get_dataloader(self, dataset, batch_size, num_workers):
+        """Reference strategy.py:747-760."""
+        from torch.utils.data import DataLoader, DistributedSampler
+
+        return DataLoader(dataset, batch_size=batch_size, num_workers=num_workers, sampler=DistributedSampler(dataset))
+
+    @staticmethod
+    def _compute_batch_heatmap(pose_estimator, data):
+        """Reference strategy.py:771-782 (the forward stays in PyTorch/cuDNN)."""
+        images = data["images"].cuda()
+        return pose_estimator(images.reshape([-1, images.shape[2], images.shape[3], images.shape[4]]))
+
+    def _frame_al_metric(self, heatmaps, joint_valid, tri):
+        """AL metric of every frame of the batch as (numpy values, is_float64) -- strategy.py:1072-1094."""
+        cfg = self.al_cfg.AL
+        B = heatmaps.shape[0]
+        if cfg.STRATEGY == "RANDOM":
+            return np.array([_item32(torch.rand(1).item()) for _ in range(B)]), False
+        if cfg.STRATEGY == "TRIANGULATION":
+            return tri["metric"].cpu().numpy(), True
+        if cfg.STRATEGY == "CORESET":
+            return np.zeros(B), False
+        if cfg.STRATEGY == "HP":
+            vals = self._compute_hp_batch(heatmaps, joint_valid)
+            return np.asarray(vals, dtype=np.float64), cfg.HP_CONFIG == "STD"
+        if cfg.STRATEGY in ("MPE", "BSB"):
+            raise NotImplementedError("AL.STRATEGY=%s (skimage peak_local_max scores) is not built yet" % cfg.STRATEGY)
+        raise NotImplementedError()
+
+    def _compute_hp_batch(self, heatmaps, joint_valid):
+        """strategy.py:1178-1193 for a batch: per-map 1 - max(row softmax) on the device, AVG / STD on the host with
+        the reference's float64 accumulation over (view, valid joint)."""
+        valid = (torch.as_tensor(joint_valid) != 0)
+        hp = ops.score_hp(heatmaps, valid).cpu().numpy().astype(np.float64)  # [B, V, J], NaN for invalid joints
+        v = valid.cpu().numpy()
+        out = []
+        for b in range(hp.shape[0]):
+            vals = hp[b][:, v[b]].reshape(-1)
+            if self.al_cfg.AL.HP_CONFIG == "AVG":
+                out.append(sum(vals.tolist()) / len(vals))  # Python float sum, like the reference's sum(hps)/len(hps)
+            elif self.al_cfg.AL.HP_CONFIG == "STD":
+                out.append(np.std(vals))
+            else:
+                out.append(None)  # the reference falls off the end of _compute_hp and returns None
+        return out
+
+    def _compute_hp(self, heatmaps, joint_valid):
+        """Reference signature (strategy.py:1178): heatmaps [V, J, H, W] of one frame."""
+        hm = heatmaps if heatmaps.is_cuda else heatmaps.cuda()
+        return self._compute_hp_batch(hm.unsqueeze(0), torch.as_tensor(joint_valid).unsqueeze(0))[0]
+
+    def _compute_mpe(self, heatmaps, joint_valid):
+        raise NotImplementedError("MPE (skimage peak_local_max) is a 'next' row of SURVEY.md section 8")
+
+    def _compute_bsb(self, heatmaps, joint_valid):
+        raise NotImplementedError("BSB (skimage peak_local_max) is a 'next' row of SURVEY.md section 8")
+
+    def _compute_sal_dict(self, data_loader, pose_estimator):
+        """Reference strategy.py:1004-1147, batched (see module docstring)."""
+        cfg = self.al_cfg
+        acc = {k: [] for k in ("sal", "inl", "al", "pred", "gt", "valid", "pose", "frame")}
+        al_is_f64 = False
+        n_done = 0
+        rank_base = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank_base = torch.distributed.get_rank() << 32  # distinct pair-subset streams per rank (V >= 12 only)
+        for dp in data_loader:
+            with torch.no_grad():
+                heatmaps = self._compute_batch_heatmap(pose_estimator, dp)
+                _, kp, w, h = heatmaps.shape
+                B = dp["proj_matrices"].shape[0]
+                heatmaps = heatmaps.reshape([B, -1, kp, w, h]).float()
+                joint_valid = dp["joint_valid"]
+                if cfg.AL.USE_REPROJECTION_XE:
+                    raise NotImplementedError("AL.USE_REPROJECTION_XE is a 'next' row of SURVEY.md section 8")
+                tri = triangulation.triangulation_batch(
+                    heatmaps, dp["proj_matrices"], cfg.POSE_ESTIMATOR.STRIDE, joint_valid,
+                    use_soft_argmax=cfg.AL.USE_SOFTARGMAX, pair_seed=getattr(cfg, "RANDOM_SEED", 0),
+                    frame_offset=rank_base + n_done)
+                n_done += B
+                al, al_is_f64 = self._frame_al_metric(heatmaps, joint_valid, tri)
+                acc["sal"].append(tri["metric"].float())  # torch.Tensor([metric]) -> float32 (:1061)
+                acc["inl"].append(tri["inlier_count"].float())
+                acc["al"].append(torch.from_numpy(np.asarray(al, dtype=np.float64)).cuda())
+                acc["pred"].append(tri["keypoints_3d"].float())  # torch.Tensor(keypoints_3d) -> float32 (:1046)
+                acc["gt"].append(dp["3d_keypoints"].cuda().float())
+                acc["valid"].append(torch.as_tensor(joint_valid).cuda().float())
+                acc["pose"].append(torch.as_tensor(np.array(dp["pose"])).reshape(-1).cuda().long())
+                acc["frame"].append(torch.as_tensor(np.array(dp["frame_id"])).reshape(-1).cuda().long())
+        fields = {k: (torch.cat(v) if v else torch.zeros(0).cuda()) for k, v in acc.items()}
+        fields = self._gather_interleaved(fields)
+        return self._build_sal_dict(fields, al_is_f64)
+
+    @staticmethod
+    def _gather_interleaved(fields):
+        """One all_gather per field; result ordered as the reference's per-frame gathers would have inserted them:
+        local position t of rank r lands at t * world + r (strategy.py:1106-1133)."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return fields
+        world = dist.get_world_size()
+        out = {}
+        for k, t in fields.items():
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t.contiguous())
+            out[k] = torch.stack(parts, dim=1).reshape((-1,) + tuple(t.shape[1:]))
+        return out
+
+    @staticmethod
+    def _build_sal_dict(f, al_is_f64):
+        sal_dict = {k: OrderedDict() for k in ("al_metric", "sal_metric", "inlier_count", "pred_3d_keypoints", "mkpe")}
+        n = f["sal"].shape[0]
+        if n == 0:
+            return sal_dict
+        # utils/evaluation.py:198-208 compute_mkpe([pred], [gt], [valid]) per frame, float32
+        d = torch.square(f["pred"].permute(0, 2, 1) - f["gt"][:, :3, :])
+        d = torch.where(f["valid"].bool().unsqueeze(1), d, torch.zeros_like(d))
+        mkpe = torch.mean(torch.sqrt(torch.sum(d, dim=1)) / f["valid"], dim=1).cpu().tolist()
+        poses, frames = f["pose"].cpu().tolist(), f["frame"].cpu().tolist()
+        sal = f["sal"].cpu().tolist()
+        inl = f["inl"].cpu().tolist()
+        al = f["al"].cpu().numpy()
+        al = al.tolist() if al_is_f64 else al.astype(np.float32).astype(np.float64).tolist()
+        pred = f["pred"].cpu().numpy().tolist()
+        for i in range(n):
+            guid = "%s-%s" % (poses[i], frames[i])
+            sal_dict["sal_metric"][guid] = sal[i]
+            sal_dict["inlier_count"][guid] = inl[i]
+            sal_dict["pred_3d_keypoints"][guid] = pred[i]
+            sal_dict["al_metric"][guid] = al[i]
+            sal_dict["mkpe"][guid] = mkpe[i]
+        return sal_dict
+
+
+class ActiveLearningStrategy(ScoringSelectionMixin):
+    """Stand-alone strategy object exposing only the scoring-and-selection path (reference strategy.py:28-52 for
+    the constructor fields that path reads)."""
+
+    def __init__(self, al_cfg):
+        self.al_cfg = al_cfg
+        self.num_joints = al_cfg.DATA.NUM_JOINTS
+        self.joint_root_index = 2 if al_cfg.DATA.TYPE == "panoptic" else 21
+        self.kmeans = None

@@ -1,0 +1,152 @@
+"""Drop-in check of the strategy hot path: ``_compute_sal_dict`` / ``_sal_pseudo_labeling`` /
+``sample_next_batch`` against an emulation of the reference's per-frame loop driven by the CPU oracle."""
+import math
+from collections import OrderedDict
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+import torch
+
+from multi_view_active_learning_b200 import synthetic as S
+from oracle import coreset_oracle as CO
+from oracle import scores_oracle as SO
+from oracle import triangulation_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def make_cfg(strategy="TRIANGULATION", expr="AL", hp="AVG"):
+    return NS(EXPR_TYPE=expr, RANDOM_SEED=1307, DATA=NS(NUM_JOINTS=19, TYPE="panoptic"),
+              POSE_ESTIMATOR=NS(STRIDE=4),
+              SAL=NS(INLIER_THRESHOLD=4, CLUSTER_FILE_PATH="", NUM_CLUSTERS=10),
+              AL=NS(STRATEGY=strategy, USE_SOFTARGMAX=False, USE_REPROJECTION_XE=False, REPROJECTION_SIGMA=1.0,
+                    HP_CONFIG=hp, MPE_CONFIG="AVG", BSB_CONFIG="AVG", INFERENCE=NS(BATCH_SIZE=3, NUM_WORKERS=0)))
+
+
+class FakeDataset(torch.utils.data.Dataset):
+    """Same surface as dataset/dataset.py's ActiveLearningDataset as far as the strategy touches it."""
+
+    def __init__(self, n, V=8, J=19, seed=0, n_labeled=6):
+        pool = S.make_pool(n + n_labeled, V, J, seed=seed, valid_prob=0.95, p_outlier=0.12)
+        hm = S.render_heatmaps(pool["centres"], noise=0.05, seed=seed + 1)
+        gt = np.concatenate([pool["X"].transpose(0, 2, 1), np.ones((n + n_labeled, 1, J))], axis=1)  # [4, J]
+        frames = [{"images": torch.from_numpy(hm[i]), "proj_matrices": torch.from_numpy(pool["P"][i]),
+                   "joint_valid": torch.from_numpy(pool["valid"][i].astype(np.float32)),
+                   "3d_keypoints": torch.from_numpy(gt[i].astype(np.float32)), "pose": 160422 + i % 3, "frame_id": 100 + i}
+                  for i in range(n + n_labeled)]
+        self.unlabeled_data = OrderedDict(("%d-%d" % (f["pose"], f["frame_id"]), f) for f in frames[:n])
+        self.labeled_data = [dict(f, **{"3d_keypoints": f["3d_keypoints"].numpy()}) for f in frames[n:]]
+        self.pseudo_label_guids, self.pseudo_labeled_data, self.data = [], [], []
+        self.hm, self.pool = hm, pool
+
+    def resample_unlabeled_data(self):
+        self.data = list(self.unlabeled_data.values())
+
+    def get_al_dict_for_coreset(self):
+        return {i: np.array(self.labeled_data[i]["3d_keypoints"]).transpose([1, 0]) for i in range(len(self.labeled_data))}
+
+    def label_by_frame_guids(self, guids):
+        for g in guids:
+            self.labeled_data.append(self.unlabeled_data[g])
+            del self.unlabeled_data[g]
+
+    def pseudo_label_by_frame_guids(self, guids, pseudo_labels):
+        self.pseudo_label_guids = guids
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, i):
+        return self.data[i]
+
+
+def make_strategy(cfg):
+    from multi_view_active_learning_b200.strategy import ActiveLearningStrategy
+
+    st = ActiveLearningStrategy(cfg)
+    # single process: plain loader in dataset order (the reference's own test swaps the sampler out the same way,
+    # tests/test_strategy.py:41-43)
+    st._get_dataloader = lambda ds, bs, nw: torch.utils.data.DataLoader(ds, batch_size=bs, num_workers=0)
+    return st
+
+
+def reference_emulation(ds, cfg):
+    """What strategy.py:1004-1147 leaves in sal_dict, computed from the oracle frame by frame."""
+    n = len(ds.unlabeled_data)
+    ref = O.triangulate_pool(ds.hm[:n], ds.pool["P"][:n], 4, ds.pool["valid"][:n])
+    sal = {k: OrderedDict() for k in ("al_metric", "sal_metric", "inlier_count", "pred_3d_keypoints", "mkpe")}
+    for i, (guid, f) in enumerate(ds.unlabeled_data.items()):
+        sal["sal_metric"][guid] = float(np.float32(ref["metric"][i]))
+        sal["inlier_count"][guid] = float(ref["inlier_count"][i])
+        pred32 = ref["keypoints_3d"][i].astype(np.float32)
+        sal["pred_3d_keypoints"][guid] = pred32.tolist()
+        if cfg.AL.STRATEGY == "TRIANGULATION":
+            sal["al_metric"][guid] = float(ref["metric"][i])
+        elif cfg.AL.STRATEGY == "HP":
+            m = SO.hp_metric(ds.hm[i], ds.pool["valid"][i], cfg.AL.HP_CONFIG)
+            sal["al_metric"][guid] = float(np.float32(m)) if cfg.AL.HP_CONFIG == "AVG" else float(m)
+        else:
+            sal["al_metric"][guid] = 0.0
+        sal["mkpe"][guid] = float(SO.mkpe(pred32, f["3d_keypoints"].numpy(), ds.pool["valid"][i]))
+    return sal
+
+
+@pytest.mark.parametrize("strategy,hp", [("TRIANGULATION", "AVG"), ("HP", "AVG"), ("HP", "STD"), ("CORESET", "AVG")])
+def test_compute_sal_dict_and_selection(strategy, hp):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = make_cfg(strategy, hp=hp)
+    ds = FakeDataset(40, seed=5)
+    st = make_strategy(cfg)
+    ref = reference_emulation(ds, cfg)
+    ds.resample_unlabeled_data()
+    sal = st._compute_sal_dict(st._get_dataloader(ds, 3, 0), torch.nn.Identity())
+    assert list(sal["al_metric"].keys()) == list(ref["al_metric"].keys())
+    for g in ref["sal_metric"]:
+        assert sal["inlier_count"][g] == ref["inlier_count"][g]
+        assert abs(sal["sal_metric"][g] - ref["sal_metric"][g]) <= 1e-4
+        np.testing.assert_allclose(sal["pred_3d_keypoints"][g], ref["pred_3d_keypoints"][g], rtol=1e-3, atol=1e-2)
+        tol = 1e-4 if strategy == "TRIANGULATION" else 2e-6
+        assert abs(sal["al_metric"][g] - ref["al_metric"][g]) <= tol
+        a, b = sal["mkpe"][g], ref["mkpe"][g]
+        assert (math.isnan(a) and math.isnan(b)) or abs(a - b) <= 1e-2 * max(1.0, abs(b))
+    # selection through the reference's entry point
+    n_sel = 7
+    ds2 = FakeDataset(40, seed=5)
+    st.sample_next_batch(ds2, n_sel, 0, torch.nn.Identity(), iteration=1, rank=0)
+    if strategy == "CORESET":
+        keys = list(ref["pred_3d_keypoints"])
+        F = CO.stacked_features(ref["pred_3d_keypoints"].values(), FakeDataset(40, seed=5).get_al_dict_for_coreset().values(), 2)
+        exp = [keys[i] for i in CO.kcenter_greedy_f32(F, len(keys), n_sel)[0]]
+        assert exp == [keys[i] for i in CO.kcenter_greedy_f64(F, len(keys), n_sel)[0]]
+    else:
+        exp = SO.rank_nlargest(ref["al_metric"], n_sel)
+    assert st.last_al_guids == exp
+    assert len(ds2.unlabeled_data) == 40 - n_sel and len(ds2.labeled_data) == 6 + n_sel
+
+
+def test_sal_pseudo_label_filter_and_iteration0():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import random
+
+    cfg = make_cfg("TRIANGULATION", expr="SAL")
+    st = make_strategy(cfg)
+    ds = FakeDataset(30, seed=9)
+    ref = reference_emulation(ds, cfg)
+    random.seed(3)
+    _, al_guids, sal_guids, sal_dict = st._sal_pseudo_labeling(ds, 5, 4, torch.nn.Identity())
+    exp_al = SO.rank_nlargest(ref["al_metric"], 5)
+    assert al_guids == exp_al
+    cand = {g: m for g, m in ref["sal_metric"].items()
+            if g not in exp_al and not math.isnan(m) and ref["inlier_count"][g] > cfg.SAL.INLIER_THRESHOLD}
+    best = sorted(cand, key=cand.get)[:8]
+    assert len(sal_guids) == 4 and set(sal_guids) <= set(best)
+    assert ds.pseudo_label_guids == sal_guids
+    # iteration 0 = seeded random sampling, identical to the reference's random.sample (strategy.py:868-878)
+    ds0 = FakeDataset(30, seed=9)
+    keys = list(ds0.unlabeled_data.keys())
+    st.sample_next_batch(ds0, 6, 0, None, iteration=0)
+    random.seed(cfg.RANDOM_SEED)
+    assert st.last_al_guids == random.sample(keys, 6)
