@@ -52,54 +52,69 @@ def workload_config(args, n_gpus):
 # clocks sampling (B200_PROFILING.md recipe)
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region.  In-process NVML polling from a thread (a
+    spawned `nvidia-smi -lms` takes the driver lock on every query and was measured to stall kernel launches of
+    a 36 ms step by tens of ms); falls back to one nvidia-smi query if NVML is unavailable."""
 
-    def __init__(self, index):
-        self.path = tempfile.mktemp(prefix="mval_clocks_", suffix=".csv")
-        self.index = index
-        self.proc = None
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, index, period_s=0.05):
+        self.index, self.period = index, period_s
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _run(self):
+        nv, h = self._nvml, self._handle
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[self.index])
+                except Exception:
+                    phys = self.index
+            self._handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self._handle, nv.NVML_CLOCK_SM))
+            self._nvml = nv
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._nvml = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvml"}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        if self.sm:
+            out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.max_mhz, samples=len(self.sm),
+                       reasons=sorted(self.reasons))
             return out
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for line in open(self.path):
-                p = [x.strip() for x in line.split(",")]
-                if len(p) < 7:
-                    continue
-                try:
-                    sm.append(float(p[0]))
-                    mx.append(float(p[1]))
-                except ValueError:
-                    continue
-                for name, flag in zip(names, p[3:7]):
-                    if flag.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
+        try:  # fallback: a single nvidia-smi query right after the timed region
+            q = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            a, b = [float(x) for x in q.strip().split(",")[:2]]
+            out.update(sm_mhz=a, sm_max_mhz=b, samples=1, source="nvidia-smi (after the timed region)")
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
-        out["reasons"] = sorted(reasons)
         return out
 
 
@@ -240,17 +255,20 @@ def run_ours(args):
         sel = step()
     barrier()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev0.record()
-    for _ in range(args.steps):
+    for k in range(args.steps):
         sel = step()
+        marks[k].record()
     ev1.record()
     barrier()
     launches = _lib.launch_count() - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
+    step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([ev0] + marks[:-1], marks)]
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
@@ -282,18 +300,24 @@ def run_ours(args):
     dec_ms = time_ms(lambda: ops.decode_argmax(hm, STRIDE), 5)
     tri_ms = time_ms(lambda: ops.triangulate_ransac(xy, P), 5)
     pool_ms = time_ms(lambda: ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False), 5)
-    dec_bytes = R * FRAME_HEATMAP_BYTES
-    dec_gbs = dec_bytes / (dec_ms * 1e-3) / 1e9
-    pool_gbs = R * FRAME_ALGO_BYTES / (pool_ms * 1e-3) / 1e9
+    fused = os.environ.get("MVAL_FUSED", "1") != "0"
+    dec_gbs = R * FRAME_HEATMAP_BYTES / (dec_ms * 1e-3) / 1e9
+    pool_bytes = R * FRAME_ALGO_BYTES
+    pool_gbs = pool_bytes / (pool_ms * 1e-3) / 1e9
+    # dominant kernel: the fused persistent kernel does the whole scoring pass of a chunk in one launch
     roofline = {
-        "bound": "hbm", "kernel": "decode_argmax_kernel", "achieved": dec_gbs, "peak": hbm_peak, "unit": "GB/s",
-        "frac": dec_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": dec_bytes, "avg_launch_ms": dec_ms,
-        "share_of_step": dec_ms / pool_ms,
-        "other_kernels": {"ransac_vote+final+frame_reduce_ms_per_resident_chunk": tri_ms,
-                          "triangulation_share_of_step": tri_ms / pool_ms},
-        "whole_scoring_step": {"achieved": pool_gbs, "frac": pool_gbs / hbm_peak, "ms_per_resident_chunk": pool_ms,
-                               "algorithmic_bytes_per_frame": FRAME_ALGO_BYTES},
+        "bound": "hbm",
+        "kernel": "score_pool_fused_kernel" if fused else "decode_argmax_kernel + ransac_vote/final/frame_reduce",
+        "achieved": pool_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pool_gbs / hbm_peak, "traffic": None,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": pool_bytes,
+        "algorithmic_bytes_per_frame": FRAME_ALGO_BYTES, "frames_per_launch": R, "avg_launch_ms": pool_ms,
+        "share_of_step": pool_ms * (pool_frames / R) / ms_per_step,
+        "other_kernels": {
+            "decode_argmax_kernel": {"achieved": dec_gbs, "frac": dec_gbs / hbm_peak, "avg_launch_ms": dec_ms,
+                                     "algorithmic_bytes_per_launch": R * FRAME_HEATMAP_BYTES},
+            "ransac_vote+final+frame_reduce (stand-alone, from key-points)": {"avg_ms_per_resident_chunk": tri_ms,
+                                                                             "bound": "fp64 pipe"},
+        },
     }
 
     line = None
@@ -312,11 +336,12 @@ def run_ours(args):
             torch.cuda.synchronize()
             if it > 0:
                 e2e_times.append(time.perf_counter() - t0)
-        e2e_val = E / (sum(e2e_times) / len(e2e_times))
+        e2e_val = E / float(np.median(e2e_times))
         h2d = E * (FRAME_HEATMAP_BYTES + V * 96)
         d2h = sum(t.numel() * t.element_size() for t in outs.values()) + idx_h.numel() * 8
         e2e = {"value": e2e_val * n_gpus if n_gpus > 1 else e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "frames_per_step": E, "steps": args.e2e_steps,
+               "d2h_bytes_per_step": d2h, "frames_per_step": E, "steps": args.e2e_steps, "aggregate": "median over steps",
+               "step_ms": [round(1e3 * t, 2) for t in e2e_times],
                "call": "mval_score_pool_host (pinned host heat maps -> chunked H2D on 2 streams -> kernels -> D2H) + "
                        "mval_topk_desc; measured on rank 0" + (", scaled by n_gpus" if n_gpus > 1 else "")}
         # ---- CPU baseline (oracle port, one core) on a bounded sample of the same frames, N = 1 only
@@ -337,7 +362,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": dict(workload_config(args, n_gpus), seed=1234),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "step_ms": step_ms, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "selected_head": [int(i) for i in sel[0][:5]],
         }
         print(json.dumps(line))
@@ -350,15 +375,16 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pool-frames", type=int, default=POOL_FRAMES_PER_GPU)
     ap.add_argument("--resident-frames", type=int, default=16384)
     ap.add_argument("--e2e-frames", type=int, default=4096)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=4096)
     ap.add_argument("--ref-frames-per-core", type=int, default=128)
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

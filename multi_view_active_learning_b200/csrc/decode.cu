@@ -34,31 +34,8 @@ decode_argmax_kernel(const float* __restrict__ hm, int64_t n_maps, int V, int J,
     return;
   }
   const float4* __restrict__ p = reinterpret_cast<const float4*>(hm) + map * hw4;
-  uint32_t best_key = 0u, best_idx = 0u;  // every real key is >= 0x007fffff, so the first element always wins
-  for (int base = lane; base < hw4; base += kWarp * kUnroll) {
-    float4 v[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int i = base + u * kWarp;
-      if (i < hw4) v[u] = ld_stream_f4(p + i);
-    }
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int i = base + u * kWarp;
-      if (i < hw4) {
-        const uint32_t e = (uint32_t)i * 4u;
-        uint32_t k;
-        k = argmax_key(v[u].x); if (k > best_key) { best_key = k; best_idx = e; }
-        k = argmax_key(v[u].y); if (k > best_key) { best_key = k; best_idx = e + 1; }
-        k = argmax_key(v[u].z); if (k > best_key) { best_key = k; best_idx = e + 2; }
-        k = argmax_key(v[u].w); if (k > best_key) { best_key = k; best_idx = e + 3; }
-      }
-    }
-  }
-  // lanes scanned their elements in increasing index order with a strict compare, so each lane holds its first
-  // maximum; across lanes: highest key, then lowest index.
-  const uint32_t top = __reduce_max_sync(kFull, best_key);
-  const uint32_t idx = __reduce_min_sync(kFull, best_key == top ? best_idx : 0xffffffffu);
+  uint32_t top;
+  const uint32_t idx = warp_argmax_map<kUnroll, false>([&](int i) { return ld_stream_f4(p + i); }, hw4, lane, &top);
   if (lane == 0) {
     reinterpret_cast<int2*>(out_xy)[map] = make_int2((int)(idx % (uint32_t)H) * stride, (int)(idx / (uint32_t)H) * stride);
     if (out_peak) out_peak[map] = argmax_key_to_float(top);

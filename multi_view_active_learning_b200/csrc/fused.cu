@@ -1,0 +1,358 @@
+// Fused persistent pool-scoring kernel (sm_100a): heat-map decode + RANSAC/DLT triangulation + per-frame
+// uncertainty in ONE launch, so that the float64 Jacobi work (FP64-pipe bound) runs underneath the heat-map
+// stream (HBM bound) instead of after it, and the key-points never leave the SM.
+//
+// One CTA per SM, persistent over frames  f = blockIdx.x, blockIdx.x + gridDim.x, ...  Warp roles:
+//
+//   warp 0           TMA producer: one elected lane issues cp.async.bulk (global -> shared, mbarrier complete_tx)
+//                    for every 16 KiB map of the frame into a ring of S stages (S*16 KiB in flight per SM, no
+//                    registers spent on staging), plus the frame's V*96 B of projection matrices.
+//   warps 1..6       decode: wait full[stage], arg-max the map out of shared memory (conflict-free LDS.128, same
+//                    monotone-key / REDUX reduction as decode_argmax_kernel), release empty[stage], publish the
+//                    key-point into the frame slot and arrive on kp_ready[slot].
+//   warps 7..14      RANSAC: the (frame, joint) vote tasks form one stream t = i*J + j dealt round-robin to the 8
+//                    warps (balanced for any J); lane = view pair as in ransac_vote_kernel.  The warp i % 8 then
+//                    runs the final solves of frame i with lane = joint, reduces metric / inlier_count and frees
+//                    the slot.
+//
+// Four frame slots (key-points, P, masks) decouple the roles: decode may run up to 3 frames ahead of the finals.
+// Every hand-off is an mbarrier in shared memory; there is no __syncthreads after set-up.
+//
+// Arithmetic is shared with the stand-alone kernels (ransac.cuh), so the results are bit-identical to
+// mval_decode_argmax + mval_triangulate_ransac (tests/test_gpu_parity.py::test_fused_equals_unfused).
+#include <stdlib.h>
+
+#include "ransac.cuh"
+
+namespace mval {
+
+constexpr int kFusedDecodeWarps = 6;
+constexpr int kFusedRansacWarps = 8;
+constexpr int kFusedThreads = kWarp * (1 + kFusedDecodeWarps + kFusedRansacWarps);  // 480
+constexpr int kFrameSlots = 4;
+constexpr int kMaxStages = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Watchdog: a wait that lasts longer than ~5 s of SM clocks is a protocol bug, not load.  Instead of hanging the
+// device the waiter records who/what/where in g_fused_abort, raises the abort flag, and every role drains out of
+// its loops; the host reports MVAL_ERR_CUDA with the record (see launch_score_pool_fused).
+__device__ unsigned long long g_fused_abort[8];  // [0] flag, [1] code, [2] block, [3] warp, [4] frame iter, [5] index
+
+// kBackoff: the waiter expects to wait long (a RANSAC warp waiting for the next frame's key-points); it sleeps
+// between polls so that it does not take issue slots from the decode warps of its scheduler.
+template <bool kBackoff = false>
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t code, long long iter, int index) {
+  uint32_t ok;
+  long long t0 = 0;
+  uint32_t polls = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return true;
+    if (kBackoff) __nanosleep(256);
+    if ((++polls & 255u) == 0u) {
+      if (*((volatile unsigned long long*)&g_fused_abort[0]) != 0ull) return false;
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 10000000000ll) {
+        if (atomicCAS(&g_fused_abort[0], 0ull, 1ull) == 0ull) {
+          g_fused_abort[1] = code;
+          g_fused_abort[2] = blockIdx.x;
+          g_fused_abort[3] = threadIdx.x >> 5;
+          g_fused_abort[4] = (unsigned long long)iter;
+          g_fused_abort[5] = (unsigned long long)index;
+          __threadfence();
+        }
+        return false;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct FusedSmem {  // byte offsets into dynamic shared memory
+  uint32_t ring, proj, kp, mask, red_reproj, red_inl, pair, perm, pxy, bars, total;
+  int stages;
+  uint32_t stage_bytes;
+};
+
+__host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline FusedSmem fused_layout(int V, int J, int HW, int stages) {
+  FusedSmem L;
+  const int n_all = V * (V - 1) / 2;
+  L.stage_bytes = (uint32_t)HW * 4u;
+  L.stages = stages;
+  uint32_t o = 0;
+  L.ring = o;        o = align_up(o + (uint32_t)stages * L.stage_bytes, 128);
+  L.proj = o;        o = align_up(o + kFrameSlots * V * 96u, 16);
+  L.kp = o;          o = align_up(o + kFrameSlots * V * J * 8u, 16);
+  L.mask = o;        o = align_up(o + kFrameSlots * J * 4u, 16);
+  L.red_reproj = o;  o = align_up(o + kFusedRansacWarps * J * 8u, 16);
+  L.red_inl = o;     o = align_up(o + kFusedRansacWarps * J * 4u, 16);
+  L.pair = o;        o = align_up(o + 2u * n_all, 16);
+  L.perm = o;        o = align_up(o + kFusedRansacWarps * n_all * 2u, 16);
+  L.pxy = o;         o = align_up(o + kFusedRansacWarps * 2u * V * 8u, 16);
+  L.bars = o;        o = o + (2u * stages + 3u * kFrameSlots) * 8u;
+  L.total = o;
+  return L;
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__ proj, const uint8_t* __restrict__ valid,
+                        int64_t n_frames, int V, int J, int H, int HW, int stride, int stages, int n_iters, double eps,
+                        uint64_t seed, int64_t frame_offset, int32_t* __restrict__ out_xy, double* __restrict__ out_xyz,
+                        double* __restrict__ out_reproj, int32_t* __restrict__ out_inliers, double* __restrict__ out_metric,
+                        int32_t* __restrict__ out_inlier_count) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const FusedSmem L = fused_layout(V, J, HW, stages);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* empty = full + stages;
+  uint64_t* kp_ready = empty + stages;
+  uint64_t* kp_free = kp_ready + kFrameSlots;
+  uint64_t* masks_ready = kp_free + kFrameSlots;
+  const int VJ = V * J;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_all = V * (V - 1) / 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < kFrameSlots; ++s) {
+      mbar_init(&kp_ready[s], (uint32_t)VJ + 1u);
+      mbar_init(&kp_free[s], (uint32_t)J + 1u);
+      mbar_init(&masks_ready[s], (uint32_t)J);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  build_pair_table(smem + L.pair, V, threadIdx.x, blockDim.x);
+  __syncthreads();
+
+  // frames of this CTA: blockIdx.x + i * gridDim.x
+  const int64_t nf = (n_frames > (int64_t)blockIdx.x) ? (n_frames - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------- producer
+    if (lane == 0) {
+      int64_t c = 0;
+      for (int64_t i = 0; i < nf; ++i) {
+        const int64_t frame = blockIdx.x + i * (int64_t)gridDim.x;
+        const int sl = (int)(i % kFrameSlots);
+        const uint32_t ku = (uint32_t)(i / kFrameSlots);
+        if (!mbar_wait(&kp_free[sl], (ku & 1u) ^ 1u, 1, i, sl)) return;
+        mbar_arrive_expect_tx(&kp_ready[sl], (uint32_t)V * 96u);
+        bulk_g2s(smem + L.proj + sl * V * 96, proj + frame * V * 12, (uint32_t)V * 96u, &kp_ready[sl]);
+        const float* src = hm + frame * (int64_t)VJ * HW;
+        for (int m = 0; m < VJ; ++m, ++c) {
+          const int st = (int)(c % stages);
+          const uint32_t kf = (uint32_t)(c / stages);
+          if (!mbar_wait(&empty[st], (kf & 1u) ^ 1u, 2, i, st)) return;
+          mbar_arrive_expect_tx(&full[st], L.stage_bytes);
+          bulk_g2s(smem + L.ring + (uint32_t)st * L.stage_bytes, src + (int64_t)m * HW, L.stage_bytes, &full[st]);
+        }
+      }
+    }
+  } else if (warp <= kFusedDecodeWarps) {
+    // ------------------------------------------------------------------------------------------- decode
+    const int d = warp - 1;
+    const int hw4 = HW >> 2;
+    int2* kp_all = reinterpret_cast<int2*>(smem + L.kp);
+    for (int64_t i = 0; i < nf; ++i) {
+      const int64_t frame = blockIdx.x + i * (int64_t)gridDim.x;
+      const int sl = (int)(i % kFrameSlots);
+      const uint32_t ku = (uint32_t)(i / kFrameSlots);
+      // every decode warp passes every frame's slot gate (even with no map in it) so that no warp can run a full
+      // barrier phase ahead of the others
+      if (!mbar_wait(&kp_free[sl], (ku & 1u) ^ 1u, 3, i, sl)) return;
+      const int64_t c0 = i * VJ;
+      // first map of this frame owned by this warp: smallest m with (c0 + m) % D == d
+      int m = (int)(((int64_t)d - c0 % kFusedDecodeWarps + kFusedDecodeWarps) % kFusedDecodeWarps);
+      for (; m < VJ; m += kFusedDecodeWarps) {
+        const int64_t c = c0 + m;
+        const int st = (int)(c % stages);
+        const uint32_t kf = (uint32_t)(c / stages);
+        if (!mbar_wait(&full[st], kf & 1u, 4, i, st)) return;
+        const float4* __restrict__ p = reinterpret_cast<const float4*>(smem + L.ring + (uint32_t)st * L.stage_bytes);
+        const uint32_t idx = warp_argmax_map<8, true>([&](int q) { return p[q]; }, hw4, lane, nullptr);
+        if (lane == 0) {
+          mbar_arrive(&empty[st]);  // every lane's loads were consumed by the reductions above
+          const int j = m % J;
+          int2 xy = make_int2((int)(idx % (uint32_t)H) * stride, (int)(idx / (uint32_t)H) * stride);
+          if (valid != nullptr && valid[frame * J + j] == 0) xy = make_int2(0, 0);  // evaluation.py:21-23
+          kp_all[sl * VJ + m] = xy;
+          if (out_xy) reinterpret_cast<int2*>(out_xy)[frame * VJ + m] = xy;
+          mbar_arrive(&kp_ready[sl]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------- RANSAC
+    const int w = warp - 1 - kFusedDecodeWarps;
+    const bool subset = n_all > n_iters;
+    const int n_pairs = subset ? n_iters : n_all;
+    const uint8_t* sPair = smem + L.pair;
+    uint16_t* perm = reinterpret_cast<uint16_t*>(smem + L.perm) + w * n_all;
+    double* px = reinterpret_cast<double*>(smem + L.pxy) + w * 2 * V;
+    double* py = px + V;
+    double* red_reproj = reinterpret_cast<double*>(smem + L.red_reproj) + w * J;
+    int32_t* red_inl = reinterpret_cast<int32_t*>(smem + L.red_inl) + w * J;
+    const int2* kp_all = reinterpret_cast<const int2*>(smem + L.kp);
+    uint32_t* mask_all = reinterpret_cast<uint32_t*>(smem + L.mask);
+    for (int64_t i = 0; i < nf; ++i) {
+      const int64_t frame = blockIdx.x + i * (int64_t)gridDim.x;
+      const int sl = (int)(i % kFrameSlots);
+      const uint32_t ku = (uint32_t)(i / kFrameSlots);
+      const double* P = reinterpret_cast<const double*>(smem + L.proj + sl * V * 96);
+      const int2* kp = kp_all + sl * VJ;
+      uint32_t* masks = mask_all + sl * J;
+      if (!mbar_wait<true>(&kp_ready[sl], ku & 1u, 5, i, sl)) return;  // every RANSAC warp, every frame (same reason)
+      const int64_t t0 = i * J;
+      int j = (int)(((int64_t)w - t0 % kFusedRansacWarps + kFusedRansacWarps) % kFusedRansacWarps);
+      for (; j < J; j += kFusedRansacWarps) {
+        uint32_t mask = 0u;
+        if (valid == nullptr || valid[frame * J + j] != 0) {
+          __syncwarp();
+          for (int v = lane; v < V; v += kWarp) {
+            const int2 q = kp[v * J + j];
+            px[v] = (double)q.x;
+            py[v] = (double)q.y;
+          }
+          if (subset) draw_pair_subset(perm, n_all, n_iters, seed, frame_offset + frame, j, lane);
+          __syncwarp();
+          mask = ransac_vote_warp(
+              P, px, py, V, n_pairs, eps,
+              [&](int pi, int& a, int& b) {
+                const int li = subset ? (int)perm[pi] : pi;
+                a = sPair[2 * li];
+                b = sPair[2 * li + 1];
+              },
+              lane);
+        }
+        if (lane == 0) {
+          masks[j] = mask;
+          mbar_arrive(&masks_ready[sl]);
+          mbar_arrive(&kp_free[sl]);
+        }
+      }
+      if ((int)(i % kFusedRansacWarps) == w) {
+        // final solves of this frame: lane = joint
+        if (!mbar_wait<true>(&masks_ready[sl], ku & 1u, 7, i, sl)) return;
+        for (int jb = 0; jb < J; jb += kWarp) {
+          const int jj = jb + lane;
+          if (jj < J) {
+            const int64_t task = frame * J + jj;
+            const uint32_t mask = masks[jj];
+            if (valid != nullptr && valid[task] == 0) {
+              out_xyz[3 * task] = 0.0;
+              out_xyz[3 * task + 1] = 0.0;
+              out_xyz[3 * task + 2] = 0.0;
+              if (out_reproj) out_reproj[task] = __longlong_as_double(0x7ff8000000000000ll);
+              if (out_inliers) out_inliers[task] = 0;
+              red_inl[jj] = -1;
+            } else {
+              double X, Y, Z, rm;
+              ransac_final_thread(
+                  P,
+                  [&](int v, double& x, double& y) {
+                    const int2 q = kp[v * J + jj];
+                    x = (double)q.x;
+                    y = (double)q.y;
+                  },
+                  mask, V, X, Y, Z, rm);
+              out_xyz[3 * task] = X;
+              out_xyz[3 * task + 1] = Y;
+              out_xyz[3 * task + 2] = Z;
+              if (out_reproj) out_reproj[task] = rm;
+              if (out_inliers) out_inliers[task] = __popc(mask);
+              red_reproj[jj] = rm;
+              red_inl[jj] = __popc(mask);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&kp_free[sl]);  // slot inputs are no longer needed
+          double sum = 0.0;           // same sequential order as frame_reduce_kernel
+          int cnt = 0, mn = 0x7fffffff;
+          for (int q = 0; q < J; ++q) {
+            if (red_inl[q] >= 0) {
+              sum += red_reproj[q];
+              mn = min(mn, red_inl[q]);
+              ++cnt;
+            }
+          }
+          out_metric[frame] = cnt ? sum / (double)cnt : __longlong_as_double(0x7ff8000000000000ll);
+          out_inlier_count[frame] = cnt ? mn : 0;
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// Returns MVAL_ERR_UNSUPPORTED (without setting an error) when the shape does not fit the fused kernel; the caller
+// then takes the three-launch path.
+int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
+                            int H, int W, int stride, const mval_ransac_params& prm, int32_t* out_xy, double* out_xyz,
+                            double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
+                            cudaStream_t stream) {
+  const int HW = H * W;
+  if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(hm) & 15) != 0 || (reinterpret_cast<uintptr_t>(proj) & 15) != 0 ||
+      prm.pairs != nullptr)
+    return MVAL_ERR_UNSUPPORTED;
+  int dev = 0, max_smem = 0;
+  MVAL_CUDA(cudaGetDevice(&dev));
+  MVAL_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  // The ring depth must be a multiple of the number of decode warps: map c lives in stage c % S and is decoded by warp
+  // c % D, so D | S pins every stage to one warp, which visits it in order.  (Otherwise a warp can wait on a phase two
+  // ahead of the barrier and the parity test aliases with the phase before -- seen as stale reads / deadlock.)
+  int stages = kMaxStages / kFusedDecodeWarps * kFusedDecodeWarps;
+  while (stages >= kFusedDecodeWarps && fused_layout(V, J, HW, stages).total > (uint32_t)max_smem)
+    stages -= kFusedDecodeWarps;
+  if (stages < kFusedDecodeWarps) return MVAL_ERR_UNSUPPORTED;
+  const FusedSmem L = fused_layout(V, J, HW, stages);
+  MVAL_CUDA(cudaFuncSetAttribute(score_pool_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const int64_t sms = num_sms();
+  const int grid = (int)(n_frames < sms ? n_frames : sms);
+  score_pool_fused_kernel<<<grid, kFusedThreads, L.total, stream>>>(hm, proj, valid, n_frames, V, J, H, HW, stride, stages,
+                                                                  prm.n_iters, prm.epsilon, prm.pair_seed, prm.frame_offset,
+                                                                  out_xy, out_xyz, out_reproj, out_inliers, out_metric,
+                                                                  out_inlier_count);
+  MVAL_LAUNCH_CHECK("score_pool_fused");
+  static const bool debug_sync = getenv("MVAL_DEBUG_SYNC") != nullptr;
+  if (debug_sync) {
+    MVAL_CUDA(cudaStreamSynchronize(stream));
+    unsigned long long rec[8] = {0};
+    MVAL_CUDA(cudaMemcpyFromSymbol(rec, g_fused_abort, sizeof(rec)));
+    if (rec[0] != 0ull) {
+      unsigned long long zero[8] = {0};
+      cudaMemcpyToSymbol(g_fused_abort, zero, sizeof(zero));
+      set_error("score_pool_fused watchdog: wait code %llu timed out (block %llu warp %llu frame-iter %llu index %llu)", rec[1],
+                rec[2], rec[3], rec[4], rec[5]);
+      return MVAL_ERR_CUDA;
+    }
+  }
+  return MVAL_OK;
+}
+
+}  // namespace mval

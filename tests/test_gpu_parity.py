@@ -251,6 +251,27 @@ def test_full_size_properties(ops):
     _check_tri(out, ref, pool["valid"][sample])
 
 
+@pytest.mark.parametrize("N,V,J,vp", [(1500, 8, 19, 1.0), (700, 5, 19, 0.8), (300, 20, 42, 0.8), (200, 31, 19, 1.0),
+                                      (333, 2, 3, 0.7), (5, 8, 19, 1.0)])
+def test_fused_equals_unfused(ops, N, V, J, vp):
+    """mval_score_pool (one persistent fused kernel: TMA ring + decode warps + RANSAC warps) must be bit-identical
+    to mval_decode_argmax followed by mval_triangulate_ransac (three launches), for every output."""
+    pool = S.make_pool(N, V, J, seed=N + V, valid_prob=vp, p_outlier=0.15)
+    hm = ops.synth_heatmaps(_cuda(pool["centres"]), noise=0.05, seed=11)
+    P, valid = _cuda(pool["P"]), torch.from_numpy(pool["valid"])
+    fused = ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345)
+    xy = ops.decode_argmax(hm, 4, valid)
+    ref = ops.triangulate_ransac(xy, P, valid, pair_seed=3, frame_offset=12345)
+    assert torch.equal(fused["keypoints_2d"], xy)
+    for k in ("keypoints_3d", "inliers", "inlier_count"):
+        assert torch.equal(fused[k], ref[k]), k
+    for k in ("metric", "reproj_mean"):
+        assert torch.equal(torch.nan_to_num(fused[k], nan=-1.0), torch.nan_to_num(ref[k], nan=-1.0)), k
+    # optional outputs may be omitted
+    lean = ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345, return_keypoints_2d=False)
+    assert torch.equal(torch.nan_to_num(lean["metric"], nan=-1.0), torch.nan_to_num(ref["metric"], nan=-1.0))
+
+
 # ------------------------------------------------------------------------------------------------ ranking
 def test_topk_matches_nlargest(ops):
     rng = np.random.default_rng(0)
