@@ -157,6 +157,19 @@ int mval_kcenter_norms(const float* features, int64_t n, int d, float* row_norms
 int mval_kcenter_update(const float* features, const float* row_norms, int64_t n, int d, const float* centre,
                         float* min_dist, int64_t index_offset, float* out_best_val, int64_t* out_best_idx,
                         void* stream);
+/* Multi-GPU greedy step (features row-sharded across ranks, contiguous).  Same fused update as
+ * mval_kcenter_update, plus the two halves of the per-step exchange so that the loop needs no host round trip:
+ *   input  : the centre is either `centre` (d floats; used for the labeled set) or the best of the `n_cands`
+ *            candidate records in `cands_in` (the all-gathered records of the previous step; highest value, lowest
+ *            global index wins = np.argmax over the concatenated shards, coreset.py:90); in that case the chosen
+ *            global index is also written to *out_selected (may be NULL);
+ *   output : `cand_out` receives this rank's record {float32 val; int32 pad; int64 global idx; float32 row[d4]}
+ *            (mval_kcenter_record_bytes(d) bytes, idx = -1 for an empty shard) of its updated local arg-max, feature
+ *            row included, ready to be all-gathered. */
+size_t mval_kcenter_record_bytes(int d);
+int mval_kcenter_update_exchange(const float* features, const float* row_norms, int64_t n, int d, const float* centre,
+                                 const void* cands_in, int n_cands, float* min_dist, int64_t index_offset,
+                                 void* cand_out, int64_t* out_selected, void* stream);
 /* Single-device greedy loop (coreset.py:86-93) run entirely on the device: `budget` dependent steps without
  * host round trips.  labeled rows are [n_unlabeled, n); out_selected int64 device [budget]. */
 int mval_kcenter_greedy(const float* features, int64_t n, int64_t n_unlabeled, int d, int32_t budget,

@@ -40,6 +40,8 @@ PROTOTYPES = {
     "mval_topk_desc": (C.c_int, [_p, _i64, _i64, C.c_int32, _p, _p, _p, _p]),
     "mval_kcenter_norms": (C.c_int, [_p, _i64, _i, _p, _p]),
     "mval_kcenter_update": (C.c_int, [_p, _p, _i64, _i, _p, _p, _i64, _p, _p, _p]),
+    "mval_kcenter_record_bytes": (C.c_size_t, [_i]),
+    "mval_kcenter_update_exchange": (C.c_int, [_p, _p, _i64, _i, _p, _p, _i, _p, _i64, _p, _p, _p]),
     "mval_kcenter_greedy": (C.c_int, [_p, _i64, _i64, _i, C.c_int32, _p, _p, _p]),
     "mval_synth_heatmaps": (C.c_int, [_p, _i64, _i, _i, _f, _f, _u64, _p, _p]),
 }

@@ -71,20 +71,59 @@ __device__ __forceinline__ bool kc_better(float v, int64_t i, float bv, int64_t 
   return v > bv || (v == bv && i < bi);
 }
 
-// centre_idx != nullptr: the centre is row (*centre_idx - index_offset) of `feat` (device-side chaining of greedy
-// steps); otherwise `centre` points to d floats.
+// Candidate record exchanged between ranks in the multi-GPU loop: {float val; int32 pad; int64 idx; float row[d4]}
+// with d4 = d rounded up to a multiple of 4 (16-byte aligned records).  idx < 0 marks an empty shard.
+__host__ __device__ inline size_t kc_record_bytes(int d) { return 16 + sizeof(float) * (size_t)((d + 3) & ~3); }
+
+struct KcArgs {
+  const float* feat;
+  const float* norms;
+  int64_t n;
+  int d;
+  const float* centre;        // explicit centre (d floats), or
+  const int64_t* centre_idx;  // row (*centre_idx - index_offset) of feat, or
+  const char* cands_in;       // the best of n_cands candidate records (highest val, lowest idx)
+  int n_cands;
+  float* min_dist;
+  int64_t index_offset;
+  KcPartial* partials;
+  unsigned int* done_counter;
+  float* out_best_val;    // local arg-max of the updated min_dist (may be null)
+  int64_t* out_best_idx;  // global index = local + index_offset (may be null)
+  int64_t* also_idx;      // second copy of out_best_idx, or -- with cands_in -- the index of the chosen centre
+  char* cand_out;         // candidate record of the local arg-max, row included (may be null)
+};
+
 template <bool kVec>
-__global__ void __launch_bounds__(kKcThreads)
-kcenter_update_kernel(const float* __restrict__ feat, const float* __restrict__ norms, int64_t n, int d,
-                      const float* __restrict__ centre, const int64_t* __restrict__ centre_idx, float* __restrict__ min_dist,
-                      int64_t index_offset, KcPartial* __restrict__ partials, unsigned int* __restrict__ done_counter,
-                      float* __restrict__ out_best_val, int64_t* __restrict__ out_best_idx, int64_t* __restrict__ also_idx) {
+__global__ void __launch_bounds__(kKcThreads) kcenter_update_kernel(const KcArgs a) {
   extern __shared__ __align__(16) float s_centre[];  // d floats (+ padding)
   __shared__ float s_cc;
   __shared__ KcPartial s_part[kKcWarps];
   __shared__ bool s_last;
+  __shared__ int s_win;
+  __shared__ KcPartial s_best;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* c = centre_idx ? feat + (*centre_idx - index_offset) * d : centre;
+  const int d = a.d;
+  const float* c = a.centre;
+  if (a.cands_in != nullptr) {
+    if (threadIdx.x == 0) {
+      const size_t rb = kc_record_bytes(d);
+      int win = -1;
+      float bv = 0.f;
+      int64_t bi = 0;
+      for (int r = 0; r < a.n_cands; ++r) {
+        const float v = *reinterpret_cast<const float*>(a.cands_in + r * rb);
+        const int64_t i = *reinterpret_cast<const int64_t*>(a.cands_in + r * rb + 8);
+        if (i >= 0 && (win < 0 || kc_better(v, i, bv, bi))) { win = r; bv = v; bi = i; }
+      }
+      s_win = win < 0 ? 0 : win;
+      if (blockIdx.x == 0 && a.also_idx) *a.also_idx = win < 0 ? -1 : bi;
+    }
+    __syncthreads();
+    c = reinterpret_cast<const float*>(a.cands_in + s_win * kc_record_bytes(d) + 16);
+  } else if (a.centre_idx != nullptr) {
+    c = a.feat + (*a.centre_idx - a.index_offset) * d;
+  }
   for (int i = threadIdx.x; i < d; i += kKcThreads) s_centre[i] = c[i];
   __syncthreads();
   if (warp == 0) {
@@ -96,13 +135,13 @@ kcenter_update_kernel(const float* __restrict__ feat, const float* __restrict__ 
   float best_v = -INFINITY;
   int64_t best_i = INT64_MAX;
   const int64_t warps = (int64_t)gridDim.x * kKcWarps;
-  for (int64_t row = (int64_t)blockIdx.x * kKcWarps + warp; row < n; row += warps) {
-    const float dot = canonical_dot<kVec>(feat + row * d, s_centre, d, lane);
+  for (int64_t row = (int64_t)blockIdx.x * kKcWarps + warp; row < a.n; row += warps) {
+    const float dot = canonical_dot<kVec>(a.feat + row * d, s_centre, d, lane);
     if (lane == 0) {
-      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), norms[row]), cc);
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, dot), a.norms[row]), cc);
       const float dist = __fsqrt_rn(fmaxf(d2, 0.0f));
-      const float m = fminf(min_dist[row], dist);
-      min_dist[row] = m;
+      const float m = fminf(a.min_dist[row], dist);
+      a.min_dist[row] = m;
       if (kc_better(m, row, best_v, best_i)) { best_v = m; best_i = row; }
     }
   }
@@ -112,18 +151,19 @@ kcenter_update_kernel(const float* __restrict__ feat, const float* __restrict__ 
     KcPartial b = s_part[0];
     for (int w = 1; w < kKcWarps; ++w)
       if (kc_better(s_part[w].val, s_part[w].idx, b.val, b.idx)) b = s_part[w];
-    partials[blockIdx.x] = b;
+    a.partials[blockIdx.x] = b;
     __threadfence();
-    const unsigned int ticket = atomicAdd(done_counter, 1u);
+    const unsigned int ticket = atomicAdd(a.done_counter, 1u);
     s_last = (ticket == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last && warp == 0) {
+  if (!s_last) return;
+  if (warp == 0) {
     __threadfence();
     KcPartial b{-INFINITY, INT64_MAX};
     for (int i = lane; i < (int)gridDim.x; i += kWarp) {
-      const float pv = __ldcg(&partials[i].val);
-      const int64_t pi = __ldcg(&partials[i].idx);
+      const float pv = __ldcg(&a.partials[i].val);
+      const int64_t pi = __ldcg(&a.partials[i].idx);
       if (kc_better(pv, pi, b.val, b.idx)) { b.val = pv; b.idx = pi; }
     }
 #pragma unroll
@@ -133,12 +173,23 @@ kcenter_update_kernel(const float* __restrict__ feat, const float* __restrict__ 
       if (kc_better(ov, oi, b.val, b.idx)) { b.val = ov; b.idx = oi; }
     }
     if (lane == 0) {
-      const int64_t g = (b.idx == INT64_MAX) ? -1 : b.idx + index_offset;
-      *out_best_val = b.val;
-      *out_best_idx = g;
-      if (also_idx) *also_idx = g;
-      *done_counter = 0u;  // ready for the next launch on this stream
+      const int64_t g = (b.idx == INT64_MAX) ? -1 : b.idx + a.index_offset;
+      if (a.out_best_val) *a.out_best_val = b.val;
+      if (a.out_best_idx) *a.out_best_idx = g;
+      if (a.also_idx && a.cands_in == nullptr) *a.also_idx = g;
+      if (a.cand_out) {
+        *reinterpret_cast<float*>(a.cand_out) = b.val;
+        *reinterpret_cast<int64_t*>(a.cand_out + 8) = g;
+      }
+      s_best = b;
+      *a.done_counter = 0u;  // ready for the next launch on this stream
     }
+  }
+  __syncthreads();
+  if (a.cand_out != nullptr && s_best.idx != INT64_MAX) {  // ship the local winner's row with its record
+    const float* row = a.feat + s_best.idx * d;
+    float* dst = reinterpret_cast<float*>(a.cand_out + 16);
+    for (int i = threadIdx.x; i < d; i += kKcThreads) dst[i] = row[i];
   }
 }
 
@@ -182,28 +233,34 @@ static int kc_grid(int64_t n) {
 
 static bool vec_ok(const float* feat, int d) { return d % 4 == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0; }
 
-int kcenter_update(const float* feat, const float* norms, int64_t n, int d, const float* centre,
-                   const int64_t* centre_idx, float* min_dist, int64_t index_offset, float* out_best_val,
-                   int64_t* out_best_idx, int64_t* also_idx, cudaStream_t stream) {
-  const int grid = kc_grid(n);
+static int kcenter_launch(KcArgs a, cudaStream_t stream) {
+  const int grid = kc_grid(a.n);
   KcScratch* s = nullptr;
   if (int rc = get_scratch(num_sms() * 8, &s)) return rc;
-  const size_t smem = sizeof(float) * ((d + 3) & ~3);
-  if (vec_ok(feat, d)) {
+  a.partials = s->partials;
+  a.done_counter = s->counter;
+  const size_t smem = sizeof(float) * ((a.d + 3) & ~3);
+  if (vec_ok(a.feat, a.d)) {
     if (smem > 48 * 1024)
       MVAL_CUDA(cudaFuncSetAttribute(kcenter_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kcenter_update_kernel<true><<<grid, kKcThreads, smem, stream>>>(feat, norms, n, d, centre, centre_idx, min_dist,
-                                                                   index_offset, s->partials, s->counter, out_best_val,
-                                                                   out_best_idx, also_idx);
+    kcenter_update_kernel<true><<<grid, kKcThreads, smem, stream>>>(a);
   } else {
     if (smem > 48 * 1024)
       MVAL_CUDA(cudaFuncSetAttribute(kcenter_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kcenter_update_kernel<false><<<grid, kKcThreads, smem, stream>>>(feat, norms, n, d, centre, centre_idx, min_dist,
-                                                                    index_offset, s->partials, s->counter, out_best_val,
-                                                                    out_best_idx, also_idx);
+    kcenter_update_kernel<false><<<grid, kKcThreads, smem, stream>>>(a);
   }
   MVAL_LAUNCH_CHECK("kcenter_update");
   return MVAL_OK;
+}
+
+int kcenter_update(const float* feat, const float* norms, int64_t n, int d, const float* centre,
+                   const int64_t* centre_idx, float* min_dist, int64_t index_offset, float* out_best_val,
+                   int64_t* out_best_idx, int64_t* also_idx, cudaStream_t stream) {
+  KcArgs a{};
+  a.feat = feat; a.norms = norms; a.n = n; a.d = d; a.centre = centre; a.centre_idx = centre_idx;
+  a.min_dist = min_dist; a.index_offset = index_offset; a.out_best_val = out_best_val; a.out_best_idx = out_best_idx;
+  a.also_idx = also_idx;
+  return kcenter_launch(a, stream);
 }
 
 }  // namespace mval
@@ -272,4 +329,23 @@ extern "C" int mval_kcenter_greedy(const float* features, int64_t n, int64_t n_u
   cudaError_t e = cudaFreeAsync(ws, stream);
   if (rc == MVAL_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");
   return rc;
+}
+
+extern "C" size_t mval_kcenter_record_bytes(int d) { return mval::kc_record_bytes(d); }
+
+extern "C" int mval_kcenter_update_exchange(const float* features, const float* row_norms, int64_t n, int d,
+                                            const float* centre, const void* cands_in, int n_cands, float* min_dist,
+                                            int64_t index_offset, void* cand_out, int64_t* out_selected, void* stream) {
+  using namespace mval;
+  if (int rc = require_device()) return rc;
+  MVAL_REQUIRE(n >= 0 && d > 0, "mval_kcenter_update_exchange: bad shape");
+  MVAL_REQUIRE((centre != nullptr) != (cands_in != nullptr), "mval_kcenter_update_exchange: give exactly one of centre / cands_in");
+  MVAL_REQUIRE(cands_in == nullptr || n_cands > 0, "mval_kcenter_update_exchange: n_cands must be positive");
+  MVAL_REQUIRE(n == 0 || (features && row_norms && min_dist), "mval_kcenter_update_exchange: null pointer");
+  MVAL_REQUIRE((size_t)d * 4 <= 200 * 1024, "mval_kcenter_update_exchange: feature dimension too large for shared memory");
+  KcArgs a{};
+  a.feat = features; a.norms = row_norms; a.n = n; a.d = d; a.centre = centre;
+  a.cands_in = static_cast<const char*>(cands_in); a.n_cands = n_cands; a.min_dist = min_dist;
+  a.index_offset = index_offset; a.also_idx = out_selected; a.cand_out = static_cast<char*>(cand_out);
+  return kcenter_launch(a, static_cast<cudaStream_t>(stream));
 }

@@ -250,3 +250,18 @@ def synth_heatmaps(centres, H=64, W=64, sigma=1.0, noise=0.05, seed=0, out=None)
 
 def to_numpy(d):
     return {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
+
+
+def kcenter_record_bytes(d):
+    return int(_lib.load().mval_kcenter_record_bytes(int(d)))
+
+
+def kcenter_update_exchange(features, norms, min_dist, index_offset, cand_out, centre=None, cands_in=None, n_cands=0,
+                            out_selected=None):
+    """One multi-GPU greedy step on this rank's shard (see include/mval_b200.h:mval_kcenter_update_exchange).
+    All arguments are CUDA tensors; nothing is returned to the host."""
+    n, d = features.shape
+    with torch.cuda.device(features.device):
+        check(_lib.load().mval_kcenter_update_exchange(_ptr(features), _ptr(norms), n, d, _ptr(centre), _ptr(cands_in),
+                                                       int(n_cands), _ptr(min_dist), int(index_offset), _ptr(cand_out),
+                                                       _ptr(out_selected), _stream()))

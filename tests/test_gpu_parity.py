@@ -327,3 +327,23 @@ def test_coreset_class_matches_reference_golden(ops, golden):
     sal2 = {"k%d" % i: pose for i in range(20)}
     cs3 = CoreSet(sal2, {i: pose for i in range(5)}, 2)
     assert cs3.select_batch(5) == ["k%d" % i for i in g2["picked"]] == ["k0"] * 5
+
+
+def test_kcenter_sharded_loop_bit_exact(ops):
+    """The multi-GPU greedy loop (per-shard fused update -> candidate records -> device-side winner pick) with the
+    ranks emulated as shards on one device: uneven shards, an empty shard, duplicate rows across shards."""
+    from multi_view_active_learning_b200 import pool as P
+
+    rng = np.random.default_rng(7)
+    n, L, d, budget = 900, 12, 57, 60
+    F = (rng.normal(size=(n + L, d)) * 30).astype(np.float32)
+    F[700] = F[10]  # the same row in two different shards: the lower global index must win the tie
+    exp_sel, exp_min = CO.kcenter_greedy_f32(F, n, budget)
+    cuts = [0, 250, 250, 610, 900]  # shard 1 is empty
+    shards = [(_cuda(F[a:b]), a) for a, b in zip(cuts[:-1], cuts[1:])]
+    sel, mins = P.kcenter_greedy_sharded(shards, _cuda(F[n:]), budget)
+    assert sel.cpu().tolist() == exp_sel
+    assert np.array_equal(torch.cat(mins).cpu().numpy(), exp_min[:n])
+    # one shard == the single-device loop
+    sel1, _ = P.kcenter_greedy_sharded([(_cuda(F[:n]), 0)], _cuda(F[n:]), budget)
+    assert sel1.cpu().tolist() == exp_sel
