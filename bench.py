@@ -382,6 +382,80 @@ def run_ours(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# secondary workload: coreset k-center greedy (BASELINE.json configs[3], "C4"): not the driver's default line
+# ----------------------------------------------------------------------------------------------------------------
+def run_coreset(args):
+    import torch
+    import torch.distributed as dist
+
+    from multi_view_active_learning_b200 import _lib, ops, pool as poolmod
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_total, d, L, budget = args.coreset_rows, args.coreset_dim, args.coreset_labeled, args.coreset_budget
+    lo, hi = poolmod.shard_range(n_total, world, rank)
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    feat = torch.randn((hi - lo, d), generator=g, device=dev, dtype=torch.float32)
+    gl = torch.Generator(device=dev).manual_seed(7)
+    labeled = torch.randn((L, d), generator=gl, device=dev, dtype=torch.float32)
+    # per-step kernel roofline: one fused update over the local shard
+    norms = ops.kcenter_norms(feat)
+    min_d = torch.full((hi - lo,), float("inf"), dtype=torch.float32, device=dev)
+    best = ops.kcenter_update(feat, norms, labeled[0], min_d)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(20):
+        ops.kcenter_update(feat, norms, labeled[i % L], min_d, out_best=best)
+    b.record()
+    torch.cuda.synchronize()
+    step_ms = a.elapsed_time(b) / 20
+    step_bytes = (hi - lo) * (d * 4 + 12)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # the whole selection (labeled fold-in + budget greedy steps), device-timed, max over ranks
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    a.record()
+    sel, _ = poolmod.kcenter_greedy_sharded([(feat, lo)], labeled, budget)
+    b.record()
+    torch.cuda.synchronize()
+    total_ms = a.elapsed_time(b)
+    launches = _lib.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    if rank == 0:
+        gbs = step_bytes / (step_ms * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": "coreset k-center greedy: pool rows selected-from / sec", "value": n_total / (total_ms * 1e-3),
+            "unit": "rows/s", "n_gpus": world, "ms_total": total_ms, "ms_per_greedy_step": total_ms / (L + budget),
+            "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4-style coreset: %d x %d float32 features, %d labeled centres folded in one by one, "
+                                   "budget %d, rows sharded over %d GPU(s)" % (n_total, d, L, budget, world)},
+            "roofline": {"bound": "hbm", "kernel": "kcenter_update_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": gbs / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": step_bytes,
+                         "avg_launch_ms": step_ms},
+            "gpu_launches": int(launches), "selected_head": sel[:5].cpu().tolist()}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -394,11 +468,18 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=4096)
     ap.add_argument("--ref-frames-per-core", type=int, default=128)
+    ap.add_argument("--workload", default="scoring", choices=["scoring", "coreset"])
+    ap.add_argument("--coreset-rows", type=int, default=1_000_000)
+    ap.add_argument("--coreset-dim", type=int, default=2048)
+    ap.add_argument("--coreset-labeled", type=int, default=64)
+    ap.add_argument("--coreset-budget", type=int, default=256)
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "coreset":
+        return run_coreset(args)
     return run_ours(args)
 
 
