@@ -78,6 +78,16 @@ int mval_decode_softargmax(const float* heatmaps, int64_t n_frames, int V, int J
 int mval_score_hp(const float* heatmaps, int64_t n_frames, int V, int J, int H, int W, const uint8_t* valid,
                   float* out_hp, void* stream);
 
+/* Replaces the per-map loops of strategy.py:1160-1175 (_compute_mpes, mode 0) and :1195-1209 (_compute_bsb, mode 1):
+ * local peaks as skimage.feature.peak_local_max(map, min_distance=2) defines them (equal to the 5x5 window maximum,
+ * strictly above the map minimum, 2 pixels off the border), then
+ *   mode 0 (MPE): entropy of softmax over all peak values of the raw map (0 when there is no peak);
+ *   mode 1 (BSB): |p0 - p1| of the two highest peaks of the ROW-softmaxed map (NaN with fewer than two peaks; the
+ *                 reference raises IndexError there).
+ * Maps of invalid joints get NaN.  W <= 64.  out_score float32 device [n_frames][V][J]. */
+int mval_score_peaks(const float* heatmaps, int64_t n_frames, int V, int J, int H, int W, int mode,
+                     const uint8_t* valid, float* out_score, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * (2) multi-view RANSAC + DLT triangulation and reprojection uncertainty
  * ---------------------------------------------------------------------------------------------------- */

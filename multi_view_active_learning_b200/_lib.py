@@ -34,6 +34,7 @@ PROTOTYPES = {
     "mval_decode_argmax": (C.c_int, [_p, _i64, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "mval_decode_softargmax": (C.c_int, [_p, _i64, _i, _i, _i, _i, _f, _p, _p]),
     "mval_score_hp": (C.c_int, [_p, _i64, _i, _i, _i, _i, _p, _p, _p]),
+    "mval_score_peaks": (C.c_int, [_p, _i64, _i, _i, _i, _i, _i, _p, _p, _p]),
     "mval_triangulate_ransac": (C.c_int, [_p, _i, _p, _p, _i64, _i, _i, C.POINTER(RansacParams), _p, _p, _p, _p, _p, _p, _p]),
     "mval_score_pool": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _p, _p, _p, _p, _p, _p, _p]),
     "mval_score_pool_host": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _i64, _p, _p, _p, _p, _p, _p]),

@@ -90,6 +90,19 @@ def score_hp(heatmaps, valid=None):
     return out
 
 
+def score_peaks(heatmaps, mode, valid=None):
+    """heatmaps [N, V, J, H, W] -> float32 [N, V, J].  mode "MPE": entropy of softmax over the local-peak values
+    (strategy.py:1160-1175); mode "BSB": |p0 - p1| of the two best peaks of the row-softmaxed map (:1195-1209)."""
+    hm = _cuda(heatmaps, torch.float32, "heatmaps")
+    N, V, J, H, W = hm.shape
+    v = _valid_u8(valid, N, J, hm.device)
+    out = torch.empty((N, V, J), dtype=torch.float32, device=hm.device)
+    code = {"MPE": 0, "BSB": 1}[mode]
+    with torch.cuda.device(hm.device):
+        check(_lib.load().mval_score_peaks(_ptr(hm), N, V, J, H, W, code, _ptr(v), _ptr(out), _stream()))
+    return out
+
+
 def _alloc_tri_outputs(N, J, device):
     return {
         "keypoints_3d": torch.empty((N, J, 3), dtype=torch.float64, device=device),

@@ -131,40 +131,54 @@ class ScoringSelectionMixin:
             return tri["metric"].cpu().numpy(), True
         if cfg.STRATEGY == "CORESET":
             return np.zeros(B), False
-        if cfg.STRATEGY == "HP":
-            vals = self._compute_hp_batch(heatmaps, joint_valid)
-            return np.asarray(vals, dtype=np.float64), cfg.HP_CONFIG == "STD"
-        if cfg.STRATEGY in ("MPE", "BSB"):
-            raise NotImplementedError("AL.STRATEGY=%s (skimage peak_local_max scores) is not built yet" % cfg.STRATEGY)
+        if cfg.STRATEGY in ("HP", "MPE", "BSB"):
+            config = {"HP": cfg.HP_CONFIG, "MPE": cfg.MPE_CONFIG, "BSB": cfg.BSB_CONFIG}[cfg.STRATEGY]
+            vals = self._compute_map_score_batch(cfg.STRATEGY, config, heatmaps, joint_valid)
+            return np.asarray(vals, dtype=np.float64), config == "STD"
         raise NotImplementedError()
 
-    def _compute_hp_batch(self, heatmaps, joint_valid):
-        """strategy.py:1178-1193 for a batch: per-map 1 - max(row softmax) on the device, AVG / STD on the host with
-        the reference's float64 accumulation over (view, valid joint)."""
+    @staticmethod
+    def _compute_map_score_batch(kind, config, heatmaps, joint_valid):
+        """strategy.py:1149-1215 for a batch: the per-map score (HP / MPE / BSB) on the device, then AVG (Python float
+        sum / len, like the reference's sum(x)/len(x)) or STD (np.std) over (view, valid joint) on the host."""
         valid = (torch.as_tensor(joint_valid) != 0)
-        hp = ops.score_hp(heatmaps, valid).cpu().numpy().astype(np.float64)  # [B, V, J], NaN for invalid joints
+        if kind == "HP":
+            per_map = ops.score_hp(heatmaps, valid)
+        else:
+            per_map = ops.score_peaks(heatmaps, kind, valid)
+        per_map = per_map.cpu().numpy().astype(np.float64)  # [B, V, J], NaN for invalid joints
         v = valid.cpu().numpy()
         out = []
-        for b in range(hp.shape[0]):
-            vals = hp[b][:, v[b]].reshape(-1)
-            if self.al_cfg.AL.HP_CONFIG == "AVG":
-                out.append(sum(vals.tolist()) / len(vals))  # Python float sum, like the reference's sum(hps)/len(hps)
-            elif self.al_cfg.AL.HP_CONFIG == "STD":
+        for b in range(per_map.shape[0]):
+            vals = per_map[b][:, v[b]].reshape(-1)
+            if config == "AVG":
+                out.append(sum(vals.tolist()) / len(vals))
+            elif config == "STD":
                 out.append(np.std(vals))
+            elif kind == "MPE":
+                raise NotImplementedError("AL.MPE_CONFIG should be either AVG or STD.")  # reference :1157-1158
             else:
-                out.append(None)  # the reference falls off the end of _compute_hp and returns None
+                out.append(None)  # the reference falls off the end of _compute_hp / _compute_bsb and returns None
         return out
+
+    def _one_frame(self, kind, config, heatmaps, joint_valid):
+        hm = heatmaps if heatmaps.is_cuda else heatmaps.cuda()
+        res = self._compute_map_score_batch(kind, config, hm.unsqueeze(0), torch.as_tensor(joint_valid).unsqueeze(0))[0]
+        if kind == "BSB" and res is not None and np.isnan(res):
+            raise IndexError("list index out of range")  # reference :1208 probs[1] with fewer than two peaks
+        return res
 
     def _compute_hp(self, heatmaps, joint_valid):
         """Reference signature (strategy.py:1178): heatmaps [V, J, H, W] of one frame."""
-        hm = heatmaps if heatmaps.is_cuda else heatmaps.cuda()
-        return self._compute_hp_batch(hm.unsqueeze(0), torch.as_tensor(joint_valid).unsqueeze(0))[0]
+        return self._one_frame("HP", self.al_cfg.AL.HP_CONFIG, heatmaps, joint_valid)
 
     def _compute_mpe(self, heatmaps, joint_valid):
-        raise NotImplementedError("MPE (skimage peak_local_max) is a 'next' row of SURVEY.md section 8")
+        """Reference signature (strategy.py:1149)."""
+        return self._one_frame("MPE", self.al_cfg.AL.MPE_CONFIG, heatmaps, joint_valid)
 
     def _compute_bsb(self, heatmaps, joint_valid):
-        raise NotImplementedError("BSB (skimage peak_local_max) is a 'next' row of SURVEY.md section 8")
+        """Reference signature (strategy.py:1195)."""
+        return self._one_frame("BSB", self.al_cfg.AL.BSB_CONFIG, heatmaps, joint_valid)
 
     def _compute_sal_dict(self, data_loader, pose_estimator):
         """Reference strategy.py:1004-1147, batched (see module docstring)."""
@@ -196,8 +210,8 @@ class ScoringSelectionMixin:
                 acc["pred"].append(tri["keypoints_3d"].float())  # torch.Tensor(keypoints_3d) -> float32 (:1046)
                 acc["gt"].append(dp["3d_keypoints"].cuda().float())
                 acc["valid"].append(torch.as_tensor(joint_valid).cuda().float())
-                acc["pose"].append(torch.as_tensor(np.array(dp["pose"])).reshape(-1).cuda().long())
-                acc["frame"].append(torch.as_tensor(np.array(dp["frame_id"])).reshape(-1).cuda().long())
+                acc["pose"].append(torch.as_tensor(dp["pose"]).reshape(-1).cuda().long())
+                acc["frame"].append(torch.as_tensor(dp["frame_id"]).reshape(-1).cuda().long())
         fields = {k: (torch.cat(v) if v else torch.zeros(0).cuda()) for k, v in acc.items()}
         fields = self._gather_interleaved(fields)
         return self._build_sal_dict(fields, al_is_f64)

@@ -49,3 +49,84 @@ def mkpe(pred_3d, gt_3d, valid):
     with np.errstate(invalid="ignore", divide="ignore"):
         per_joint = d / v
     return np.float32(per_joint.mean(dtype=np.float32))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# MPE / BSB (strategy.py:1149-1176, 1195-1215).  parity unpinned: the reference calls
+# skimage.feature.peak_local_max(..., indices=True) (skimage <= 0.19, not installed anywhere we can run); restated
+# here from its published algorithm with scipy.ndimage, which IS what skimage uses underneath.
+# ----------------------------------------------------------------------------------------------------------------
+def peak_local_max(image, min_distance=2, num_peaks=np.inf):
+    """skimage 0.18/0.19 peak_local_max(image, min_distance, indices=True, num_peaks) with the defaults the
+    reference relies on (threshold_abs=None -> image.min(), threshold_rel=None, exclude_border=True -> min_distance,
+    footprint = ones(2*min_distance+1), p_norm=inf): candidates = pixels equal to the maximum of their footprint
+    (scipy maximum_filter, mode='constant'), strictly above the threshold, outside the border; sorted by descending
+    intensity; greedy spacing (a peak removes later peaks at Chebyshev distance < min_distance); first num_peaks."""
+    from scipy import ndimage as ndi
+
+    image = np.asarray(image)
+    size = 2 * min_distance + 1
+    image_max = ndi.maximum_filter(image, footprint=np.ones((size, size), dtype=bool), mode="constant")
+    mask = image == image_max
+    if np.all(mask):
+        mask[:] = False
+    mask &= image > image.min()
+    bw = min_distance
+    mask[:bw, :] = mask[-bw:, :] = False
+    mask[:, :bw] = mask[:, -bw:] = False
+    coord = np.nonzero(mask)
+    intensities = image[coord]
+    order = np.argsort(-intensities, kind="stable")
+    coord = np.transpose(coord)[order]
+    keep, rejected = [], set()
+    max_out = int(num_peaks) if np.isfinite(num_peaks) else None
+    for i in range(len(coord)):
+        if i in rejected:
+            continue
+        keep.append(i)
+        if max_out is not None and len(keep) >= max_out:
+            break
+        d = np.abs(coord[i + 1:] - coord[i]).max(axis=1) if i + 1 < len(coord) else np.zeros(0)
+        rejected.update((i + 1 + np.nonzero(d < min_distance)[0]).tolist())
+    return coord[keep]
+
+
+def mpe_scores(heatmaps):
+    """[..., H, W] float32 -> float32 [...]: entropy of softmax over the local-peak values (strategy.py:1168-1175);
+    a map without peaks scores 0 (sum over an empty list)."""
+    hm = np.asarray(heatmaps, dtype=np.float32)
+    out = np.zeros(hm.shape[:-2], dtype=np.float32)
+    for idx in np.ndindex(*hm.shape[:-2]):
+        pk = peak_local_max(hm[idx], min_distance=2)
+        if len(pk) == 0:
+            continue
+        v = hm[idx][pk[:, 0], pk[:, 1]].astype(np.float64)
+        p = np.exp(v - v.max())
+        p /= p.sum()
+        out[idx] = np.float32(-(p * np.log(p)).sum())
+    return out
+
+
+def bsb_scores(heatmaps):
+    """[..., H, W] float32 -> float32 [...]: |p0 - p1| of the two highest local peaks of the ROW-softmaxed map
+    (strategy.py:1202-1208); NaN where the map has fewer than two peaks (the reference raises IndexError there)."""
+    hm = np.asarray(heatmaps, dtype=np.float32)
+    e = np.exp(hm - hm.max(axis=-1, keepdims=True))
+    sm = (e / e.sum(axis=-1, keepdims=True, dtype=np.float32)).astype(np.float32)
+    out = np.full(hm.shape[:-2], np.nan, dtype=np.float32)
+    for idx in np.ndindex(*hm.shape[:-2]):
+        pk = peak_local_max(sm[idx], min_distance=2, num_peaks=2)
+        if len(pk) >= 2:
+            out[idx] = abs(sm[idx][pk[0, 0], pk[0, 1]] - sm[idx][pk[1, 0], pk[1, 1]])
+    return out
+
+
+def reduce_frame_score(per_map, joint_valid, config="AVG"):
+    """per_map [V, J] -> AVG (Python float sum / len) or STD (np.std) over (view, valid joint), reference
+    :1151-1158, :1188-1193, :1210-1215."""
+    vals = [float(per_map[v, k]) for v in range(per_map.shape[0]) for k in range(per_map.shape[1]) if joint_valid[k]]
+    if config == "AVG":
+        return sum(vals) / len(vals)
+    if config == "STD":
+        return np.std(np.array(vals))
+    raise NotImplementedError

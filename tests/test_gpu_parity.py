@@ -106,6 +106,34 @@ def test_hp_scores(ops, golden):
     np.testing.assert_allclose(ops.score_hp(_cuda(hm)).cpu().numpy(), SO.hp_scores(hm), rtol=0, atol=2e-6)
 
 
+def test_mpe_bsb_scores_vs_restatement(ops):
+    """MPE / BSB against the scipy restatement of skimage.peak_local_max (parity unpinned: skimage is not installed).
+    Tolerance: float32 softmax / entropy of ~130 peak values -> 2e-5 absolute."""
+    pool = S.make_pool(3, 4, 5, seed=12)
+    hm = S.render_heatmaps(pool["centres"], noise=0.05, seed=13)
+    hm[0, 0, 0] = 0.0                      # flat map: no peak at all
+    hm[0, 0, 1] = 0.0
+    hm[0, 0, 1, 20, 30] = 1.0              # one-hot: a single peak
+    hm[0, 0, 2] = 0.0
+    hm[0, 0, 2, 10, 10], hm[0, 0, 2, 40, 50], hm[0, 0, 2, 1, 1] = 2.0, 1.5, 9.0  # the 9.0 sits on the excluded border
+    valid = np.ones((3, 5), dtype=bool)
+    valid[1, 3] = False
+    mpe = ops.score_peaks(_cuda(hm), "MPE", torch.from_numpy(valid)).cpu().numpy()
+    bsb = ops.score_peaks(_cuda(hm), "BSB", torch.from_numpy(valid)).cpu().numpy()
+    exp_m, exp_b = SO.mpe_scores(hm), SO.bsb_scores(hm)
+    v = np.broadcast_to(valid[:, None, :], mpe.shape)
+    assert np.isnan(mpe[~v]).all() and np.isnan(bsb[~v]).all()
+    np.testing.assert_allclose(mpe[v], exp_m[v], rtol=0, atol=2e-5)
+    assert mpe[0, 0, 0] == 0.0 and mpe[0, 0, 1] == 0.0 and abs(mpe[0, 0, 2] - exp_m[0, 0, 2]) < 1e-6
+    both = v & ~np.isnan(exp_b)
+    np.testing.assert_allclose(bsb[both], exp_b[both], rtol=0, atol=2e-6)
+    assert np.array_equal(np.isnan(bsb[v]), np.isnan(exp_b[v]))  # fewer than two peaks -> NaN on both sides
+    # narrower maps go through the same kernel
+    hm2 = np.random.default_rng(3).normal(size=(1, 2, 3, 24, 20)).astype(np.float32)
+    np.testing.assert_allclose(ops.score_peaks(_cuda(hm2), "MPE").cpu().numpy(), SO.mpe_scores(hm2), rtol=0, atol=2e-5)
+    np.testing.assert_allclose(ops.score_peaks(_cuda(hm2), "BSB").cpu().numpy(), SO.bsb_scores(hm2), rtol=0, atol=2e-6)
+
+
 # ------------------------------------------------------------------------------------------------ triangulation
 def test_reference_unit_test_known_answer(ops, golden):
     from multi_view_active_learning_b200.utils.triangulation import triangulation
