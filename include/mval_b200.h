@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MVAL_ABI_VERSION 1
+#define MVAL_ABI_VERSION 2
 #define MVAL_MAX_VIEWS 32
 
 enum mval_status {
@@ -154,34 +154,57 @@ int mval_score_pool_host(const float* heatmaps, const double* proj, const uint8_
 int mval_topk_desc(const double* scores, int64_t n, int64_t index_offset, int32_t k, int64_t* out_idx,
                    double* out_val, int32_t* out_count, void* stream);
 
-/* Coreset (utils/coreset.py:49-95) on float32 features in the canonical summation order documented in
- * oracle/coreset_oracle.py.  features float32 device [n][d] row-major.
- *   mval_kcenter_norms       : row_norms[i] = <x_i, x_i>
- *   mval_kcenter_update      : min_dist[i] = min(min_dist[i], dist(x_i, centre)) for the local rows, and the
- *                              local arg-max (value, lowest index) of the updated min_dist ->
- *                              out_best_val float32 device[1], out_best_idx int64 device[1] (index_offset added)
- *                              (coreset.py:64-69 followed by :90).  `centre` float32 device [d].
- * The caller seeds min_dist with +inf and calls update once per labeled centre (coreset.py:83-84), then
- * budget times with the row the (global) arg-max selected. */
+/* Coreset k-center greedy (utils/coreset.py:49-95) on float32 features.  features float32 device [n][d] row-major.
+ * The distance is sklearn's expansion evaluated in float32 in the canonical order that oracle/coreset_oracle.c
+ * defines (one fma chain over k ascending per (row, centre); d2 = ((-2 dot) + |x|^2) + |c|^2; sqrt(max(d2, 0))),
+ * so selected indices and running minima are bit-reproducible on the CPU.  Ties: lowest index (np.argmax, :90).
+ *
+ *   mval_kcenter_norms        : row_norms[i] = dot(x_i, x_i)
+ *   mval_kcenter_update       : one centre (coreset.py:64-69 with a single cluster centre):
+ *                               min_dist[i] = min(min_dist[i], dist(x_i, centre)), then the arg-max of the updated
+ *                               min_dist -> out_best_val float32 device[1], out_best_idx int64 device[1] (index_offset
+ *                               added; -1 for n = 0) = the next `ind` of coreset.py:90.  `centre` float32 device [d].
+ *   mval_kcenter_update_batch : the same fold for n_centres centres in ONE pass over the features (what coreset.py:83-84
+ *                               does for the labeled set, and what a round of greedy picks needs).  centres float32
+ *                               device [n_centres][d], centre_norms their canonical squared norms.  flags: 0 = choose
+ *                               (tcgen05 TF32 screening GEMM + exact recheck when d is large and 16-byte aligned,
+ *                               register-tiled FFMA pass otherwise), 1 = force the FFMA pass, 2 = force the tensor-core
+ *                               path whenever it is applicable.  The result does not depend on the path. */
 int mval_kcenter_norms(const float* features, int64_t n, int d, float* row_norms, void* stream);
 int mval_kcenter_update(const float* features, const float* row_norms, int64_t n, int d, const float* centre,
                         float* min_dist, int64_t index_offset, float* out_best_val, int64_t* out_best_idx,
                         void* stream);
-/* Multi-GPU greedy step (features row-sharded across ranks, contiguous).  Same fused update as
- * mval_kcenter_update, plus the two halves of the per-step exchange so that the loop needs no host round trip:
- *   input  : the centre is either `centre` (d floats; used for the labeled set) or the best of the `n_cands`
- *            candidate records in `cands_in` (the all-gathered records of the previous step; highest value, lowest
- *            global index wins = np.argmax over the concatenated shards, coreset.py:90); in that case the chosen
- *            global index is also written to *out_selected (may be NULL);
- *   output : `cand_out` receives this rank's record {float32 val; int32 pad; int64 global idx; float32 row[d4]}
- *            (mval_kcenter_record_bytes(d) bytes, idx = -1 for an empty shard) of its updated local arg-max, feature
- *            row included, ready to be all-gathered. */
-size_t mval_kcenter_record_bytes(int d);
-int mval_kcenter_update_exchange(const float* features, const float* row_norms, int64_t n, int d, const float* centre,
-                                 const void* cands_in, int n_cands, float* min_dist, int64_t index_offset,
-                                 void* cand_out, int64_t* out_selected, void* stream);
-/* Single-device greedy loop (coreset.py:86-93) run entirely on the device: `budget` dependent steps without
- * host round trips.  labeled rows are [n_unlabeled, n); out_selected int64 device [budget]. */
+int mval_kcenter_update_batch(const float* features, const float* row_norms, int64_t n, int d, const float* centres,
+                              const float* centre_norms, int n_centres, float* min_dist, int flags, void* stream);
+
+/* The greedy loop of coreset.py:86-93 in ROUNDS (csrc/kcenter.cu header): each round yields the next T >= 1 picks of
+ * the sequential algorithm, exactly, for one pass over the features.  Multi-GPU (rows sharded contiguously): every
+ * rank calls select on its shard, the record blocks are all-gathered (the only exchange, once per round), every rank
+ * calls resolve on the gathered blocks -- all ranks compute the same picks -- and update_batch on its own shard.
+ *
+ *   mval_kcenter_records_bytes : size of one shard's record block for k_slots candidates of dimension d
+ *   mval_kcenter_select        : writes this shard's block: up to k_slots - 1 rows whose running minimum is above the
+ *                                shard's k_slots-th largest value kappa (all rows if n < k_slots), each with value,
+ *                                global index (index_offset + local), squared norm and feature row, plus kappa
+ *   mval_kcenter_resolve       : records = n_blocks consecutive blocks.  Replays the greedy loop on the union of the
+ *                                candidates while the best candidate is provably the arg-max of the whole pool (value
+ *                                above every shard's kappa; the first pick always is).  Writes the global indices of
+ *                                the picks to selected_out (int64 device [max_picks]), their rows and squared norms
+ *                                to centres_out (float32 device [max_picks][d]) / centre_norms_out, and the number of
+ *                                picks (1..max_picks) to *n_picks_host (HOST int32) -- this call synchronises `stream`.
+ *                                workspace: device, mval_kcenter_resolve_workspace_bytes(n_blocks, k_slots, d) bytes.
+ *                                n_blocks * k_slots <= 1024. */
+size_t mval_kcenter_records_bytes(int k_slots, int d);
+int mval_kcenter_select(const float* features, const float* row_norms, const float* min_dist, int64_t n, int d,
+                        int64_t index_offset, int k_slots, void* records_out, void* stream);
+size_t mval_kcenter_resolve_workspace_bytes(int n_blocks, int k_slots, int d);
+int mval_kcenter_resolve(const void* records, int n_blocks, int k_slots, int d, int max_picks, void* workspace,
+                         float* centres_out, float* centre_norms_out, int64_t* selected_out, int32_t* n_picks_host,
+                         void* stream);
+
+/* Single-device selection (coreset.py:71-95): norms, the labeled rows [n_unlabeled, n) folded in, then `budget`
+ * picks in rounds.  min_dist float32 device [n] (out), out_selected int64 device [budget].  Synchronises `stream`
+ * once per round. */
 int mval_kcenter_greedy(const float* features, int64_t n, int64_t n_unlabeled, int d, int32_t budget,
                         float* min_dist, int64_t* out_selected, void* stream);
 

@@ -12,6 +12,7 @@ MVAL_ERR_CUDA = -3
 MVAL_ERR_NO_DEVICE = -4
 MVAL_ERR_OUT_OF_MEMORY = -5
 MAX_VIEWS = 32
+ABI_VERSION = 2
 
 
 class MvalError(RuntimeError):
@@ -41,8 +42,11 @@ PROTOTYPES = {
     "mval_topk_desc": (C.c_int, [_p, _i64, _i64, C.c_int32, _p, _p, _p, _p]),
     "mval_kcenter_norms": (C.c_int, [_p, _i64, _i, _p, _p]),
     "mval_kcenter_update": (C.c_int, [_p, _p, _i64, _i, _p, _p, _i64, _p, _p, _p]),
-    "mval_kcenter_record_bytes": (C.c_size_t, [_i]),
-    "mval_kcenter_update_exchange": (C.c_int, [_p, _p, _i64, _i, _p, _p, _i, _p, _i64, _p, _p, _p]),
+    "mval_kcenter_update_batch": (C.c_int, [_p, _p, _i64, _i, _p, _p, _i, _p, _i, _p]),
+    "mval_kcenter_records_bytes": (C.c_size_t, [_i, _i]),
+    "mval_kcenter_select": (C.c_int, [_p, _p, _p, _i64, _i, _i64, _i, _p, _p]),
+    "mval_kcenter_resolve_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
+    "mval_kcenter_resolve": (C.c_int, [_p, _i, _i, _i, _i, _p, _p, _p, _p, C.POINTER(C.c_int32), _p]),
     "mval_kcenter_greedy": (C.c_int, [_p, _i64, _i64, _i, C.c_int32, _p, _p, _p]),
     "mval_synth_heatmaps": (C.c_int, [_p, _i64, _i, _i, _f, _f, _u64, _p, _p]),
 }
@@ -66,7 +70,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.mval_version() != 1:
+    if lib.mval_version() != ABI_VERSION:
         raise MvalError(MVAL_ERR_UNSUPPORTED, "ABI version mismatch")
     _lib = lib
     return lib

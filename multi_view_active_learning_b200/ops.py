@@ -265,16 +265,53 @@ def to_numpy(d):
     return {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
 
 
-def kcenter_record_bytes(d):
-    return int(_lib.load().mval_kcenter_record_bytes(int(d)))
+def kcenter_update_batch(features, norms, centres, centre_norms, min_dist, flags=0):
+    """In place: min_dist[i] = min(min_dist[i], dist(features[i], centres[t]) for every t) in one pass over the features
+    (utils/coreset.py:64-69 for a list of cluster centres).  flags: 0 choose, 1 force the FFMA pass, 2 force tcgen05."""
+    f = _cuda(features, torch.float32, "features")
+    n, d = f.shape
+    c = _cuda(centres, torch.float32, "centres").reshape(-1, d)
+    cn = _cuda(centre_norms, torch.float32, "centre_norms").reshape(-1)
+    assert cn.numel() == c.shape[0] and min_dist.dtype == torch.float32 and min_dist.is_contiguous() and min_dist.numel() == n
+    with torch.cuda.device(f.device):
+        check(_lib.load().mval_kcenter_update_batch(_ptr(f), _ptr(norms), n, d, _ptr(c), _ptr(cn), c.shape[0], _ptr(min_dist),
+                                                    int(flags), _stream()))
 
 
-def kcenter_update_exchange(features, norms, min_dist, index_offset, cand_out, centre=None, cands_in=None, n_cands=0,
-                            out_selected=None):
-    """One multi-GPU greedy step on this rank's shard (see include/mval_b200.h:mval_kcenter_update_exchange).
-    All arguments are CUDA tensors; nothing is returned to the host."""
+def kcenter_records_bytes(k_slots, d):
+    return int(_lib.load().mval_kcenter_records_bytes(int(k_slots), int(d)))
+
+
+def kcenter_select(features, norms, min_dist, index_offset, k_slots, out=None):
+    """Candidate record block of this shard for one greedy round (include/mval_b200.h:mval_kcenter_select)."""
     n, d = features.shape
+    if out is None:
+        out = torch.empty(kcenter_records_bytes(k_slots, d), dtype=torch.uint8, device=features.device)
     with torch.cuda.device(features.device):
-        check(_lib.load().mval_kcenter_update_exchange(_ptr(features), _ptr(norms), n, d, _ptr(centre), _ptr(cands_in),
-                                                       int(n_cands), _ptr(min_dist), int(index_offset), _ptr(cand_out),
-                                                       _ptr(out_selected), _stream()))
+        check(_lib.load().mval_kcenter_select(_ptr(features), _ptr(norms), _ptr(min_dist), n, d, int(index_offset),
+                                              int(k_slots), _ptr(out), _stream()))
+    return out
+
+
+class KcenterResolver:
+    """Workspace + outputs of mval_kcenter_resolve for a fixed (n_blocks, k_slots, d)."""
+
+    def __init__(self, n_blocks, k_slots, d, device):
+        self.n_blocks, self.k_slots, self.d = int(n_blocks), int(k_slots), int(d)
+        kc = self.n_blocks * self.k_slots
+        lib = _lib.load()
+        self.workspace = torch.empty(int(lib.mval_kcenter_resolve_workspace_bytes(self.n_blocks, self.k_slots, self.d)),
+                                     dtype=torch.uint8, device=device)
+        self.centres = torch.empty((kc, self.d), dtype=torch.float32, device=device)
+        self.centre_norms = torch.empty((kc,), dtype=torch.float32, device=device)
+        self._n = C.c_int32(0)
+
+    def resolve(self, records, max_picks, selected_out):
+        """records: the n_blocks gathered record blocks (uint8 CUDA).  Writes the picks' global indices to
+        selected_out[:T] and returns (T, centres[:T], centre_norms[:T]).  Synchronises the current stream."""
+        with torch.cuda.device(records.device):
+            check(_lib.load().mval_kcenter_resolve(_ptr(records), self.n_blocks, self.k_slots, self.d, int(max_picks),
+                                                   _ptr(self.workspace), _ptr(self.centres), _ptr(self.centre_norms),
+                                                   _ptr(selected_out), C.byref(self._n), _stream()))
+        t = int(self._n.value)
+        return t, self.centres[:t], self.centre_norms[:t]

@@ -51,50 +51,83 @@ def distributed_topk(local_topk, k, group=None):
 # ----------------------------------------------------------------------------------------------------------------
 # coreset k-center greedy over row-sharded features (utils/coreset.py:71-95 across ranks)
 # ----------------------------------------------------------------------------------------------------------------
-def kcenter_greedy_sharded(shards, labeled, budget, group=None):
+INIT_CHUNK = 256  # labeled centres folded in per pass over the features
+
+
+def kcenter_fold_centres(state, centres, centre_norms=None, flags=0):
+    """min_dist of every shard in ``state`` <- min over the given centre rows too (coreset.py:83-84)."""
+    from . import ops
+
+    if centres.shape[0] == 0:
+        return
+    centres = centres.float().contiguous()
+    if centre_norms is None:
+        centre_norms = ops.kcenter_norms(centres)
+    for c0 in range(0, centres.shape[0], INIT_CHUNK):
+        for s in state:
+            ops.kcenter_update_batch(s["feat"], s["norms"], centres[c0:c0 + INIT_CHUNK], centre_norms[c0:c0 + INIT_CHUNK],
+                                     s["min"], flags)
+
+
+def kcenter_rounds(state, budget, group=None, k_slots=None, flags=0, stats=None):
+    """``budget`` greedy picks over the shards in ``state`` (dicts with feat / norms / min / off), in rounds: every
+    shard contributes its candidate record block, the blocks are exchanged with ONE all_gather per round (not per
+    pick), every rank replays the greedy loop on the union -- identical picks everywhere -- and folds the new centres
+    into its own shards.  Returns the selected global indices (int64 CUDA [budget])."""
+    from . import ops
+
+    dev = state[0]["feat"].device
+    d = state[0]["feat"].shape[1]
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if multi else 1
+    n_local = len(state)
+    n_blocks = world * n_local
+    if k_slots is None:
+        k_slots = max(4, min(256, (1024 // n_blocks) // 4 * 4))
+    assert k_slots % 4 == 0 and n_blocks * k_slots <= 1024, "n_blocks * k_slots must be <= 1024 and k_slots % 4 == 0"
+    rb = ops.kcenter_records_bytes(k_slots, d)
+    local = torch.empty(n_local * rb, dtype=torch.uint8, device=dev)
+    gathered = torch.empty(world * n_local * rb, dtype=torch.uint8, device=dev) if multi else local
+    resolver = ops.KcenterResolver(n_blocks, k_slots, d, dev)
+    selected = torch.empty(max(int(budget), 1), dtype=torch.int64, device=dev)
+    done = 0
+    while done < budget:
+        for i, s in enumerate(state):
+            ops.kcenter_select(s["feat"], s["norms"], s["min"], s["off"], k_slots, out=local[i * rb:(i + 1) * rb])
+        if multi:
+            dist.all_gather_into_tensor(gathered, local, group=group)
+        t, centres, cnorms = resolver.resolve(gathered, budget - done, selected[done:])
+        assert t >= 1
+        for s in state:
+            ops.kcenter_update_batch(s["feat"], s["norms"], centres, cnorms, s["min"], flags)
+        done += t
+        if stats is not None:
+            stats.append(t)
+    return selected[: int(budget)]
+
+
+def kcenter_greedy_sharded(shards, labeled, budget, group=None, k_slots=None, flags=0, stats=None):
     """Greedy k-center selection over UNLABELED feature rows that are row-sharded contiguously.
 
     shards : list of (features float32 CUDA [n_s, d], global_row_offset) owned by THIS process -- one entry per
              rank in a torch.distributed job, several entries to emulate ranks on one device (tests).
     labeled: float32 CUDA [L, d], the labeled centres, replicated on every rank (coreset.py:83-84).
-    Per greedy step every shard updates its running minimum against the new centre and reduces to its local
-    (max min-distance, lowest global index, feature row) record inside one kernel; the records are exchanged with ONE
-    all_gather (<= world * (16 + 4 d) bytes) and the next launch picks the global winner on the device -- "first
-    index wins" across contiguous shards is "lowest global index among equal maxima", i.e. np.argmax (coreset.py:90).
-    No host synchronisation inside the loop.  Returns (selected global indices int64 CUDA [budget], list of
-    per-shard min_dist tensors).  Labeled rows never compete: their min-distance is exactly 0 and an all-zero pool
-    resolves to global index 0 in the reference too.
+    "First index wins" across contiguous shards is "lowest global index among equal maxima", i.e. np.argmax
+    (coreset.py:90).  Returns (selected global indices int64 CUDA [budget], list of per-shard min_dist tensors).
+    Labeled rows never compete: their min-distance is exactly 0 and an all-zero pool resolves to global index 0 in
+    the reference too.
     """
     from . import ops
 
     assert len(shards) >= 1 and labeled.shape[0] >= 1, "need at least one shard and one labeled centre"
     dev = labeled.device
-    d = labeled.shape[1]
-    rb = ops.kcenter_record_bytes(d)
-    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-    world = dist.get_world_size(group) if multi else 1
-    labeled = labeled.float().contiguous()
     state = []
     for feat, off in shards:
         feat = feat.float().contiguous()
         n = feat.shape[0]
         norms = ops.kcenter_norms(feat) if n else torch.empty(0, dtype=torch.float32, device=dev)
         state.append({"feat": feat, "off": int(off), "norms": norms,
-                      "min": torch.full((n,), float("inf"), dtype=torch.float32, device=dev),
-                      "cand": torch.zeros(rb, dtype=torch.uint8, device=dev)})
-    n_local = len(state)
-    local_cands = torch.empty(n_local * rb, dtype=torch.uint8, device=dev)
-    all_cands = torch.empty(world * n_local * rb, dtype=torch.uint8, device=dev) if multi else local_cands
-    selected = torch.empty(max(int(budget), 1), dtype=torch.int64, device=dev)
-    for c in range(labeled.shape[0]):
-        for s in state:
-            ops.kcenter_update_exchange(s["feat"], s["norms"], s["min"], s["off"], s["cand"], centre=labeled[c])
-    for t in range(int(budget)):
-        for i, s in enumerate(state):
-            local_cands[i * rb:(i + 1) * rb].copy_(s["cand"], non_blocking=True)
-        if multi:
-            dist.all_gather_into_tensor(all_cands, local_cands, group=group)
-        for i, s in enumerate(state):
-            ops.kcenter_update_exchange(s["feat"], s["norms"], s["min"], s["off"], s["cand"], cands_in=all_cands,
-                                        n_cands=world * n_local, out_selected=selected[t:] if i == 0 else None)
-    return selected[: int(budget)], [s["min"] for s in state]
+                      "min": torch.full((n,), float("inf"), dtype=torch.float32, device=dev)})
+    kcenter_fold_centres(state, labeled, flags=flags)
+    selected = kcenter_rounds(state, int(budget), group=group, k_slots=k_slots, flags=flags, stats=stats)
+    return selected, [s["min"] for s in state]

@@ -29,7 +29,6 @@ class CoreSet:
         self._feat = torch.from_numpy(np.ascontiguousarray(self.features, dtype=np.float32)).to(self._device)
         self._norms = None
         self._min_dist = None
-        self._best = None
 
     def _compute_stacked_features(self, root_idx):
         # reference :35-47: rows = unlabeled poses (dict order) then labeled; root-relative x.., y.., z.. per row
@@ -49,6 +48,8 @@ class CoreSet:
     def update_distances(self, cluster_centers, only_new=True, reset_dist=False):
         """Reference :49-69.  (With several centres and an existing min_distances the reference broadcasts to an
         [n, c] matrix; here the minimum over all given centres is folded into the [n, 1] vector.)"""
+        from .. import pool
+
         if reset_dist:
             self._min_dist = None
         if only_new:
@@ -58,27 +59,29 @@ class CoreSet:
                 self._norms = ops.kcenter_norms(self._feat)
             if self._min_dist is None:
                 self._min_dist = torch.full((self.n_obs,), float("inf"), dtype=torch.float32, device=self._device)
-            for c in cluster_centers:
-                self._best = ops.kcenter_update(self._feat, self._norms, self._feat[int(c)], self._min_dist)
+            idx = torch.as_tensor([int(c) for c in cluster_centers], dtype=torch.int64, device=self._device)
+            pool.kcenter_fold_centres([self._state()], self._feat[idx].contiguous(), self._norms[idx].contiguous())
+
+    def _state(self):
+        return {"feat": self._feat, "norms": self._norms, "min": self._min_dist, "off": 0}
 
     def select_batch(self, N, **kwargs):
-        """Reference :71-95: fold in the labeled set, then N times {argmax, assert, update}."""
+        """Reference :71-95: fold in the labeled set, then N times {argmax, assert, update} -- executed in exact
+        rounds on the device (csrc/kcenter.cu)."""
+        from .. import pool
+
         already_selected = self.al_indices
         if self._min_dist is None and len(already_selected) > 0 and not self.already_selected:
-            # whole loop on the device, no host round trip per step
+            # whole selection in one C call
             sel, self._min_dist = ops.kcenter_greedy(self._feat, len(self.sal_dict), N)
             new_batch = [int(i) for i in sel.cpu().tolist()]
-            for ind in new_batch:
-                assert ind not in already_selected
         else:
             self.update_distances(already_selected, only_new=True, reset_dist=False)
-            new_batch = []
-            for _ in range(N):
-                if self._best is None:  # no labeled centre at all: np.argmax(None) in the reference, undefined
-                    raise ValueError("CoreSet.select_batch needs at least one labeled pose")
-                ind = int(self._best[1].item())
-                assert ind not in already_selected
-                self.update_distances([ind], only_new=True, reset_dist=False)
-                new_batch.append(ind)
+            if self._min_dist is None:  # no labeled centre at all: np.argmax(None) in the reference, undefined
+                raise ValueError("CoreSet.select_batch needs at least one labeled pose")
+            sel = pool.kcenter_rounds([self._state()], int(N))
+            new_batch = [int(i) for i in sel.cpu().tolist()]
+        for ind in new_batch:
+            assert ind not in already_selected
         self.already_selected = already_selected
         return [self.sal_keys[i] for i in new_batch]

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(lib, name), "libmval_b200.so does not export %s" % name
         assert name in _lib.PROTOTYPES, "%s has no ctypes prototype" % name
     assert sorted(_lib.PROTOTYPES) == names
-    assert lib.mval_version() == 1
+    assert lib.mval_version() == _lib.ABI_VERSION
     assert lib.mval_last_error() is not None
 
 

@@ -319,7 +319,7 @@ def test_topk_matches_nlargest(ops):
 
 # ------------------------------------------------------------------------------------------------ coreset
 @pytest.mark.parametrize("n,L,d,budget", [(700, 30, 57, 40), (300, 10, 126, 25), (513, 7, 2048, 30), (200, 5, 130, 20),
-                                          (100, 3, 3, 10)])
+                                          (100, 3, 3, 10), (5000, 300, 57, 400), (3000, 20, 128, 300)])
 def test_kcenter_bit_exact_vs_f32_oracle(ops, n, L, d, budget):
     rng = np.random.default_rng(n + d)
     F = (rng.normal(size=(n + L, d)) * 50).astype(np.float32)
@@ -328,7 +328,58 @@ def test_kcenter_bit_exact_vs_f32_oracle(ops, n, L, d, budget):
     sel, min_d = ops.kcenter_greedy(_cuda(F), n, budget)
     assert sel.cpu().tolist() == exp_sel
     assert np.array_equal(min_d.cpu().numpy(), exp_min)  # bit-exact float32 distances, not only indices
-    assert np.array_equal(ops.kcenter_norms(_cuda(F)).cpu().numpy(), CO.canonical_dot_f32(F, F))
+    assert np.array_equal(ops.kcenter_norms(_cuda(F)).cpu().numpy(), CO.canonical_dot_f32(F))
+
+
+@pytest.mark.parametrize("kind", ["clustered", "lattice", "all_equal", "few_distinct"])
+def test_kcenter_rounds_on_hard_pools(ops, kind):
+    """Pools where a greedy round must stop early (clusters: one pick collapses its neighbours' minima) or where
+    almost everything ties (integer lattice, identical rows): the rounds still equal the sequential loop."""
+    rng = np.random.default_rng(11)
+    n, L, d, budget = 2500, 6, 57, 120
+    if kind == "clustered":
+        centres = rng.normal(size=(12, d)) * 100
+        F = centres[rng.integers(0, 12, n + L)] + rng.normal(size=(n + L, d)) * 0.5
+    elif kind == "lattice":
+        F = rng.integers(0, 3, size=(n + L, d)).astype(np.float64)
+    elif kind == "all_equal":
+        F = np.ones((n + L, d))
+        budget = 7
+    else:
+        F = rng.normal(size=(5, d))[rng.integers(0, 5, n + L)] * 10
+        budget = 12
+    F = F.astype(np.float32)
+    exp_sel, exp_min = CO.kcenter_greedy_f32(F, n, budget)
+    sel, min_d = ops.kcenter_greedy(_cuda(F), n, budget)
+    assert sel.cpu().tolist() == exp_sel
+    assert np.array_equal(min_d.cpu().numpy(), exp_min)
+
+
+def test_kcenter_update_paths_agree(ops):
+    """Single-centre update, batched FFMA update (all tile widths, aligned and unaligned d) and the oracle give the same
+    running minima bit for bit."""
+    rng = np.random.default_rng(3)
+    for d in (57, 64, 130, 256):
+        n = 1000
+        F = (rng.normal(size=(n, d)) * 20).astype(np.float32)
+        X = _cuda(F)
+        norms = ops.kcenter_norms(X)
+        xx = CO.canonical_dot_f32(F)
+        assert np.array_equal(norms.cpu().numpy(), xx)
+        for T in (1, 2, 16, 17, 64, 65, 200):
+            cidx = rng.integers(0, n, T)
+            exp = np.full(n, np.inf, dtype=np.float32)
+            for c in cidx:
+                exp = np.minimum(exp, CO.canonical_dist_f32(F, xx, F[c], xx[c]))
+            m = torch.full((n,), float("inf"), dtype=torch.float32, device="cuda")
+            ci = torch.as_tensor(cidx, device="cuda")
+            ops.kcenter_update_batch(X, norms, X[ci].contiguous(), norms[ci].contiguous(), m, flags=1)
+            assert np.array_equal(m.cpu().numpy(), exp), (d, T)
+        m = torch.full((n,), float("inf"), dtype=torch.float32, device="cuda")
+        best = ops.kcenter_update(X, norms, X[17], m)
+        exp = CO.canonical_dist_f32(F, xx, F[17], xx[17])
+        assert np.array_equal(m.cpu().numpy(), exp)
+        assert int(best[1].item()) == int(np.argmax(exp)) and float(best[0].item()) == float(exp.max())
 
 
 def test_coreset_class_matches_reference_golden(ops, golden):
@@ -358,8 +409,8 @@ def test_coreset_class_matches_reference_golden(ops, golden):
 
 
 def test_kcenter_sharded_loop_bit_exact(ops):
-    """The multi-GPU greedy loop (per-shard fused update -> candidate records -> device-side winner pick) with the
-    ranks emulated as shards on one device: uneven shards, an empty shard, duplicate rows across shards."""
+    """The multi-GPU greedy rounds (per-shard candidate records -> replay on the union -> batched update) with the ranks
+    emulated as shards on one device: uneven shards, an empty shard, duplicate rows across shards."""
     from multi_view_active_learning_b200 import pool as P
 
     rng = np.random.default_rng(7)
@@ -373,5 +424,10 @@ def test_kcenter_sharded_loop_bit_exact(ops):
     assert sel.cpu().tolist() == exp_sel
     assert np.array_equal(torch.cat(mins).cpu().numpy(), exp_min[:n])
     # one shard == the single-device loop
-    sel1, _ = P.kcenter_greedy_sharded([(_cuda(F[:n]), 0)], _cuda(F[n:]), budget)
+    stats = []
+    sel1, _ = P.kcenter_greedy_sharded([(_cuda(F[:n]), 0)], _cuda(F[n:]), budget, stats=stats)
     assert sel1.cpu().tolist() == exp_sel
+    assert sum(stats) == budget and len(stats) < budget  # rounds really batch several picks
+    # tiny candidate sets (k_slots = 4): many short rounds, same answer
+    sel2, _ = P.kcenter_greedy_sharded(shards, _cuda(F[n:]), budget, k_slots=4)
+    assert sel2.cpu().tolist() == exp_sel

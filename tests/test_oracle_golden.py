@@ -109,8 +109,33 @@ def test_canonical_dot_is_order_defined():
         np.testing.assert_allclose(got, X.astype(np.float64) @ c.astype(np.float64), rtol=2e-4, atol=1e-4)
         assert got.dtype == np.float32
     x = rng.normal(size=(1, 2048)).astype(np.float32)
-    xx = C.canonical_dot_f32(x, x[0])
+    xx = C.canonical_dot_f32(x)
     assert C.canonical_dist_f32(x, xx, x[0])[0] == 0.0  # a row is at distance exactly 0 from itself
+
+
+def test_c_oracle_equals_numpy_fma_emulation():
+    """Two independent statements of the canonical float32 arithmetic (C99 fmaf vs float64 + TwoSum + round-to-odd)
+    give the same bits: norms, distances, selected rows, final minima."""
+    rng = np.random.default_rng(1)
+    for n, L, d, b in [(300, 5, 57, 20), (120, 3, 126, 12), (64, 2, 2048, 6), (50, 1, 7, 8)]:
+        F = (rng.standard_normal((n + L, d)) * rng.choice([1e-2, 1.0, 300.0])).astype(np.float32)
+        F[7] = F[2]
+        assert np.array_equal(C.canonical_dot_f32(F), C.fma_dot_f32_numpy(F, F))
+        s1, m1 = C.kcenter_greedy_f32(F, n, b)
+        s2, m2 = C.kcenter_greedy_f32_numpy(F, n, b)
+        assert s1 == s2 and np.array_equal(m1, m2)
+    # the emulated fma itself on operands of very different magnitude (where double rounding would bite)
+    x = rng.standard_normal(200000).astype(np.float32)
+    c = rng.standard_normal(200000).astype(np.float32)
+    a = (rng.standard_normal(200000) * rng.choice([1e-6, 1e-3, 1.0, 1e3, 1e6], 200000)).astype(np.float32)
+    got = C._fma_f32(x, c, a)
+    import fractions
+
+    for i in range(0, 200000, 997):
+        exact = fractions.Fraction(float(x[i])) * fractions.Fraction(float(c[i])) + fractions.Fraction(float(a[i]))
+        lo, hi = np.nextafter(got[i], np.float32(-np.inf)), np.nextafter(got[i], np.float32(np.inf))
+        err = abs(fractions.Fraction(float(got[i])) - exact)
+        assert err <= abs(fractions.Fraction(float(lo)) - exact) and err <= abs(fractions.Fraction(float(hi)) - exact)
 
 
 def test_ranking():
