@@ -385,7 +385,24 @@ def run_ours(args):
 # ----------------------------------------------------------------------------------------------------------------
 # secondary workload: coreset k-center greedy (BASELINE.json configs[3], "C4"): not the driver's default line
 # ----------------------------------------------------------------------------------------------------------------
+def _timed(fn, iters=1):
+    import torch
+
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        out = fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters, out
+
+
 def run_coreset(args):
+    """C4-style workload: k-center greedy over n x d float32 features sharded by rows.  Reports the whole selection
+    (norms + labeled fold-in + budget picks in exact rounds) and the roofline of its dominant kernel (the batched
+    update: tcgen05 TF32 screening GEMM when applicable, register-tiled FFMA pass otherwise)."""
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -399,57 +416,111 @@ def run_coreset(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_total, d, L, budget = args.coreset_rows, args.coreset_dim, args.coreset_labeled, args.coreset_budget
+    flags = {"auto": 0, "ffma": 1, "tc": 2}[args.coreset_path]
     lo, hi = poolmod.shard_range(n_total, world, rank)
+    n = hi - lo
     g = torch.Generator(device=dev).manual_seed(99 + rank)
-    feat = torch.randn((hi - lo, d), generator=g, device=dev, dtype=torch.float32)
+    feat = torch.randn((n, d), generator=g, device=dev, dtype=torch.float32)
     gl = torch.Generator(device=dev).manual_seed(7)
     labeled = torch.randn((L, d), generator=gl, device=dev, dtype=torch.float32)
-    # per-step kernel roofline: one fused update over the local shard
-    norms = ops.kcenter_norms(feat)
-    min_d = torch.full((hi - lo,), float("inf"), dtype=torch.float32, device=dev)
-    best = ops.kcenter_update(feat, norms, labeled[0], min_d)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for i in range(20):
-        ops.kcenter_update(feat, norms, labeled[i % L], min_d, out_best=best)
-    b.record()
-    torch.cuda.synchronize()
-    step_ms = a.elapsed_time(b) / 20
-    step_bytes = (hi - lo) * (d * 4 + 12)
+    if args.coreset_data == "clustered":  # 64 tight clusters: a pick collapses the minima of its whole cluster
+        gc = torch.Generator(device=dev).manual_seed(5)
+        cent = torch.randn((64, d), generator=gc, device=dev, dtype=torch.float32) * 4.0
+        feat = feat * 0.25 + cent[torch.randint(0, 64, (n,), generator=g, device=dev)]
+        labeled = labeled * 0.25 + cent[torch.randint(0, 64, (L,), generator=gl, device=dev)]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    # the whole selection (labeled fold-in + budget greedy steps), device-timed, max over ranks
+
+    # ---- kernels timed alone on this rank's shard (CUDA events on the launching stream, after a warm-up call)
+    norms = ops.kcenter_norms(feat)
+    lab_norms = ops.kcenter_norms(labeled)
+    norms_ms, _ = _timed(lambda: ops.kcenter_norms(feat), 3)
+    min_d = torch.full((n,), float("inf"), dtype=torch.float32, device=dev)
+    ops.kcenter_update(feat, norms, labeled[0], min_d)
+    single_ms, _ = _timed(lambda: ops.kcenter_update_batch(feat, norms, labeled[:1], lab_norms[:1], min_d, 1), 5)
+    T = min(256, n)
+    cidx = torch.randint(0, n, (T,), generator=g, device=dev)
+    cent_rows, cent_norms = feat[cidx].contiguous(), norms[cidx].contiguous()
+    poolmod.kcenter_fold_centres([{"feat": feat, "norms": norms, "min": min_d, "off": lo}], labeled, lab_norms, flags=1)
+    ops.kcenter_update_batch(feat, norms, cent_rows, cent_norms, min_d.clone(), 1)
+    ffma_ms, _ = _timed(lambda: ops.kcenter_update_batch(feat, norms, cent_rows, cent_norms, min_d.clone(), 1), 2)
+    auto_ms, tc_survivors, tc_capacity = None, None, None
+    if flags != 1:
+        ops.kcenter_update_batch(feat, norms, cent_rows, cent_norms, min_d.clone(), flags)
+        auto_ms, _ = _timed(lambda: ops.kcenter_update_batch(feat, norms, cent_rows, cent_norms, min_d.clone(), flags), 3)
+        tc_survivors, tc_capacity = ops.kcenter_tc_stats()
+    clone_ms, _ = _timed(lambda: min_d.clone(), 3)
+    rec = ops.kcenter_select(feat, norms, min_d, lo, 256)
+    select_ms, _ = _timed(lambda: ops.kcenter_select(feat, norms, min_d, lo, 256, out=rec), 5)
+
+    # ---- the whole selection, device-timed, max over ranks
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     l0 = _lib.launch_count()
-    a.record()
-    sel, _ = poolmod.kcenter_greedy_sharded([(feat, lo)], labeled, budget)
-    b.record()
-    torch.cuda.synchronize()
-    total_ms = a.elapsed_time(b)
+    stats = []
+    total_ms, (sel, _) = _timed(lambda: poolmod.kcenter_greedy_sharded([(feat, lo)], labeled, budget, flags=flags, stats=stats))
     launches = _lib.launch_count() - l0
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
+
+    # ---- CPU arm on a bounded sample (rank 0): the C oracle (same arithmetic) on all host cores
+    cpu = None
+    if rank == 0 and args.cpu_frames > 0:
+        from oracle import coreset_oracle as CO
+
+        ns = min(n, args.coreset_cpu_rows)
+        Fs = np.concatenate([feat[:ns].cpu().numpy(), labeled[: min(L, 8)].cpu().numpy()])
+        steps = 8
+        t0 = time.perf_counter()
+        cpu_sel, _ = CO.kcenter_greedy_f32(Fs, ns, steps)
+        cpu_s = time.perf_counter() - t0
+        passes = min(L, 8) + steps + 1  # centre passes + the norms pass
+        cpu_rows_per_s = ns * passes / cpu_s  # row-passes per second
+        full_passes = L + budget + 1
+        cpu = {"value": n_total / (full_passes * n_total / cpu_rows_per_s), "unit": "rows/s", "cores": os.cpu_count(),
+               "kind": "port", "sample": "C oracle (OpenMP, fmaf) on %d x %d rows: %d centre passes in %.2f s; extrapolated "
+               "linearly to %d passes over %d rows (the sequential algorithm has no batching)" % (ns, d, passes, cpu_s,
+                                                                                                   full_passes, n_total)}
+        # parity of the sample against the GPU on the same rows
+        gsel, _ = ops.kcenter_greedy(torch.from_numpy(Fs).to(dev), ns, steps)
+        cpu["gpu_matches_oracle_on_sample"] = bool(gsel.cpu().tolist() == cpu_sel)
     if rank == 0:
-        gbs = step_bytes / (step_ms * 1e-3) / 1e9
-        print(json.dumps({
+        upd_ms = (auto_ms if auto_ms is not None else ffma_ms) - clone_ms
+        ffma_only = ffma_ms - clone_ms
+        flops = 2.0 * n * T * d
+        step_bytes = n * (d * 4 + 12)
+        out = {
             "metric": "coreset k-center greedy: pool rows selected-from / sec", "value": n_total / (total_ms * 1e-3),
-            "unit": "rows/s", "n_gpus": world, "ms_total": total_ms, "ms_per_greedy_step": total_ms / (L + budget),
-            "higher_is_better": True, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C4-style coreset: %d x %d float32 features, %d labeled centres folded in one by one, "
-                                   "budget %d, rows sharded over %d GPU(s)" % (n_total, d, L, budget, world)},
-            "roofline": {"bound": "hbm", "kernel": "kcenter_update_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": gbs / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": step_bytes,
-                         "avg_launch_ms": step_ms},
-            "gpu_launches": int(launches), "selected_head": sel[:5].cpu().tolist()}))
+            "unit": "rows/s", "n_gpus": world, "ms_total": total_ms, "higher_is_better": True, "dtype": "f32",
+            "data": "synthetic (%s)" % args.coreset_data,
+            "config": {"workload": "C4-style coreset: %d x %d float32 features, %d labeled centres, budget %d, rows sharded "
+                                   "over %d GPU(s); exact greedy in rounds" % (n_total, d, L, budget, world),
+                       "update_path": args.coreset_path},
+            "rounds": {"count": len(stats), "picks_per_round_mean": float(np.mean(stats)), "picks_per_round_min": int(min(stats)),
+                       "picks_per_round_max": int(max(stats))},
+            "ms_per_pick": total_ms / budget,
+            "equivalent_sequential_ms": (L + budget) * single_ms,
+            "kernels_ms": {"norms": norms_ms, "single_centre_update": single_ms, "update_256_centres_ffma": ffma_only,
+                           "update_256_centres_selected_path": upd_ms, "select_256": select_ms},
+            "roofline": {"bound": "hbm", "kernel": "kc_rowdot_kernel<1> (single-centre update, one greedy step of the reference)",
+                         "achieved": step_bytes / (single_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": step_bytes / (single_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": step_bytes, "avg_launch_ms": single_ms,
+                         "batched_update": {"centres": T, "ffma_tflops": flops / (ffma_only * 1e-3) / 1e12,
+                                            "selected_path_tflops_equiv": flops / (upd_ms * 1e-3) / 1e12,
+                                            "selected_path_gbs": step_bytes / (upd_ms * 1e-3) / 1e9,
+                                            "tc_survivor_pairs": tc_survivors, "tc_pair_capacity": tc_capacity}},
+            "gpu_launches": int(launches), "selected_head": sel[:5].cpu().tolist()}
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -472,7 +543,10 @@ def main():
     ap.add_argument("--coreset-rows", type=int, default=1_000_000)
     ap.add_argument("--coreset-dim", type=int, default=2048)
     ap.add_argument("--coreset-labeled", type=int, default=64)
-    ap.add_argument("--coreset-budget", type=int, default=256)
+    ap.add_argument("--coreset-budget", type=int, default=2048)
+    ap.add_argument("--coreset-path", default="auto", choices=["auto", "ffma", "tc"])
+    ap.add_argument("--coreset-data", default="gaussian", choices=["gaussian", "clustered"])
+    ap.add_argument("--coreset-cpu-rows", type=int, default=50000)
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -177,6 +177,11 @@ int mval_kcenter_update(const float* features, const float* row_norms, int64_t n
 int mval_kcenter_update_batch(const float* features, const float* row_norms, int64_t n, int d, const float* centres,
                               const float* centre_norms, int n_centres, float* min_dist, int flags, void* stream);
 
+/* Diagnostics of the tensor-core path: number of (row, centre) pairs that survived the LAST screening GEMM on the
+ * current device and had to be re-evaluated exactly, and the capacity of the survivor list (beyond it the FFMA pass
+ * takes over).  Host pointers; synchronises `stream`. */
+int mval_kcenter_tc_stats(uint64_t* survivors, uint64_t* capacity, void* stream);
+
 /* The greedy loop of coreset.py:86-93 in ROUNDS (csrc/kcenter.cu header): each round yields the next T >= 1 picks of
  * the sequential algorithm, exactly, for one pass over the features.  Multi-GPU (rows sharded contiguously): every
  * rank calls select on its shard, the record blocks are all-gathered (the only exchange, once per round), every rank

@@ -43,6 +43,7 @@ PROTOTYPES = {
     "mval_kcenter_norms": (C.c_int, [_p, _i64, _i, _p, _p]),
     "mval_kcenter_update": (C.c_int, [_p, _p, _i64, _i, _p, _p, _i64, _p, _p, _p]),
     "mval_kcenter_update_batch": (C.c_int, [_p, _p, _i64, _i, _p, _p, _i, _p, _i, _p]),
+    "mval_kcenter_tc_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _p]),
     "mval_kcenter_records_bytes": (C.c_size_t, [_i, _i]),
     "mval_kcenter_select": (C.c_int, [_p, _p, _p, _i64, _i, _i64, _i, _p, _p]),
     "mval_kcenter_resolve_workspace_bytes": (C.c_size_t, [_i, _i, _i]),

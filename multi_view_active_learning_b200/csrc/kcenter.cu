@@ -145,8 +145,9 @@ template <int TN, bool kStore, bool kVec>
 __global__ void __launch_bounds__(kBatchThreads, 2)
 kc_batch_kernel(const float* __restrict__ X, const float* __restrict__ xx, int64_t n, int d, const float* __restrict__ C,
                 const float* __restrict__ cc, int T, int n_col_tiles, float* __restrict__ min_dist, float* __restrict__ out,
-                int64_t ld_out) {
+                int64_t ld_out, const unsigned int* __restrict__ gate, unsigned int gate_capacity) {
   constexpr int BN = 16 * TN;
+  if (gate != nullptr && *gate <= gate_capacity) return;  // fallback pass of the tensor-core path: nothing overflowed
   constexpr int XS = kBM + 4, CS = BN + 4;
   __shared__ __align__(16) float xs[2][kBK][XS];
   __shared__ __align__(16) float cs[2][kBK][CS];
@@ -305,7 +306,8 @@ kc_batch_kernel(const float* __restrict__ X, const float* __restrict__ xx, int64
 
 template <int TN, bool kStore>
 static int launch_batch_tn(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T,
-                           float* min_dist, float* out, int64_t ld_out, cudaStream_t stream) {
+                           float* min_dist, float* out, int64_t ld_out, cudaStream_t stream,
+                           const unsigned int* gate = nullptr, unsigned int gate_capacity = 0) {
   constexpr int BN = 16 * TN;
   const int n_col_tiles = (T + BN - 1) / BN;
   const int64_t n_row_tiles = (n + kBM - 1) / kBM;
@@ -314,10 +316,10 @@ static int launch_batch_tn(const float* X, const float* xx, int64_t n, int d, co
   const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
   if (vec)
     kc_batch_kernel<TN, kStore, true><<<(unsigned)blocks, kBatchThreads, 0, stream>>>(X, xx, n, d, C, cc, T, n_col_tiles,
-                                                                                        min_dist, out, ld_out);
+                                                                                        min_dist, out, ld_out, gate, gate_capacity);
   else
     kc_batch_kernel<TN, kStore, false><<<(unsigned)blocks, kBatchThreads, 0, stream>>>(X, xx, n, d, C, cc, T, n_col_tiles,
-                                                                                         min_dist, out, ld_out);
+                                                                                         min_dist, out, ld_out, gate, gate_capacity);
   MVAL_LAUNCH_CHECK("kc_batch");
   return MVAL_OK;
 }
@@ -333,6 +335,13 @@ int kc_update_batch_exact(const float* X, const float* xx, int64_t n, int d, con
   if (T <= 16) return launch_batch_tn<1, false>(X, xx, n, d, C, cc, T, min_dist, nullptr, 0, stream);
   if (T <= 64) return launch_batch_tn<4, false>(X, xx, n, d, C, cc, T, min_dist, nullptr, 0, stream);
   return launch_batch_tn<8, false>(X, xx, n, d, C, cc, T, min_dist, nullptr, 0, stream);
+}
+
+// The same pass, executed only if *count > capacity on the device (overflow of the tensor-core path's pair list).
+int kc_update_batch_exact_if(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T,
+                             float* min_dist, const unsigned int* count, unsigned int capacity, cudaStream_t stream) {
+  if (T <= 64) return launch_batch_tn<4, false>(X, xx, n, d, C, cc, T, min_dist, nullptr, 0, stream, count, capacity);
+  return launch_batch_tn<8, false>(X, xx, n, d, C, cc, T, min_dist, nullptr, 0, stream, count, capacity);
 }
 
 int kc_pairwise_exact(const float* X, const float* xx, int n, int d, float* out_t, cudaStream_t stream) {
@@ -722,14 +731,6 @@ kc_argmax_kernel(const float* __restrict__ m, int64_t n, int64_t index_offset, K
   }
 }
 
-#ifndef MVAL_HAVE_KCENTER_TC
-int kc_update_batch(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T, float* min_dist,
-                    int flags, cudaStream_t stream) {
-  (void)flags;
-  return kc_update_batch_exact(X, xx, n, d, C, cc, T, min_dist, stream);
-}
-#endif
-
 int kc_norms(const float* X, int64_t n, int d, float* out, cudaStream_t stream) {
   if (n == 0) return MVAL_OK;
   kc_rowdot_kernel<0><<<rowdot_grid(n), kRdWarps * 32, 0, stream>>>(X, n, d, nullptr, nullptr, nullptr, out);
@@ -788,6 +789,12 @@ extern "C" int mval_kcenter_update_batch(const float* features, const float* row
   MVAL_REQUIRE(features && row_norms && centres && centre_norms && min_dist, "mval_kcenter_update_batch: null pointer");
   return kc_update_batch(features, row_norms, n, d, centres, centre_norms, n_centres, min_dist, flags,
                          static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mval_kcenter_tc_stats(uint64_t* survivors, uint64_t* capacity, void* stream) {
+  if (int rc = require_device()) return rc;
+  MVAL_REQUIRE(survivors && capacity, "mval_kcenter_tc_stats: null pointer");
+  return kc_tc_last_stats(survivors, capacity, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" size_t mval_kcenter_records_bytes(int k_slots, int d) { return kc_records_bytes(k_slots, d); }

@@ -1,0 +1,427 @@
+// Coreset batched update on the 5th-generation tensor cores (sm_100a): a tcgen05 TF32 GEMM as an error-bounded SCREEN,
+// followed by an exact float32 re-evaluation of the few (row, centre) pairs that survive it.
+//
+// Goal of a batched update (kcenter.cu header):  m_i <- min(m_i, min_t dist(x_i, c_t))  for T new centres, with dist in
+// the canonical float32 order.  tcgen05 has no true-float32 MMA, so the tensor cores cannot produce dist itself; they
+// can, however, PROVE for almost every pair that it cannot change m_i:
+//
+//   dot_tc(i,t)   = TF32 tensor-core dot product (operands truncated to 10 mantissa bits, float32 accumulation in TMEM)
+//   |dot_tc - dot_canonical| <= E,  2E <= (2^-9 + d 2^-21) (|x|^2 + |c|^2)            (derivation in DESIGN.md section 4)
+//   => canonical d2(i,t) lies within s_i = alpha (|x_i|^2 + max_t |c_t|^2) of  D~(i,t) = |x_i|^2 - 2 val,
+//      val = dot_tc - |c_t|^2 / 2,  alpha = 2^-8 + d 2^-20 (twice the bound)
+//
+// A pair can lower m_i only if (A) D~ - s_i < m_i^2 (it may beat the current minimum) and (B) D~ - s_i <= min_t' D~ + s_i
+// (it may be the best of this batch).  The epilogue evaluates A and B straight out of TMEM -- one sweep for the row
+// maximum of val, one sweep that appends the surviving (i, t) to a global list -- and kc_recheck_kernel evaluates the
+// canonical distance of the survivors (typically 1-3 per row while minima are still falling, ~0 later) and applies
+// atomicMin.  The result is bit-identical to the exact FFMA pass; if the list overflows, a device-side flag makes the
+// FFMA pass (always launched, normally a no-op) do the work instead.  No host synchronisation.
+//
+// Kernel anatomy (one persistent CTA per SM, 192 threads):
+//   warp 0     TMA producer: cp.async.bulk.tensor 2-D tiles, 128-byte swizzle, 4-stage ring
+//              A = 128 feature rows x 32 floats (16 KiB), B = 256 centres x 32 floats (32 KiB; rows >= T zero-filled)
+//   warp 1     allocates 512 TMEM columns, issues tcgen05.mma.cta_group::1.kind::tf32 M=128 N=256 K=8 (4 per stage),
+//              tcgen05.commit -> stage-empty / accumulator-full mbarriers
+//   warps 2-5  epilogue: tcgen05.ld 32x32b of the 128 x 256 float32 accumulator (two TMEM buffers, so the MMAs of the next
+//              row tile overlap the epilogue of this one)
+#include <cuda.h>
+
+#include "kcenter.cuh"
+
+namespace mval {
+
+namespace {
+
+constexpr int kTcBlockM = 128, kTcBlockN = 256, kTcBlockK = 32, kTcStages = 4, kTcUmmaK = 8;
+constexpr int kTcThreads = 192;
+constexpr uint32_t kTcABytes = kTcBlockM * kTcBlockK * 4, kTcBBytes = kTcBlockN * kTcBlockK * 4;
+constexpr uint32_t kTcStageBytes = kTcABytes + kTcBBytes;
+constexpr uint32_t kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*hcc*/ + 256 /*barriers etc.*/ + 1024 /*alignment*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// A wait that lasts ~4 s of SM clocks is a protocol bug: trap (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  long long t0 = 0;
+  for (uint32_t polls = 0;; ++polls) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((polls & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 8000000000ll) asm volatile("trap;");
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, float32 accumulate, issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// K-major operand tile, rows of 128 bytes, 128-byte swizzle, 8-row groups 1024 bytes apart (SBO); LBO unused.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major, N >> 3 at 17, M >> 4 at 24
+constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBlockN >> 3) << 17) | ((uint32_t)(kTcBlockM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+struct TcPair {
+  uint32_t row, t;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+kc_screen_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
+                    const float* __restrict__ xx, const float* __restrict__ cc, const float* __restrict__ min_dist, int64_t n,
+                    int d, int T, float alpha, TcPair* __restrict__ pairs, unsigned int* __restrict__ pair_count,
+                    unsigned int pair_capacity) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* hcc = reinterpret_cast<float*>(smem + kTcStages * kTcStageBytes);  // |c_t|^2 / 2, +inf for t >= T
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes + 1024);
+  uint64_t* full = bars;                       // [kTcStages]
+  uint64_t* empty = bars + kTcStages;          // [kTcStages]
+  uint64_t* tmem_full = bars + 2 * kTcStages;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* cc_max_slot = reinterpret_cast<float*>(tmem_base_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (n + kTcBlockM - 1) / kTcBlockM;
+  const int nkb = (d + kTcBlockK - 1) / kTcBlockK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int t = threadIdx.x; t < kTcBlockN; t += kTcThreads) hcc[t] = (t < T) ? 0.5f * __ldg(cc + t) : INFINITY;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 2) {
+    float m = 0.0f;
+    for (int t = lane; t < T; t += 32) m = fmaxf(m, __ldg(cc + t));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    if (lane == 0) *cc_max_slot = m;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  const float cc_max = *cc_max_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], kTcStageBytes);
+          unsigned char* a_dst = smem + stage * kTcStageBytes;
+          tma_load_2d(a_dst, &map_x, kb * kTcBlockK, (int)(tile * kTcBlockM), &full[stage]);
+          tma_load_2d(a_dst + kTcABytes, &map_c, kb * kTcBlockK, 0, &full[stage]);
+          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kTcBlockN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kTcStageBytes);
+          const uint32_t b_addr = a_addr + kTcABytes;
+#pragma unroll
+          for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k) {
+            umma_tf32(tmem_d, umma_smem_desc(a_addr + k * kTcUmmaK * 4), umma_smem_desc(b_addr + k * kTcUmmaK * 4), kTcIdesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    const int n_chunks = (T + 31) / 32;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      const int64_t row = tile * kTcBlockM + quarter * 32 + lane;
+      const bool rok = row < n;
+      const float xr = rok ? __ldg(xx + row) : 0.0f;
+      const float mi = rok ? __ldg(min_dist + row) : 0.0f;
+      const float m2 = __fmul_ru(mi, mi);
+      const float s_i = alpha * (xr + cc_max);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * kTcBlockN + ((uint32_t)(quarter * 32) << 16);
+      float v[32];
+      float vmax = -INFINITY;
+      for (int c = 0; c < n_chunks; ++c) {
+        tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, v[j] - hcc[c * 32 + j]);
+      }
+      // pair (i, t) survives iff val >= max(0.5 (|x|^2 - s - m^2), max_t val - s)
+      const float thr = fmaxf(0.5f * ((xr - s_i) - m2), vmax - s_i);
+      for (int c = 0; c < n_chunks; ++c) {
+        tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (rok && (v[j] - hcc[c * 32 + j]) >= thr) {
+            const unsigned int pos = atomicAdd(pair_count, 1u);
+            if (pos < pair_capacity) pairs[pos] = TcPair{(uint32_t)row, (uint32_t)(c * 32 + j)};
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// Exact canonical distance of the surviving pairs; 32 pairs per warp, coalesced through a shared-memory transpose.
+constexpr int kRcWarps = 4;
+__global__ void __launch_bounds__(kRcWarps * 32)
+kc_recheck_kernel(const float* __restrict__ X, const float* __restrict__ xx, int d, const float* __restrict__ C,
+                  const float* __restrict__ cc, const TcPair* __restrict__ pairs, const unsigned int* __restrict__ pair_count,
+                  unsigned int pair_capacity, float* __restrict__ min_dist) {
+  __shared__ float tx[kRcWarps][32][33];
+  __shared__ float tc[kRcWarps][32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned int total = *pair_count;
+  if (total > pair_capacity) total = pair_capacity;  // overflow: the FFMA fallback pass redoes everything
+  const unsigned int n_groups = (total + 31) / 32;
+  for (unsigned int g = blockIdx.x * kRcWarps + warp; g < n_groups; g += gridDim.x * kRcWarps) {
+    const unsigned int p = g * 32 + lane;
+    const bool ok = p < total;
+    const TcPair pr = ok ? pairs[p] : TcPair{0u, 0u};
+    const float* xrow = X + (int64_t)pr.row * d;
+    const float* crow = C + (int64_t)pr.t * d;
+    float acc = 0.0f;
+    for (int k0 = 0; k0 < d; k0 += 32) {
+      const int k = k0 + lane;
+      float vx[32], vc[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const float* xr = reinterpret_cast<const float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(xrow), r));
+        const float* cr = reinterpret_cast<const float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(crow), r));
+        vx[r] = (k < d) ? __ldg(xr + k) : 0.0f;
+        vc[r] = (k < d) ? __ldg(cr + k) : 0.0f;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        tx[warp][r][lane] = vx[r];
+        tc[warp][r][lane] = vc[r];
+      }
+      __syncwarp();
+      const int kk = (d - k0) < 32 ? (d - k0) : 32;
+      if (kk == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc = __fmaf_rn(tx[warp][lane][j], tc[warp][lane][j], acc);
+      } else {
+        for (int j = 0; j < kk; ++j) acc = __fmaf_rn(tx[warp][lane][j], tc[warp][lane][j], acc);
+      }
+    }
+    if (ok) {
+      const float dist = kc_dist(acc, __ldg(xx + pr.row), __ldg(cc + pr.t));
+      if (dist < min_dist[pr.row]) atomicMin(reinterpret_cast<unsigned int*>(min_dist + pr.row), __float_as_uint(dist));
+    }
+  }
+}
+
+__global__ void kc_tc_reset_kernel(unsigned int* pair_count) { *pair_count = 0u; }
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int d, int box_rows) {
+  static PFN_encodeTiled encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MVAL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return MVAL_ERR_CUDA;
+    }
+    encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)d * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)kTcBlockK, (cuuint32_t)box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld, d %d)", (int)r, (long long)rows, d);
+    return MVAL_ERR_CUDA;
+  }
+  return MVAL_OK;
+}
+
+}  // namespace
+
+// ffma fallback that only runs when the pair list overflowed (kcenter.cu)
+int kc_update_batch_exact_if(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T,
+                             float* min_dist, const unsigned int* count, unsigned int capacity, cudaStream_t stream);
+
+bool kc_tc_applicable(const float* X, int64_t n, int d, const float* C, int T) {
+  return d % 4 == 0 && d >= 64 && n >= 1024 && T >= 2 && T <= kTcBlockN && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+}
+
+int kc_update_batch_tc(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T, float* min_dist,
+                       cudaStream_t stream) {
+  KcDeviceScratch* s = nullptr;
+  if (int rc = kc_scratch(&s)) return rc;
+  size_t want = (size_t)n * 4;
+  if (want < (1u << 20)) want = 1u << 20;
+  if (want > (16u << 20)) want = 16u << 20;
+  if (s->tc_pairs_capacity < want) {
+    if (s->tc_pairs) cudaFree(s->tc_pairs);
+    s->tc_pairs = nullptr;
+    s->tc_pairs_capacity = 0;
+    MVAL_CUDA(cudaMalloc(&s->tc_pairs, want * sizeof(TcPair)));
+    s->tc_pairs_capacity = want;
+  }
+  if (s->tc_count == nullptr) MVAL_CUDA(cudaMalloc(&s->tc_count, sizeof(unsigned int)));
+  MVAL_CUDA(cudaFuncSetAttribute(kc_screen_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  CUtensorMap map_x, map_c;
+  if (int rc = make_map(&map_x, X, n, d, kTcBlockM)) return rc;
+  if (int rc = make_map(&map_c, C, T, d, kTcBlockN)) return rc;
+  const unsigned int cap = (unsigned int)s->tc_pairs_capacity;
+  kc_tc_reset_kernel<<<1, 1, 0, stream>>>(s->tc_count);
+  MVAL_LAUNCH_CHECK("kc_tc_reset");
+  const int64_t n_tiles = (n + kTcBlockM - 1) / kTcBlockM;
+  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  const float alpha = ldexpf(1.0f, -8) + (float)d * ldexpf(1.0f, -20);
+  kc_screen_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(map_x, map_c, xx, cc, min_dist, n, d, T, alpha,
+                                                                  static_cast<TcPair*>(s->tc_pairs), s->tc_count, cap);
+  MVAL_LAUNCH_CHECK("kc_screen_tc");
+  kc_recheck_kernel<<<num_sms() * 4, kRcWarps * 32, 0, stream>>>(X, xx, d, C, cc, static_cast<const TcPair*>(s->tc_pairs),
+                                                                 s->tc_count, cap, min_dist);
+  MVAL_LAUNCH_CHECK("kc_recheck");
+  return kc_update_batch_exact_if(X, xx, n, d, C, cc, T, min_dist, s->tc_count, cap, stream);
+}
+
+int kc_tc_last_stats(uint64_t* survivors, uint64_t* capacity, cudaStream_t stream) {
+  KcDeviceScratch* s = nullptr;
+  if (int rc = kc_scratch(&s)) return rc;
+  *survivors = 0;
+  *capacity = s->tc_pairs_capacity;
+  if (s->tc_count == nullptr) return MVAL_OK;
+  unsigned int c = 0;
+  MVAL_CUDA(cudaMemcpyAsync(&c, s->tc_count, sizeof(c), cudaMemcpyDeviceToHost, stream));
+  MVAL_CUDA(cudaStreamSynchronize(stream));
+  *survivors = c;
+  return MVAL_OK;
+}
+
+int kc_update_batch(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T, float* min_dist,
+                    int flags, cudaStream_t stream) {
+  if (n == 0 || T == 0) return MVAL_OK;
+  const bool force_exact = (flags & kKcFlagForceExact) != 0;
+  const bool force_tc = (flags & kKcFlagForceTc) != 0;
+  for (int t0 = 0; t0 < T; t0 += kTcBlockN) {
+    const int tn = (T - t0) < kTcBlockN ? (T - t0) : kTcBlockN;
+    const float* Cb = C + (int64_t)t0 * d;
+    const bool can = kc_tc_applicable(X, n, d, Cb, tn);
+    // the tensor-core pass costs one sweep of the features whatever tn is; the FFMA pass costs ~ tn / 256 of 16 sweeps
+    const bool use_tc = !force_exact && can && (force_tc || ((int64_t)tn * d >= 16 * 1024 && n >= 16384));
+    int rc;
+    if (use_tc) rc = kc_update_batch_tc(X, xx, n, d, Cb, cc + t0, tn, min_dist, stream);
+    else rc = kc_update_batch_exact(X, xx, n, d, Cb, cc + t0, tn, min_dist, stream);
+    if (rc) return rc;
+  }
+  return MVAL_OK;
+}
+
+}  // namespace mval

@@ -278,6 +278,13 @@ def kcenter_update_batch(features, norms, centres, centre_norms, min_dist, flags
                                                     int(flags), _stream()))
 
 
+def kcenter_tc_stats():
+    """(survivors of the last tensor-core screen on the current device, capacity of the survivor list)."""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    check(_lib.load().mval_kcenter_tc_stats(C.byref(a), C.byref(b), _stream()))
+    return int(a.value), int(b.value)
+
+
 def kcenter_records_bytes(k_slots, d):
     return int(_lib.load().mval_kcenter_records_bytes(int(k_slots), int(d)))
 

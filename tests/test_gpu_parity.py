@@ -382,6 +382,56 @@ def test_kcenter_update_paths_agree(ops):
         assert int(best[1].item()) == int(np.argmax(exp)) and float(best[0].item()) == float(exp.max())
 
 
+@pytest.mark.parametrize("n,d", [(5000, 64), (20000, 256), (3000, 2048), (4097, 100)])
+def test_kcenter_tensor_core_screen_equals_exact_pass(ops, n, d):
+    """tcgen05 TF32 screening GEMM + exact recheck must give the same running minima, bit for bit, as the FFMA pass:
+    from +inf (every row has survivors), after some centres (few survivors), with duplicate rows (distance exactly 0)."""
+    rng = np.random.default_rng(d)
+    F = (rng.normal(size=(n, d)) * 3).astype(np.float32)
+    F[n // 2] = F[11]
+    X = _cuda(F)
+    norms = ops.kcenter_norms(X)
+    m_tc = torch.full((n,), float("inf"), dtype=torch.float32, device="cuda")
+    m_ex = m_tc.clone()
+    for T in (256, 37, 3, 200):
+        ci = torch.as_tensor(rng.integers(0, n, T), device="cuda")
+        ci[0] = 11
+        C, cn = X[ci].contiguous(), norms[ci].contiguous()
+        ops.kcenter_update_batch(X, norms, C, cn, m_tc, flags=2)
+        survivors, capacity = ops.kcenter_tc_stats()
+        ops.kcenter_update_batch(X, norms, C, cn, m_ex, flags=1)
+        assert torch.equal(m_tc, m_ex), (n, d, T)
+        # the screen really screens: far fewer survivors than pairs, and never the overflow fallback
+        assert 0 < survivors <= capacity and survivors <= max(4 * n, n * T // 8), (n, d, T, survivors)
+    assert float(m_tc[n // 2].item()) == 0.0
+    # against the oracle for one batch
+    xx = CO.canonical_dot_f32(F)
+    exp = np.full(n, np.inf, dtype=np.float32)
+    cidx = rng.integers(0, n, 40)
+    for c in cidx:
+        exp = np.minimum(exp, CO.canonical_dist_f32(F, xx, F[c], xx[c]))
+    m = torch.full((n,), float("inf"), dtype=torch.float32, device="cuda")
+    ci = torch.as_tensor(cidx, device="cuda")
+    ops.kcenter_update_batch(X, norms, X[ci].contiguous(), norms[ci].contiguous(), m, flags=2)
+    assert np.array_equal(m.cpu().numpy(), exp)
+
+
+def test_kcenter_greedy_with_tensor_core_updates(ops):
+    """Whole selection with the tensor-core update path (auto-selected at this size) against the C oracle."""
+    from multi_view_active_learning_b200 import pool as P
+
+    rng = np.random.default_rng(21)
+    n, L, d, budget = 20000, 40, 128, 300
+    F = (rng.normal(size=(n + L, d)) * 2).astype(np.float32)
+    exp_sel, exp_min = CO.kcenter_greedy_f32(F, n, budget)
+    sel, min_d = ops.kcenter_greedy(_cuda(F), n, budget)
+    assert sel.cpu().tolist() == exp_sel
+    assert np.array_equal(min_d.cpu().numpy(), exp_min)
+    sel2, mins = P.kcenter_greedy_sharded([(_cuda(F[:9000]), 0), (_cuda(F[9000:n]), 9000)], _cuda(F[n:]), budget, flags=2)
+    assert sel2.cpu().tolist() == exp_sel
+    assert np.array_equal(torch.cat(mins).cpu().numpy(), exp_min[:n])
+
+
 def test_coreset_class_matches_reference_golden(ops, golden):
     from multi_view_active_learning_b200.utils.coreset import CoreSet
 
