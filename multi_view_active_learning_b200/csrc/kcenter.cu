@@ -657,7 +657,11 @@ int kc_resolve(const void* records, int n_blocks, int K, int d, int max_picks, v
   kc_unpack_kernel<<<Kc, 128, 0, stream>>>(static_cast<const char*>(records), n_blocks, K, d, kc_records_bytes(K, d), rows, val,
                                            xx, gidx, tau);
   MVAL_LAUNCH_CHECK("kc_unpack");
-  if (int rc = kc_pairwise_exact(rows, xx, Kc, d, dt, stream)) return rc;
+  if (kc_pairwise_tc_applicable(rows, Kc, d)) {
+    if (int rc = kc_pairwise_tc(rows, xx, val, Kc, d, dt, stream)) return rc;
+  } else {
+    if (int rc = kc_pairwise_exact(rows, xx, Kc, d, dt, stream)) return rc;
+  }
   const int threads = (Kc + 31) / 32 * 32;
   kc_replay_kernel<<<1, threads, 0, stream>>>(val, gidx, dt, Kc, tau, max_picks, selected_out, pick_slots, n_picks);
   MVAL_LAUNCH_CHECK("kc_replay");

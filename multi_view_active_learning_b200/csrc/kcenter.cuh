@@ -92,6 +92,10 @@ constexpr int kKcFlagForceTc = 2;
 int kc_update_batch(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T, float* min_dist,
                     int flags, cudaStream_t stream);
 
+// candidate pairwise matrix through the tensor-core screen (kcenter_tc.cu)
+bool kc_pairwise_tc_applicable(const float* X, int n, int d);
+int kc_pairwise_tc(const float* X, const float* xx, const float* val, int n, int d, float* out_t, cudaStream_t stream);
+
 // survivors of the last tensor-core screen on this device (synchronises `stream`) and the capacity of the pair list
 int kc_tc_last_stats(uint64_t* survivors, uint64_t* capacity, cudaStream_t stream);
 

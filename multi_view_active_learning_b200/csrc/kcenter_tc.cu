@@ -126,7 +126,7 @@ struct TcPair {
 __global__ void __launch_bounds__(kTcThreads, 1)
 kc_screen_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
                     const float* __restrict__ xx, const float* __restrict__ cc, const float* __restrict__ min_dist, int64_t n,
-                    int d, int T, float alpha, TcPair* __restrict__ pairs, unsigned int* __restrict__ pair_count,
+                    int d, int T, float alpha, int batch_min, TcPair* __restrict__ pairs, unsigned int* __restrict__ pair_count,
                     unsigned int pair_capacity) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -234,12 +234,15 @@ kc_screen_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const uint32_t taddr = tmem_base + acc * kTcBlockN + ((uint32_t)(quarter * 32) << 16);
       float v[32];
       float vmax = -INFINITY;
-      for (int c = 0; c < n_chunks; ++c) {
-        tmem_ld32(taddr + c * 32, v);
+      if (batch_min) {
+        for (int c = 0; c < n_chunks; ++c) {
+          tmem_ld32(taddr + c * 32, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, v[j] - hcc[c * 32 + j]);
+          for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, v[j] - hcc[c * 32 + j]);
+        }
       }
-      // pair (i, t) survives iff val >= max(0.5 (|x|^2 - s - m^2), max_t val - s)
+      // pair (i, t) survives iff val >= max(0.5 (|x|^2 - s - m^2), max_t val - s); without batch_min (every pair
+      // that may beat m_i is wanted, not only the best of the batch) the second term is dropped
       const float thr = fmaxf(0.5f * ((xr - s_i) - m2), vmax - s_i);
       for (int c = 0; c < n_chunks; ++c) {
         tmem_ld32(taddr + c * 32, v);
@@ -265,11 +268,14 @@ kc_screen_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 }
 
 // Exact canonical distance of the surviving pairs; 32 pairs per warp, coalesced through a shared-memory transpose.
+//   kStore = false: min_dist[row] = min(min_dist[row], dist)
+//   kStore = true : out[(t0 + t) * ld_out + row] = dist        (candidate pairwise matrix of the replay)
 constexpr int kRcWarps = 4;
+template <bool kStore>
 __global__ void __launch_bounds__(kRcWarps * 32)
 kc_recheck_kernel(const float* __restrict__ X, const float* __restrict__ xx, int d, const float* __restrict__ C,
                   const float* __restrict__ cc, const TcPair* __restrict__ pairs, const unsigned int* __restrict__ pair_count,
-                  unsigned int pair_capacity, float* __restrict__ min_dist) {
+                  unsigned int pair_capacity, float* __restrict__ min_dist, int t0, int64_t ld_out) {
   __shared__ float tx[kRcWarps][32][33];
   __shared__ float tc[kRcWarps][32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -310,7 +316,11 @@ kc_recheck_kernel(const float* __restrict__ X, const float* __restrict__ xx, int
     }
     if (ok) {
       const float dist = kc_dist(acc, __ldg(xx + pr.row), __ldg(cc + pr.t));
-      if (dist < min_dist[pr.row]) atomicMin(reinterpret_cast<unsigned int*>(min_dist + pr.row), __float_as_uint(dist));
+      if (kStore) {
+        min_dist[(int64_t)(t0 + (int)pr.t) * ld_out + pr.row] = dist;
+      } else if (dist < min_dist[pr.row]) {
+        atomicMin(reinterpret_cast<unsigned int*>(min_dist + pr.row), __float_as_uint(dist));
+      }
     }
   }
 }
@@ -354,40 +364,77 @@ int kc_update_batch_exact_if(const float* X, const float* xx, int64_t n, int d, 
                              float* min_dist, const unsigned int* count, unsigned int capacity, cudaStream_t stream);
 
 bool kc_tc_applicable(const float* X, int64_t n, int d, const float* C, int T) {
-  return d % 4 == 0 && d >= 64 && n >= 1024 && T >= 2 && T <= kTcBlockN && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+  return d % 4 == 0 && d >= 64 && n >= 128 && T >= 2 && T <= kTcBlockN && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
          (reinterpret_cast<uintptr_t>(C) & 15) == 0;
 }
 
-int kc_update_batch_tc(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T, float* min_dist,
-                       cudaStream_t stream) {
+static int tc_prepare(KcDeviceScratch** out, size_t want_pairs) {
   KcDeviceScratch* s = nullptr;
   if (int rc = kc_scratch(&s)) return rc;
-  size_t want = (size_t)n * 4;
-  if (want < (1u << 20)) want = 1u << 20;
-  if (want > (16u << 20)) want = 16u << 20;
-  if (s->tc_pairs_capacity < want) {
+  if (want_pairs < (1u << 20)) want_pairs = 1u << 20;
+  if (want_pairs > (16u << 20)) want_pairs = 16u << 20;
+  if (s->tc_pairs_capacity < want_pairs) {
     if (s->tc_pairs) cudaFree(s->tc_pairs);
     s->tc_pairs = nullptr;
     s->tc_pairs_capacity = 0;
-    MVAL_CUDA(cudaMalloc(&s->tc_pairs, want * sizeof(TcPair)));
-    s->tc_pairs_capacity = want;
+    MVAL_CUDA(cudaMalloc(&s->tc_pairs, want_pairs * sizeof(TcPair)));
+    s->tc_pairs_capacity = want_pairs;
   }
   if (s->tc_count == nullptr) MVAL_CUDA(cudaMalloc(&s->tc_count, sizeof(unsigned int)));
   MVAL_CUDA(cudaFuncSetAttribute(kc_screen_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  *out = s;
+  return MVAL_OK;
+}
+
+static int tc_screen(KcDeviceScratch* s, const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T,
+                     const float* min_dist, int batch_min, cudaStream_t stream) {
   CUtensorMap map_x, map_c;
   if (int rc = make_map(&map_x, X, n, d, kTcBlockM)) return rc;
   if (int rc = make_map(&map_c, C, T, d, kTcBlockN)) return rc;
-  const unsigned int cap = (unsigned int)s->tc_pairs_capacity;
   kc_tc_reset_kernel<<<1, 1, 0, stream>>>(s->tc_count);
   MVAL_LAUNCH_CHECK("kc_tc_reset");
   const int64_t n_tiles = (n + kTcBlockM - 1) / kTcBlockM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   const float alpha = ldexpf(1.0f, -8) + (float)d * ldexpf(1.0f, -20);
-  kc_screen_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(map_x, map_c, xx, cc, min_dist, n, d, T, alpha,
-                                                                  static_cast<TcPair*>(s->tc_pairs), s->tc_count, cap);
+  kc_screen_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(map_x, map_c, xx, cc, min_dist, n, d, T, alpha, batch_min,
+                                                                  static_cast<TcPair*>(s->tc_pairs), s->tc_count,
+                                                                  (unsigned int)s->tc_pairs_capacity);
   MVAL_LAUNCH_CHECK("kc_screen_tc");
-  kc_recheck_kernel<<<num_sms() * 4, kRcWarps * 32, 0, stream>>>(X, xx, d, C, cc, static_cast<const TcPair*>(s->tc_pairs),
-                                                                 s->tc_count, cap, min_dist);
+  return MVAL_OK;
+}
+
+__global__ void kc_fill_inf_kernel(float* __restrict__ p, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = INFINITY;
+}
+
+// Candidate pairwise matrix of the replay through the tensor-core screen: out_t[s * n + j] = dist(candidate j, centre s)
+// wherever that distance may be below val[j] (the only entries the replay can ever act on), +inf elsewhere.
+bool kc_pairwise_tc_applicable(const float* X, int n, int d) { return kc_tc_applicable(X, n, d, X, 2) && d >= 512; }
+
+int kc_pairwise_tc(const float* X, const float* xx, const float* val, int n, int d, float* out_t, cudaStream_t stream) {
+  KcDeviceScratch* s = nullptr;
+  if (int rc = tc_prepare(&s, (size_t)n * kTcBlockN)) return rc;
+  kc_fill_inf_kernel<<<64, 256, 0, stream>>>(out_t, (int64_t)n * n);
+  MVAL_LAUNCH_CHECK("kc_fill_inf");
+  for (int t0 = 0; t0 < n; t0 += kTcBlockN) {
+    const int tn = (n - t0) < kTcBlockN ? (n - t0) : kTcBlockN;
+    if (int rc = tc_screen(s, X, xx, n, d, X + (int64_t)t0 * d, xx + t0, tn, val, 0, stream)) return rc;
+    kc_recheck_kernel<true><<<num_sms(), kRcWarps * 32, 0, stream>>>(X, xx, d, X + (int64_t)t0 * d, xx + t0,
+                                                                     static_cast<const TcPair*>(s->tc_pairs), s->tc_count,
+                                                                     (unsigned int)s->tc_pairs_capacity, out_t, t0, n);
+    MVAL_LAUNCH_CHECK("kc_recheck_store");
+  }
+  return MVAL_OK;
+}
+
+int kc_update_batch_tc(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T, float* min_dist,
+                       cudaStream_t stream) {
+  KcDeviceScratch* s = nullptr;
+  if (int rc = tc_prepare(&s, (size_t)n * 4)) return rc;
+  if (int rc = tc_screen(s, X, xx, n, d, C, cc, T, min_dist, 1, stream)) return rc;
+  const unsigned int cap = (unsigned int)s->tc_pairs_capacity;
+  kc_recheck_kernel<false><<<num_sms() * 4, kRcWarps * 32, 0, stream>>>(X, xx, d, C, cc, static_cast<const TcPair*>(s->tc_pairs),
+                                                                        s->tc_count, cap, min_dist, 0, 0);
   MVAL_LAUNCH_CHECK("kc_recheck");
   return kc_update_batch_exact_if(X, xx, n, d, C, cc, T, min_dist, s->tc_count, cap, stream);
 }
