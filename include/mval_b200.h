@@ -143,6 +143,16 @@ int mval_score_pool_host(const float* heatmaps, const double* proj, const uint8_
                          int64_t chunk_frames, int32_t* out_xy, double* out_xyz, double* out_reproj,
                          int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count);
 
+/* Replaces utils/triangulation.py:236-257 (_compute_xe, the metric of triangulation() when use_reprojection_xe=True /
+ * AL.USE_REPROJECTION_XE): per (view, joint) the triangulated 3-D joint is reprojected (P [X,1], w == 0 -> 1), a Gaussian
+ * exp(-|pixel - reprojection|^2 / (2 sigma^2)) is rendered on the H x W heat-map pixel grid in float64, and
+ * sum((heatmap - render)^2) / (H W) is added up over views, then joints (all joints: the reference also renders the
+ * joints triangulation() left at the origin).  xyz float64 device [n_frames][J][3] (out_xyz of the calls above).
+ * out_map    float64 device [n_frames][V][J] per-map terms (may be NULL)
+ * out_metric float64 device [n_frames]. */
+int mval_score_xe(const float* heatmaps, const double* proj, const double* xyz, int64_t n_frames, int V, int J, int H, int W,
+                  double sigma, double* out_map, double* out_metric, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * (3) ranking and coreset k-center greedy selection
  * ---------------------------------------------------------------------------------------------------- */

@@ -39,6 +39,7 @@ PROTOTYPES = {
     "mval_triangulate_ransac": (C.c_int, [_p, _i, _p, _p, _i64, _i, _i, C.POINTER(RansacParams), _p, _p, _p, _p, _p, _p, _p]),
     "mval_score_pool": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _p, _p, _p, _p, _p, _p, _p]),
     "mval_score_pool_host": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _i64, _p, _p, _p, _p, _p, _p]),
+    "mval_score_xe": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _d, _p, _p, _p]),
     "mval_topk_desc": (C.c_int, [_p, _i64, _i64, C.c_int32, _p, _p, _p, _p]),
     "mval_kcenter_norms": (C.c_int, [_p, _i64, _i, _p, _p]),
     "mval_kcenter_update": (C.c_int, [_p, _p, _i64, _i, _p, _p, _i64, _p, _p, _p]),

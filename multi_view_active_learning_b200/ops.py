@@ -199,6 +199,22 @@ def score_pool_host(heatmaps, proj, stride, valid=None, n_iters=DEFAULT_N_ITERS,
     return out
 
 
+def score_xe(heatmaps, proj, keypoints_3d, sigma, return_per_map=False):
+    """Reprojection-XE metric (utils/triangulation.py:236-257) for a batch: heatmaps [N, V, J, H, W] float32 CUDA,
+    proj [N, V, 3, 4], keypoints_3d [N, J, 3] float64 -> float64 [N] (and the per-map terms [N, V, J])."""
+    hm = _cuda(heatmaps, torch.float32, "heatmaps")
+    N, V, J, H, W = hm.shape
+    P = _cuda(proj.to(hm.device) if not proj.is_cuda else proj, torch.float64, "proj")
+    X = _cuda(keypoints_3d, torch.float64, "keypoints_3d")
+    if tuple(P.shape) != (N, V, 3, 4) or tuple(X.shape) != (N, J, 3):
+        raise ValueError("proj / keypoints_3d shapes do not match the heat maps")
+    out = torch.empty((N,), dtype=torch.float64, device=hm.device)
+    per_map = torch.empty((N, V, J), dtype=torch.float64, device=hm.device) if return_per_map else None
+    with torch.cuda.device(hm.device):
+        check(_lib.load().mval_score_xe(_ptr(hm), _ptr(P), _ptr(X), N, V, J, H, W, float(sigma), _ptr(per_map), _ptr(out), _stream()))
+    return (out, per_map) if return_per_map else out
+
+
 def topk_desc(scores, k, index_offset=0):
     """scores float64 CUDA [n] -> (idx int64 [m], val float64 [m]), m = min(k, #non-NaN): descending score, ties by
     ascending index, NaN dropped (strategy.py:932-949)."""

@@ -196,12 +196,11 @@ class ScoringSelectionMixin:
                 B = dp["proj_matrices"].shape[0]
                 heatmaps = heatmaps.reshape([B, -1, kp, w, h]).float()
                 joint_valid = dp["joint_valid"]
-                if cfg.AL.USE_REPROJECTION_XE:
-                    raise NotImplementedError("AL.USE_REPROJECTION_XE is a 'next' row of SURVEY.md section 8")
                 tri = triangulation.triangulation_batch(
                     heatmaps, dp["proj_matrices"], cfg.POSE_ESTIMATOR.STRIDE, joint_valid,
                     use_soft_argmax=cfg.AL.USE_SOFTARGMAX, pair_seed=getattr(cfg, "RANDOM_SEED", 0),
-                    frame_offset=rank_base + n_done)
+                    frame_offset=rank_base + n_done, use_reprojection_xe=cfg.AL.USE_REPROJECTION_XE,
+                    sigma=cfg.AL.REPROJECTION_SIGMA)
                 n_done += B
                 al, al_is_f64 = self._frame_al_metric(heatmaps, joint_valid, tri)
                 acc["sal"].append(tri["metric"].float())  # torch.Tensor([metric]) -> float32 (:1061)

@@ -37,9 +37,9 @@ def triangulation(
     """Same contract as the reference: heatmaps [V, J, H, W], proj_matricies [V, 3, 4], valid_joints [J] ->
     {"keypoints_3d": np.float64 [J, 3], "keypoints_2d": np [V, J, 2], "metric": np.float64, "inlier_count": np.int64}.
     """
-    if use_reprojection_xe or direct_optimization:
-        # SURVEY.md section 8f row 3: optional flags of the same API, scheduled after the default path.
-        raise NotImplementedError("use_reprojection_xe / direct_optimization are not built yet in mval_b200")
+    if direct_optimization:
+        # SURVEY.md section 8f row 3: never enabled by the reference's own callers (strategy.py:607, 1037).
+        raise NotImplementedError("direct_optimization (Huber refinement, utils/triangulation.py:319-336) is not built")
     if not torch.is_tensor(heatmaps):
         heatmaps = torch.as_tensor(np.asarray(heatmaps))
     if len(proj_matricies) != heatmaps.shape[0]:
@@ -64,23 +64,34 @@ def triangulation(
         raise ValueError("zero-size array to reduction operation minimum which has no identity")
     out = ops.triangulate_ransac(kp, P, torch.from_numpy(valid), n_iters, float(reprojection_error_epsilon), pairs=pairs)
     kp_np = kp[0].cpu().numpy()
+    if use_reprojection_xe:
+        # reference :223-224: the metric becomes the 0-d CUDA tensor _compute_xe returns (float64 by promotion)
+        metric = ops.score_xe(hm5, P, out["keypoints_3d"], sigma)[0]
+    else:
+        metric = np.float64(out["metric"][0].item())
     return {
         "keypoints_3d": out["keypoints_3d"][0].cpu().numpy(),
         "keypoints_2d": kp_np if use_soft_argmax else kp_np.astype(np.int64),
-        "metric": np.float64(out["metric"][0].item()),
+        "metric": metric,
         "inlier_count": np.int64(out["inlier_count"][0].item()),
     }
 
 
 def triangulation_batch(heatmaps, proj_matricies, stride, valid_joints, use_soft_argmax=False, n_iters=64,
-                        reprojection_error_epsilon=5, pair_seed=0, frame_offset=0):
+                        reprojection_error_epsilon=5, pair_seed=0, frame_offset=0, use_reprojection_xe=False, sigma=None):
     """Pool-level entry: heatmaps [N, V, J, H, W] (CUDA), proj_matricies [N, V, 3, 4], valid_joints [N, J] or [J].
     Returns a dict of CUDA tensors (keypoints_3d [N,J,3] f64, keypoints_2d, metric [N] f64, inlier_count [N] i32,
     reproj_mean [N,J], inliers [N,J]).  For C(V,2) > n_iters the view-pair subsets are the counter-based ones keyed
     by (pair_seed, frame_offset + frame, joint) -- see include/mval_b200.h."""
     if use_soft_argmax:
         kp = ops.decode_softargmax(heatmaps, stride)
-        return ops.triangulate_ransac(kp, proj_matricies, valid_joints, n_iters, float(reprojection_error_epsilon),
-                                      pair_seed, frame_offset)
-    return ops.score_pool(heatmaps, proj_matricies, stride, valid_joints, n_iters, float(reprojection_error_epsilon),
-                          pair_seed, frame_offset)
+        out = ops.triangulate_ransac(kp, proj_matricies, valid_joints, n_iters, float(reprojection_error_epsilon),
+                                     pair_seed, frame_offset)
+    else:
+        out = ops.score_pool(heatmaps, proj_matricies, stride, valid_joints, n_iters, float(reprojection_error_epsilon),
+                             pair_seed, frame_offset)
+    if use_reprojection_xe:
+        # utils/triangulation.py:223-224: metric = _compute_xe(...) replaces the mean reprojection error
+        out["reproj_metric"] = out["metric"]
+        out["metric"] = ops.score_xe(heatmaps, proj_matricies, out["keypoints_3d"], sigma)
+    return out

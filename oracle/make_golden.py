@@ -177,6 +177,30 @@ def case_coreset(cs):
     print("coreset", [keys.index(k) for k in picked][:8], [keys2.index(k) for k in picked2])
 
 
+def case_xe(tri):
+    """_compute_xe (utils/triangulation.py:236-257).  The function moves its rendered maps with .cuda(); there is no
+    GPU in the dev container, so Tensor.cuda is patched to the identity for this call (the arithmetic -- float64
+    render, float32 prediction promoted by MSELoss -- is device independent)."""
+    N, V, J, sigma = 6, 4, 5, 2.5
+    pool = S.make_pool(N, V, J, seed=77, valid_prob=1.0)
+    hm = S.render_heatmaps(pool["centres"], noise=0.05, seed=78)
+    P = pool["P"].copy()
+    P[:3, :, :2, :] /= S.STRIDE  # first three frames: projections land inside the 64 x 64 grid (non-trivial renders)
+    kp3d = pool["X"].copy()
+    kp3d[:, 1] = 0.0  # an "invalid joint": keypoints_3d row left at zero by triangulation()
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        xe = np.array([float(tri._compute_xe(kp3d[n], P[n], torch.from_numpy(hm[n]), sigma)) for n in range(N)])
+    finally:
+        torch.Tensor.cuda = real_cuda
+    m, _ = O.compute_xe(kp3d, P, hm, sigma)
+    np.testing.assert_allclose(m, xe, rtol=1e-12)
+    np.savez_compressed(os.path.join(OUT, "xe_metric.npz"), P=P, keypoints_3d=kp3d, centres=pool["centres"], sigma=sigma,
+                        noise=0.05, heatmap_seed=78, xe=xe)
+    print("xe", xe)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     tri, ev, cs = load_reference()
@@ -190,6 +214,7 @@ def main():
     case_decode(ev)
     case_hp(st)
     case_coreset(cs)
+    case_xe(tri)
 
 
 if __name__ == "__main__":

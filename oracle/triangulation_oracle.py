@@ -287,3 +287,39 @@ def triangulate_pool(heatmaps, P, stride, valid, n_iters=64, eps=5.0, pair_seed=
         "inliers": inliers,
         "inlier_mask": inlier_mask,
     }
+
+
+def compute_xe(keypoints_3d, P, heatmaps, sigma):
+    """Restatement of reference utils/triangulation.py:236-257 (_compute_xe) for a pool.
+
+    keypoints_3d [N, J, 3] f64 (zeros for invalid joints -- the reference renders those too), P [N, V, 3, 4] f64,
+    heatmaps [N, V, J, H, W] f32.  Per (view, joint): project the 3-D point (:240-242, :459-484; w == 0 -> 1), render
+    exp(-((x - u)^2 + (y - v)^2) / (2 sigma^2)) on the H x W pixel grid IN FLOAT64 (float32 grid minus float64 point
+    promotes), and add sum((pred - render)^2) / (1 * H * W) (pose_estimators/loss.py:14-20; float32 pred up-cast).
+    The reference compares the HEATMAP pixel grid with a point in IMAGE pixels (no division by the stride); kept.
+    Returns (metric [N] f64 = sum over views then joints in that order, per_map [N, V, J] f64)."""
+    kp = np.asarray(keypoints_3d, dtype=np.float64)
+    P = np.asarray(P, dtype=np.float64)
+    hm = np.asarray(heatmaps)
+    N, V, J, H, W = hm.shape
+    per_map = np.zeros((N, V, J))
+    xs = np.arange(W, dtype=np.float32).astype(np.float64)
+    ys = np.arange(H, dtype=np.float32).astype(np.float64)
+    for n in range(N):
+        Xh = np.hstack([kp[n], np.ones((J, 1))])
+        for v in range(V):
+            ph = Xh @ P[n, v].T
+            z = np.where(ph[:, 2] == 0, 1.0, ph[:, 2])
+            uv = ph[:, :2] / z[:, None]
+            for j in range(J):
+                expo = (xs[None, :] - uv[j, 0]) ** 2 + (ys[:, None] - uv[j, 1]) ** 2
+                render = np.exp(-expo / (2.0 * sigma ** 2))
+                per_map[n, v, j] = np.sum((hm[n, v, j].astype(np.float64) - render) ** 2) / (H * W)
+    metric = np.zeros(N)
+    for n in range(N):
+        acc = 0.0
+        for v in range(V):
+            for j in range(J):
+                acc += per_map[n, v, j]
+        metric[n] = acc
+    return metric, per_map

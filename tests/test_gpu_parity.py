@@ -317,6 +317,45 @@ def test_topk_matches_nlargest(ops):
     assert idx.cpu().tolist() == [1000 + int(g[1:]) for g in SO.rank_nlargest(d, 5)]
 
 
+# ------------------------------------------------------------------------------------------------ reprojection XE
+def test_reprojection_xe_golden_and_oracle(ops, golden):
+    """utils/triangulation.py:236-257 (_compute_xe): golden values of the reference, then a larger random pool against
+    the oracle, then the per-frame drop-in with use_reprojection_xe=True.  float64 sums of 4096 terms in a different
+    order: rtol 1e-11."""
+    from multi_view_active_learning_b200.utils import triangulation as T
+
+    g = golden("xe_metric")
+    hm = S.render_heatmaps(g["centres"], noise=float(g["noise"]), seed=int(g["heatmap_seed"]))
+    xe, per_map = ops.score_xe(_cuda(hm), _cuda(g["P"]), _cuda(g["keypoints_3d"]), float(g["sigma"]), return_per_map=True)
+    np.testing.assert_allclose(xe.cpu().numpy(), g["xe"], rtol=1e-11, atol=0)
+    exp, exp_map = O.compute_xe(g["keypoints_3d"], g["P"], hm, float(g["sigma"]))
+    np.testing.assert_allclose(per_map.cpu().numpy(), exp_map, rtol=1e-11, atol=1e-300)
+    # random pool, projections inside and outside the grid, a joint at the origin, w == 0
+    N, V, J = 9, 5, 7
+    pool = S.make_pool(N, V, J, seed=5)
+    P = pool["P"].copy()
+    P[:5, :, :2, :] /= S.STRIDE
+    X = pool["X"].copy()
+    X[:, 2] = 0.0
+    P[8, 0, 2, :] = 0.0  # w == 0 for every point of that view -> w := 1
+    hm = S.render_heatmaps(pool["centres"], noise=0.1, seed=6)
+    for sigma in (1.0, 3.0):
+        got = ops.score_xe(_cuda(hm), _cuda(P), _cuda(X), sigma).cpu().numpy()
+        np.testing.assert_allclose(got, O.compute_xe(X, P, hm, sigma)[0], rtol=1e-11, atol=0)
+    # drop-in: metric is the XE of the triangulated joints (a 0-d float64 CUDA tensor, like the reference's)
+    n = 2
+    r = T.triangulation(_cuda(hm[n]), torch.from_numpy(P[n]), 4, torch.from_numpy(pool["valid"][n]), False, True, 2.0)
+    ref = O.triangulate_pool(hm[n:n + 1], P[n:n + 1], 4, pool["valid"][n:n + 1])
+    exp = O.compute_xe(r["keypoints_3d"][None], P[n:n + 1], hm[n:n + 1], 2.0)[0][0]
+    assert torch.is_tensor(r["metric"]) and r["metric"].is_cuda and r["metric"].dtype == torch.float64
+    np.testing.assert_allclose(float(r["metric"].item()), exp, rtol=1e-11)
+    np.testing.assert_allclose(r["keypoints_3d"], ref["keypoints_3d"][0], rtol=XYZ_RTOL, atol=XYZ_ATOL_MM)
+    # batch entry
+    b = T.triangulation_batch(_cuda(hm), _cuda(P), 4, _cuda(pool["valid"]), use_reprojection_xe=True, sigma=2.0)
+    expb = O.compute_xe(b["keypoints_3d"].cpu().numpy(), P, hm, 2.0)[0]
+    np.testing.assert_allclose(b["metric"].cpu().numpy(), expb, rtol=1e-11)
+
+
 # ------------------------------------------------------------------------------------------------ coreset
 @pytest.mark.parametrize("n,L,d,budget", [(700, 30, 57, 40), (300, 10, 126, 25), (513, 7, 2048, 30), (200, 5, 130, 20),
                                           (100, 3, 3, 10), (5000, 300, 57, 400), (3000, 20, 128, 300)])

@@ -138,6 +138,18 @@ def test_c_oracle_equals_numpy_fma_emulation():
         assert err <= abs(fractions.Fraction(float(lo)) - exact) and err <= abs(fractions.Fraction(float(hi)) - exact)
 
 
+def test_xe_oracle_matches_reference(golden):
+    """oracle compute_xe against the values the reference's _compute_xe produced (oracle/make_golden.py:case_xe)."""
+    from multi_view_active_learning_b200 import synthetic as S
+    from oracle import triangulation_oracle as O
+
+    g = golden("xe_metric")
+    hm = S.render_heatmaps(g["centres"], noise=float(g["noise"]), seed=int(g["heatmap_seed"]))
+    m, per_map = O.compute_xe(g["keypoints_3d"], g["P"], hm, float(g["sigma"]))
+    np.testing.assert_allclose(m, g["xe"], rtol=1e-12, atol=0)
+    assert per_map.shape == (6, 4, 5) and (per_map > 0).all()
+
+
 def test_ranking():
     d = {"a": 1.0, "b": float("nan"), "c": 3.0, "d": 3.0, "e": 2.0}
     assert SC.rank_nlargest(d, 3) == ["c", "d", "e"]
