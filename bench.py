@@ -351,6 +351,36 @@ def run_ours(args):
            "call": "mval_score_pool_host (pinned host heat maps -> chunked H2D on 2 streams -> fused kernel -> D2H) + "
                    "mval_topk_desc + ranking merge, on every rank concurrently"}
     del h_hm
+    # Variant at the reference's own boundary: triangulation() receives the heat maps as CUDA tensors straight from
+    # the backbone (strategy.py:1027-1045) and only the projection matrices / validity masks live on the host.  Per step:
+    # H2D of P (+ valid) from pinned memory, fused kernel over the resident heat maps, ranking, D2H of every result.
+    h_P_all = P.cpu().pin_memory()
+    dv_times = []
+    res_host = None
+    for it in range(1 + args.e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        dP = h_P_all.to(dev, non_blocking=True)
+        out_dv = ops.score_pool(hm, dP, STRIDE, None, frame_offset=shard_start, return_keypoints_2d=True)
+        local = ops.topk_desc(out_dv["metric"], TOPK, index_offset=shard_start)
+        res_host = {k: v.to("cpu", non_blocking=True) for k, v in out_dv.items()}
+        sel_dv = poolmod.distributed_topk(local, TOPK)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        if it > 0:
+            dv_times.append(dt)
+    e2e["device_heatmaps_variant"] = {
+        "value": R * n_gpus / float(np.median(dv_times)), "unit": UNIT, "frames_per_step": R * n_gpus,
+        "h2d_bytes_per_step": R * V * 96 * n_gpus,
+        "d2h_bytes_per_step": (sum(t.numel() * t.element_size() for t in res_host.values()) + len(sel_dv[0]) * 16) * n_gpus,
+        "step_ms": [round(1e3 * t, 2) for t in dv_times],
+        "call": "ops.score_pool on CUDA heat maps (the reference's triangulation() boundary: heat maps come from the "
+                "backbone on the device, strategy.py:1027-1045) with P copied from pinned host memory and all results "
+                "copied back, + mval_topk_desc + ranking merge"}
 
     line = None
     if rank == 0:
@@ -527,6 +557,166 @@ def run_coreset(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# secondary workload: hybrid selection (BASELINE.json configs[4] / north-star target): uncertainty scoring of the whole
+# pool + top-k ranking + coreset k-center over the predicted poses, end to end
+# ----------------------------------------------------------------------------------------------------------------
+def run_hybrid(args):
+    """Every rank owns `pool_frames` frames (north-star target: 8 x 125k = 1M frames, 8 views, 19 joints).  One step =
+    fused decode + RANSAC triangulation + uncertainty over the whole shard (resident chunk passes, as in the scoring
+    workload) -> ranking (top-k by uncertainty, one all_gather) -> root-relative pose features (coreset.py:35-47,
+    d = 3J = 57) -> k-center greedy (budget picks, `coreset_labeled` labeled poses) in exact rounds (one all_gather per
+    round).  Distinct poses per pool frame: the resident heat maps repeat, the projection matrices do not (each pool
+    frame's cameras are composed with its own similarity transform of the world, which leaves every reprojection
+    error unchanged and rotates / scales the triangulated pose)."""
+    import torch
+    import torch.distributed as dist
+
+    from multi_view_active_learning_b200 import _lib, ops, pool as poolmod
+    from multi_view_active_learning_b200 import synthetic as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    R, n, L, budget = args.resident_frames, args.pool_frames, args.coreset_labeled, args.coreset_budget
+    shard_start = rank * n
+    seed = 1234 + rank
+    host_pool = S.make_pool(R, V, J, seed=seed, p_outlier=0.1)
+    hm = ops.synth_heatmaps(torch.from_numpy(host_pool["centres"]).to(dev), H, W, 1.0, 0.05, seed)
+    P_res = torch.from_numpy(host_pool["P"]).to(dev)
+    # per-pool-frame similarity transform M_f = [s R | t]: P_f = P_res[f % R] @ M_f
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    q = torch.randn((n, 4), generator=g, device=dev, dtype=torch.float64)
+    q = q / q.norm(dim=1, keepdim=True)
+    w_, x_, y_, z_ = q.unbind(1)
+    Rm = torch.stack([1 - 2 * (y_ * y_ + z_ * z_), 2 * (x_ * y_ - z_ * w_), 2 * (x_ * z_ + y_ * w_),
+                      2 * (x_ * y_ + z_ * w_), 1 - 2 * (x_ * x_ + z_ * z_), 2 * (y_ * z_ - x_ * w_),
+                      2 * (x_ * z_ - y_ * w_), 2 * (y_ * z_ + x_ * w_), 1 - 2 * (x_ * x_ + y_ * y_)], dim=1).reshape(n, 3, 3)
+    sc = 0.5 + torch.rand((n, 1, 1), generator=g, device=dev, dtype=torch.float64)
+    M = torch.zeros((n, 4, 4), dtype=torch.float64, device=dev)
+    M[:, :3, :3] = Rm * sc
+    M[:, :3, 3] = torch.randn((n, 3), generator=g, device=dev, dtype=torch.float64) * 100
+    M[:, 3, 3] = 1.0
+    idx = torch.arange(n, device=dev) % R
+    P_pool = torch.matmul(P_res[idx], M[:, None])  # [n, V, 3, 4]
+    gl = torch.Generator(device=dev).manual_seed(7)
+    labeled = (torch.randn((L, J, 3), generator=gl, device=dev) * 300.0)
+    root = 2
+    labeled = (labeled - labeled[:, root:root + 1]).permute(0, 2, 1).reshape(L, 3 * J).contiguous()
+    chunks = [(o, min(R, n - o)) for o in range(0, n, R)]
+
+    def step(stats=None):
+        metrics, feats = [], []
+        for off, m in chunks:
+            out = ops.score_pool(hm[:m], P_pool[off:off + m], STRIDE, None, pair_seed=0, frame_offset=shard_start + off,
+                                 return_keypoints_2d=False)
+            metrics.append(out["metric"])
+            kp = out["keypoints_3d"]
+            feats.append((kp - kp[:, root:root + 1]).permute(0, 2, 1).reshape(m, 3 * J).float())
+        metric = torch.cat(metrics)
+        ranked = poolmod.distributed_topk(ops.topk_desc(metric, TOPK, index_offset=shard_start), TOPK)
+        feat = torch.cat(feats)
+        sel, _ = poolmod.kcenter_greedy_sharded([(feat, shard_start)], labeled, budget, stats=stats)
+        return ranked, sel
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = _lib.launch_count()
+    times, stats = [], []
+    for _ in range(args.steps):
+        barrier()
+        stats = []
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ranked, sel = step(stats)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    launches = (_lib.launch_count() - l0) // max(args.steps, 1)
+    score_ms, _ = _timed(lambda: [ops.score_pool(hm[:m], P_pool[o:o + m], STRIDE, None, frame_offset=shard_start + o,
+                                                 return_keypoints_2d=False) for o, m in chunks])
+    if rank == 0:
+        ms = float(np.median(times))
+        print(json.dumps({
+            "metric": "hybrid selection: pool frames scored + ranked + coreset-selected / sec", "value": n * world / (ms * 1e-3),
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "step_ms": times,
+            "higher_is_better": True, "scaling": "weak", "dtype": "f64 (triangulation) / f32 (coreset)", "data": "synthetic",
+            "config": {"workload": "north-star target / C5-style hybrid: %d frames per GPU x %d GPU(s), %d views, %d joints: "
+                                   "fused decode + RANSAC triangulation + uncertainty, top-%d ranking, coreset k-center over "
+                                   "root-relative predicted poses (d = %d), %d labeled, budget %d"
+                                   % (n, world, V, J, TOPK, 3 * J, L, budget), "resident_frames": R},
+            "breakdown_ms": {"scoring_kernels": score_ms, "ranking_features_coreset": ms - score_ms},
+            "coreset_rounds": {"count": len(stats), "picks_per_round_mean": float(np.mean(stats)) if stats else None},
+            "gpu_launches": int(launches), "selected_head": sel[:5].cpu().tolist(), "ranked_head": [int(i) for i in ranked[0][:5]]}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# secondary workload: the per-map heat-map kernels (soft-arg-max, HP, MPE, BSB, XE) on a resident chunk
+# ----------------------------------------------------------------------------------------------------------------
+def run_scores(args):
+    """Roofline of every per-map kernel of SURVEY.md rows a1/a3/a8/a9: one launch over `resident_frames` frames of
+    V x J heat maps (16 KiB each, read once), CUDA events, algorithmic bytes = maps x H*W*4."""
+    import torch
+
+    from multi_view_active_learning_b200 import ops
+    from multi_view_active_learning_b200 import synthetic as S
+
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    n = args.resident_frames
+    pool = S.make_pool(min(n, 2048), V, J, seed=1234)
+    reps = (n + pool["centres"].shape[0] - 1) // pool["centres"].shape[0]
+    centres = torch.from_numpy(np.tile(pool["centres"], (reps, 1, 1, 1))[:n]).to(dev)
+    P = torch.from_numpy(np.tile(pool["P"], (reps, 1, 1, 1))[:n]).to(dev)
+    hm = ops.synth_heatmaps(centres, noise=0.05, seed=1)
+    xyz = torch.from_numpy(np.tile(pool["X"], (reps, 1, 1))[:n]).to(dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    algo = n * FRAME_HEATMAP_BYTES
+    kernels = {
+        "decode_argmax_kernel (a1)": lambda: ops.decode_argmax(hm, STRIDE),
+        "decode_softargmax_kernel (a3)": lambda: ops.decode_softargmax(hm, STRIDE),
+        "score_hp_w64_kernel (a8 HP)": lambda: ops.score_hp(hm),
+        "score_peaks_kernel MPE (a8)": lambda: ops.score_peaks(hm, "MPE"),
+        "score_peaks_kernel BSB (a8)": lambda: ops.score_peaks(hm, "BSB"),
+        "score_xe_kernel (a9)": lambda: ops.score_xe(hm, P, xyz, 2.0),
+        "score_pool_fused_kernel (a1+a4..a7)": lambda: ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False),
+    }
+    out = {}
+    for name, fn in kernels.items():
+        for _ in range(3):
+            fn()
+        ms, _ = _timed(fn, 5)
+        out[name] = {"avg_launch_ms": ms, "achieved": algo / (ms * 1e-3) / 1e9, "frac": algo / (ms * 1e-3) / 1e9 / hbm_peak}
+    print(json.dumps({"metric": "per-map heat-map kernels: algorithmic GB/s", "unit": "GB/s", "n_gpus": 1,
+                      "config": {"workload": "%d frames x %d views x %d joints x %dx%d float32 heat maps resident (%.1f GB), "
+                                 "one launch each" % (n, V, J, H, W, algo / 1e9)},
+                      "roofline": {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "algorithmic_bytes_per_launch": algo,
+                                   "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)", "kernels": out}}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -539,7 +729,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=4096)
     ap.add_argument("--ref-frames-per-core", type=int, default=128)
-    ap.add_argument("--workload", default="scoring", choices=["scoring", "coreset"])
+    ap.add_argument("--workload", default="scoring", choices=["scoring", "coreset", "scores", "hybrid"])
     ap.add_argument("--coreset-rows", type=int, default=1_000_000)
     ap.add_argument("--coreset-dim", type=int, default=2048)
     ap.add_argument("--coreset-labeled", type=int, default=64)
@@ -554,6 +744,10 @@ def main():
         return run_reference_arm(args)
     if args.workload == "coreset":
         return run_coreset(args)
+    if args.workload == "scores":
+        return run_scores(args)
+    if args.workload == "hybrid":
+        return run_hybrid(args)
     return run_ours(args)
 
 
