@@ -241,6 +241,11 @@ score_hp_generic_kernel(const float* __restrict__ hm, int64_t n_maps, int V, int
   if (lane == 0) out_hp[map] = bad ? __int_as_float(0x7fc00000) : 1.0f - 1.0f / min_s;
 }
 
+// mapstream.cu: persistent TMA-ring kernels for 64 x 64 maps
+bool map_stream_applicable(const float* hm, int H, int W);
+int stream_softargmax(const float* hm, int64_t n_maps, float stride, float* out_xy, cudaStream_t stream);
+int stream_hp(const float* hm, int64_t n_maps, int V, int J, const uint8_t* valid, float* out, cudaStream_t stream);
+
 }  // namespace mval
 
 extern "C" int mval_decode_argmax(const float* heatmaps, int64_t n_frames, int V, int J, int H, int W, int stride,
@@ -260,6 +265,8 @@ extern "C" int mval_decode_softargmax(const float* heatmaps, int64_t n_frames, i
   const int64_t n_maps = n_frames * V * J;
   if (n_maps == 0) return MVAL_OK;
   MVAL_REQUIRE(heatmaps && out_xy, "mval_decode_softargmax: null pointer");
+  if (mval::map_stream_applicable(heatmaps, H, W))
+    return mval::stream_softargmax(heatmaps, n_maps, stride, out_xy, static_cast<cudaStream_t>(stream));
   if (W % 4 != 0 || (reinterpret_cast<uintptr_t>(heatmaps) & 15) != 0) {
     mval::set_error("mval_decode_softargmax: W must be a multiple of 4 and the maps 16-byte aligned");
     return MVAL_ERR_UNSUPPORTED;
@@ -282,6 +289,7 @@ extern "C" int mval_score_hp(const float* heatmaps, int64_t n_frames, int V, int
   const int64_t blocks = (n_maps + mval::kDecodeWarps - 1) / mval::kDecodeWarps;
   MVAL_REQUIRE(blocks <= 0x7fffffffLL, "mval_score_hp: too many maps for one launch; chunk the pool");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mval::map_stream_applicable(heatmaps, H, W)) return mval::stream_hp(heatmaps, n_maps, V, J, valid, out_hp, st);
   if (W == 64 && (reinterpret_cast<uintptr_t>(heatmaps) & 15) == 0)
     mval::score_hp_w64_kernel<<<(unsigned)blocks, mval::kDecodeThreads, 0, st>>>(heatmaps, n_maps, V, J, H, valid, out_hp);
   else

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include "ransac.cuh"
+#include "tma.cuh"
 
 namespace mval {
 
@@ -32,61 +33,8 @@ constexpr int kFusedThreads = kWarp * (1 + kFusedDecodeWarps + kFusedRansacWarps
 constexpr int kFrameSlots = 4;
 constexpr int kMaxStages = 64;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Watchdog: a wait that lasts longer than ~5 s of SM clocks is a protocol bug, not load.  Instead of hanging the
-// device the waiter records who/what/where in g_fused_abort, raises the abort flag, and every role drains out of
-// its loops; the host reports MVAL_ERR_CUDA with the record (see launch_score_pool_fused).
-__device__ unsigned long long g_fused_abort[8];  // [0] flag, [1] code, [2] block, [3] warp, [4] frame iter, [5] index
-
-// kBackoff: the waiter expects to wait long (a RANSAC warp waiting for the next frame's key-points); it sleeps
-// between polls so that it does not take issue slots from the decode warps of its scheduler.
-template <bool kBackoff = false>
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t code, long long iter, int index) {
-  uint32_t ok;
-  long long t0 = 0;
-  uint32_t polls = 0;
-  for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) return true;
-    if (kBackoff) __nanosleep(256);
-    if ((++polls & 255u) == 0u) {
-      if (*((volatile unsigned long long*)&g_fused_abort[0]) != 0ull) return false;
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      if (now - t0 > 10000000000ll) {
-        if (atomicCAS(&g_fused_abort[0], 0ull, 1ull) == 0ull) {
-          g_fused_abort[1] = code;
-          g_fused_abort[2] = blockIdx.x;
-          g_fused_abort[3] = threadIdx.x >> 5;
-          g_fused_abort[4] = (unsigned long long)iter;
-          g_fused_abort[5] = (unsigned long long)index;
-          __threadfence();
-        }
-        return false;
-      }
-    }
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
+// Abort record of the mbarrier watchdog (tma.cuh): [0] flag, [1] code, [2] block, [3] warp, [4] frame iter, [5] index
+__device__ unsigned long long g_fused_abort[8];
 
 struct FusedSmem {  // byte offsets into dynamic shared memory
   uint32_t ring, proj, kp, mask, red_reproj, red_inl, pair, perm, pxy, bars, total;
@@ -143,7 +91,7 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
       mbar_init(&kp_free[s], (uint32_t)J + 1u);
       mbar_init(&masks_ready[s], (uint32_t)J);
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   build_pair_table(smem + L.pair, V, threadIdx.x, blockDim.x);
   __syncthreads();
@@ -159,14 +107,14 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
         const int64_t frame = blockIdx.x + i * (int64_t)gridDim.x;
         const int sl = (int)(i % kFrameSlots);
         const uint32_t ku = (uint32_t)(i / kFrameSlots);
-        if (!mbar_wait(&kp_free[sl], (ku & 1u) ^ 1u, 1, i, sl)) return;
+        if (!mbar_wait(&kp_free[sl], (ku & 1u) ^ 1u, g_fused_abort, 1, i, sl)) return;
         mbar_arrive_expect_tx(&kp_ready[sl], (uint32_t)V * 96u);
         bulk_g2s(smem + L.proj + sl * V * 96, proj + frame * V * 12, (uint32_t)V * 96u, &kp_ready[sl]);
         const float* src = hm + frame * (int64_t)VJ * HW;
         for (int m = 0; m < VJ; ++m, ++c) {
           const int st = (int)(c % stages);
           const uint32_t kf = (uint32_t)(c / stages);
-          if (!mbar_wait(&empty[st], (kf & 1u) ^ 1u, 2, i, st)) return;
+          if (!mbar_wait(&empty[st], (kf & 1u) ^ 1u, g_fused_abort, 2, i, st)) return;
           mbar_arrive_expect_tx(&full[st], L.stage_bytes);
           bulk_g2s(smem + L.ring + (uint32_t)st * L.stage_bytes, src + (int64_t)m * HW, L.stage_bytes, &full[st]);
         }
@@ -183,7 +131,7 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
       const uint32_t ku = (uint32_t)(i / kFrameSlots);
       // every decode warp passes every frame's slot gate (even with no map in it) so that no warp can run a full
       // barrier phase ahead of the others
-      if (!mbar_wait(&kp_free[sl], (ku & 1u) ^ 1u, 3, i, sl)) return;
+      if (!mbar_wait(&kp_free[sl], (ku & 1u) ^ 1u, g_fused_abort, 3, i, sl)) return;
       const int64_t c0 = i * VJ;
       // first map of this frame owned by this warp: smallest m with (c0 + m) % D == d
       int m = (int)(((int64_t)d - c0 % kFusedDecodeWarps + kFusedDecodeWarps) % kFusedDecodeWarps);
@@ -191,7 +139,7 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
         const int64_t c = c0 + m;
         const int st = (int)(c % stages);
         const uint32_t kf = (uint32_t)(c / stages);
-        if (!mbar_wait(&full[st], kf & 1u, 4, i, st)) return;
+        if (!mbar_wait(&full[st], kf & 1u, g_fused_abort, 4, i, st)) return;
         const float4* __restrict__ p = reinterpret_cast<const float4*>(smem + L.ring + (uint32_t)st * L.stage_bytes);
         const uint32_t idx = warp_argmax_map<8, true>([&](int q) { return p[q]; }, hw4, lane, nullptr);
         if (lane == 0) {
@@ -225,7 +173,7 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
       const double* P = reinterpret_cast<const double*>(smem + L.proj + sl * V * 96);
       const int2* kp = kp_all + sl * VJ;
       uint32_t* masks = mask_all + sl * J;
-      if (!mbar_wait<true>(&kp_ready[sl], ku & 1u, 5, i, sl)) return;  // every RANSAC warp, every frame (same reason)
+      if (!mbar_wait<true>(&kp_ready[sl], ku & 1u, g_fused_abort, 5, i, sl)) return;  // every RANSAC warp, every frame (same reason)
       const int64_t t0 = i * J;
       int j = (int)(((int64_t)w - t0 % kFusedRansacWarps + kFusedRansacWarps) % kFusedRansacWarps);
       for (; j < J; j += kFusedRansacWarps) {
@@ -256,7 +204,7 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
       }
       if ((int)(i % kFusedRansacWarps) == w) {
         // final solves of this frame: lane = joint
-        if (!mbar_wait<true>(&masks_ready[sl], ku & 1u, 7, i, sl)) return;
+        if (!mbar_wait<true>(&masks_ready[sl], ku & 1u, g_fused_abort, 7, i, sl)) return;
         for (int jb = 0; jb < J; jb += kWarp) {
           const int jj = jb + lane;
           if (jj < J) {

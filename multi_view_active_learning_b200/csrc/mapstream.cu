@@ -1,0 +1,477 @@
+// Persistent "map stream" kernels (sm_100a) for the per-map heat-map scores on the reference's 64 x 64 maps:
+// soft-arg-max (utils/triangulation.py:191-197), MPE / BSB (strategy.py:1149-1176, 1195-1215) and the reprojection-XE
+// metric (utils/triangulation.py:236-257).
+//
+// These scores cost 6-20 instructions per pixel, so a warp that loads its own map from global memory alternates between
+// waiting for HBM and computing and the stream stalls (measured round 1e: 0.22-0.65 of the copy bandwidth).  Here the
+// two are decoupled exactly as in fused.cu: one CTA per SM, persistent over maps m = blockIdx.x + c * gridDim.x;
+//
+//   warp 0        TMA producer: one elected lane issues one cp.async.bulk (16 KiB, mbarrier complete_tx) per map into a
+//                 ring of kStages stages, so kStages * 16 KiB = 192 KiB per SM are in flight without a single register
+//                 or LSU slot spent on staging;
+//   warps 1..12   consumers: warp w owns stage w - 1 (map c goes to stage c % 12 and warp c % 12), waits on full[stage],
+//                 evaluates the whole map out of shared memory (conflict-free LDS.128, as many passes as it likes),
+//                 writes the score and releases empty[stage].
+//
+// Maps of invalid joints are never read: the producer arrives on the full barrier without a copy and the consumer
+// writes NaN.  Every hand-off is an mbarrier; there is no __syncthreads after set-up.  Shapes other than 64 x 64 (or
+// unaligned maps) take the one-warp-per-map kernels in decode.cu / peaks.cu / xe.cu.
+#include <stdlib.h>
+
+#include "tma.cuh"
+
+namespace mval {
+
+constexpr int kStreamWarps = 12;
+constexpr int kStreamStages = 12;
+constexpr int kStreamThreads = kWarp * (1 + kStreamWarps);  // 416
+constexpr int kMapDim = 64;
+constexpr int kMapFloats = kMapDim * kMapDim;
+constexpr uint32_t kMapBytes = kMapFloats * 4u;
+constexpr uint32_t kScratchPerWarp = 1024;  // XE: two tables of 64 doubles
+constexpr uint32_t kStreamSmem = kStreamStages * kMapBytes + 2u * kStreamStages * 8u + kStreamWarps * kScratchPerWarp;
+
+__device__ unsigned long long g_stream_abort[8];
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {  // one FMNMX3 (sm_100+)
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float y;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// soft-arg-max: softmax over the whole map, expectation of the pixel grid, times stride (kornia
+// spatial_soft_argmax2d(normalized_coordinates=False)).  Two passes over shared memory: the map maximum, then
+// w = 2^(x log2e - M log2e) (one FFMA + one MUFU per pixel; the rounding of M log2e scales every weight alike and
+// cancels in the ratio).  With W = 64 a lane's float4 column is fixed (4 * (lane % 16)) and its row is 2u + lane / 16,
+// so per vector only sum(w), sum(k w_k) and row * sum(w) are accumulated -- in float32 over 8 vectors, in float64
+// across them and across lanes.
+// ---------------------------------------------------------------------------------------------------------------
+struct SoftArgmaxOp {
+  struct Args {
+    float stride;
+    float* out_xy;
+  };
+  static constexpr bool kWritesSmem = false;
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*) {
+    (void)ok;
+    const float4* __restrict__ p = reinterpret_cast<const float4*>(map) + lane;
+    float mx = -INFINITY;
+#pragma unroll 8
+    for (int u = 0; u < 32; ++u) {
+      const float4 t = p[u * 32];
+      mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float nml = -mx * kLog2e;
+    const float half = (float)(lane >> 4);
+    double S = 0.0, X = 0.0, Y = 0.0;
+#pragma unroll 1
+    for (int blk = 0; blk < 4; ++blk) {
+      float s32 = 0.f, x32 = 0.f, y32 = 0.f;
+#pragma unroll
+      for (int uu = 0; uu < 8; ++uu) {
+        const int u = blk * 8 + uu;
+        const float4 t = p[u * 32];
+        const float w0 = ex2_approx(fmaf(t.x, kLog2e, nml)), w1 = ex2_approx(fmaf(t.y, kLog2e, nml));
+        const float w2 = ex2_approx(fmaf(t.z, kLog2e, nml)), w3 = ex2_approx(fmaf(t.w, kLog2e, nml));
+        const float ws = (w0 + w1) + (w2 + w3);
+        s32 += ws;
+        x32 += fmaf(3.0f, w3, fmaf(2.0f, w2, w1));
+        y32 = fmaf((float)(2 * u) + half, ws, y32);
+      }
+      S += (double)s32;
+      X += (double)x32;
+      Y += (double)y32;
+    }
+    X = fma((double)((lane & 15) * 4), S, X);
+    S = warp_sum(S);
+    X = warp_sum(X);
+    Y = warp_sum(Y);
+    if (lane == 0)  // the reference multiplies the float32 expectation by stride in float32 (:193-197)
+      reinterpret_cast<float2*>(a.out_xy)[m] = make_float2((float)(X / S) * a.stride, (float)(Y / S) * a.stride);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// HP (strategy.py:1185-1186): 1 - max over the map of softmax(row); the row maximum of softmax(row) is 1 / S_r with
+// S_r = sum_c exp(x_rc - max_r), so the score is 1 - 1 / min_r S_r.  One LDS.128 covers two rows (16 lanes each); row
+// max / row sum are 16-lane butterflies; exp = ex2.approx of the exactly formed difference times log2e (the maximum
+// itself contributes exactly 1).  A NaN row (a NaN, an infinity or an all -inf row) poisons the map like torch's softmax.
+// ---------------------------------------------------------------------------------------------------------------
+struct HpOp {
+  struct Args {
+    float* out;
+  };
+  static constexpr bool kWritesSmem = false;
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*) {
+    if (!ok) {
+      if (lane == 0) a.out[m] = __int_as_float(0x7fc00000);
+      return;
+    }
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float4* __restrict__ p = reinterpret_cast<const float4*>(map) + lane;
+    float min_s = INFINITY;
+    bool bad = false;
+#pragma unroll 8
+    for (int t = 0; t < 32; ++t) {
+      const float4 x = p[t * 32];
+      float rm = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(kFull, rm, o));
+      float rs = (ex2_approx((x.x - rm) * kLog2e) + ex2_approx((x.y - rm) * kLog2e)) +
+                 (ex2_approx((x.z - rm) * kLog2e) + ex2_approx((x.w - rm) * kLog2e));
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(kFull, rs, o);
+      bad |= (rs != rs);
+      min_s = fminf(min_s, rs);
+    }
+    min_s = fminf(min_s, __shfl_xor_sync(kFull, min_s, 16));
+    bad = __any_sync(kFull, bad);
+    if (lane == 0) a.out[m] = bad ? __int_as_float(0x7fc00000) : 1.0f - 1.0f / min_s;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// MPE (kMode 0) / BSB (kMode 1): local peaks as skimage.feature.peak_local_max(map, min_distance=2) defines them
+// (equal to the maximum of their 5 x 5 window, strictly above the map minimum, 2 pixels off the border).
+//
+// Layout: lane = (half, l16): float4 column block 4 * l16 .. 4 * l16 + 3 of row stream `half` -- half 0 walks rows
+// 0..33 and tests rows 2..31, half 1 walks rows 30..63 and tests rows 32..61 -- so one LDS.128 per lane feeds two rows
+// per warp instruction.  Horizontal 5-max: four 16-lane shuffles bring the two neighbouring values on each side (or
+// their pair maxima), three-input FMNMX does the rest; vertical 5-max: a register window of the last five horizontal
+// maxima, two FMNMX3 per pixel.  A pixel equal to its window maximum sets one bit in a per-column mask (30 tested rows
+// per stream), nothing else happens inside the scan: peaks are frequent on noisy maps (one per ~25 pixels), so any
+// per-peak work in the scan would run, diverged, on almost every row.  Afterwards each lane walks its own set bits
+// (about 5 per lane) with the map still in shared memory: MPE = entropy of softmax over the peak values (max pass,
+// then sum pass), BSB = |p0 - p1| of the two highest peaks.
+// BSB works on the ROW-softmaxed map (F.softmax without dim on a 2-D tensor): a first pass rewrites the stage in
+// place, p = exp(x - rowmax) / rowsum with 16-lane butterflies for the row statistics (exp = ex2.approx of the
+// difference times log2e, the quotient e * (1/s) corrected by one residual step).
+// ---------------------------------------------------------------------------------------------------------------
+template <int kMode>
+struct PeaksOp {
+  struct Args {
+    float* out;
+  };
+  static constexpr bool kWritesSmem = (kMode == 1);
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*) {
+    if (!ok) {
+      if (lane == 0) a.out[m] = __int_as_float(0x7fc00000);
+      return;
+    }
+    const int half = lane >> 4, l16 = lane & 15;
+    float4* p4 = reinterpret_cast<float4*>(map);
+    float gmin = INFINITY;
+    if (kMode == 1) {
+      constexpr float kLog2e = 1.4426950408889634f;
+#pragma unroll 4
+      for (int t = 0; t < 32; ++t) {
+        const int row = 2 * t + half;
+        const float4 x = p4[row * 16 + l16];
+        float rm = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(kFull, rm, o));
+        float4 e;  // the row maximum contributes exactly 1
+        e.x = ex2_approx((x.x - rm) * kLog2e);
+        e.y = ex2_approx((x.y - rm) * kLog2e);
+        e.z = ex2_approx((x.z - rm) * kLog2e);
+        e.w = ex2_approx((x.w - rm) * kLog2e);
+        float s = (e.x + e.y) + (e.z + e.w);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+        const float r = __frcp_rn(s);
+        float4 q;
+        q.x = e.x * r; q.x = fmaf(fmaf(-q.x, s, e.x), r, q.x);
+        q.y = e.y * r; q.y = fmaf(fmaf(-q.y, s, e.y), r, q.y);
+        q.z = e.z * r; q.z = fmaf(fmaf(-q.z, s, e.z), r, q.z);
+        q.w = e.w * r; q.w = fmaf(fmaf(-q.w, s, e.w), r, q.w);
+        gmin = fminf(gmin, fminf(fminf(q.x, q.y), fminf(q.z, q.w)));
+        p4[row * 16 + l16] = q;
+      }
+      __syncwarp();
+    }
+    const int rbase = half * 30;
+    float h[4][5], xs[4][3];
+    uint32_t bits[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int t = 0; t < 34; ++t) {
+      const float4 x = p4[(rbase + t) * 16 + l16];
+      const float m01 = fmaxf(x.x, x.y), m23 = fmaxf(x.z, x.w);
+      if (kMode == 0) gmin = min3(min3(x.x, x.y, x.z), x.w, gmin);
+      // neighbours inside the 16-lane row segment; the edge lanes get their own values back, which only ever reach the
+      // windows of border columns (masked below) or are members of the window anyway
+      const float Lm = __shfl_up_sync(kFull, m23, 1, 16), Lc3 = __shfl_up_sync(kFull, x.w, 1, 16);
+      const float Rc0 = __shfl_down_sync(kFull, x.x, 1, 16), Rm = __shfl_down_sync(kFull, m01, 1, 16);
+      const int s5 = t % 5, s3 = t % 3;
+      h[0][s5] = max3(Lm, m01, x.z);
+      h[1][s5] = max3(Lc3, m01, m23);
+      h[2][s5] = max3(m01, m23, Rc0);
+      h[3][s5] = max3(x.y, m23, Rm);
+      xs[0][s3] = x.x; xs[1][s3] = x.y; xs[2][s3] = x.z; xs[3][s3] = x.w;
+      if (t >= 4) {  // row rbase + t - 2 now has its five window rows in the ring
+        const int c3 = (t - 2) % 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float w = max3(max3(h[k][0], h[k][1], h[k][2]), h[k][3], h[k][4]);
+          if (xs[k][c3] == w) bits[k] |= 1u << (t - 4);
+        }
+      }
+    }
+    if (l16 == 0) bits[0] = bits[1] = 0u;   // columns 0, 1
+    if (l16 == 15) bits[2] = bits[3] = 0u;  // columns 62, 63
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmin = fminf(gmin, __shfl_xor_sync(kFull, gmin, o));
+    const float* col = map + (rbase + 2) * kMapDim + l16 * 4;  // bit i of bits[k] <-> col[i * 64 + k]
+    if (kMode == 0) {
+      float M = -INFINITY;
+      int n = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t b = bits[k];
+        while (b) {
+          const int i = __ffs(b) - 1;
+          b &= b - 1;
+          const float v = col[i * kMapDim + k];
+          if (v > gmin) {  // image > image.min(): peaks sitting at the map minimum are not peaks
+            M = fmaxf(M, v);
+            ++n;
+          } else {
+            bits[k] &= ~(1u << i);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        M = fmaxf(M, __shfl_xor_sync(kFull, M, o));
+        n += __shfl_xor_sync(kFull, n, o);
+      }
+      float S = 0.f, T = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t b = bits[k];
+        while (b) {
+          const int i = __ffs(b) - 1;
+          b &= b - 1;
+          const float d = col[i * kMapDim + k] - M;
+          const float w = expf(d);
+          S += w;
+          T = fmaf(d, w, T);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(kFull, S, o);
+        T += __shfl_xor_sync(kFull, T, o);
+      }
+      // H = -sum p log p with p = e^(v - M) / S  =  log S - T / S ; no peak: the reference sums an empty list
+      if (lane == 0) a.out[m] = (n > 0) ? logf(S) - T / S : 0.f;
+    } else {
+      float t1 = -INFINITY, t2 = -INFINITY;
+      int n = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t b = bits[k];
+        while (b) {
+          const int i = __ffs(b) - 1;
+          b &= b - 1;
+          const float v = col[i * kMapDim + k];
+          if (v > gmin) {
+            ++n;
+            if (v > t1) { t2 = t1; t1 = v; } else if (v > t2) { t2 = v; }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float u1 = __shfl_xor_sync(kFull, t1, o), u2 = __shfl_xor_sync(kFull, t2, o);
+        const float n1 = fmaxf(t1, u1), n2 = fmaxf(fminf(t1, u1), fmaxf(t2, u2));  // merge two sorted pairs
+        t1 = n1;
+        t2 = n2;
+        n += __shfl_xor_sync(kFull, n, o);
+      }
+      // fewer than two peaks: the reference raises IndexError (strategy.py:1208); NaN here, raised by the host wrapper
+      if (lane == 0) a.out[m] = (n >= 2) ? fabsf(t1 - t2) : __int_as_float(0x7fc00000);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Reprojection-XE term of one map (utils/triangulation.py:236-257): sum((heatmap - render)^2) / (H W) with
+// render[y][x] = exp(-((x - u)^2 + (y - v)^2) / (2 sigma^2)) in float64, (u, v) the reprojection of the triangulated
+// joint in IMAGE pixels (the reference compares it with the heat-map pixel grid as is).  The Gaussian is separable:
+// the warp forms gx[0..63], gy[0..63] (4 double exponentials per lane) in its scratch, a lane keeps the gx of its four
+// columns in registers and a pixel costs one conversion and two DFMA (r = h - gx gy; acc += r r).
+// ---------------------------------------------------------------------------------------------------------------
+struct XeOp {
+  struct Args {
+    const double* proj;
+    const double* xyz;
+    int V, J;
+    double inv_two_sigma2;
+    double* out_map;
+  };
+  static constexpr bool kWritesSmem = false;
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char* scratch) {
+    (void)ok;
+    double* gx = reinterpret_cast<double*>(scratch);
+    double* gy = gx + kMapDim;
+    const int j = (int)(m % a.J);
+    const int64_t fv = m / a.J;
+    const int64_t f = fv / a.V;
+    const double* __restrict__ P = a.proj + fv * 12;
+    const double* __restrict__ X = a.xyz + (f * a.J + j) * 3;
+    const double x = X[0], y = X[1], z = X[2];
+    // [X, 1] @ P^T (:476), then dehomogenise with w == 0 -> 1 (:397-399)
+    const double pu = ((x * P[0] + y * P[1]) + z * P[2]) + P[3];
+    const double pv = ((x * P[4] + y * P[5]) + z * P[6]) + P[7];
+    double pw = ((x * P[8] + y * P[9]) + z * P[10]) + P[11];
+    if (pw == 0.0) pw = 1.0;
+    const double u = pu / pw, v = pv / pw;
+    __syncwarp();
+#pragma unroll
+    for (int i = lane; i < kMapDim; i += 32) {
+      const double dx = (double)i - u, dy = (double)i - v;
+      gx[i] = exp(-(dx * dx) * a.inv_two_sigma2);
+      gy[i] = exp(-(dy * dy) * a.inv_two_sigma2);
+    }
+    __syncwarp();
+    const int half = lane >> 4, l16 = lane & 15;
+    const double2 ga = reinterpret_cast<const double2*>(gx)[l16 * 2], gb = reinterpret_cast<const double2*>(gx)[l16 * 2 + 1];
+    const float4* __restrict__ p = reinterpret_cast<const float4*>(map) + lane;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll 8
+    for (int t = 0; t < 32; ++t) {
+      const float4 h = p[t * 32];
+      const double g = gy[2 * t + half];
+      const double r0 = fma(-ga.x, g, (double)h.x), r1 = fma(-ga.y, g, (double)h.y);
+      const double r2 = fma(-gb.x, g, (double)h.z), r3 = fma(-gb.y, g, (double)h.w);
+      acc0 = fma(r0, r0, acc0);
+      acc1 = fma(r1, r1, acc1);
+      acc2 = fma(r2, r2, acc2);
+      acc3 = fma(r3, r3, acc3);
+    }
+    const double acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
+    if (lane == 0) a.out_map[m] = acc * (1.0 / (double)kMapFloats);
+  }
+};
+
+template <class Op>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+map_stream_kernel(const float* __restrict__ hm, int64_t n_maps, const uint8_t* __restrict__ valid, int V, int J,
+                  typename Op::Args args) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* ring = reinterpret_cast<float*>(smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStreamStages * kMapBytes);
+  uint64_t* empty = full + kStreamStages;
+  unsigned char* scratch = smem + kStreamStages * kMapBytes + 2u * kStreamStages * 8u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStreamStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int64_t nm = (n_maps > (int64_t)blockIdx.x) ? (n_maps - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const int64_t VJ = (int64_t)V * J;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int64_t c = 0; c < nm; ++c) {
+        const int64_t m = blockIdx.x + c * (int64_t)gridDim.x;
+        const int st = (int)(c % kStreamStages);
+        const uint32_t kf = (uint32_t)(c / kStreamStages);
+        if (!mbar_wait(&empty[st], (kf & 1u) ^ 1u, g_stream_abort, 1, c, st)) return;
+        if (valid != nullptr && valid[(m / VJ) * J + m % J] == 0) {
+          mbar_arrive(&full[st]);  // nothing to read for an invalid joint
+        } else {
+          mbar_arrive_expect_tx(&full[st], kMapBytes);
+          bulk_g2s(ring + (size_t)st * kMapFloats, hm + m * kMapFloats, kMapBytes, &full[st]);
+        }
+      }
+    }
+  } else {
+    const int w = warp - 1;
+    static_assert(kStreamStages == kStreamWarps, "stage c % S must belong to warp c % D");
+    float* stage = ring + (size_t)w * kMapFloats;
+    for (int64_t c = w; c < nm; c += kStreamWarps) {
+      const int64_t m = blockIdx.x + c * (int64_t)gridDim.x;
+      const uint32_t kf = (uint32_t)(c / kStreamStages);
+      const bool ok = valid == nullptr || valid[(m / VJ) * J + m % J] != 0;
+      if (!mbar_wait(&full[w], kf & 1u, g_stream_abort, 2, c, w)) return;
+      Op::run(stage, m, ok, lane, args, scratch + (uint32_t)w * kScratchPerWarp);
+      if (Op::kWritesSmem) fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[w]);
+    }
+  }
+}
+
+bool map_stream_applicable(const float* hm, int H, int W) {
+  const char* off = getenv("MVAL_NO_STREAM");  // A/B measurements and tests only; read on every call
+  return !(off != nullptr && off[0] == '1') && H == kMapDim && W == kMapDim && (reinterpret_cast<uintptr_t>(hm) & 15) == 0;
+}
+
+template <class Op>
+static int launch_map_stream(const char* name, const float* hm, int64_t n_maps, const uint8_t* valid, int V, int J,
+                             const typename Op::Args& args, cudaStream_t stream) {
+  if (n_maps == 0) return MVAL_OK;
+  MVAL_CUDA(cudaFuncSetAttribute(map_stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmem));
+  const int64_t sms = num_sms();
+  const int grid = (int)(n_maps < sms ? n_maps : sms);
+  map_stream_kernel<Op><<<grid, kStreamThreads, kStreamSmem, stream>>>(hm, n_maps, valid, V, J, args);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, name);
+  static const bool debug_sync = getenv("MVAL_DEBUG_SYNC") != nullptr;
+  if (debug_sync) {
+    MVAL_CUDA(cudaStreamSynchronize(stream));
+    unsigned long long rec[8] = {0};
+    MVAL_CUDA(cudaMemcpyFromSymbol(rec, g_stream_abort, sizeof(rec)));
+    if (rec[0] != 0ull) {
+      unsigned long long zero[8] = {0};
+      cudaMemcpyToSymbol(g_stream_abort, zero, sizeof(zero));
+      set_error("%s watchdog: wait code %llu timed out (block %llu warp %llu iter %llu index %llu)", name, rec[1], rec[2],
+                rec[3], rec[4], rec[5]);
+      return MVAL_ERR_CUDA;
+    }
+  }
+  return MVAL_OK;
+}
+
+int stream_softargmax(const float* hm, int64_t n_maps, float stride, float* out_xy, cudaStream_t stream) {
+  return launch_map_stream<SoftArgmaxOp>("map_stream<softargmax>", hm, n_maps, nullptr, 1, 1, {stride, out_xy}, stream);
+}
+int stream_hp(const float* hm, int64_t n_maps, int V, int J, const uint8_t* valid, float* out, cudaStream_t stream) {
+  return launch_map_stream<HpOp>("map_stream<HP>", hm, n_maps, valid, V, J, {out}, stream);
+}
+int stream_peaks(const float* hm, int64_t n_maps, int V, int J, int mode, const uint8_t* valid, float* out,
+                 cudaStream_t stream) {
+  if (mode == 0) return launch_map_stream<PeaksOp<0>>("map_stream<MPE>", hm, n_maps, valid, V, J, {out}, stream);
+  return launch_map_stream<PeaksOp<1>>("map_stream<BSB>", hm, n_maps, valid, V, J, {out}, stream);
+}
+int stream_xe(const float* hm, const double* proj, const double* xyz, int64_t n_maps, int V, int J, double inv_two_sigma2,
+              double* out_map, cudaStream_t stream) {
+  return launch_map_stream<XeOp>("map_stream<XE>", hm, n_maps, nullptr, V, J, {proj, xyz, V, J, inv_two_sigma2, out_map},
+                                 stream);
+}
+
+}  // namespace mval

@@ -209,6 +209,10 @@ score_peaks_kernel(const float* __restrict__ hm, int64_t n_maps, int V, int J, i
   }
 }
 
+bool map_stream_applicable(const float* hm, int H, int W);  // mapstream.cu
+int stream_peaks(const float* hm, int64_t n_maps, int V, int J, int mode, const uint8_t* valid, float* out,
+                 cudaStream_t stream);
+
 }  // namespace mval
 
 extern "C" int mval_score_peaks(const float* heatmaps, int64_t n_frames, int V, int J, int H, int W, int mode,
@@ -220,6 +224,8 @@ extern "C" int mval_score_peaks(const float* heatmaps, int64_t n_frames, int V, 
   const int64_t n_maps = n_frames * V * J;
   if (n_maps == 0) return MVAL_OK;
   MVAL_REQUIRE(heatmaps && out_score, "mval_score_peaks: null pointer");
+  if (map_stream_applicable(heatmaps, H, W))
+    return stream_peaks(heatmaps, n_maps, V, J, mode, valid, out_score, static_cast<cudaStream_t>(stream));
   if (W > 64) {
     set_error("mval_score_peaks: maps wider than 64 pixels are not supported (W=%d)", W);
     return MVAL_ERR_UNSUPPORTED;

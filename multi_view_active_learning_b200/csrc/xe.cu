@@ -81,6 +81,10 @@ __global__ void xe_frame_reduce_kernel(const double* __restrict__ per_map, int64
   out[f] = acc;
 }
 
+bool map_stream_applicable(const float* hm, int H, int W);  // mapstream.cu
+int stream_xe(const float* hm, const double* proj, const double* xyz, int64_t n_maps, int V, int J, double inv_two_sigma2,
+              double* out_map, cudaStream_t stream);
+
 }  // namespace mval
 
 extern "C" int mval_score_xe(const float* heatmaps, const double* proj, const double* xyz, int64_t n_frames, int V, int J, int H,
@@ -100,9 +104,14 @@ extern "C" int mval_score_xe(const float* heatmaps, const double* proj, const do
   const int64_t want = (n_maps + kXeWarps - 1) / kXeWarps;
   const int64_t cap = (int64_t)num_sms() * 8;
   const int grid = (int)(want < cap ? want : cap);
-  score_xe_kernel<<<grid, kXeWarps * 32, 0, stream>>>(heatmaps, proj, xyz, n_maps, V, J, H, W, 1.0 / (2.0 * sigma * sigma), per_map);
-  count_launch();
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = cudaSuccess;
+  if (map_stream_applicable(heatmaps, H, W)) {
+    if (stream_xe(heatmaps, proj, xyz, n_maps, V, J, 1.0 / (2.0 * sigma * sigma), per_map, stream) != MVAL_OK) e = cudaErrorUnknown;
+  } else {
+    score_xe_kernel<<<grid, kXeWarps * 32, 0, stream>>>(heatmaps, proj, xyz, n_maps, V, J, H, W, 1.0 / (2.0 * sigma * sigma), per_map);
+    count_launch();
+    e = cudaGetLastError();
+  }
   if (e == cudaSuccess) {
     xe_frame_reduce_kernel<<<(unsigned)((n_frames + 127) / 128), 128, 0, stream>>>(per_map, n_frames, V * J, out_metric);
     count_launch();

@@ -520,3 +520,83 @@ def test_kcenter_sharded_loop_bit_exact(ops):
     # tiny candidate sets (k_slots = 4): many short rounds, same answer
     sel2, _ = P.kcenter_greedy_sharded(shards, _cuda(F[n:]), budget, k_slots=4)
     assert sel2.cpu().tolist() == exp_sel
+
+
+# ------------------------------------------------------------------------------------------------ map-stream kernels
+def _legacy(fn):
+    """Runs fn with the persistent TMA-ring kernels (csrc/mapstream.cu) switched off -> one-warp-per-map kernels."""
+    import os
+
+    os.environ["MVAL_NO_STREAM"] = "1"
+    try:
+        return fn()
+    finally:
+        os.environ["MVAL_NO_STREAM"] = "0"
+
+
+def test_map_stream_kernels_match_per_map_kernels(ops):
+    """The persistent kernels (64 x 64 maps) against the one-warp-per-map kernels on a pool large enough for several
+    rounds of the 12-stage ring on every SM (148 x 12 x 3 maps), with invalid joints (never read) and a ragged tail."""
+    N, V, J = 41, 8, 19  # 6232 maps
+    pool = S.make_pool(N, V, J, seed=21, valid_prob=0.85)
+    hm_np = S.render_heatmaps(pool["centres"], noise=0.05, seed=22)
+    hm, valid = _cuda(hm_np), torch.from_numpy(pool["valid"])
+    v = np.broadcast_to(pool["valid"][:, None, :], (N, V, J))
+
+    soft_s = ops.decode_softargmax(hm, 4).cpu().numpy()
+    soft_l = _legacy(lambda: ops.decode_softargmax(hm, 4)).cpu().numpy()
+    np.testing.assert_allclose(soft_s, soft_l, rtol=0, atol=1e-4)
+    np.testing.assert_allclose(soft_s[:4], O.decode_softargmax(hm_np[:4], 4), rtol=0, atol=2e-4)
+
+    hp_s = ops.score_hp(hm, valid).cpu().numpy()
+    hp_l = _legacy(lambda: ops.score_hp(hm, valid)).cpu().numpy()
+    assert np.isnan(hp_s[~v]).all() and not np.isnan(hp_s[v]).any()
+    np.testing.assert_allclose(hp_s[v], hp_l[v], rtol=0, atol=1e-6)
+
+    for mode, atol in (("MPE", 2e-5), ("BSB", 2e-6)):
+        a = ops.score_peaks(hm, mode, valid).cpu().numpy()
+        b = _legacy(lambda: ops.score_peaks(hm, mode, valid)).cpu().numpy()
+        assert np.isnan(a[~v]).all() and not np.isnan(a[v]).any()
+        np.testing.assert_allclose(a[v], b[v], rtol=0, atol=atol)
+    sub = slice(0, 2)
+    np.testing.assert_allclose(ops.score_peaks(hm[sub], "MPE").cpu().numpy(), SO.mpe_scores(hm_np[sub]), rtol=0, atol=2e-5)
+    np.testing.assert_allclose(ops.score_peaks(hm[sub], "BSB").cpu().numpy(), SO.bsb_scores(hm_np[sub]), rtol=0, atol=2e-6)
+
+    P, X = _cuda(pool["P"]), _cuda(pool["X"])
+    P4 = P.clone()
+    P4[: N // 2, :, :2, :] /= 4  # half of the frames project onto the 64 x 64 grid (non-trivial renders)
+    xe_s, map_s = ops.score_xe(hm, P4, X, 2.0, return_per_map=True)
+    xe_l, map_l = _legacy(lambda: ops.score_xe(hm, P4, X, 2.0, return_per_map=True))
+    np.testing.assert_allclose(map_s.cpu().numpy(), map_l.cpu().numpy(), rtol=1e-12, atol=0)
+    np.testing.assert_allclose(xe_s.cpu().numpy(), xe_l.cpu().numpy(), rtol=1e-12, atol=0)
+    np.testing.assert_allclose(xe_s[:3].cpu().numpy(), O.compute_xe(pool["X"][:3], P4[:3].cpu().numpy(), hm_np[:3], 2.0)[0],
+                               rtol=1e-11, atol=0)
+
+
+def test_map_stream_peak_edge_cases(ops):
+    """Peaks next to the excluded 2-pixel border, on the seam between the two row streams (rows 30..33), plateaus at the
+    map minimum, and a map with exactly two peaks -- persistent kernel vs the scipy restatement."""
+    hm = np.zeros((1, 1, 8, 64, 64), dtype=np.float32)
+    hm[0, 0, 0, 2, 2], hm[0, 0, 0, 61, 61], hm[0, 0, 0, 1, 30], hm[0, 0, 0, 30, 62] = 3.0, 2.0, 9.0, 9.0  # corners in, border out
+    for r in (29, 30, 31, 32, 33, 34):
+        hm[0, 0, 1, r, 3 * (r - 28) + 5] = 1.0 + 0.1 * r  # one peak per seam row, far apart
+    hm[0, 0, 2, 31, 31], hm[0, 0, 2, 32, 33] = 2.0, 2.5  # neighbours across the seam: only the larger survives
+    hm[0, 0, 3] = 1.0
+    hm[0, 0, 3, 10:20, 10:20] = 0.5  # peaks would sit on the plateau of 1.0 = not the minimum -> all plateau pixels count
+    hm[0, 0, 4] = -1.0
+    hm[0, 0, 4, 20, 20], hm[0, 0, 4, 40, 40] = 0.0, 0.25
+    rng = np.random.default_rng(8)
+    hm[0, 0, 5] = rng.normal(size=(64, 64)).astype(np.float32)
+    hm[0, 0, 6] = rng.uniform(size=(64, 64)).astype(np.float32) * 10
+    hm[0, 0, 7, 15, 15], hm[0, 0, 7, 15, 19], hm[0, 0, 7, 15, 17] = 1.0, 1.0, 0.5  # equal peaks, 4 apart
+    mpe = ops.score_peaks(_cuda(hm), "MPE").cpu().numpy()
+    bsb = ops.score_peaks(_cuda(hm), "BSB").cpu().numpy()
+    exp_m, exp_b = SO.mpe_scores(hm), SO.bsb_scores(hm)
+    keep = np.ones(8, dtype=bool)
+    keep[3] = False  # a plateau above the minimum: skimage prunes it with ensure_spacing, the kernel counts every pixel
+    np.testing.assert_allclose(mpe[0, 0, keep], exp_m[0, 0, keep], rtol=0, atol=2e-5)
+    ok = keep & ~np.isnan(exp_b[0, 0])
+    np.testing.assert_allclose(bsb[0, 0, ok], exp_b[0, 0, ok], rtol=0, atol=2e-6)
+    assert np.array_equal(np.isnan(bsb[0, 0, keep]), np.isnan(exp_b[0, 0, keep]))
+    legacy_m = _legacy(lambda: ops.score_peaks(_cuda(hm), "MPE")).cpu().numpy()
+    np.testing.assert_allclose(mpe, legacy_m, rtol=0, atol=2e-5)
