@@ -693,14 +693,15 @@ def run_scores(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     algo = n * FRAME_HEATMAP_BYTES
     kernels = {
         "decode_argmax_kernel (a1)": lambda: ops.decode_argmax(hm, STRIDE),
-        "decode_softargmax_kernel (a3)": lambda: ops.decode_softargmax(hm, STRIDE),
-        "score_hp_w64_kernel (a8 HP)": lambda: ops.score_hp(hm),
-        "score_peaks_kernel MPE (a8)": lambda: ops.score_peaks(hm, "MPE"),
-        "score_peaks_kernel BSB (a8)": lambda: ops.score_peaks(hm, "BSB"),
-        "score_xe_kernel (a9)": lambda: ops.score_xe(hm, P, xyz, 2.0),
+        "map_stream_kernel<SoftArgmaxOp> (a3)": lambda: ops.decode_softargmax(hm, STRIDE),
+        "map_stream_kernel<HpOp> (a8 HP)": lambda: ops.score_hp(hm),
+        "map_stream_kernel<PeaksOp<0>> MPE (a8)": lambda: ops.score_peaks(hm, "MPE"),
+        "map_stream_kernel<PeaksOp<1>> BSB (a8)": lambda: ops.score_peaks(hm, "BSB"),
+        "map_stream_kernel<XeOp> + xe_frame_reduce (a9)": lambda: ops.score_xe(hm, P, xyz, 2.0),
         "score_pool_fused_kernel (a1+a4..a7)": lambda: ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False),
     }
     out = {}
@@ -713,7 +714,7 @@ def run_scores(args):
                       "config": {"workload": "%d frames x %d views x %d joints x %dx%d float32 heat maps resident (%.1f GB), "
                                  "one launch each" % (n, V, J, H, W, algo / 1e9)},
                       "roofline": {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "algorithmic_bytes_per_launch": algo,
-                                   "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)", "kernels": out}}))
+                                   "peak_source": peak_src, "kernels": out}}))
     return 0
 
 

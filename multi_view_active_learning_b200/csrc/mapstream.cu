@@ -153,19 +153,37 @@ struct HpOp {
 // MPE (kMode 0) / BSB (kMode 1): local peaks as skimage.feature.peak_local_max(map, min_distance=2) defines them
 // (equal to the maximum of their 5 x 5 window, strictly above the map minimum, 2 pixels off the border).
 //
-// Layout: lane = (half, l16): float4 column block 4 * l16 .. 4 * l16 + 3 of row stream `half` -- half 0 walks rows
+// Scan layout: lane = (half, l16): float4 column block 4 * l16 .. 4 * l16 + 3 of row stream `half` -- half 0 walks rows
 // 0..33 and tests rows 2..31, half 1 walks rows 30..63 and tests rows 32..61 -- so one LDS.128 per lane feeds two rows
 // per warp instruction.  Horizontal 5-max: four 16-lane shuffles bring the two neighbouring values on each side (or
 // their pair maxima), three-input FMNMX does the rest; vertical 5-max: a register window of the last five horizontal
 // maxima, two FMNMX3 per pixel.  A pixel equal to its window maximum sets one bit in a per-column mask (30 tested rows
 // per stream), nothing else happens inside the scan: peaks are frequent on noisy maps (one per ~25 pixels), so any
-// per-peak work in the scan would run, diverged, on almost every row.  Afterwards each lane walks its own set bits
-// (about 5 per lane) with the map still in shared memory: MPE = entropy of softmax over the peak values (max pass,
-// then sum pass), BSB = |p0 - p1| of the two highest peaks.
-// BSB works on the ROW-softmaxed map (F.softmax without dim on a 2-D tensor): a first pass rewrites the stage in
-// place, p = exp(x - rowmax) / rowsum with 16-lane butterflies for the row statistics (exp = ex2.approx of the
-// difference times log2e, the quotient e * (1/s) corrected by one residual step).
+// per-peak work in the scan would run, diverged, on almost every row.  Afterwards each lane walks its own set bits,
+// one bit of each of its four column masks per trip (about 2-3 trips), with the map still in shared memory:
+//   MPE = entropy of softmax over the peak values = log S - T / S with S = sum e^(v - c), T = sum (v - c) e^(v - c);
+//         the shift c is the maximum of the whole map (known from the scan, >= every peak), so one pass suffices; should
+//         every term underflow (a border pixel ~100 above every peak) a second pass shifts by the largest peak instead;
+//   BSB = |p0 - p1| of the two highest peaks.
+// Warp-wide minima / maxima / counts go through REDUX on monotone integer keys (one instruction instead of a five-step
+// shuffle butterfly); only the two float sums of MPE use a butterfly.
+// BSB works on the ROW-softmaxed map (F.softmax without dim on a 2-D tensor), so a first pass rewrites the stage in
+// place, p = exp(x - rowmax) / rowsum.  That pass runs with lane = row (rows l and l + 32): a lane holds its whole row in
+// 64 registers, so the row statistics need no shuffles at all; the float4 column blocks are visited in the rotated
+// order (k + lane) % 16, which keeps every quarter-warp on eight distinct 16-byte bank groups (conflict-free LDS.128 /
+// STS.128).  exp = ex2.approx of the exactly formed difference times log2e (the row maximum contributes exactly 1), the
+// quotient is e * (1/s) corrected by one residual step.
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t order_key(float x) {  // monotone float -> uint (no NaN handling needed here)
+  const uint32_t u = __float_as_uint(x);
+  return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float order_key_inv(uint32_t k) {
+  return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu));
+}
+__device__ __forceinline__ float warp_min_f(float v) { return order_key_inv(__reduce_min_sync(kFull, order_key(v))); }
+__device__ __forceinline__ float warp_max_f(float v) { return order_key_inv(__reduce_max_sync(kFull, order_key(v))); }
+
 template <int kMode>
 struct PeaksOp {
   struct Args {
@@ -179,32 +197,41 @@ struct PeaksOp {
     }
     const int half = lane >> 4, l16 = lane & 15;
     float4* p4 = reinterpret_cast<float4*>(map);
-    float gmin = INFINITY;
+    float gmin = INFINITY, gmax = -INFINITY;
     if (kMode == 1) {
       constexpr float kLog2e = 1.4426950408889634f;
-#pragma unroll 4
-      for (int t = 0; t < 32; ++t) {
-        const int row = 2 * t + half;
-        const float4 x = p4[row * 16 + l16];
-        float rm = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+#pragma unroll 1
+      for (int rr = 0; rr < 2; ++rr) {
+        float4* row = p4 + (lane + 32 * rr) * 16;
+        float4 x[16];
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(kFull, rm, o));
-        float4 e;  // the row maximum contributes exactly 1
-        e.x = ex2_approx((x.x - rm) * kLog2e);
-        e.y = ex2_approx((x.y - rm) * kLog2e);
-        e.z = ex2_approx((x.z - rm) * kLog2e);
-        e.w = ex2_approx((x.w - rm) * kLog2e);
-        float s = (e.x + e.y) + (e.z + e.w);
+        for (int k = 0; k < 16; ++k) x[k] = row[(k + lane) & 15];
+        float rm = -INFINITY;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+        for (int k = 0; k < 16; k += 2)
+          rm = max3(rm, max3(x[k].x, x[k].y, x[k].z), max3(x[k].w, x[k + 1].x, max3(x[k + 1].y, x[k + 1].z, x[k + 1].w)));
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          x[k].x = ex2_approx((x[k].x - rm) * kLog2e);
+          x[k].y = ex2_approx((x[k].y - rm) * kLog2e);
+          x[k].z = ex2_approx((x[k].z - rm) * kLog2e);
+          x[k].w = ex2_approx((x[k].w - rm) * kLog2e);
+          s0 += x[k].x + x[k].y;
+          s1 += x[k].z + x[k].w;
+        }
+        const float s = s0 + s1;
         const float r = __frcp_rn(s);
-        float4 q;
-        q.x = e.x * r; q.x = fmaf(fmaf(-q.x, s, e.x), r, q.x);
-        q.y = e.y * r; q.y = fmaf(fmaf(-q.y, s, e.y), r, q.y);
-        q.z = e.z * r; q.z = fmaf(fmaf(-q.z, s, e.z), r, q.z);
-        q.w = e.w * r; q.w = fmaf(fmaf(-q.w, s, e.w), r, q.w);
-        gmin = fminf(gmin, fminf(fminf(q.x, q.y), fminf(q.z, q.w)));
-        p4[row * 16 + l16] = q;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          float4 q;
+          q.x = x[k].x * r; q.x = fmaf(fmaf(-q.x, s, x[k].x), r, q.x);
+          q.y = x[k].y * r; q.y = fmaf(fmaf(-q.y, s, x[k].y), r, q.y);
+          q.z = x[k].z * r; q.z = fmaf(fmaf(-q.z, s, x[k].z), r, q.z);
+          q.w = x[k].w * r; q.w = fmaf(fmaf(-q.w, s, x[k].w), r, q.w);
+          gmin = min3(min3(q.x, q.y, q.z), q.w, gmin);
+          row[(k + lane) & 15] = q;
+        }
       }
       __syncwarp();
     }
@@ -215,7 +242,10 @@ struct PeaksOp {
     for (int t = 0; t < 34; ++t) {
       const float4 x = p4[(rbase + t) * 16 + l16];
       const float m01 = fmaxf(x.x, x.y), m23 = fmaxf(x.z, x.w);
-      if (kMode == 0) gmin = min3(min3(x.x, x.y, x.z), x.w, gmin);
+      if (kMode == 0) {
+        gmin = min3(min3(x.x, x.y, x.z), x.w, gmin);
+        gmax = max3(m01, m23, gmax);
+      }
       // neighbours inside the 16-lane row segment; the edge lanes get their own values back, which only ever reach the
       // windows of border columns (masked below) or are members of the window anyway
       const float Lm = __shfl_up_sync(kFull, m23, 1, 16), Lc3 = __shfl_up_sync(kFull, x.w, 1, 16);
@@ -237,78 +267,96 @@ struct PeaksOp {
     }
     if (l16 == 0) bits[0] = bits[1] = 0u;   // columns 0, 1
     if (l16 == 15) bits[2] = bits[3] = 0u;  // columns 62, 63
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) gmin = fminf(gmin, __shfl_xor_sync(kFull, gmin, o));
+    gmin = warp_min_f(gmin);
     const float* col = map + (rbase + 2) * kMapDim + l16 * 4;  // bit i of bits[k] <-> col[i * 64 + k]
     if (kMode == 0) {
-      float M = -INFINITY;
+      constexpr float kLog2e = 1.4426950408889634f;
+      gmax = warp_max_f(gmax);
+      float S = 0.f, T = 0.f, M = -INFINITY;
       int n = 0;
+      uint32_t b0 = bits[0], b1 = bits[1], b2 = bits[2], b3 = bits[3];
+      while (b0 | b1 | b2 | b3) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t b = bits[k];
-        while (b) {
-          const int i = __ffs(b) - 1;
-          b &= b - 1;
-          const float v = col[i * kMapDim + k];
-          if (v > gmin) {  // image > image.min(): peaks sitting at the map minimum are not peaks
-            M = fmaxf(M, v);
-            ++n;
-          } else {
-            bits[k] &= ~(1u << i);
+        for (int k = 0; k < 4; ++k) {
+          uint32_t& b = (k == 0) ? b0 : (k == 1) ? b1 : (k == 2) ? b2 : b3;
+          if (b) {
+            const int i = __ffs(b) - 1;
+            b &= b - 1;
+            const float v = col[i * kMapDim + k];
+            if (v > gmin) {  // image > image.min(): peaks sitting at the map minimum are not peaks
+              const float d = v - gmax;
+              const float w = ex2_approx(d * kLog2e);
+              S += w;
+              T = fmaf(d, w, T);
+              M = fmaxf(M, v);
+              ++n;
+            }
           }
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        M = fmaxf(M, __shfl_xor_sync(kFull, M, o));
-        n += __shfl_xor_sync(kFull, n, o);
-      }
-      float S = 0.f, T = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t b = bits[k];
-        while (b) {
-          const int i = __ffs(b) - 1;
-          b &= b - 1;
-          const float d = col[i * kMapDim + k] - M;
-          const float w = expf(d);
-          S += w;
-          T = fmaf(d, w, T);
-        }
-      }
+      n = __reduce_add_sync(kFull, n);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         S += __shfl_xor_sync(kFull, S, o);
         T += __shfl_xor_sync(kFull, T, o);
       }
-      // H = -sum p log p with p = e^(v - M) / S  =  log S - T / S ; no peak: the reference sums an empty list
+      if (n > 0 && !(S >= 1e-30f)) {  // every term underflowed: shift by the largest peak instead (never on real maps)
+        M = warp_max_f(M);
+        S = 0.f;
+        T = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t b = bits[k];
+          while (b) {
+            const int i = __ffs(b) - 1;
+            b &= b - 1;
+            const float v = col[i * kMapDim + k];
+            if (v > gmin) {
+              const float d = v - M;
+              const float w = expf(d);
+              S += w;
+              T = fmaf(d, w, T);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          S += __shfl_xor_sync(kFull, S, o);
+          T += __shfl_xor_sync(kFull, T, o);
+        }
+      }
+      // H = -sum p log p with p = e^(v - c) / S  =  log S - T / S ; no peak: the reference sums an empty list
       if (lane == 0) a.out[m] = (n > 0) ? logf(S) - T / S : 0.f;
     } else {
       float t1 = -INFINITY, t2 = -INFINITY;
       int n = 0;
+      uint32_t b0 = bits[0], b1 = bits[1], b2 = bits[2], b3 = bits[3];
+      while (b0 | b1 | b2 | b3) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t b = bits[k];
-        while (b) {
-          const int i = __ffs(b) - 1;
-          b &= b - 1;
-          const float v = col[i * kMapDim + k];
-          if (v > gmin) {
-            ++n;
-            if (v > t1) { t2 = t1; t1 = v; } else if (v > t2) { t2 = v; }
+        for (int k = 0; k < 4; ++k) {
+          uint32_t& b = (k == 0) ? b0 : (k == 1) ? b1 : (k == 2) ? b2 : b3;
+          if (b) {
+            const int i = __ffs(b) - 1;
+            b &= b - 1;
+            const float v = col[i * kMapDim + k];
+            if (v > gmin) {
+              ++n;
+              t2 = fmaxf(t2, fminf(t1, v));  // (t1, t2) = the two largest of {t1, t2, v}
+              t1 = fmaxf(t1, v);
+            }
           }
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float u1 = __shfl_xor_sync(kFull, t1, o), u2 = __shfl_xor_sync(kFull, t2, o);
-        const float n1 = fmaxf(t1, u1), n2 = fmaxf(fminf(t1, u1), fmaxf(t2, u2));  // merge two sorted pairs
-        t1 = n1;
-        t2 = n2;
-        n += __shfl_xor_sync(kFull, n, o);
-      }
+      n = __reduce_add_sync(kFull, n);
+      // two largest values over all lanes: the maximum, then either the maximum again (held by two lanes, or twice by
+      // one lane: then that lane's t2 equals it) or the largest remaining value
+      const float top = warp_max_f(t1);
+      const bool mine = (t1 == top);
+      const int owners = __popc(__ballot_sync(kFull, mine));
+      float second = warp_max_f(mine ? t2 : t1);
+      if (owners >= 2) second = top;
       // fewer than two peaks: the reference raises IndexError (strategy.py:1208); NaN here, raised by the host wrapper
-      if (lane == 0) a.out[m] = (n >= 2) ? fabsf(t1 - t2) : __int_as_float(0x7fc00000);
+      if (lane == 0) a.out[m] = (n >= 2) ? fabsf(top - second) : __int_as_float(0x7fc00000);
     }
   }
 };
