@@ -615,8 +615,7 @@ def run_hybrid(args):
             out = ops.score_pool(hm[:m], P_pool[off:off + m], STRIDE, None, pair_seed=0, frame_offset=shard_start + off,
                                  return_keypoints_2d=False)
             metrics.append(out["metric"])
-            kp = out["keypoints_3d"]
-            feats.append((kp - kp[:, root:root + 1]).permute(0, 2, 1).reshape(m, 3 * J).float())
+            feats.append(ops.pose_features(out["keypoints_3d"], root))  # utils/coreset.py:35-47 (mval_pose_features)
         metric = torch.cat(metrics)
         ranked = poolmod.distributed_topk(ops.topk_desc(metric, TOPK, index_offset=shard_start), TOPK)
         feat = torch.cat(feats)
@@ -727,7 +726,7 @@ def main():
     ap.add_argument("--pool-frames", type=int, default=POOL_FRAMES_PER_GPU)
     ap.add_argument("--resident-frames", type=int, default=16384)
     ap.add_argument("--e2e-frames", type=int, default=4096)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=9)
     ap.add_argument("--cpu-frames", type=int, default=4096)
     ap.add_argument("--ref-frames-per-core", type=int, default=128)
     ap.add_argument("--workload", default="scoring", choices=["scoring", "coreset", "scores", "hybrid"])

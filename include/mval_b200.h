@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MVAL_ABI_VERSION 2
+#define MVAL_ABI_VERSION 3
 #define MVAL_MAX_VIEWS 32
 
 enum mval_status {
@@ -127,6 +127,17 @@ int mval_triangulate_ransac(const void* xy, int xy_is_float, const double* proj,
                             double* out_reproj, int32_t* out_inliers, uint32_t* out_mask, double* out_metric,
                             int32_t* out_inlier_count, void* stream);
 
+/* Replaces the direct_optimization=True branch of _triangulate_ransac (utils/triangulation.py:319-336:
+ * scipy.optimize.least_squares(residuals, x0, loss="huber", method="trf") on the inlier views, then the mean error at
+ * the refined point).  Call after mval_triangulate_ransac with its outputs: every valid (frame, joint) minimises
+ * sum_v phi(0.5 ||kp_v - proj_v(x)||), phi = Huber with f_scale 1, over the views in inlier_mask, starting from xyz,
+ * by a damped Newton iteration run to convergence (csrc/refine.cu).  xyz and reproj are updated in place; when
+ * out_metric / out_inlier_count are given they are recomputed (inliers = out_inliers of the triangulation call).
+ * out_iters int32 device [n_frames][J] (may be NULL) receives the iteration counts. */
+int mval_refine_huber(const void* xy, int xy_is_float, const double* proj, const uint8_t* valid,
+                      const uint32_t* inlier_mask, const int32_t* inliers, int64_t n_frames, int V, int J, double* xyz,
+                      double* reproj, double* out_metric, int32_t* out_inlier_count, int32_t* out_iters, void* stream);
+
 /* Fused pool scoring = mval_decode_argmax + mval_triangulate_ransac on device-resident heat maps
  * (what strategy.py:1036-1045 does per frame, for a batch of frames).  out_xy may be NULL. */
 int mval_score_pool(const float* heatmaps, const double* proj, const uint8_t* valid, int64_t n_frames, int V,
@@ -163,6 +174,29 @@ int mval_score_xe(const float* heatmaps, const double* proj, const double* xyz, 
  * out_val float64 device [k]. */
 int mval_topk_desc(const double* scores, int64_t n, int64_t index_offset, int32_t k, int64_t* out_idx,
                    double* out_val, int32_t* out_count, void* stream);
+
+/* Replaces strategy.py:957-975 (the pseudo-label candidate filter and its sort): frames with a non-NaN sal_metric,
+ * inlier_count > inlier_threshold (SAL.INLIER_THRESHOLD) and excluded[i] == 0 (the caller marks frames already picked by
+ * the AL step or already pseudo-labelled), in ascending sal_metric order, ties in pool order (sorted() is stable).
+ * sal_metric / inlier_count float32 device [n] (strategy.py:1061-1063 stores both as float32); excluded uint8 device [n]
+ * or NULL.  Writes the first min(k, #candidates) pool indices to out_idx (int64 device [k]) and their number to
+ * *out_count (device int32). */
+int mval_sal_rank(const float* sal_metric, const float* inlier_count, const uint8_t* excluded, int64_t n,
+                  float inlier_threshold, int32_t k, int64_t* out_idx, int32_t* out_count, void* stream);
+
+/* Replaces utils/evaluation.py:198-208 compute_mkpe([pred], [gt], [valid]) per frame (strategy.py:1134-1145), float32:
+ * mean over joints of sqrt(sum_c where(valid, (pred - gt)^2, 0)) / valid  (NaN as soon as one joint is invalid, like the
+ * reference).  pred float32 device [n][J][3]; gt float32 device [n][gt_rows][J], rows 0..2 = x, y, z
+ * (dataset/dataset.py:148 stores 4 rows); valid float32 device [n][J]; out_mkpe float32 device [n]. */
+int mval_mkpe(const float* pred, const float* gt, const float* valid, int64_t n_frames, int J, int gt_rows, float* out_mkpe,
+              void* stream);
+
+/* Replaces utils/coreset.py:35-47 (_compute_stacked_features) for poses that are already on the device: row f =
+ * (x_0..x_{J-1}, y.., z..) of frame f relative to joint `root`, from the float32 roundings of the joints
+ * (strategy.py:1046), subtracted in float64 and rounded to float32.  xyz device [n][J][3], float64 (xyz_is_double = 1) or
+ * float32; out_features float32 device [n][3 J]. */
+int mval_pose_features(const void* xyz, int xyz_is_double, int64_t n_frames, int J, int root, float* out_features,
+                       void* stream);
 
 /* Coreset k-center greedy (utils/coreset.py:49-95) on float32 features.  features float32 device [n][d] row-major.
  * The distance is sklearn's expansion evaluated in float32 in the canonical order that oracle/coreset_oracle.c

@@ -8,7 +8,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmval_b200.so")
-SOURCES = ["capi.cu", "decode.cu", "peaks.cu", "xe.cu", "mapstream.cu", "triangulate.cu", "fused.cu", "select.cu", "kcenter.cu", "kcenter_tc.cu", "synth.cu"]
+SOURCES = ["capi.cu", "decode.cu", "peaks.cu", "xe.cu", "mapstream.cu", "triangulate.cu", "refine.cu", "fused.cu", "select.cu", "sal.cu", "kcenter.cu", "kcenter_tc.cu", "synth.cu"]
 
 
 def nvcc_path():

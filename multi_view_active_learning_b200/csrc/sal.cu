@@ -1,0 +1,118 @@
+// Per-frame bookkeeping kernels around the scoring pass (reference strategy.py:952-975, 1134-1145;
+// utils/evaluation.py:198-208; utils/coreset.py:35-47).  All are O(n J) element-wise work on results that already live
+// on the device; they exist so that a pool's scores never have to visit the host before the selection is made.
+#include "common.cuh"
+
+namespace mval {
+
+// utils/coreset.py:41-46: feature row = (pose^T[0:3, :] - pose^T[0:3, root]).flatten() = x_0..x_{J-1}, y.., z.. relative to
+// the root joint.  The reference builds it from sal_dict["pred_3d_keypoints"], i.e. from the float32 roundings of the
+// triangulated joints (strategy.py:1046), subtracts in float64 and CoreSet's device copy rounds to float32 once more.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pose_features_kernel(const T* __restrict__ xyz, int64_t n, int J, int root, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t d = 3ll * J;
+  if (i >= n * d) return;
+  const int64_t f = i / d;
+  const int r = (int)(i - f * d);
+  const int c = r / J, j = r - c * J;
+  const float a = (float)xyz[(f * J + j) * 3 + c], b = (float)xyz[(f * J + root) * 3 + c];
+  out[i] = (float)((double)a - (double)b);
+}
+
+// utils/evaluation.py:198-208 compute_mkpe([pred], [gt], [valid]) for every frame (strategy.py:1134-1145), float32 like
+// the reference's tensors: per joint sqrt(sum_c where(valid, (pred - gt)^2, 0)) / valid (0 / 0 = NaN for an invalid
+// joint, exactly as the reference), then the mean over joints (accumulated in float64, rounded once).
+// pred float32 [n][J][3]; gt float32 [n][gt_rows][J] (rows 0..2 = x, y, z; the dataset stores 4 rows); valid float32 [n][J].
+__global__ void __launch_bounds__(128)
+mkpe_kernel(const float* __restrict__ pred, const float* __restrict__ gt, const float* __restrict__ valid, int64_t n, int J,
+            int gt_rows, float* __restrict__ out) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const float* p = pred + f * J * 3;
+  const float* g = gt + f * gt_rows * J;
+  const float* v = valid + f * J;
+  double acc = 0.0;
+  for (int j = 0; j < J; ++j) {
+    float s = 0.f;
+    if (v[j] != 0.f) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float d = __fsub_rn(p[j * 3 + c], g[c * J + j]);
+        s = __fadd_rn(s, __fmul_rn(d, d));
+      }
+    }
+    acc += (double)__fdiv_rn(sqrtf(s), v[j]);
+  }
+  out[f] = (float)(acc / (double)J);
+}
+
+// strategy.py:957-975: candidates for pseudo-labelling are the frames that were not picked by the AL step, are not
+// already pseudo-labelled (both folded into `excluded` by the caller), have a non-NaN sal_metric and
+// inlier_count > threshold; they are visited in ascending sal_metric order, ties in pool order (Python's sorted is
+// stable).  Written as a descending ranking key for mval_topk_desc: NaN drops a frame, -metric + 0 orders the rest.
+__global__ void __launch_bounds__(256)
+sal_key_kernel(const float* __restrict__ sal_metric, const float* __restrict__ inlier_count, const uint8_t* __restrict__ excluded,
+               int64_t n, float inlier_threshold, double* __restrict__ key) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float m = sal_metric[i];
+  const bool keep = !(m != m) && !(excluded != nullptr && excluded[i] != 0) && inlier_count[i] > inlier_threshold;
+  key[i] = keep ? (-(double)m + 0.0) : __longlong_as_double(0x7ff8000000000000ll);
+}
+
+}  // namespace mval
+
+extern "C" int mval_pose_features(const void* xyz, int xyz_is_double, int64_t n_frames, int J, int root, float* out_features,
+                                  void* stream) {
+  using namespace mval;
+  if (int rc = require_device()) return rc;
+  MVAL_REQUIRE(n_frames >= 0 && J > 0 && root >= 0 && root < J, "mval_pose_features: bad shape or root joint");
+  if (n_frames == 0) return MVAL_OK;
+  MVAL_REQUIRE(xyz && out_features, "mval_pose_features: null pointer");
+  const int64_t total = n_frames * 3 * J;
+  const int64_t blocks = (total + 255) / 256;
+  MVAL_REQUIRE(blocks <= 0x7fffffffLL, "mval_pose_features: too many frames for one launch; chunk the pool");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (xyz_is_double)
+    pose_features_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const double*>(xyz), n_frames, J, root, out_features);
+  else
+    pose_features_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(xyz), n_frames, J, root, out_features);
+  MVAL_LAUNCH_CHECK("pose_features");
+  return MVAL_OK;
+}
+
+extern "C" int mval_mkpe(const float* pred, const float* gt, const float* valid, int64_t n_frames, int J, int gt_rows,
+                         float* out_mkpe, void* stream) {
+  using namespace mval;
+  if (int rc = require_device()) return rc;
+  MVAL_REQUIRE(n_frames >= 0 && J > 0 && gt_rows >= 3, "mval_mkpe: bad shape (gt needs at least the x, y, z rows)");
+  if (n_frames == 0) return MVAL_OK;
+  MVAL_REQUIRE(pred && gt && valid && out_mkpe, "mval_mkpe: null pointer");
+  mkpe_kernel<<<(unsigned)((n_frames + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(pred, gt, valid, n_frames, J,
+                                                                                                gt_rows, out_mkpe);
+  MVAL_LAUNCH_CHECK("mkpe");
+  return MVAL_OK;
+}
+
+extern "C" int mval_sal_rank(const float* sal_metric, const float* inlier_count, const uint8_t* excluded, int64_t n,
+                             float inlier_threshold, int32_t k, int64_t* out_idx, int32_t* out_count, void* stream_) {
+  using namespace mval;
+  if (int rc = require_device()) return rc;
+  MVAL_REQUIRE(n >= 0 && k >= 0, "mval_sal_rank: bad sizes");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n == 0 || k == 0) return mval_topk_desc(nullptr, 0, 0, k, out_idx, nullptr, out_count, stream_);
+  MVAL_REQUIRE(sal_metric && inlier_count && out_idx, "mval_sal_rank: null pointer");
+  double* key = nullptr;
+  MVAL_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&key), sizeof(double) * n, stream));
+  sal_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(sal_metric, inlier_count, excluded, n, inlier_threshold, key);
+  count_launch();
+  int rc = MVAL_OK;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) rc = cuda_fail(e, "launch sal_key");
+  if (rc == MVAL_OK) rc = mval_topk_desc(key, n, 0, k, out_idx, nullptr, out_count, stream_);
+  e = cudaFreeAsync(key, stream);
+  if (rc == MVAL_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");
+  return rc;
+}

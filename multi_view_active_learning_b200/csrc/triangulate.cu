@@ -142,6 +142,14 @@ frame_reduce_kernel(const double* __restrict__ reproj, const int32_t* __restrict
   out_inlier_count[frame] = cnt ? mn : 0;
 }
 
+int launch_frame_reduce(const double* reproj, const int32_t* inliers, const uint8_t* valid, int64_t n_frames, int J,
+                        double* out_metric, int32_t* out_inlier_count, cudaStream_t stream) {
+  frame_reduce_kernel<<<(unsigned)((n_frames + 127) / 128), 128, 0, stream>>>(reproj, inliers, valid, n_frames, J, out_metric,
+                                                                            out_inlier_count);
+  MVAL_LAUNCH_CHECK("frame_reduce");
+  return MVAL_OK;
+}
+
 static size_t vote_smem_bytes(int V) {
   const int n_all = V * (V - 1) / 2;
   return sizeof(double) * kVoteWarps * V * 14 + ((2 * n_all + 15) & ~15) + sizeof(uint16_t) * kVoteWarps * n_all;

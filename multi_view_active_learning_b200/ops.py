@@ -114,9 +114,11 @@ def _alloc_tri_outputs(N, J, device):
 
 
 def triangulate_ransac(keypoints_2d, proj, valid=None, n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0,
-                       frame_offset=0, pairs=None):
+                       frame_offset=0, pairs=None, direct_optimization=False):
     """keypoints_2d [N, V, J, 2] int32/float32 CUDA, proj [N, V, 3, 4] -> dict of CUDA tensors
-    (utils/triangulation.py:205-232 for N frames at once)."""
+    (utils/triangulation.py:205-232 for N frames at once).  direct_optimization=True adds the Huber refinement of
+    :319-336 on the inlier views (keypoints_3d, reproj_mean and metric are then those of the refined points;
+    "refine_iters" [N, J] holds the iteration counts)."""
     kp = keypoints_2d
     if not kp.is_cuda:
         raise RuntimeError("keypoints_2d is on %s: mval_b200 has no CPU fallback" % kp.device)
@@ -139,6 +141,12 @@ def triangulate_ransac(keypoints_2d, proj, valid=None, n_iters=DEFAULT_N_ITERS, 
                                                   _ptr(out["keypoints_3d"]), _ptr(out["reproj_mean"]),
                                                   _ptr(out["inliers"]), _ptr(out["inlier_mask"]), _ptr(out["metric"]),
                                                   _ptr(out["inlier_count"]), _stream()))
+        if direct_optimization:
+            out["refine_iters"] = torch.zeros((N, J), dtype=torch.int32, device=kp.device)
+            check(_lib.load().mval_refine_huber(_ptr(kp), int(is_float), _ptr(P), _ptr(v), _ptr(out["inlier_mask"]),
+                                                _ptr(out["inliers"]), N, V, J, _ptr(out["keypoints_3d"]),
+                                                _ptr(out["reproj_mean"]), _ptr(out["metric"]), _ptr(out["inlier_count"]),
+                                                _ptr(out["refine_iters"]), _stream()))
     out["keypoints_2d"] = kp
     return out
 
@@ -228,6 +236,48 @@ def topk_desc(scores, k, index_offset=0):
         check(_lib.load().mval_topk_desc(_ptr(s), n, int(index_offset), k, _ptr(idx), _ptr(val), _ptr(cnt), _stream()))
     m = int(cnt.item())
     return idx[:m], val[:m]
+
+
+def sal_rank(sal_metric, inlier_count, excluded, inlier_threshold, k):
+    """strategy.py:957-975 on the device: pool indices (int64 CUDA [m]) of the pseudo-label candidates -- non-NaN
+    sal_metric, inlier_count > threshold, not excluded -- in ascending sal_metric order (ties in pool order), first k."""
+    m = _cuda(sal_metric, torch.float32, "sal_metric").reshape(-1)
+    c = _cuda(inlier_count, torch.float32, "inlier_count").reshape(-1)
+    n = m.numel()
+    ex = None if excluded is None else _cuda(excluded, torch.uint8, "excluded").reshape(-1)
+    k = int(min(k, n))
+    idx = torch.empty((max(k, 1),), dtype=torch.int64, device=m.device)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=m.device)
+    with torch.cuda.device(m.device):
+        check(_lib.load().mval_sal_rank(_ptr(m), _ptr(c), _ptr(ex), n, float(inlier_threshold), k, _ptr(idx), _ptr(cnt), _stream()))
+    return idx[: int(cnt.item())]
+
+
+def mkpe(pred, gt, valid):
+    """utils/evaluation.py:198-208 per frame: pred [N, J, 3], gt [N, R >= 3, J], valid [N, J] (CUDA) -> float32 [N]."""
+    p = _cuda(pred, torch.float32, "pred")
+    g = _cuda(gt, torch.float32, "gt")
+    v = _cuda(valid, torch.float32, "valid")
+    N, J, _ = p.shape
+    if g.shape[0] != N or g.shape[2] != J or tuple(v.shape) != (N, J):
+        raise ValueError("gt / valid shapes do not match pred")
+    out = torch.empty((N,), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        check(_lib.load().mval_mkpe(_ptr(p), _ptr(g), _ptr(v), N, J, int(g.shape[1]), _ptr(out), _stream()))
+    return out
+
+
+def pose_features(keypoints_3d, root):
+    """utils/coreset.py:35-47 for device-resident poses: [N, J, 3] float64/float32 CUDA -> float32 [N, 3 J]."""
+    x = keypoints_3d
+    if not x.is_cuda:
+        raise RuntimeError("keypoints_3d is on %s: mval_b200 has no CPU fallback" % x.device)
+    x = x.contiguous() if x.dtype in (torch.float32, torch.float64) else x.double().contiguous()
+    N, J, _ = x.shape
+    out = torch.empty((N, 3 * J), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mval_pose_features(_ptr(x), int(x.dtype == torch.float64), N, J, int(root), _ptr(out), _stream()))
+    return out
 
 
 def kcenter_norms(features):

@@ -13,7 +13,9 @@ What changes relative to the reference's ``_compute_sal_dict`` (strategy.py:1004
   * the guid-keyed OrderedDicts are built once, in the order the reference would have inserted them (for each
     local position, rank 0..G-1), with the reference's float32 / float64 roundings.
 """
+import json
 import math
+import os
 import random
 from collections import OrderedDict
 
@@ -73,16 +75,12 @@ class ScoringSelectionMixin:
         train_dataset.label_by_frame_guids(al_guids)
         sal_sampled_guids = []
         if cfg.EXPR_TYPE == "SAL":
-            # reference :957-1001 -- host-side dict filtering, kept literal (SURVEY.md 8f row 2 moves it on device)
-            chosen = set(al_guids)
-            already = set(train_dataset.pseudo_label_guids)
-            sal_metric_dict = {
-                guid: m for guid, m in sal_dict["sal_metric"].items()
-                if guid not in chosen and not math.isnan(m) and guid not in already
-                and sal_dict["inlier_count"][guid] > cfg.SAL.INLIER_THRESHOLD
-            }
-            sal_guids = sorted(sal_metric_dict, key=sal_metric_dict.get)
-            if cfg.SAL.CLUSTER_FILE_PATH != "":
+            clustered = cfg.SAL.CLUSTER_FILE_PATH != ""
+            # reference :957-975: filter + ascending sort, on the device (mval_sal_rank).  Without clusters only the best
+            # 2n candidates are ever looked at (:993-995); the cluster-balanced walk may need the whole order.
+            sal_guids = self._sal_candidates(sal_dict, al_guids, train_dataset.pseudo_label_guids, cfg.SAL.INLIER_THRESHOLD,
+                                             None if clustered else 2 * pseudo_num_frames)
+            if clustered:
                 counter = [0 for _ in range(cfg.SAL.NUM_CLUSTERS)]
                 per_cluster_count = pseudo_num_frames // cfg.SAL.NUM_CLUSTERS
                 for guid in sal_guids:
@@ -96,6 +94,20 @@ class ScoringSelectionMixin:
                 sal_sampled_guids = random.sample(sal_guids[:2 * pseudo_num_frames], pseudo_num_frames)
             train_dataset.pseudo_label_by_frame_guids(sal_sampled_guids, sal_dict["pred_3d_keypoints"])
         return train_dataset, al_guids, sal_sampled_guids, sal_dict
+
+    @staticmethod
+    def _sal_candidates(sal_dict, al_guids, pseudo_label_guids, inlier_threshold, limit=None):
+        """strategy.py:957-975: guids with a non-NaN sal_metric and inlier_count > threshold that were neither picked by
+        the AL step nor pseudo-labelled before, by ascending sal_metric (ties in dict order); the first ``limit``."""
+        keys = list(sal_dict["sal_metric"].keys())
+        if not keys:
+            return []
+        taken = set(al_guids) | set(pseudo_label_guids)
+        excluded = torch.tensor([k in taken for k in keys], dtype=torch.uint8).cuda()
+        metric = torch.tensor(list(sal_dict["sal_metric"].values()), dtype=torch.float32).cuda()
+        inliers = torch.tensor([sal_dict["inlier_count"][k] for k in keys], dtype=torch.float32).cuda()
+        idx = ops.sal_rank(metric, inliers, excluded, float(inlier_threshold), len(keys) if limit is None else int(limit))
+        return [keys[i] for i in idx.cpu().tolist()]
 
     @staticmethod
     def _rank_nlargest(al_metric, n):
@@ -237,10 +249,8 @@ class ScoringSelectionMixin:
         n = f["sal"].shape[0]
         if n == 0:
             return sal_dict
-        # utils/evaluation.py:198-208 compute_mkpe([pred], [gt], [valid]) per frame, float32
-        d = torch.square(f["pred"].permute(0, 2, 1) - f["gt"][:, :3, :])
-        d = torch.where(f["valid"].bool().unsqueeze(1), d, torch.zeros_like(d))
-        mkpe = torch.mean(torch.sqrt(torch.sum(d, dim=1)) / f["valid"], dim=1).cpu().tolist()
+        # utils/evaluation.py:198-208 compute_mkpe([pred], [gt], [valid]) per frame, float32 (mval_mkpe)
+        mkpe = ops.mkpe(f["pred"], f["gt"], f["valid"]).cpu().tolist()
         poses, frames = f["pose"].cpu().tolist(), f["frame"].cpu().tolist()
         sal = f["sal"].cpu().tolist()
         inl = f["inl"].cpu().tolist()
@@ -257,7 +267,48 @@ class ScoringSelectionMixin:
         return sal_dict
 
 
-class ActiveLearningStrategy(ScoringSelectionMixin):
+class SelectionLogMixin:
+    """The files either side of the path: what ``sample_next_batch`` leaves on disk for rank 0
+    (strategy.py:112-134) and how ``restore_dataset`` replays them (strategy.py:315-336).  Same names, same JSON
+    payloads -- a run started with the reference can be resumed here and vice versa.  TensorBoard histograms
+    (:82-108) stay with the reference class."""
+
+    def _log_path(self, name):
+        return os.path.join(self.al_cfg.LOG_DIR, self.al_cfg.EXPR_NAME, name)
+
+    def _open(self, path, mode):
+        mgr = getattr(self, "_pathmgr", None)
+        if mgr is not None:
+            return mgr.open(path, mode)
+        if "w" in mode:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+        return open(path, mode)
+
+    def _after_sampling(self, iteration, rank, al_guids, sal_guids, sal_dict):
+        if rank != 0 or not hasattr(self.al_cfg, "LOG_DIR"):
+            return
+        if iteration != 0:
+            if len(sal_guids) != 0:
+                with self._open(self._log_path("SAL-GUID-ITER-%d" % iteration), "w") as f:
+                    f.write(json.dumps(sal_guids))
+            with self._open(self._log_path("SAL-DICT-ITER-%d" % iteration), "w") as f:
+                f.write(json.dumps(sal_dict))
+        with self._open(self._log_path("SAMPLED-GUID-ITER-%d" % iteration), "w") as f:
+            f.write(json.dumps(al_guids))
+
+    def restore_dataset(self, train_dataset, iteration):
+        """Reference strategy.py:315-336."""
+        for i in range(0, iteration):
+            with self._open(self._log_path("SAMPLED-GUID-ITER-%d" % i), "r") as f:
+                guids = json.loads(f.readline())
+            train_dataset.label_by_frame_guids(guids)
+        if self.al_cfg.EXPR_TYPE == "SAL" and iteration > 1:
+            with self._open(self._log_path("SAL-GUID-ITER-%d" % (iteration - 1)), "r") as f:
+                train_dataset.pseudo_label_guids = json.loads(f.readline())
+        return train_dataset
+
+
+class ActiveLearningStrategy(SelectionLogMixin, ScoringSelectionMixin):
     """Stand-alone strategy object exposing only the scoring-and-selection path (reference strategy.py:28-52 for
     the constructor fields that path reads)."""
 
@@ -266,3 +317,14 @@ class ActiveLearningStrategy(ScoringSelectionMixin):
         self.num_joints = al_cfg.DATA.NUM_JOINTS
         self.joint_root_index = 2 if al_cfg.DATA.TYPE == "panoptic" else 21
         self.kmeans = None
+        if al_cfg.EXPR_TYPE == "SAL" and getattr(al_cfg.SAL, "CLUSTER_FILE_PATH", "") != "":
+            # reference :37-52: k-means over the root-relative poses of the cluster file
+            from sklearn.cluster import KMeans
+
+            with self._open(al_cfg.SAL.CLUSTER_FILE_PATH, "r") as f:
+                clusters = json.load(f)
+            kp_values = []
+            for guid in clusters:
+                kp = np.array(clusters[guid])
+                kp_values.append((kp[0:3, :] - kp[0:3, self.joint_root_index:self.joint_root_index + 1]).flatten())
+            self.kmeans = KMeans(al_cfg.SAL.NUM_CLUSTERS, random_state=al_cfg.RANDOM_SEED).fit(kp_values)

@@ -37,9 +37,6 @@ def triangulation(
     """Same contract as the reference: heatmaps [V, J, H, W], proj_matricies [V, 3, 4], valid_joints [J] ->
     {"keypoints_3d": np.float64 [J, 3], "keypoints_2d": np [V, J, 2], "metric": np.float64, "inlier_count": np.int64}.
     """
-    if direct_optimization:
-        # SURVEY.md section 8f row 3: never enabled by the reference's own callers (strategy.py:607, 1037).
-        raise NotImplementedError("direct_optimization (Huber refinement, utils/triangulation.py:319-336) is not built")
     if not torch.is_tensor(heatmaps):
         heatmaps = torch.as_tensor(np.asarray(heatmaps))
     if len(proj_matricies) != heatmaps.shape[0]:
@@ -62,7 +59,8 @@ def triangulation(
     if not valid.any():
         # np.min([]) in the reference (:231)
         raise ValueError("zero-size array to reduction operation minimum which has no identity")
-    out = ops.triangulate_ransac(kp, P, torch.from_numpy(valid), n_iters, float(reprojection_error_epsilon), pairs=pairs)
+    out = ops.triangulate_ransac(kp, P, torch.from_numpy(valid), n_iters, float(reprojection_error_epsilon), pairs=pairs,
+                                 direct_optimization=bool(direct_optimization))
     kp_np = kp[0].cpu().numpy()
     if use_reprojection_xe:
         # reference :223-224: the metric becomes the 0-d CUDA tensor _compute_xe returns (float64 by promotion)
@@ -78,15 +76,17 @@ def triangulation(
 
 
 def triangulation_batch(heatmaps, proj_matricies, stride, valid_joints, use_soft_argmax=False, n_iters=64,
-                        reprojection_error_epsilon=5, pair_seed=0, frame_offset=0, use_reprojection_xe=False, sigma=None):
+                        reprojection_error_epsilon=5, pair_seed=0, frame_offset=0, use_reprojection_xe=False, sigma=None,
+                        direct_optimization=False):
     """Pool-level entry: heatmaps [N, V, J, H, W] (CUDA), proj_matricies [N, V, 3, 4], valid_joints [N, J] or [J].
     Returns a dict of CUDA tensors (keypoints_3d [N,J,3] f64, keypoints_2d, metric [N] f64, inlier_count [N] i32,
     reproj_mean [N,J], inliers [N,J]).  For C(V,2) > n_iters the view-pair subsets are the counter-based ones keyed
     by (pair_seed, frame_offset + frame, joint) -- see include/mval_b200.h."""
-    if use_soft_argmax:
-        kp = ops.decode_softargmax(heatmaps, stride)
+    if use_soft_argmax or direct_optimization:
+        # the refinement (utils/triangulation.py:319-336) needs the inlier masks, which only the unfused path keeps
+        kp = ops.decode_softargmax(heatmaps, stride) if use_soft_argmax else ops.decode_argmax(heatmaps, stride, valid_joints)
         out = ops.triangulate_ransac(kp, proj_matricies, valid_joints, n_iters, float(reprojection_error_epsilon),
-                                     pair_seed, frame_offset)
+                                     pair_seed, frame_offset, direct_optimization=bool(direct_optimization))
     else:
         out = ops.score_pool(heatmaps, proj_matricies, stride, valid_joints, n_iters, float(reprojection_error_epsilon),
                              pair_seed, frame_offset)

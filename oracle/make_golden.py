@@ -35,13 +35,13 @@ def load_strategy():
     return importlib.import_module("strategy")
 
 
-def run_reference_triangulation(tri, heatmaps, P, stride, valid, pair_seed):
+def run_reference_triangulation(tri, heatmaps, P, stride, valid, pair_seed, **kw):
     """Calls the reference's triangulation() frame by frame, exactly like strategy.py:1036-1045."""
     N, V, J = heatmaps.shape[:3]
     sched = [(n, j) for n in range(N) for j in range(J) if valid[n, j]]
     tri.random = O.DeterministicShuffle(pair_seed, sched)
     res = [tri.triangulation(torch.from_numpy(heatmaps[n]), torch.from_numpy(P[n]), stride,
-                             torch.from_numpy(valid[n])) for n in range(N)]
+                             torch.from_numpy(valid[n]), **kw) for n in range(N)]
     return {
         "keypoints_3d": np.stack([r["keypoints_3d"] for r in res]),
         "keypoints_2d": np.stack([r["keypoints_2d"] for r in res]),
@@ -93,6 +93,22 @@ def case_pool(tri, name, N, V, J, seed, valid_prob, pair_seed, p_outlier=0.12):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), P=pool["P"], valid=pool["valid"], stride=S.STRIDE,
                         pair_seed=pair_seed, keypoints_2d_unmasked=kp, **out)
     print(name, "metric[:3]", out["metric"][:3], "inlier_count", out["inlier_count"][:8])
+
+
+def case_huber(tri):
+    """triangulation(..., direct_optimization=True): the Huber refinement of utils/triangulation.py:319-336 run by
+    the reference itself (scipy least_squares) on a pool with outlier views, so that many residuals sit in the
+    linear zone of the loss."""
+    N, V, J = 6, 8, 19
+    pool = S.make_pool(N, V, J, seed=301, valid_prob=0.9, p_outlier=0.15)
+    rng = np.random.default_rng(302)
+    kp = (np.round(pool["centres"] + rng.normal(scale=0.6, size=pool["centres"].shape)).astype(np.int64)).clip(0, 63) * S.STRIDE
+    hm = S.onehot_heatmaps(kp)
+    out = run_reference_triangulation(tri, hm, pool["P"], S.STRIDE, pool["valid"], 0, direct_optimization=True)
+    base = run_reference_triangulation(tri, hm, pool["P"], S.STRIDE, pool["valid"], 0)
+    np.savez_compressed(os.path.join(OUT, "huber_v8_j19.npz"), P=pool["P"], valid=pool["valid"], stride=S.STRIDE,
+                        keypoints_2d_unmasked=kp, keypoints_3d_dlt=base["keypoints_3d"], metric_dlt=base["metric"], **out)
+    print("huber: max shift from DLT (mm)", np.abs(out["keypoints_3d"] - base["keypoints_3d"]).max(), "metric", out["metric"][:3])
 
 
 def case_decode(ev):
@@ -211,6 +227,7 @@ def main():
     case_pool(tri, "pool_v20_j42", N=4, V=20, J=42, seed=103, valid_prob=0.8, pair_seed=1234)
     case_pool(tri, "pool_v31_j19", N=3, V=31, J=19, seed=104, valid_prob=1.0, pair_seed=99)
     case_pool(tri, "pool_v2_j3", N=8, V=2, J=3, seed=105, valid_prob=0.7, pair_seed=0, p_outlier=0.3)
+    case_huber(tri)
     case_decode(ev)
     case_hp(st)
     case_coreset(cs)

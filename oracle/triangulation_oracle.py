@@ -10,7 +10,8 @@ Restates, vectorised over (frame, joint, view pair), what the upstream reference
                           kornia is not installed anywhere we can run; restated from kornia's dsnt docs]
   dlt_solve            <- utils/triangulation.py:341-368 (_triangulate_dlt) + :387-399
   reprojection_error   <- utils/triangulation.py:371-384, :459-484, :408-430
-  ransac_pool          <- utils/triangulation.py:260-316 (_triangulate_ransac, direct_optimization=False)
+  ransac_pool          <- utils/triangulation.py:260-316 (_triangulate_ransac)
+  refine_huber         <- utils/triangulation.py:319-336 (direct_optimization=True: scipy least_squares, Huber, trf)
   triangulate_pool     <- utils/triangulation.py:168-233 (triangulation) applied to every frame of a pool
 
 The SVD is numpy's (LAPACK gesdd), exactly the routine the reference calls (:363), on matrices of
@@ -168,7 +169,29 @@ def reprojection_error(X, pts, P):
     return 0.5 * np.sqrt(np.sum((np.asarray(pts, dtype=np.float64) - proj) ** 2, axis=-1))
 
 
-def ransac_pool(P, pts, valid, pairs, eps=5.0):
+def huber_cost(X, pts, P):
+    """0.5 * sum rho(r^2) with rho = Huber, f_scale = 1: the objective scipy minimises for reference :319-330."""
+    r = reprojection_error(X, pts, P)
+    z = r * r
+    return 0.5 * np.sum(np.where(z <= 1.0, z, 2.0 * np.sqrt(z) - 1.0), axis=-1)
+
+
+def refine_huber(P_inl, pts_inl, x0):
+    """Reference :319-336 for one joint: the very call the reference makes (same residual function, same scipy
+    routine and defaults), then the mean error at the refined point.  Returns (x [3], reproj_mean)."""
+    from scipy.optimize import least_squares
+
+    P_inl = np.asarray(P_inl, dtype=np.float64)
+    pts_inl = np.asarray(pts_inl, dtype=np.float64)
+
+    def residual_function(x):
+        return reprojection_error(np.array([x]), pts_inl[None], P_inl[None])[0]
+
+    res = least_squares(residual_function, np.array(x0, dtype=np.float64), loss="huber", method="trf")
+    return res.x, float(np.mean(residual_function(res.x)))
+
+
+def ransac_pool(P, pts, valid, pairs, eps=5.0, direct_optimization=False):
     """RANSAC over view pairs + final DLT on the inlier set, for every valid (frame, joint).
 
     P [N, V, 3, 4] f64; pts [N, V, J, 2]; valid [N, J] bool; pairs [n_pairs, 2] (shared) or
@@ -225,6 +248,10 @@ def ransac_pool(P, pts, valid, pairs, eps=5.0):
         pi = pm[sel[:, None], views]
         Xc = dlt_solve(Pi, pi)
         ec = reprojection_error(Xc, pi, Pi)
+        if direct_optimization:
+            for i in range(len(sel)):
+                Xc[i], m_i = refine_huber(Pi[i], pi[i], Xc[i])
+                ec[i] = m_i  # broadcast: the mean below returns m_i
         Xf[sel] = Xc
         rm[sel] = np.mean(ec, axis=-1)
     kp3d[nn, jj] = Xf
@@ -235,8 +262,9 @@ def ransac_pool(P, pts, valid, pairs, eps=5.0):
 
 
 def triangulate_pool(heatmaps, P, stride, valid, n_iters=64, eps=5.0, pair_seed=0, frame_offset=0,
-                     use_soft_argmax=False, keypoints_2d=None, chunk=256):
-    """Pool-level restatement of reference utils/triangulation.py:168-233 (use_reprojection_xe=False).
+                     use_soft_argmax=False, keypoints_2d=None, chunk=256, direct_optimization=False):
+    """Pool-level restatement of reference utils/triangulation.py:168-233 (use_reprojection_xe=False;
+    direct_optimization=True adds the Huber refinement of :319-336 through scipy, exactly as the reference does).
 
     heatmaps [N, V, J, H, W] f32 (or None when ``keypoints_2d`` [N, V, J, 2] is given); P [N, V, 3, 4];
     valid [N, J].  Returns dict with keypoints_3d [N,J,3] f64, keypoints_2d, metric [N] f64 (mean over valid
@@ -267,7 +295,7 @@ def triangulate_pool(heatmaps, P, stride, valid, n_iters=64, eps=5.0, pair_seed=
                 for j in range(J):
                     if valid[n, j]:
                         pairs[n - s, j] = allp[pair_subset_indices(n_all, n_iters, pair_seed, frame_offset + n, j)]
-        r = ransac_pool(P[s:e], keypoints_2d[s:e], valid[s:e], pairs, eps)
+        r = ransac_pool(P[s:e], keypoints_2d[s:e], valid[s:e], pairs, eps, direct_optimization)
         for o, x in zip(outs, r):
             o.append(x)
     kp3d, reproj_mean, inliers, inlier_mask = [np.concatenate(o, axis=0) for o in outs]

@@ -600,3 +600,47 @@ def test_map_stream_peak_edge_cases(ops):
     assert np.array_equal(np.isnan(bsb[0, 0, keep]), np.isnan(exp_b[0, 0, keep]))
     legacy_m = _legacy(lambda: ops.score_peaks(_cuda(hm), "MPE")).cpu().numpy()
     np.testing.assert_allclose(mpe, legacy_m, rtol=0, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------ Huber refinement
+def test_huber_refinement_golden_and_oracle(ops, golden):
+    """direct_optimization=True (utils/triangulation.py:319-336).  scipy stops at ftol = xtol = 1e-8, the kernel runs
+    its damped Newton iteration to convergence, so the two differ by scipy's termination slack (observed < 5e-3 mm):
+    inside the 1e-2 mm / 1e-3 relative contract, and the kernel's Huber cost is never above scipy's."""
+    g = golden("huber_v8_j19")
+    valid, P = g["valid"], g["P"]
+    kp = np.where(valid[:, None, :, None], g["keypoints_2d_unmasked"], 0)
+    out = ops.triangulate_ransac(_cuda(kp.astype(np.int32)), _cuda(P), torch.from_numpy(valid), direct_optimization=True)
+    got = ops.to_numpy(out)
+    np.testing.assert_allclose(got["keypoints_3d"], g["keypoints_3d"], rtol=XYZ_RTOL, atol=XYZ_ATOL_MM)
+    assert np.abs(got["keypoints_3d"] - g["keypoints_3d"]).max() < 1e-2
+    np.testing.assert_allclose(got["metric"], g["metric"], rtol=0, atol=REPROJ_ATOL_PX)
+    assert np.array_equal(got["inlier_count"], g["inlier_count"])
+    assert (got["keypoints_3d"][~valid] == 0).all()
+    assert got["refine_iters"][valid].max() < 100 and got["refine_iters"][valid].min() >= 1
+    # cost at the kernel's point <= cost at the reference's point, joint by joint
+    base = O.triangulate_pool(None, P, 4, valid, keypoints_2d=kp)
+    N, V, J = kp.shape[:3]
+    for n in range(N):
+        for j in range(J):
+            if not valid[n, j]:
+                continue
+            views = [v for v in range(V) if base["inlier_mask"][n, j] >> v & 1]
+            pts, Pi = kp[n, views, j].astype(np.float64), P[n, views]
+            assert O.huber_cost(got["keypoints_3d"][n, j], pts, Pi) <= O.huber_cost(g["keypoints_3d"][n, j], pts, Pi) + 1e-12
+    # drop-in entry point and the batched entry
+    from multi_view_active_learning_b200.utils import triangulation as T
+
+    hm = S.onehot_heatmaps(g["keypoints_2d_unmasked"][:2], 4)
+    r = T.triangulation(torch.from_numpy(hm[1]), torch.from_numpy(P[1]), 4, torch.from_numpy(valid[1]), direct_optimization=True)
+    np.testing.assert_allclose(r["keypoints_3d"], g["keypoints_3d"][1], rtol=XYZ_RTOL, atol=XYZ_ATOL_MM)
+    np.testing.assert_allclose(r["metric"], g["metric"][1], rtol=0, atol=REPROJ_ATOL_PX)
+    b = T.triangulation_batch(_cuda(hm), _cuda(P[:2]), 4, _cuda(valid[:2]), direct_optimization=True)
+    np.testing.assert_allclose(b["keypoints_3d"].cpu().numpy(), got["keypoints_3d"][:2], rtol=0, atol=1e-9)
+    # float key-points (soft-arg-max path) against the scipy oracle
+    pool = S.make_pool(5, 6, 7, seed=41, p_outlier=0.2)
+    kpf = (pool["centres"] * 4 + np.random.default_rng(1).normal(scale=1.5, size=pool["centres"].shape)).astype(np.float32)
+    o2 = ops.to_numpy(ops.triangulate_ransac(_cuda(kpf), _cuda(pool["P"]), torch.from_numpy(pool["valid"]), direct_optimization=True))
+    e2 = O.triangulate_pool(None, pool["P"], 4, pool["valid"], keypoints_2d=kpf, direct_optimization=True)
+    np.testing.assert_allclose(o2["keypoints_3d"], e2["keypoints_3d"], rtol=XYZ_RTOL, atol=XYZ_ATOL_MM)
+    np.testing.assert_allclose(o2["metric"], e2["metric"], rtol=0, atol=REPROJ_ATOL_PX)

@@ -163,3 +163,46 @@ def test_sal_pseudo_label_filter_and_iteration0():
     st.sample_next_batch(ds0, 6, 0, None, iteration=0)
     random.seed(cfg.RANDOM_SEED)
     assert st.last_al_guids == random.sample(keys, 6)
+
+
+def test_sal_rank_mkpe_and_pose_features_kernels():
+    """mval_sal_rank / mval_mkpe / mval_pose_features against literal restatements of strategy.py:957-975,
+    utils/evaluation.py:198-208 and utils/coreset.py:35-47."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from multi_view_active_learning_b200 import ops
+
+    rng = np.random.default_rng(17)
+    n = 5000
+    metric = rng.uniform(0, 3, size=n).astype(np.float32)
+    metric[rng.integers(0, n, 200)] = np.float32(0.5)   # ties -> pool order
+    metric[rng.integers(0, n, 50)] = 0.0
+    metric[rng.integers(0, n, 100)] = np.nan
+    inl = rng.integers(2, 9, size=n).astype(np.float32)
+    excl = rng.uniform(size=n) < 0.2
+    cand = {i: float(metric[i]) for i in range(n) if not excl[i] and not math.isnan(metric[i]) and inl[i] > 4}
+    exp = sorted(cand, key=cand.get)
+    got = ops.sal_rank(torch.from_numpy(metric).cuda(), torch.from_numpy(inl).cuda(), torch.from_numpy(excl).cuda(), 4.0, n)
+    assert got.cpu().tolist() == exp
+    got = ops.sal_rank(torch.from_numpy(metric).cuda(), torch.from_numpy(inl).cuda(), None, 4.0, 64)
+    cand = {i: float(metric[i]) for i in range(n) if not math.isnan(metric[i]) and inl[i] > 4}
+    assert got.cpu().tolist() == sorted(cand, key=cand.get)[:64]
+    assert ops.sal_rank(torch.full((7,), float("nan")).cuda(), torch.ones(7).cuda(), None, 0.0, 3).numel() == 0
+
+    N, J = 300, 19
+    pred = (rng.normal(size=(N, J, 3)) * 300).astype(np.float32)
+    gt = np.concatenate([(pred.transpose(0, 2, 1) + rng.normal(size=(N, 3, J)) * 20), np.ones((N, 1, J))], axis=1).astype(np.float32)
+    valid = (rng.uniform(size=(N, J)) < 0.97).astype(np.float32)
+    valid[:200] = 1.0
+    got = ops.mkpe(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(valid).cuda()).cpu().numpy()
+    exp = np.array([SO.mkpe(pred[i], gt[i], valid[i]) for i in range(N)], dtype=np.float32)
+    assert np.array_equal(np.isnan(got), np.isnan(exp)) and np.isnan(exp).sum() > 0
+    ok = ~np.isnan(exp)
+    np.testing.assert_allclose(got[ok], exp[ok], rtol=3e-7, atol=0)  # 1-2 ulp: float32 mean in a different order
+
+    xyz = rng.normal(size=(N, J, 3)) * 300
+    feats = ops.pose_features(torch.from_numpy(xyz).cuda(), 2).cpu().numpy()
+    poses32 = [xyz[i].astype(np.float32).tolist() for i in range(N)]  # what sal_dict["pred_3d_keypoints"] holds
+    exp = CO.stacked_features(poses32, [], 2).astype(np.float32)
+    assert feats.shape == (N, 3 * J) and np.array_equal(feats, exp)
+    assert np.array_equal(ops.pose_features(torch.from_numpy(xyz.astype(np.float32)).cuda(), 2).cpu().numpy(), exp)

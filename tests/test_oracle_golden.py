@@ -154,3 +154,15 @@ def test_ranking():
     d = {"a": 1.0, "b": float("nan"), "c": 3.0, "d": 3.0, "e": 2.0}
     assert SC.rank_nlargest(d, 3) == ["c", "d", "e"]
     assert SC.rank_nlargest(d, 10) == ["c", "d", "e", "a"]
+
+
+def test_huber_refinement_matches_reference(golden):
+    """direct_optimization=True (utils/triangulation.py:319-336): the oracle makes the reference's own scipy call, so it
+    reproduces the reference's refined joints to rounding; the refinement really moves the points (several mm)."""
+    g = golden("huber_v8_j19")
+    kp = np.where(g["valid"][:, None, :, None], g["keypoints_2d_unmasked"], 0)
+    out = O.triangulate_pool(None, g["P"], int(g["stride"]), g["valid"], keypoints_2d=kp, direct_optimization=True)
+    np.testing.assert_allclose(out["keypoints_3d"], g["keypoints_3d"], rtol=1e-9, atol=1e-7)
+    np.testing.assert_allclose(out["metric"], g["metric"], rtol=1e-9)
+    assert np.array_equal(out["inlier_count"], g["inlier_count"])
+    assert np.abs(g["keypoints_3d"] - g["keypoints_3d_dlt"]).max() > 1.0

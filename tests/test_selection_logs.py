@@ -1,0 +1,64 @@
+"""Host logic either side of the path (no GPU): the SAMPLED-GUID / SAL-GUID / SAL-DICT files sample_next_batch leaves
+behind (reference strategy.py:112-134) and their replay by restore_dataset (strategy.py:315-336)."""
+import json
+import os
+from collections import OrderedDict
+from types import SimpleNamespace as NS
+
+from multi_view_active_learning_b200.strategy import ActiveLearningStrategy
+
+
+class _Dataset:
+    def __init__(self, n):
+        self.unlabeled_data = OrderedDict(("160422-%d" % i, {"frame_id": i}) for i in range(n))
+        self.labeled_data, self.pseudo_label_guids = [], []
+
+    def label_by_frame_guids(self, guids):
+        for g in guids:
+            self.labeled_data.append(self.unlabeled_data.pop(g))
+
+
+def _cfg(tmp_path, expr="SAL"):
+    return NS(EXPR_TYPE=expr, EXPR_NAME="run0", LOG_DIR=str(tmp_path), RANDOM_SEED=1307, DATA=NS(NUM_JOINTS=19, TYPE="panoptic"),
+              SAL=NS(INLIER_THRESHOLD=7, CLUSTER_FILE_PATH="", NUM_CLUSTERS=10), AL=NS(STRATEGY="TRIANGULATION"))
+
+
+def test_iteration_files_and_restore(tmp_path):
+    st = ActiveLearningStrategy(_cfg(tmp_path))
+    ds = _Dataset(12)
+    st.sample_next_batch(ds, 3, 0, None, iteration=0, rank=0)  # iteration 0: seeded random sample (strategy.py:868-878)
+    first = st.last_al_guids
+    run = os.path.join(str(tmp_path), "run0")
+    assert json.loads(open(os.path.join(run, "SAMPLED-GUID-ITER-0")).readline()) == first
+    assert not os.path.exists(os.path.join(run, "SAL-DICT-ITER-0"))  # only written for iteration > 0 (:112-125)
+
+    sal_dict = {"al_metric": OrderedDict(a=1.5, b=float("nan")), "sal_metric": OrderedDict(a=0.25, b=0.5),
+                "inlier_count": OrderedDict(a=8.0, b=3.0), "pred_3d_keypoints": OrderedDict(a=[[0.0, 1.0, 2.0]], b=[[3.0, 4.0, 5.0]]),
+                "mkpe": OrderedDict(a=1.0, b=2.0)}
+    rest = [g for g in ds.unlabeled_data]
+    second, pseudo = rest[:2], rest[2:3]
+    st._after_sampling(1, 0, second, pseudo, sal_dict)
+    assert json.loads(open(os.path.join(run, "SAMPLED-GUID-ITER-1")).read()) == second
+    assert json.loads(open(os.path.join(run, "SAL-GUID-ITER-1")).read()) == pseudo
+    back = json.loads(open(os.path.join(run, "SAL-DICT-ITER-1")).read())
+    assert list(back) == list(sal_dict) and back["pred_3d_keypoints"]["b"] == [[3.0, 4.0, 5.0]] and back["al_metric"]["b"] != back["al_metric"]["b"]
+    st._after_sampling(2, 1, ["x"], [], {})  # other ranks write nothing (:81, :126)
+    assert not os.path.exists(os.path.join(run, "SAMPLED-GUID-ITER-2"))
+
+    ds2 = _Dataset(12)
+    st.restore_dataset(ds2, 2)
+    assert [f["frame_id"] for f in ds2.labeled_data] == [int(g.split("-")[1]) for g in first + second]
+    assert ds2.pseudo_label_guids == pseudo
+    assert len(ds2.unlabeled_data) == 12 - 5
+
+
+def test_al_experiment_writes_no_sal_guid_file(tmp_path):
+    st = ActiveLearningStrategy(_cfg(tmp_path, expr="AL"))
+    st._after_sampling(1, 0, ["a"], [], {"al_metric": {}})
+    run = os.path.join(str(tmp_path), "run0")
+    assert os.path.exists(os.path.join(run, "SAL-DICT-ITER-1")) and not os.path.exists(os.path.join(run, "SAL-GUID-ITER-1"))
+    ds = _Dataset(3)
+    ds.unlabeled_data["a"] = {"frame_id": 99}
+    open(os.path.join(run, "SAMPLED-GUID-ITER-0"), "w").write(json.dumps(["160422-0"]))
+    st.restore_dataset(ds, 2)
+    assert ds.pseudo_label_guids == [] and len(ds.labeled_data) == 2
