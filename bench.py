@@ -619,7 +619,8 @@ def run_hybrid(args):
         metric = torch.cat(metrics)
         ranked = poolmod.distributed_topk(ops.topk_desc(metric, TOPK, index_offset=shard_start), TOPK)
         feat = torch.cat(feats)
-        sel, _ = poolmod.kcenter_greedy_sharded([(feat, shard_start)], labeled, budget, stats=stats)
+        sel, _ = poolmod.kcenter_greedy_sharded([(feat, shard_start)], labeled, budget, stats=stats,
+                                                pad_to=args.coreset_pad or None)
         return ranked, sel
 
     def barrier():
@@ -737,6 +738,7 @@ def main():
     ap.add_argument("--coreset-path", default="auto", choices=["auto", "ffma", "tc"])
     ap.add_argument("--coreset-data", default="gaussian", choices=["gaussian", "clustered"])
     ap.add_argument("--coreset-cpu-rows", type=int, default=50000)
+    ap.add_argument("--coreset-pad", type=int, default=0, help="hybrid: zero-pad the pose features to a multiple of this")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks during the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

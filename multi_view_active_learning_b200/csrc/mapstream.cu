@@ -210,27 +210,31 @@ struct PeaksOp {
 #pragma unroll
         for (int k = 0; k < 16; k += 2)
           rm = max3(rm, max3(x[k].x, x[k].y, x[k].z), max3(x[k].w, x[k + 1].x, max3(x[k + 1].y, x[k + 1].z, x[k + 1].w)));
-        float s0 = 0.f, s1 = 0.f;
+        // packed float32x2 arithmetic (FADD2 / FMUL2 / FFMA2, sm_100): half the issue slots of the scalar forms
+        const float2 nrm = make_float2(-rm, -rm), l2e = make_float2(kLog2e, kLog2e);
+        float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          x[k].x = ex2_approx((x[k].x - rm) * kLog2e);
-          x[k].y = ex2_approx((x[k].y - rm) * kLog2e);
-          x[k].z = ex2_approx((x[k].z - rm) * kLog2e);
-          x[k].w = ex2_approx((x[k].w - rm) * kLog2e);
-          s0 += x[k].x + x[k].y;
-          s1 += x[k].z + x[k].w;
+          const float2 ta = __fmul2_rn(__fadd2_rn(make_float2(x[k].x, x[k].y), nrm), l2e);
+          const float2 tb = __fmul2_rn(__fadd2_rn(make_float2(x[k].z, x[k].w), nrm), l2e);
+          x[k].x = ex2_approx(ta.x);
+          x[k].y = ex2_approx(ta.y);
+          x[k].z = ex2_approx(tb.x);
+          x[k].w = ex2_approx(tb.y);
+          sa = __fadd2_rn(sa, make_float2(x[k].x, x[k].y));
+          sb = __fadd2_rn(sb, make_float2(x[k].z, x[k].w));
         }
-        const float s = s0 + s1;
+        const float s = (sa.x + sa.y) + (sb.x + sb.y);
         const float r = __frcp_rn(s);
+        const float2 r2 = make_float2(r, r), ns2 = make_float2(-s, -s);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          float4 q;
-          q.x = x[k].x * r; q.x = fmaf(fmaf(-q.x, s, x[k].x), r, q.x);
-          q.y = x[k].y * r; q.y = fmaf(fmaf(-q.y, s, x[k].y), r, q.y);
-          q.z = x[k].z * r; q.z = fmaf(fmaf(-q.z, s, x[k].z), r, q.z);
-          q.w = x[k].w * r; q.w = fmaf(fmaf(-q.w, s, x[k].w), r, q.w);
-          gmin = min3(min3(q.x, q.y, q.z), q.w, gmin);
-          row[(k + lane) & 15] = q;
+          const float2 ea = make_float2(x[k].x, x[k].y), eb = make_float2(x[k].z, x[k].w);
+          float2 qa = __fmul2_rn(ea, r2), qb = __fmul2_rn(eb, r2);
+          qa = __ffma2_rn(__ffma2_rn(qa, ns2, ea), r2, qa);  // q + (e - q s) / s: one residual correction step
+          qb = __ffma2_rn(__ffma2_rn(qb, ns2, eb), r2, qb);
+          gmin = min3(min3(qa.x, qa.y, qb.x), qb.y, gmin);
+          row[(k + lane) & 15] = make_float4(qa.x, qa.y, qb.x, qb.y);
         }
       }
       __syncwarp();

@@ -106,7 +106,21 @@ def kcenter_rounds(state, budget, group=None, k_slots=None, flags=0, stats=None)
     return selected[: int(budget)]
 
 
-def kcenter_greedy_sharded(shards, labeled, budget, group=None, k_slots=None, flags=0, stats=None):
+def pad_features(feat, multiple):
+    """Appends zero columns up to a multiple of ``multiple``.  The canonical float32 distance (oracle/coreset_oracle.c) is
+    unchanged by them: fma(0, 0, acc) = acc closes the dot-product chain and the squared norms gain exact zeros, so the
+    selection and the running minima are bit-identical -- but a 16-byte aligned row of at least 64 floats is what the
+    tensor-core screen (csrc/kcenter_tc.cu) needs, e.g. the reference's own d = 3 J = 57 -> 64."""
+    d = feat.shape[1]
+    pad = (-d) % int(multiple)
+    if pad == 0:
+        return feat
+    out = torch.zeros((feat.shape[0], d + pad), dtype=feat.dtype, device=feat.device)
+    out[:, :d] = feat
+    return out
+
+
+def kcenter_greedy_sharded(shards, labeled, budget, group=None, k_slots=None, flags=0, stats=None, pad_to=None):
     """Greedy k-center selection over UNLABELED feature rows that are row-sharded contiguously.
 
     shards : list of (features float32 CUDA [n_s, d], global_row_offset) owned by THIS process -- one entry per
@@ -121,9 +135,13 @@ def kcenter_greedy_sharded(shards, labeled, budget, group=None, k_slots=None, fl
 
     assert len(shards) >= 1 and labeled.shape[0] >= 1, "need at least one shard and one labeled centre"
     dev = labeled.device
+    if pad_to:
+        labeled = pad_features(labeled.float(), pad_to)
     state = []
     for feat, off in shards:
         feat = feat.float().contiguous()
+        if pad_to:
+            feat = pad_features(feat, pad_to)
         n = feat.shape[0]
         norms = ops.kcenter_norms(feat) if n else torch.empty(0, dtype=torch.float32, device=dev)
         state.append({"feat": feat, "off": int(off), "norms": norms,
