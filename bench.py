@@ -37,8 +37,10 @@ FRAME_ALGO_BYTES = FRAME_HEATMAP_BYTES + V * 96 + J + J * 24 + 16  # SURVEY.md s
 
 def workload_config(args, n_gpus):
     return {
-        "workload": "C2: Panoptic 19-joint, 8 views, 100k-frame pool per GPU: heatmap decode + RANSAC/DLT "
-                    "triangulation + reprojection uncertainty + top-k ranking",
+        "workload": ("C2: Panoptic 19-joint, 8 views, 100k-frame pool per GPU: heatmap decode + RANSAC/DLT "
+                     "triangulation + reprojection uncertainty + top-k ranking") if (V, J) == (8, 19) else
+                    ("%d-joint, %d views, %d-frame pool per GPU: heatmap decode + RANSAC/DLT triangulation + reprojection "
+                     "uncertainty + top-k ranking" % (J, V, args.pool_frames)),
         "views": V, "joints": J, "heatmap": [H, W], "pool_frames_per_gpu": args.pool_frames,
         "pool_frames_total": args.pool_frames * n_gpus, "resident_frames": args.resident_frames, "topk": TOPK,
         "n_iters": 64, "epsilon_px": 5.0,
@@ -744,7 +746,14 @@ def main():
     ap.add_argument("--coreset-cpu-rows", type=int, default=50000)
     ap.add_argument("--coreset-pad", type=int, default=0, help="hybrid: zero-pad the pose features to a multiple of this")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks during the timed region")
+    ap.add_argument("--views", type=int, default=V, help="camera views per frame (C2: 8; C3: 20; C5: 31)")
+    ap.add_argument("--joints", type=int, default=J, help="joints per frame (Panoptic 19; InterHand 42)")
     args = ap.parse_args()
+    if (args.views, args.joints) != (V, J):  # other BASELINE.json shapes (C3 / C5): same code path, different rig
+        g = globals()
+        g["V"], g["J"] = args.views, args.joints
+        g["FRAME_HEATMAP_BYTES"] = args.views * args.joints * H * W * 4
+        g["FRAME_ALGO_BYTES"] = g["FRAME_HEATMAP_BYTES"] + args.views * 96 + args.joints + args.joints * 24 + 16
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -15,7 +15,9 @@
 //                    runs the final solves of frame i with lane = joint, reduces metric / inlier_count and frees
 //                    the slot.
 //
-// Four frame slots (key-points, P, masks) decouple the roles: decode may run up to 3 frames ahead of the finals.
+// Up to four frame slots (key-points, P, masks) decouple the roles: decode may run up to slots - 1 frames ahead of the
+// finals.  A slot costs V * (96 + 8 J) bytes of shared memory, so for large rigs (20 views x 42 joints) the launcher
+// trades slots for ring stages -- bytes in flight are what keeps the HBM stream saturated.
 // Every hand-off is an mbarrier in shared memory; there is no __syncthreads after set-up.
 //
 // Arithmetic is shared with the stand-alone kernels (ransac.cuh), so the results are bit-identical to
@@ -30,7 +32,7 @@ namespace mval {
 constexpr int kFusedDecodeWarps = 6;
 constexpr int kFusedRansacWarps = 8;
 constexpr int kFusedThreads = kWarp * (1 + kFusedDecodeWarps + kFusedRansacWarps);  // 480
-constexpr int kFrameSlots = 4;
+constexpr int kMaxFrameSlots = 4;  // frame slots per CTA: 4 when they are small, fewer when V * J is large (see launcher)
 constexpr int kMaxStages = 64;
 
 // Abort record of the mbarrier watchdog (tma.cuh): [0] flag, [1] code, [2] block, [3] warp, [4] frame iter, [5] index
@@ -38,45 +40,46 @@ __device__ unsigned long long g_fused_abort[8];
 
 struct FusedSmem {  // byte offsets into dynamic shared memory
   uint32_t ring, proj, kp, mask, red_reproj, red_inl, pair, perm, pxy, bars, total;
-  int stages;
+  int stages, slots;
   uint32_t stage_bytes;
 };
 
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline FusedSmem fused_layout(int V, int J, int HW, int stages) {
+__host__ __device__ inline FusedSmem fused_layout(int V, int J, int HW, int stages, int slots) {
   FusedSmem L;
   const int n_all = V * (V - 1) / 2;
   L.stage_bytes = (uint32_t)HW * 4u;
   L.stages = stages;
+  L.slots = slots;
   uint32_t o = 0;
   L.ring = o;        o = align_up(o + (uint32_t)stages * L.stage_bytes, 128);
-  L.proj = o;        o = align_up(o + kFrameSlots * V * 96u, 16);
-  L.kp = o;          o = align_up(o + kFrameSlots * V * J * 8u, 16);
-  L.mask = o;        o = align_up(o + kFrameSlots * J * 4u, 16);
+  L.proj = o;        o = align_up(o + (uint32_t)slots * V * 96u, 16);
+  L.kp = o;          o = align_up(o + (uint32_t)slots * V * J * 8u, 16);
+  L.mask = o;        o = align_up(o + (uint32_t)slots * J * 4u, 16);
   L.red_reproj = o;  o = align_up(o + kFusedRansacWarps * J * 8u, 16);
   L.red_inl = o;     o = align_up(o + kFusedRansacWarps * J * 4u, 16);
   L.pair = o;        o = align_up(o + 2u * n_all, 16);
   L.perm = o;        o = align_up(o + kFusedRansacWarps * n_all * 2u, 16);
   L.pxy = o;         o = align_up(o + kFusedRansacWarps * 2u * V * 8u, 16);
-  L.bars = o;        o = o + (2u * stages + 3u * kFrameSlots) * 8u;
+  L.bars = o;        o = o + (2u * stages + 3u * (uint32_t)slots) * 8u;
   L.total = o;
   return L;
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1)
 score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__ proj, const uint8_t* __restrict__ valid,
-                        int64_t n_frames, int V, int J, int H, int HW, int stride, int stages, int n_iters, double eps,
+                        int64_t n_frames, int V, int J, int H, int HW, int stride, int stages, int slots, int n_iters, double eps,
                         uint64_t seed, int64_t frame_offset, int32_t* __restrict__ out_xy, double* __restrict__ out_xyz,
                         double* __restrict__ out_reproj, int32_t* __restrict__ out_inliers, double* __restrict__ out_metric,
                         int32_t* __restrict__ out_inlier_count) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const FusedSmem L = fused_layout(V, J, HW, stages);
+  const FusedSmem L = fused_layout(V, J, HW, stages, slots);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty = full + stages;
   uint64_t* kp_ready = empty + stages;
-  uint64_t* kp_free = kp_ready + kFrameSlots;
-  uint64_t* masks_ready = kp_free + kFrameSlots;
+  uint64_t* kp_free = kp_ready + slots;
+  uint64_t* masks_ready = kp_free + slots;
   const int VJ = V * J;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_all = V * (V - 1) / 2;
@@ -86,7 +89,7 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int s = 0; s < kFrameSlots; ++s) {
+    for (int s = 0; s < slots; ++s) {
       mbar_init(&kp_ready[s], (uint32_t)VJ + 1u);
       mbar_init(&kp_free[s], (uint32_t)J + 1u);
       mbar_init(&masks_ready[s], (uint32_t)J);
@@ -105,8 +108,8 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
       int64_t c = 0;
       for (int64_t i = 0; i < nf; ++i) {
         const int64_t frame = blockIdx.x + i * (int64_t)gridDim.x;
-        const int sl = (int)(i % kFrameSlots);
-        const uint32_t ku = (uint32_t)(i / kFrameSlots);
+        const int sl = (int)(i % slots);
+        const uint32_t ku = (uint32_t)(i / slots);
         if (!mbar_wait(&kp_free[sl], (ku & 1u) ^ 1u, g_fused_abort, 1, i, sl)) return;
         mbar_arrive_expect_tx(&kp_ready[sl], (uint32_t)V * 96u);
         bulk_g2s(smem + L.proj + sl * V * 96, proj + frame * V * 12, (uint32_t)V * 96u, &kp_ready[sl]);
@@ -127,8 +130,8 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
     int2* kp_all = reinterpret_cast<int2*>(smem + L.kp);
     for (int64_t i = 0; i < nf; ++i) {
       const int64_t frame = blockIdx.x + i * (int64_t)gridDim.x;
-      const int sl = (int)(i % kFrameSlots);
-      const uint32_t ku = (uint32_t)(i / kFrameSlots);
+      const int sl = (int)(i % slots);
+      const uint32_t ku = (uint32_t)(i / slots);
       // every decode warp passes every frame's slot gate (even with no map in it) so that no warp can run a full
       // barrier phase ahead of the others
       if (!mbar_wait(&kp_free[sl], (ku & 1u) ^ 1u, g_fused_abort, 3, i, sl)) return;
@@ -168,8 +171,8 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
     uint32_t* mask_all = reinterpret_cast<uint32_t*>(smem + L.mask);
     for (int64_t i = 0; i < nf; ++i) {
       const int64_t frame = blockIdx.x + i * (int64_t)gridDim.x;
-      const int sl = (int)(i % kFrameSlots);
-      const uint32_t ku = (uint32_t)(i / kFrameSlots);
+      const int sl = (int)(i % slots);
+      const uint32_t ku = (uint32_t)(i / slots);
       const double* P = reinterpret_cast<const double*>(smem + L.proj + sl * V * 96);
       const int2* kp = kp_all + sl * VJ;
       uint32_t* masks = mask_all + sl * J;
@@ -274,15 +277,20 @@ int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* 
   // The ring depth must be a multiple of the number of decode warps: map c lives in stage c % S and is decoded by warp
   // c % D, so D | S pins every stage to one warp, which visits it in order.  (Otherwise a warp can wait on a phase two
   // ahead of the barrier and the parity test aliases with the phase before -- seen as stale reads / deadlock.)
-  int stages = kMaxStages / kFusedDecodeWarps * kFusedDecodeWarps;
-  while (stages >= kFusedDecodeWarps && fused_layout(V, J, HW, stages).total > (uint32_t)max_smem)
-    stages -= kFusedDecodeWarps;
+  // Deepest ring first (bytes in flight), then as many frame slots as still fit: 4 slots / 12 stages at 8 views x 19
+  // joints, 2 slots / 12 stages at 20 x 42 (4 slots would leave 6 stages and the stream latency-bound).
+  int stages = 0, slots = 0;
+  for (int sl = kMaxFrameSlots; sl >= 2; --sl) {
+    int st = kMaxStages / kFusedDecodeWarps * kFusedDecodeWarps;
+    while (st >= kFusedDecodeWarps && fused_layout(V, J, HW, st, sl).total > (uint32_t)max_smem) st -= kFusedDecodeWarps;
+    if (st > stages) { stages = st; slots = sl; }
+  }
   if (stages < kFusedDecodeWarps) return MVAL_ERR_UNSUPPORTED;
-  const FusedSmem L = fused_layout(V, J, HW, stages);
+  const FusedSmem L = fused_layout(V, J, HW, stages, slots);
   MVAL_CUDA(cudaFuncSetAttribute(score_pool_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   const int64_t sms = num_sms();
   const int grid = (int)(n_frames < sms ? n_frames : sms);
-  score_pool_fused_kernel<<<grid, kFusedThreads, L.total, stream>>>(hm, proj, valid, n_frames, V, J, H, HW, stride, stages,
+  score_pool_fused_kernel<<<grid, kFusedThreads, L.total, stream>>>(hm, proj, valid, n_frames, V, J, H, HW, stride, stages, slots,
                                                                   prm.n_iters, prm.epsilon, prm.pair_seed, prm.frame_offset,
                                                                   out_xy, out_xyz, out_reproj, out_inliers, out_metric,
                                                                   out_inlier_count);

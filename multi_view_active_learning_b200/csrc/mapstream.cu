@@ -62,13 +62,17 @@ __device__ __forceinline__ double warp_sum(double v) {
 // so per vector only sum(w), sum(k w_k) and row * sum(w) are accumulated -- in float32 over 8 vectors, in float64
 // across them and across lanes.
 // ---------------------------------------------------------------------------------------------------------------
+struct NoPrefetch {};
+
 struct SoftArgmaxOp {
   struct Args {
     float stride;
     float* out_xy;
   };
+  using Pre = NoPrefetch;
   static constexpr bool kWritesSmem = false;
-  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*) {
+  __device__ static __forceinline__ Pre prefetch(int64_t, const Args&) { return {}; }
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*, const Pre&) {
     (void)ok;
     const float4* __restrict__ p = reinterpret_cast<const float4*>(map) + lane;
     float mx = -INFINITY;
@@ -120,8 +124,10 @@ struct HpOp {
   struct Args {
     float* out;
   };
+  using Pre = NoPrefetch;
   static constexpr bool kWritesSmem = false;
-  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*) {
+  __device__ static __forceinline__ Pre prefetch(int64_t, const Args&) { return {}; }
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*, const Pre&) {
     if (!ok) {
       if (lane == 0) a.out[m] = __int_as_float(0x7fc00000);
       return;
@@ -189,8 +195,10 @@ struct PeaksOp {
   struct Args {
     float* out;
   };
+  using Pre = NoPrefetch;
   static constexpr bool kWritesSmem = (kMode == 1);
-  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*) {
+  __device__ static __forceinline__ Pre prefetch(int64_t, const Args&) { return {}; }
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*, const Pre&) {
     if (!ok) {
       if (lane == 0) a.out[m] = __int_as_float(0x7fc00000);
       return;
@@ -380,17 +388,32 @@ struct XeOp {
     double inv_two_sigma2;
     double* out_map;
   };
+  // The projection matrix row block and the 3-D joint of a map come from global memory; they are fetched one map ahead
+  // (while the warp still waits for / works on the current stage) so that their latency never sits between the
+  // arrival of a map and its evaluation.
+  struct Pre {
+    double P[12], X[3];
+  };
   static constexpr bool kWritesSmem = false;
-  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char* scratch) {
+  __device__ static __forceinline__ Pre prefetch(int64_t m, const Args& a) {
+    Pre q;
+    const int j = (int)(m % a.J);
+    const int64_t fv = m / a.J;
+    const double* __restrict__ P = a.proj + fv * 12;
+    const double* __restrict__ X = a.xyz + ((fv / a.V) * a.J + j) * 3;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) q.P[i] = __ldg(P + i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) q.X[i] = __ldg(X + i);
+    return q;
+  }
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char* scratch,
+                                             const Pre& q) {
     (void)ok;
     double* gx = reinterpret_cast<double*>(scratch);
     double* gy = gx + kMapDim;
-    const int j = (int)(m % a.J);
-    const int64_t fv = m / a.J;
-    const int64_t f = fv / a.V;
-    const double* __restrict__ P = a.proj + fv * 12;
-    const double* __restrict__ X = a.xyz + (f * a.J + j) * 3;
-    const double x = X[0], y = X[1], z = X[2];
+    const double* P = q.P;
+    const double x = q.X[0], y = q.X[1], z = q.X[2];
     // [X, 1] @ P^T (:476), then dehomogenise with w == 0 -> 1 (:397-399)
     const double pu = ((x * P[0] + y * P[1]) + z * P[2]) + P[3];
     const double pv = ((x * P[4] + y * P[5]) + z * P[6]) + P[7];
@@ -464,12 +487,16 @@ map_stream_kernel(const float* __restrict__ hm, int64_t n_maps, const uint8_t* _
     const int w = warp - 1;
     static_assert(kStreamStages == kStreamWarps, "stage c % S must belong to warp c % D");
     float* stage = ring + (size_t)w * kMapFloats;
+    typename Op::Pre pre = Op::prefetch(w < nm ? blockIdx.x + w * (int64_t)gridDim.x : 0, args);
     for (int64_t c = w; c < nm; c += kStreamWarps) {
       const int64_t m = blockIdx.x + c * (int64_t)gridDim.x;
       const uint32_t kf = (uint32_t)(c / kStreamStages);
       const bool ok = valid == nullptr || valid[(m / VJ) * J + m % J] != 0;
+      const int64_t c_next = c + kStreamWarps;
+      const typename Op::Pre nxt = Op::prefetch(c_next < nm ? blockIdx.x + c_next * (int64_t)gridDim.x : m, args);
       if (!mbar_wait(&full[w], kf & 1u, g_stream_abort, 2, c, w)) return;
-      Op::run(stage, m, ok, lane, args, scratch + (uint32_t)w * kScratchPerWarp);
+      Op::run(stage, m, ok, lane, args, scratch + (uint32_t)w * kScratchPerWarp, pre);
+      pre = nxt;
       if (Op::kWritesSmem) fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[w]);
