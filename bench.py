@@ -499,7 +499,8 @@ def run_coreset(args):
     torch.cuda.synchronize()
     l0 = _lib.launch_count()
     stats = []
-    total_ms, (sel, _) = _timed(lambda: poolmod.kcenter_greedy_sharded([(feat, lo)], labeled, budget, flags=flags, stats=stats))
+    total_ms, (sel, _) = _timed(lambda: poolmod.kcenter_greedy_sharded([(feat, lo)], labeled, budget, flags=flags, stats=stats,
+                                                                           k_slots=args.coreset_kslots or None))
     launches = _lib.launch_count() - l0
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -626,7 +627,7 @@ def run_hybrid(args):
         ranked = poolmod.distributed_topk(ops.topk_desc(metric, TOPK, index_offset=shard_start), TOPK)
         feat = torch.cat(feats)
         sel, _ = poolmod.kcenter_greedy_sharded([(feat, shard_start)], labeled, budget, stats=stats,
-                                                pad_to=args.coreset_pad or None)
+                                                pad_to=args.coreset_pad or None, k_slots=args.coreset_kslots or None)
         return ranked, sel
 
     def barrier():
@@ -744,6 +745,7 @@ def main():
     ap.add_argument("--coreset-path", default="auto", choices=["auto", "ffma", "tc"])
     ap.add_argument("--coreset-data", default="gaussian", choices=["gaussian", "clustered"])
     ap.add_argument("--coreset-cpu-rows", type=int, default=50000)
+    ap.add_argument("--coreset-kslots", type=int, default=0, help="candidate slots per shard and round (0 = pool.py default)")
     ap.add_argument("--coreset-pad", type=int, default=0, help="hybrid: zero-pad the pose features to a multiple of this")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks during the timed region")
     ap.add_argument("--views", type=int, default=V, help="camera views per frame (C2: 8; C3: 20; C5: 31)")

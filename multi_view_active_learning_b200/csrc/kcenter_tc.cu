@@ -25,6 +25,7 @@
 //   warps 2-5  epilogue: tcgen05.ld 32x32b of the 128 x 256 float32 accumulator (two TMEM buffers, so the MMAs of the next
 //              row tile overlap the epilogue of this one)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "kcenter.cuh"
 
@@ -267,6 +268,238 @@ kc_screen_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 2-CTA variant (tcgen05 cta_group::2, one CTA pair = one TPC): the 1-CTA kernel above is bound by shared-memory
+// bandwidth -- per 32-float k-block a CTA writes 48 KiB (TMA) and the tensor core reads 48 KiB back, 96 KiB per 524 MMA
+// cycles against 128 B/clk -- and two thirds of that is the centre tile, identical for every CTA.  Here a pair of CTAs
+// screens 256 feature rows against the 256 centres with ONE M = 256, N = 256 MMA per K = 8: each CTA stages its own 128
+// feature rows (16 KiB) and only HALF of the centre tile (128 centres, 16 KiB); the tensor cores of both SMs read both
+// halves.  Per SM and k-block: 32 KiB written + 32 KiB read, and half the L2 -> SM traffic for the centres.
+//   rank 0 (leader)  warp 0 TMA producer (own A rows + centres 0..127), warp 1 lane 0 issues every MMA and commits to the
+//                    stage-empty / accumulator-full barriers of BOTH CTAs (multicast), warps 2-5 epilogue of rows 0..127
+//   rank 1           warp 0 TMA producer (own A rows + centres 128..255; its transaction bytes complete on the leader's
+//                    full barrier), warp 1 only allocates / frees TMEM, warps 2-5 epilogue of rows 128..255 (arriving on
+//                    the leader's accumulator-empty barrier through the cluster window)
+// The accumulator of a CTA is its 128 rows x 256 centres, exactly as in the 1-CTA kernel, so the epilogue is unchanged.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTc2Stages = 6;
+constexpr uint32_t kTc2HalfN = kTcBlockN / 2;
+constexpr uint32_t kTc2BBytes = kTc2HalfN * kTcBlockK * 4;
+constexpr uint32_t kTc2StageBytes = kTcABytes + kTc2BBytes;  // per CTA
+constexpr uint32_t kTc2SmemBytes = kTc2Stages * kTc2StageBytes + 1024 /*hcc*/ + 256 /*barriers etc.*/ + 1024 /*alignment*/;
+constexpr uint32_t kTc2Idesc =
+    (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBlockN >> 3) << 17) | ((uint32_t)((2 * kTcBlockM) >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with cluster-scope acquire (arrivals come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  long long t0 = 0;
+  for (uint32_t polls = 0;; ++polls) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((polls & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 8000000000ll) asm volatile("trap;");
+    }
+  }
+}
+// TMA tile load of a CTA pair: the bytes land in THIS CTA's shared memory, the transaction completes on the barrier at
+// `bar_cluster_addr` (the leader's full barrier, addressed through the cluster window).
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the MMAs issued so far have completed) on the barrier at the same shared-memory offset in both CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+kc_screen_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c_half,
+                     const float* __restrict__ xx, const float* __restrict__ cc, const float* __restrict__ min_dist, int64_t n,
+                     int d, int T, float alpha, int batch_min, TcPair* __restrict__ pairs, unsigned int* __restrict__ pair_count,
+                     unsigned int pair_capacity) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* hcc = reinterpret_cast<float*>(smem + kTc2Stages * kTc2StageBytes);  // |c_t|^2 / 2, +inf for t >= T
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTc2Stages * kTc2StageBytes + 1024);
+  uint64_t* full = bars;                        // [kTc2Stages]  used in the leader only: bytes of both CTAs
+  uint64_t* empty = bars + kTc2Stages;          // [kTc2Stages]  per CTA, arrived by the leader's multicast commit
+  uint64_t* tmem_full = bars + 2 * kTc2Stages;  // [2]           per CTA, arrived by the leader's multicast commit
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]           used in the leader only: 4 epilogue warps x 2 CTAs
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* cc_max_slot = reinterpret_cast<float*>(tmem_base_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t n_pairs = (n + 2 * kTcBlockM - 1) / (2 * kTcBlockM);
+  const int64_t first = blockIdx.x >> 1, step = gridDim.x >> 1;
+  const int nkb = (d + kTcBlockK - 1) / kTcBlockK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTc2Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int t = threadIdx.x; t < kTcBlockN; t += kTcThreads) hcc[t] = (t < T) ? 0.5f * __ldg(cc + t) : INFINITY;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp == 2) {
+    float m = 0.0f;
+    for (int t = lane; t < T; t += 32) m = fmaxf(m, __ldg(cc + t));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    if (lane == 0) *cc_max_slot = m;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  const float cc_max = *cc_max_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tp = first; tp < n_pairs; tp += step) {
+        const int row0 = (int)(tp * 2 * kTcBlockM + rank * kTcBlockM);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * kTc2StageBytes);
+          const uint32_t bar = mapa_rank(smem_u32(&full[stage]), 0u);
+          unsigned char* a_dst = smem + stage * kTc2StageBytes;
+          tma_load_2d_2sm(a_dst, &map_x, kb * kTcBlockK, row0, bar);
+          tma_load_2d_2sm(a_dst + kTcABytes, &map_c_half, kb * kTcBlockK, (int)(rank * kTc2HalfN), bar);
+          if (++stage == kTc2Stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (rank == 0 && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int64_t tp = first; tp < n_pairs; tp += step, ++it) {
+        const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+        mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kTcBlockN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_cluster(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kTc2StageBytes);
+          const uint32_t b_addr = a_addr + kTcABytes;
+#pragma unroll
+          for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k) {
+            umma_tf32_2sm(tmem_d, umma_smem_desc(a_addr + k * kTcUmmaK * 4), umma_smem_desc(b_addr + k * kTcUmmaK * 4), kTc2Idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty[stage]);
+          if (++stage == kTc2Stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===== epilogue (warps 2..5 of both CTAs): TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    const int n_chunks = (T + 31) / 32;
+    uint32_t it = 0;
+    for (int64_t tp = first; tp < n_pairs; tp += step, ++it) {
+      const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+      const int64_t row = tp * 2 * kTcBlockM + rank * kTcBlockM + quarter * 32 + lane;
+      const bool rok = row < n;
+      const float xr = rok ? __ldg(xx + row) : 0.0f;
+      const float mi = rok ? __ldg(min_dist + row) : 0.0f;
+      const float m2 = __fmul_ru(mi, mi);
+      const float s_i = alpha * (xr + cc_max);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * kTcBlockN + ((uint32_t)(quarter * 32) << 16);
+      float v[32];
+      float vmax = -INFINITY;
+      if (batch_min) {
+        for (int c = 0; c < n_chunks; ++c) {
+          tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, v[j] - hcc[c * 32 + j]);
+        }
+      }
+      const float thr = fmaxf(0.5f * ((xr - s_i) - m2), vmax - s_i);  // see kc_screen_tc_kernel
+      for (int c = 0; c < n_chunks; ++c) {
+        tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (rok && (v[j] - hcc[c * 32 + j]) >= thr) {
+            const unsigned int pos = atomicAdd(pair_count, 1u);
+            if (pos < pair_capacity) pairs[pos] = TcPair{(uint32_t)row, (uint32_t)(c * 32 + j)};
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[acc]), 0u));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the pair still works on either CTA's memory
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // Exact canonical distance of the surviving pairs; 32 pairs per warp, coalesced through a shared-memory transpose.
 //   kStore = false: min_dist[row] = min(min_dist[row], dist)
 //   kStore = true : out[(t0 + t) * ld_out + row] = dist        (candidate pairwise matrix of the replay)
@@ -386,13 +619,53 @@ static int tc_prepare(KcDeviceScratch** out, size_t want_pairs) {
   return MVAL_OK;
 }
 
+// MVAL_TC_2CTA=0 keeps the 1-CTA kernel (A/B measurements, and the tests compare the two); read on every call.
+static bool tc_use_pairs(int64_t n) {
+  const char* e = getenv("MVAL_TC_2CTA");
+  return !(e != nullptr && e[0] == '0') && n >= 4 * kTcBlockM;
+}
+
 static int tc_screen(KcDeviceScratch* s, const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T,
                      const float* min_dist, int batch_min, cudaStream_t stream) {
   CUtensorMap map_x, map_c;
   if (int rc = make_map(&map_x, X, n, d, kTcBlockM)) return rc;
-  if (int rc = make_map(&map_c, C, T, d, kTcBlockN)) return rc;
   kc_tc_reset_kernel<<<1, 1, 0, stream>>>(s->tc_count);
   MVAL_LAUNCH_CHECK("kc_tc_reset");
+  const float alpha2 = ldexpf(1.0f, -8) + (float)d * ldexpf(1.0f, -20);
+  if (tc_use_pairs(n)) {
+    if (int rc = make_map(&map_c, C, T, d, (int)kTc2HalfN)) return rc;
+    MVAL_CUDA(cudaFuncSetAttribute(kc_screen_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTc2SmemBytes));
+    const int64_t n_pairs = (n + 2 * kTcBlockM - 1) / (2 * kTcBlockM);
+    // co-resident CTA pairs (a pair needs both SMs of a TPC): asked of the driver once; every cluster walks its own tile
+    // pairs, so a smaller grid is merely slower, a larger one would leave a second wave of stragglers
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(2 * (num_sms() / 2)));
+      cfg.blockDim = dim3(kTcThreads);
+      cfg.dynamicSmemBytes = kTc2SmemBytes;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = 2;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      int q = 0;
+      if (cudaOccupancyMaxActiveClusters(&q, kc_screen_tc2_kernel, &cfg) != cudaSuccess || q <= 0) {
+        (void)cudaGetLastError();
+        q = num_sms() / 2;
+      }
+      max_clusters = q;
+    }
+    const int grid = 2 * (int)(n_pairs < max_clusters ? n_pairs : max_clusters);
+    kc_screen_tc2_kernel<<<grid, kTcThreads, kTc2SmemBytes, stream>>>(map_x, map_c, xx, cc, min_dist, n, d, T, alpha2, batch_min,
+                                                                     static_cast<TcPair*>(s->tc_pairs), s->tc_count,
+                                                                     (unsigned int)s->tc_pairs_capacity);
+    MVAL_LAUNCH_CHECK("kc_screen_tc2");
+    return MVAL_OK;
+  }
+  if (int rc = make_map(&map_c, C, T, d, kTcBlockN)) return rc;
   const int64_t n_tiles = (n + kTcBlockM - 1) / kTcBlockM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   const float alpha = ldexpf(1.0f, -8) + (float)d * ldexpf(1.0f, -20);

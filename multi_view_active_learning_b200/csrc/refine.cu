@@ -176,6 +176,7 @@ extern "C" int mval_refine_huber(const void* xy, int xy_is_float, const double* 
   using namespace mval;
   if (int rc = require_device()) return rc;
   MVAL_REQUIRE(n_frames >= 0 && J > 0, "mval_refine_huber: bad shape");
+  if (n_frames == 0) return MVAL_OK;
   MVAL_REQUIRE(V >= 2, "mval_refine_huber: need at least 2 views");
   if (V > MVAL_MAX_VIEWS) {
     set_error("mval_refine_huber: V=%d exceeds MVAL_MAX_VIEWS=%d", V, MVAL_MAX_VIEWS);

@@ -83,7 +83,8 @@ def kcenter_rounds(state, budget, group=None, k_slots=None, flags=0, stats=None)
     n_local = len(state)
     n_blocks = world * n_local
     if k_slots is None:
-        k_slots = max(4, min(256, (1024 // n_blocks) // 4 * 4))
+        # as many candidates per round as the replay CTA holds (1024 over all shards): fewer rounds, same picks
+        k_slots = max(4, (1024 // n_blocks) // 4 * 4)
     assert k_slots % 4 == 0 and n_blocks * k_slots <= 1024, "n_blocks * k_slots must be <= 1024 and k_slots % 4 == 0"
     rb = ops.kcenter_records_bytes(k_slots, d)
     local = torch.empty(n_local * rb, dtype=torch.uint8, device=dev)

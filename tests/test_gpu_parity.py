@@ -644,3 +644,38 @@ def test_huber_refinement_golden_and_oracle(ops, golden):
     e2 = O.triangulate_pool(None, pool["P"], 4, pool["valid"], keypoints_2d=kpf, direct_optimization=True)
     np.testing.assert_allclose(o2["keypoints_3d"], e2["keypoints_3d"], rtol=XYZ_RTOL, atol=XYZ_ATOL_MM)
     np.testing.assert_allclose(o2["metric"], e2["metric"], rtol=0, atol=REPROJ_ATOL_PX)
+
+
+def test_empty_inputs_and_nan_maps(ops):
+    """Zero-frame pools through every entry point (the data loader's last batch can be empty on some ranks) and the
+    NaN / infinity conventions of the per-map scores on the persistent kernels."""
+    z = torch.zeros(0, 4, 3, 64, 64).cuda()
+    P0 = torch.zeros(0, 4, 3, 4).double().cuda()
+    assert ops.decode_argmax(z, 4).shape == (0, 4, 3, 2) and ops.decode_softargmax(z, 4).shape == (0, 4, 3, 2)
+    assert ops.score_hp(z).numel() == 0 and ops.score_peaks(z, "MPE").numel() == 0 and ops.score_peaks(z, "BSB").numel() == 0
+    assert ops.score_xe(z, P0, torch.zeros(0, 3, 3).double().cuda(), 2.0).numel() == 0
+    out = ops.triangulate_ransac(torch.zeros(0, 4, 3, 2, dtype=torch.int32).cuda(), P0, direct_optimization=True)
+    assert out["keypoints_3d"].shape == (0, 3, 3) and out["metric"].numel() == 0
+    assert ops.sal_rank(torch.zeros(0).cuda(), torch.zeros(0).cuda(), None, 7.0, 5).numel() == 0
+    assert ops.mkpe(torch.zeros(0, 3, 3).cuda(), torch.zeros(0, 4, 3).cuda(), torch.zeros(0, 3).cuda()).numel() == 0
+    assert ops.pose_features(torch.zeros(0, 19, 3).double().cuda(), 2).shape == (0, 57)
+
+    rng = np.random.default_rng(2)
+    hm = rng.normal(size=(1, 1, 6, 64, 64)).astype(np.float32)
+    hm[0, 0, 1, 10, 10] = np.nan       # NaN poisons softmax-based scores of that map only
+    hm[0, 0, 2, 5, 5] = np.inf         # inf - inf = NaN inside the softmax
+    hm[0, 0, 3, 7, :] = -np.inf        # an all -inf row: NaN row sum
+    hm[0, 0, 4] = 3.0                  # constant map
+    hp = ops.score_hp(_cuda(hm)).cpu().numpy()[0, 0]
+    exp = SO.hp_scores(hm)[0, 0]
+    assert np.array_equal(np.isnan(hp), np.isnan(exp)) and np.isnan(hp[[1, 2, 3]]).all()
+    np.testing.assert_allclose(hp[[0, 4, 5]], exp[[0, 4, 5]], rtol=0, atol=2e-6)
+    assert abs(hp[4] - (1 - 1 / 64)) < 1e-6
+    soft = ops.decode_softargmax(_cuda(hm), 4).cpu().numpy()[0, 0]
+    assert np.isnan(soft[1]).all() and np.isnan(soft[2]).all() and np.isfinite(soft[[0, 3, 4, 5]]).all()
+    np.testing.assert_allclose(soft[4], [31.5 * 4, 31.5 * 4], atol=1e-3)  # uniform weights -> the grid centre
+    legacy = _legacy(lambda: ops.decode_softargmax(_cuda(hm), 4)).cpu().numpy()[0, 0]
+    assert np.array_equal(np.isnan(soft), np.isnan(legacy))
+    mpe = ops.score_peaks(_cuda(hm), "MPE").cpu().numpy()[0, 0]
+    assert mpe[4] == 0.0  # constant map: no peak (every pixel sits at the map minimum)
+    np.testing.assert_allclose(mpe[[0, 5]], SO.mpe_scores(hm[:, :, [0, 5]])[0, 0], rtol=0, atol=2e-5)
