@@ -653,6 +653,23 @@ def run_hybrid(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         times.append(float(t.item()))
     launches = (_lib.launch_count() - l0) // max(args.steps, 1)
+    verified = None
+    if args.verify:
+        # the sharded selection (one all_gather per round) against the single-device loop over the gathered features
+        feats = []
+        for off, m in chunks:
+            o = ops.score_pool(hm[:m], P_pool[off:off + m], STRIDE, None, pair_seed=0, frame_offset=shard_start + off,
+                               return_keypoints_2d=False)
+            feats.append(ops.pose_features(o["keypoints_3d"], root))
+        feat = torch.cat(feats)
+        if world > 1:
+            parts = [torch.empty_like(feat) for _ in range(world)]
+            dist.all_gather(parts, feat)
+            feat = torch.cat(parts)
+        if rank == 0:
+            ref_sel, _ = ops.kcenter_greedy(torch.cat([feat, labeled]), feat.shape[0], budget)
+            verified = bool(torch.equal(ref_sel.cpu(), sel.cpu()))
+        del feat
     score_ms, _ = _timed(lambda: [ops.score_pool(hm[:m], P_pool[o:o + m], STRIDE, None, frame_offset=shard_start + o,
                                                  return_keypoints_2d=False) for o, m in chunks])
     if rank == 0:
@@ -667,6 +684,7 @@ def run_hybrid(args):
                                    % (n, world, V, J, TOPK, 3 * J, L, budget), "resident_frames": R},
             "breakdown_ms": {"scoring_kernels": score_ms, "ranking_features_coreset": ms - score_ms},
             "coreset_rounds": {"count": len(stats), "picks_per_round_mean": float(np.mean(stats)) if stats else None},
+            "selection_matches_single_device": verified,
             "gpu_launches": int(launches), "selected_head": sel[:5].cpu().tolist(), "ranked_head": [int(i) for i in ranked[0][:5]]}))
     if world > 1:
         dist.barrier()
@@ -725,6 +743,60 @@ def run_scores(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# context only: the pose-estimator forward that produces the heat maps (stays in PyTorch / cuDNN, north star: "timed
+# separately").  Random-init PoseResNet-50 ("Simple Baselines": ResNet-50 trunk, three 256-channel stride-2 deconvolutions,
+# 1x1 head -> J x 64 x 64 for a 256 x 256 crop; the architecture pose_estimators/pose_resnet.py builds).
+# ----------------------------------------------------------------------------------------------------------------
+def run_backbone(args):
+    import torch
+    import torch.nn as nn
+
+    def bottleneck(cin, planes, stride):
+        class B(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.body = nn.Sequential(
+                    nn.Conv2d(cin, planes, 1, bias=False), nn.BatchNorm2d(planes), nn.ReLU(inplace=True),
+                    nn.Conv2d(planes, planes, 3, stride, 1, bias=False), nn.BatchNorm2d(planes), nn.ReLU(inplace=True),
+                    nn.Conv2d(planes, planes * 4, 1, bias=False), nn.BatchNorm2d(planes * 4))
+                self.down = None
+                if stride != 1 or cin != planes * 4:
+                    self.down = nn.Sequential(nn.Conv2d(cin, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
+
+            def forward(self, x):
+                return torch.relu(self.body(x) + (x if self.down is None else self.down(x)))
+        return B()
+
+    layers = [nn.Conv2d(3, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True), nn.MaxPool2d(3, 2, 1)]
+    cin = 64
+    for planes, blocks, stride in ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)):
+        for b in range(blocks):
+            layers.append(bottleneck(cin, planes, stride if b == 0 else 1))
+            cin = planes * 4
+    for _ in range(3):
+        layers += [nn.ConvTranspose2d(cin, 256, 4, 2, 1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True)]
+        cin = 256
+    layers.append(nn.Conv2d(256, J, 1))
+    torch.cuda.set_device(0)
+    model = nn.Sequential(*layers).cuda().eval().to(memory_format=torch.channels_last)
+    out = {}
+    frames = args.backbone_frames
+    for name, dtype in (("fp32 (TF32 convolutions off)", torch.float32), ("bf16 autocast", torch.bfloat16)):
+        torch.backends.cudnn.allow_tf32 = False
+        x = torch.randn((frames * V, 3, 256, 256), device="cuda").to(memory_format=torch.channels_last)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+            for _ in range(3):
+                y = model(x)
+            ms, y = _timed(lambda: model(x), 5)
+        assert tuple(y.shape) == (frames * V, J, H, W)
+        out[name] = {"ms_per_batch": ms, "frames_per_s": frames / (ms * 1e-3), "images_per_s": frames * V / (ms * 1e-3)}
+    print(json.dumps({"metric": "pose-estimator forward (context only, not part of the scoring metric)", "unit": "frames/s",
+                      "n_gpus": 1, "config": {"workload": "PoseResNet-50, random init, %d frames x %d views of 3 x 256 x 256 -> %d x "
+                                              "64 x 64 heat maps, torch/cuDNN, channels_last" % (frames, V, J)}, "results": out}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -737,7 +809,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=9)
     ap.add_argument("--cpu-frames", type=int, default=4096)
     ap.add_argument("--ref-frames-per-core", type=int, default=128)
-    ap.add_argument("--workload", default="scoring", choices=["scoring", "coreset", "scores", "hybrid"])
+    ap.add_argument("--workload", default="scoring", choices=["scoring", "coreset", "scores", "hybrid", "backbone"])
     ap.add_argument("--coreset-rows", type=int, default=1_000_000)
     ap.add_argument("--coreset-dim", type=int, default=2048)
     ap.add_argument("--coreset-labeled", type=int, default=64)
@@ -745,6 +817,9 @@ def main():
     ap.add_argument("--coreset-path", default="auto", choices=["auto", "ffma", "tc"])
     ap.add_argument("--coreset-data", default="gaussian", choices=["gaussian", "clustered"])
     ap.add_argument("--coreset-cpu-rows", type=int, default=50000)
+    ap.add_argument("--backbone-frames", type=int, default=16, help="backbone workload: frames (x views images) per batch")
+    ap.add_argument("--verify", action="store_true", help="hybrid: gather the pose features and check the sharded coreset "
+                    "selection against the single-device loop on rank 0")
     ap.add_argument("--coreset-kslots", type=int, default=0, help="candidate slots per shard and round (0 = pool.py default)")
     ap.add_argument("--coreset-pad", type=int, default=0, help="hybrid: zero-pad the pose features to a multiple of this")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks during the timed region")
@@ -765,6 +840,8 @@ def main():
         return run_scores(args)
     if args.workload == "hybrid":
         return run_hybrid(args)
+    if args.workload == "backbone":
+        return run_backbone(args)
     return run_ours(args)
 
 
