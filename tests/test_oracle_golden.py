@@ -166,3 +166,21 @@ def test_huber_refinement_matches_reference(golden):
     np.testing.assert_allclose(out["metric"], g["metric"], rtol=1e-9)
     assert np.array_equal(out["inlier_count"], g["inlier_count"])
     assert np.abs(g["keypoints_3d"] - g["keypoints_3d_dlt"]).max() > 1.0
+
+
+def test_zero_padding_leaves_the_canonical_coreset_arithmetic_unchanged():
+    """pool.pad_features: zero columns close the fma chain with fma(0, 0, acc) = acc, so the float32 selection and the
+    running minima of the C oracle are bit-identical with and without them (what makes 57 -> 64 padding legal)."""
+    import torch
+
+    from multi_view_active_learning_b200 import pool as P
+
+    rng = np.random.default_rng(4)
+    F = (rng.normal(size=(600, 57)) * 100).astype(np.float32)
+    Fp = P.pad_features(torch.from_numpy(F), 64).numpy()
+    assert Fp.shape == (600, 64) and np.array_equal(Fp[:, :57], F) and not Fp[:, 57:].any()
+    assert P.pad_features(torch.from_numpy(Fp), 32) is not None and P.pad_features(torch.from_numpy(Fp), 32).shape == (600, 64)
+    sel, mins = C.kcenter_greedy_f32(F, 560, 30)
+    sel_p, mins_p = C.kcenter_greedy_f32(Fp, 560, 30)
+    assert sel == sel_p and np.array_equal(mins, mins_p)
+    assert np.array_equal(C.canonical_dot_f32(F), C.canonical_dot_f32(Fp))
