@@ -206,3 +206,37 @@ def test_sal_rank_mkpe_and_pose_features_kernels():
     exp = CO.stacked_features(poses32, [], 2).astype(np.float32)
     assert feats.shape == (N, 3 * J) and np.array_equal(feats, exp)
     assert np.array_equal(ops.pose_features(torch.from_numpy(xyz.astype(np.float32)).cuda(), 2).cpu().numpy(), exp)
+
+
+def test_sal_cluster_balanced_pseudo_labels(tmp_path):
+    """SAL with SAL.CLUSTER_FILE_PATH (reference strategy.py:37-52, 976-992): k-means over the cluster file's
+    root-relative poses, then the ascending sal_metric order (device filter + sort) is walked and every cluster takes at
+    most pseudo_num_frames // NUM_CLUSTERS frames.  Checked against a literal walk over the oracle's sal_dict."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import json
+
+    rng = np.random.default_rng(11)
+    path = tmp_path / "clusters.json"
+    path.write_text(json.dumps({"g%d" % i: (rng.normal(size=(4, 19)) * 300).tolist() for i in range(60)}))
+    cfg = make_cfg("TRIANGULATION", expr="SAL")
+    cfg.SAL.CLUSTER_FILE_PATH, cfg.SAL.NUM_CLUSTERS = str(path), 3
+    st = make_strategy(cfg)
+    assert st.kmeans is not None and st.kmeans.cluster_centers_.shape == (3, 57)
+    ds = FakeDataset(36, seed=13)
+    ref = reference_emulation(ds, cfg)
+    _, al_guids, sal_guids, sal_dict = st._sal_pseudo_labeling(ds, 4, 9, torch.nn.Identity())
+    exp_al = SO.rank_nlargest(ref["al_metric"], 4)
+    assert al_guids == exp_al
+    cand = {g: m for g, m in sal_dict["sal_metric"].items()
+            if g not in exp_al and not math.isnan(m) and sal_dict["inlier_count"][g] > cfg.SAL.INLIER_THRESHOLD}
+    counter, exp = [0, 0, 0], []
+    for g in sorted(cand, key=cand.get):
+        kp = np.array(sal_dict["pred_3d_keypoints"][g]).T
+        kp = (kp[0:3, :] - kp[0:3, 2:3]).flatten()
+        c = st.kmeans.predict([kp])[0]
+        if counter[c] < 9 // 3:
+            counter[c] += 1
+            exp.append(g)
+    assert sal_guids == exp and 0 < len(exp) <= 9
+    assert ds.pseudo_label_guids == exp
