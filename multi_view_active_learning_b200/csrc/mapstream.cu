@@ -173,6 +173,8 @@ struct HpOp {
 //   BSB = |p0 - p1| of the two highest peaks.
 // Warp-wide minima / maxima / counts go through REDUX on monotone integer keys (one instruction instead of a five-step
 // shuffle butterfly); only the two float sums of MPE use a butterfly.
+// Equal neighbouring maxima (a plateau above the map minimum) all count as peaks; skimage's ensure_spacing would keep
+// a subset of them that depends on an unstable argsort -- see DESIGN.md section 2.
 // BSB works on the ROW-softmaxed map (F.softmax without dim on a 2-D tensor), so a first pass rewrites the stage in
 // place, p = exp(x - rowmax) / rowsum.  That pass runs with lane = row (rows l and l + 32): a lane holds its whole row in
 // 64 registers, so the row statistics need no shuffles at all; the float4 column blocks are visited in the rotated
