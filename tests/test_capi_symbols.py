@@ -56,3 +56,22 @@ def test_ransac_params_layout_matches_header():
     p = _lib.RansacParams()
     assert ctypes.sizeof(p) == 40
     assert _lib.RansacParams.epsilon.offset == 8 and _lib.RansacParams.pairs.offset == 32
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/mval_b200.h must be consumable from C (the boundary is a C ABI, not C++): compile a translation unit that
+    includes it and takes the address of every declared entry point with gcc -std=c99 -pedantic."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    names = declared_symbols()
+    src = tmp_path / "abi_check.c"
+    body = "\n".join("  p[%d] = (void (*)(void))%s;" % (i, n) for i, n in enumerate(names))
+    src.write_text('#include "mval_b200.h"\nvoid (*p[%d])(void);\nint main(void) {\n%s\n  return MVAL_ABI_VERSION == %d ? 0 : 1;\n}\n'
+                   % (len(names), body, _lib.ABI_VERSION))
+    r = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                        str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
