@@ -729,12 +729,20 @@ def run_scores(args):
         "map_stream_kernel<XeOp> + xe_frame_reduce (a9)": lambda: ops.score_xe(hm, P, xyz, 2.0),
         "score_pool_fused_kernel (a1+a4..a7)": lambda: ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False),
     }
+    # the fused pass with the AL score of the same maps evaluated by its decode warps (one read of the pool instead of
+    # two: compare with the sum of the fused line and the map_stream line of that score); alt = the 10 + 5 warp budget
+    for kind in ("HP", "MPE", "BSB"):
+        for alt in ("0", "1"):
+            kernels["score_pool_fused_kernel<%s>%s (a1+a4..a8)" % (kind, " alt" if alt == "1" else "")] = (
+                lambda kind=kind, alt=alt: (os.environ.__setitem__("MVAL_FUSED_ALT", alt),
+                                            ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False, map_score=kind)))
     out = {}
     for name, fn in kernels.items():
         for _ in range(3):
             fn()
         ms, _ = _timed(fn, 5)
         out[name] = {"avg_launch_ms": ms, "achieved": algo / (ms * 1e-3) / 1e9, "frac": algo / (ms * 1e-3) / 1e9 / hbm_peak}
+    os.environ["MVAL_FUSED_ALT"] = "0"
     print(json.dumps({"metric": "per-map heat-map kernels: algorithmic GB/s", "unit": "GB/s", "n_gpus": 1,
                       "config": {"workload": "%d frames x %d views x %d joints x %dx%d float32 heat maps resident (%.1f GB), "
                                  "one launch each" % (n, V, J, H, W, algo / 1e9)},

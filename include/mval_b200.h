@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MVAL_ABI_VERSION 3
+#define MVAL_ABI_VERSION 4
 #define MVAL_MAX_VIEWS 32
 
 enum mval_status {
@@ -145,6 +145,24 @@ int mval_score_pool(const float* heatmaps, const double* proj, const uint8_t* va
                     double* out_xyz, double* out_reproj, int32_t* out_inliers, double* out_metric,
                     int32_t* out_inlier_count, void* stream);
 
+/* Per-map heat-map score evaluated inside the fused pool pass (mval_score_pool_scored). */
+#define MVAL_MAP_SCORE_NONE 0
+#define MVAL_MAP_SCORE_HP 1  /* mval_score_hp                 (strategy.py:1178-1193) */
+#define MVAL_MAP_SCORE_MPE 2 /* mval_score_peaks, mode 0      (strategy.py:1149-1176) */
+#define MVAL_MAP_SCORE_BSB 3 /* mval_score_peaks, mode 1      (strategy.py:1195-1215) */
+
+/* mval_score_pool + one of mval_score_hp / mval_score_peaks over the SAME heat maps in a single pass: what
+ * strategy.py:1036-1045 (triangulation of every frame) and :1072-1094 (the HP / MPE / BSB metric of the same frame) do
+ * together inside _compute_sal_dict.  On 64 x 64 maps the decode warps of the fused kernel evaluate the score on the
+ * staged map right after its arg-max, so every heat-map byte is read once instead of twice; other shapes run the two
+ * calls back to back.  Results are bit-identical to the separate calls.
+ * map_score      one of MVAL_MAP_SCORE_* (NONE: out_map_score is ignored, same as mval_score_pool)
+ * out_map_score  float32 device [n_frames][V][J], NaN for invalid joints. */
+int mval_score_pool_scored(const float* heatmaps, const double* proj, const uint8_t* valid, int64_t n_frames, int V,
+                           int J, int H, int W, int stride, const mval_ransac_params* params, int map_score,
+                           int32_t* out_xy, double* out_xyz, double* out_reproj, int32_t* out_inliers,
+                           double* out_metric, int32_t* out_inlier_count, float* out_map_score, void* stream);
+
 /* Same as mval_score_pool but every pointer is HOST memory (pinned recommended): the library streams the
  * pool through the device in chunks of `chunk_frames` frames (0 = choose), double-buffered on two internal
  * streams so that host->device copies overlap the kernels, and returns after the last result has landed in
@@ -183,6 +201,16 @@ int mval_topk_desc(const double* scores, int64_t n, int64_t index_offset, int32_
  * *out_count (device int32). */
 int mval_sal_rank(const float* sal_metric, const float* inlier_count, const uint8_t* excluded, int64_t n,
                   float inlier_threshold, int32_t k, int64_t* out_idx, int32_t* out_count, void* stream);
+
+/* Replaces the per-candidate self.kmeans.predict([kp])[0] of the cluster-balanced pseudo-label walk (strategy.py:981-985)
+ * for a whole pool: kp = root-relative pose (pose^T[0:3, :] - pose^T[0:3, root]).flatten() in float64 from the float32
+ * predictions of sal_dict["pred_3d_keypoints"], label = argmin_c (|c|^2 - 2 kp.c), first centre on ties -- sklearn
+ * KMeans.predict.  pred float32 device [n_frames][J][3]; centres float64 device [k][3 J] (kmeans.cluster_centers_).
+ * out_label  int32   device [n_frames]
+ * out_margin float64 device [n_frames] runner-up score minus best score (may be NULL): the caller re-checks frames whose
+ *            margin is within rounding distance of 0 with sklearn itself, so the labels are exactly the reference's. */
+int mval_kmeans_assign(const float* pred, int64_t n_frames, int J, int root, const double* centres, int k,
+                       int32_t* out_label, double* out_margin, void* stream);
 
 /* Replaces utils/evaluation.py:198-208 compute_mkpe([pred], [gt], [valid]) per frame (strategy.py:1134-1145), float32:
  * mean over joints of sqrt(sum_c where(valid, (pred - gt)^2, 0)) / valid  (NaN as soon as one joint is invalid, like the

@@ -12,7 +12,8 @@ MVAL_ERR_CUDA = -3
 MVAL_ERR_NO_DEVICE = -4
 MVAL_ERR_OUT_OF_MEMORY = -5
 MAX_VIEWS = 32
-ABI_VERSION = 3
+ABI_VERSION = 4
+MAP_SCORE = {None: 0, "HP": 1, "MPE": 2, "BSB": 3}  # MVAL_MAP_SCORE_*
 
 
 class MvalError(RuntimeError):
@@ -39,11 +40,13 @@ PROTOTYPES = {
     "mval_triangulate_ransac": (C.c_int, [_p, _i, _p, _p, _i64, _i, _i, C.POINTER(RansacParams), _p, _p, _p, _p, _p, _p, _p]),
     "mval_refine_huber": (C.c_int, [_p, _i, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p]),
     "mval_score_pool": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _p, _p, _p, _p, _p, _p, _p]),
+    "mval_score_pool_scored": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "mval_score_pool_host": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _i64, _p, _p, _p, _p, _p, _p]),
     "mval_score_xe": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _d, _p, _p, _p]),
     "mval_topk_desc": (C.c_int, [_p, _i64, _i64, C.c_int32, _p, _p, _p, _p]),
     "mval_sal_rank": (C.c_int, [_p, _p, _p, _i64, _f, C.c_int32, _p, _p, _p]),
     "mval_mkpe": (C.c_int, [_p, _p, _p, _i64, _i, _i, _p, _p]),
+    "mval_kmeans_assign": (C.c_int, [_p, _i64, _i, _i, _p, _i, _p, _p, _p]),
     "mval_pose_features": (C.c_int, [_p, _i, _i64, _i, _i, _p, _p]),
     "mval_kcenter_norms": (C.c_int, [_p, _i64, _i, _p, _p]),
     "mval_kcenter_update": (C.c_int, [_p, _p, _i64, _i, _p, _p, _i64, _p, _p, _p]),

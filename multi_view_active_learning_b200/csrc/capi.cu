@@ -68,9 +68,9 @@ int triangulate_ransac(const void* xy, int xy_is_float, const double* proj, cons
                        cudaStream_t stream);
 
 int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
-                            int H, int W, int stride, const mval_ransac_params& prm, int32_t* out_xy, double* out_xyz,
-                            double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
-                            cudaStream_t stream);
+                            int H, int W, int stride, const mval_ransac_params& prm, int map_score, int32_t* out_xy,
+                            double* out_xyz, double* out_reproj, int32_t* out_inliers, double* out_metric,
+                            int32_t* out_inlier_count, float* out_map_score, cudaStream_t stream);
 
 // MVAL_FUSED=0 in the environment forces the three-launch path (A/B measurements only).
 static bool fused_enabled() {
@@ -96,14 +96,21 @@ static int check_pool_args(const char* who, const void* heatmaps, const void* pr
 }
 
 int score_pool(const float* heatmaps, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J, int H,
-               int W, int stride, const mval_ransac_params* params, int32_t* out_xy, double* out_xyz,
+               int W, int stride, const mval_ransac_params* params, int map_score, int32_t* out_xy, double* out_xyz,
                double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
-               cudaStream_t stream) {
+               float* out_map_score, cudaStream_t stream) {
   if (n_frames == 0) return MVAL_OK;
   if (fused_enabled()) {
-    const int rc = launch_score_pool_fused(heatmaps, proj, valid, n_frames, V, J, H, W, stride, *params, out_xy, out_xyz,
-                                           out_reproj, out_inliers, out_metric, out_inlier_count, stream);
-    if (rc != MVAL_ERR_UNSUPPORTED) return rc;  // unsupported shape: fall through to decode + triangulate launches
+    const int rc = launch_score_pool_fused(heatmaps, proj, valid, n_frames, V, J, H, W, stride, *params, map_score, out_xy,
+                                           out_xyz, out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score, stream);
+    if (rc != MVAL_ERR_UNSUPPORTED) return rc;  // unsupported shape: fall through to the separate launches
+  }
+  if (map_score != MVAL_MAP_SCORE_NONE) {  // second pass over the heat maps: the stand-alone score kernel
+    const int rc = map_score == MVAL_MAP_SCORE_HP
+                       ? mval_score_hp(heatmaps, n_frames, V, J, H, W, valid, out_map_score, stream)
+                       : mval_score_peaks(heatmaps, n_frames, V, J, H, W, map_score == MVAL_MAP_SCORE_MPE ? 0 : 1, valid,
+                                          out_map_score, stream);
+    if (rc != MVAL_OK) return rc;
   }
   int32_t* xy = out_xy;
   void* scratch = nullptr;
@@ -196,8 +203,8 @@ int score_pool_host(const float* heatmaps, const double* proj, const uint8_t* va
     mval_ransac_params p = *params;
     p.frame_offset = params->frame_offset + f0;
     if (p.pairs) p.pairs = nullptr;  // explicit pair tables are a device-pointer feature; validated by the caller below
-    rc = score_pool(s.hm, s.proj, valid ? s.valid : nullptr, n, V, J, H, W, stride, &p, s.xy, s.xyz, s.reproj, s.inliers,
-                    s.metric, s.inlier_count, s.stream);
+    rc = score_pool(s.hm, s.proj, valid ? s.valid : nullptr, n, V, J, H, W, stride, &p, MVAL_MAP_SCORE_NONE, s.xy, s.xyz,
+                    s.reproj, s.inliers, s.metric, s.inlier_count, nullptr, s.stream);
     if (rc != MVAL_OK) return fail(rc);
     if (out_xy) SLOT_CUDA(cudaMemcpyAsync(out_xy + (size_t)2 * V * J * f0, s.xy, sizeof(int32_t) * 2 * V * J * n, cudaMemcpyDeviceToHost, s.stream));
     SLOT_CUDA(cudaMemcpyAsync(out_xyz + (size_t)3 * J * f0, s.xyz, sizeof(double) * 3 * J * n, cudaMemcpyDeviceToHost, s.stream));
@@ -228,8 +235,25 @@ int mval_score_pool(const float* heatmaps, const double* proj, const uint8_t* va
   if (int rc = mval::check_pool_args("mval_score_pool", heatmaps, proj, n_frames, V, J, H, W, params, out_xyz,
                                      out_metric, out_inlier_count))
     return rc;
-  return mval::score_pool(heatmaps, proj, valid, n_frames, V, J, H, W, stride, params, out_xy, out_xyz, out_reproj,
-                          out_inliers, out_metric, out_inlier_count, static_cast<cudaStream_t>(stream));
+  return mval::score_pool(heatmaps, proj, valid, n_frames, V, J, H, W, stride, params, MVAL_MAP_SCORE_NONE, out_xy, out_xyz,
+                          out_reproj, out_inliers, out_metric, out_inlier_count, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int mval_score_pool_scored(const float* heatmaps, const double* proj, const uint8_t* valid, int64_t n_frames, int V,
+                           int J, int H, int W, int stride, const mval_ransac_params* params, int map_score,
+                           int32_t* out_xy, double* out_xyz, double* out_reproj, int32_t* out_inliers,
+                           double* out_metric, int32_t* out_inlier_count, float* out_map_score, void* stream) {
+  if (int rc = mval::require_device()) return rc;
+  if (int rc = mval::check_pool_args("mval_score_pool_scored", heatmaps, proj, n_frames, V, J, H, W, params, out_xyz,
+                                     out_metric, out_inlier_count))
+    return rc;
+  MVAL_REQUIRE(map_score >= MVAL_MAP_SCORE_NONE && map_score <= MVAL_MAP_SCORE_BSB,
+               "mval_score_pool_scored: map_score must be one of MVAL_MAP_SCORE_*");
+  MVAL_REQUIRE(map_score == MVAL_MAP_SCORE_NONE || n_frames == 0 || out_map_score != nullptr,
+               "mval_score_pool_scored: out_map_score is null");
+  return mval::score_pool(heatmaps, proj, valid, n_frames, V, J, H, W, stride, params, map_score, out_xy, out_xyz,
+                          out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score,
+                          static_cast<cudaStream_t>(stream));
 }
 
 int mval_score_pool_host(const float* heatmaps, const double* proj, const uint8_t* valid, int64_t n_frames, int V,

@@ -22,16 +22,37 @@
 //
 // Arithmetic is shared with the stand-alone kernels (ransac.cuh), so the results are bit-identical to
 // mval_decode_argmax + mval_triangulate_ransac (tests/test_gpu_parity.py::test_fused_equals_unfused).
+//
+// Scored variants (kScore = 1 HP, 2 MPE, 3 BSB; strategy.py:1149-1215): _compute_sal_dict needs BOTH the triangulation
+// of every frame (sal_metric, pred_3d_keypoints; strategy.py:1037-1063) and, for those strategies, a per-map score of
+// the same heat maps (strategy.py:1072-1094).  As two launches every heat-map byte crosses HBM twice.  Here the decode
+// warps evaluate the map_stream Op (mapops.cuh, the very same device code, hence bit-identical scores) on the staged
+// map right after its arg-max and only then hand the stage back, so the pool is read once.  The per-map work grows
+// from ~400 to 1 800-2 500 warp instructions, so these variants run 12 decode warps (one per ring stage, as
+// map_stream_kernel does) over 6 RANSAC warps.
 #include <stdlib.h>
 
+#include "mapops.cuh"
 #include "ransac.cuh"
-#include "tma.cuh"
 
 namespace mval {
 
-constexpr int kFusedDecodeWarps = 6;
-constexpr int kFusedRansacWarps = 8;
-constexpr int kFusedThreads = kWarp * (1 + kFusedDecodeWarps + kFusedRansacWarps);  // 480
+// Warp budget and per-map evaluator of each variant.  The register file is split per scheduler (16 384 registers
+// each), so 17-20 warps per CTA cap a thread at 96 registers and 13-16 warps at 128.  kAlt picks between the two
+// budgets for the scored variants: 0 = 12 decode + 6 RANSAC warps at 96 registers (one decode warp per ring stage, as
+// in map_stream_kernel; ptxas spills a few loop-invariant addresses, none of the float64 Jacobi state), 1 = 10 + 5
+// warps at 128 registers (MVAL_FUSED_ALT=1, A/B measurements).
+template <int kScore> struct FusedOp;
+template <> struct FusedOp<MVAL_MAP_SCORE_NONE> { using Op = void; };
+template <> struct FusedOp<MVAL_MAP_SCORE_HP> { using Op = HpOp; };
+template <> struct FusedOp<MVAL_MAP_SCORE_MPE> { using Op = PeaksOp<0>; };
+template <> struct FusedOp<MVAL_MAP_SCORE_BSB> { using Op = PeaksOp<1>; };
+template <int kScore, int kAlt> struct FusedCfg : FusedOp<kScore> {
+  static constexpr int kD = kAlt ? 10 : 12, kR = kAlt ? 5 : 6;  // 512 / 608 threads
+};
+template <int kAlt> struct FusedCfg<MVAL_MAP_SCORE_NONE, kAlt> : FusedOp<MVAL_MAP_SCORE_NONE> {
+  static constexpr int kD = 6, kR = 8;  // 480 threads
+};
 constexpr int kMaxFrameSlots = 4;  // frame slots per CTA: 4 when they are small, fewer when V * J is large (see launcher)
 constexpr int kMaxStages = 64;
 
@@ -46,7 +67,7 @@ struct FusedSmem {  // byte offsets into dynamic shared memory
 
 __host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline FusedSmem fused_layout(int V, int J, int HW, int stages, int slots) {
+__host__ __device__ inline FusedSmem fused_layout(int V, int J, int HW, int stages, int slots, int ransac_warps) {
   FusedSmem L;
   const int n_all = V * (V - 1) / 2;
   L.stage_bytes = (uint32_t)HW * 4u;
@@ -57,24 +78,27 @@ __host__ __device__ inline FusedSmem fused_layout(int V, int J, int HW, int stag
   L.proj = o;        o = align_up(o + (uint32_t)slots * V * 96u, 16);
   L.kp = o;          o = align_up(o + (uint32_t)slots * V * J * 8u, 16);
   L.mask = o;        o = align_up(o + (uint32_t)slots * J * 4u, 16);
-  L.red_reproj = o;  o = align_up(o + kFusedRansacWarps * J * 8u, 16);
-  L.red_inl = o;     o = align_up(o + kFusedRansacWarps * J * 4u, 16);
+  L.red_reproj = o;  o = align_up(o + (uint32_t)ransac_warps * J * 8u, 16);
+  L.red_inl = o;     o = align_up(o + (uint32_t)ransac_warps * J * 4u, 16);
   L.pair = o;        o = align_up(o + 2u * n_all, 16);
-  L.perm = o;        o = align_up(o + kFusedRansacWarps * n_all * 2u, 16);
-  L.pxy = o;         o = align_up(o + kFusedRansacWarps * 2u * V * 8u, 16);
+  L.perm = o;        o = align_up(o + (uint32_t)ransac_warps * n_all * 2u, 16);
+  L.pxy = o;         o = align_up(o + (uint32_t)ransac_warps * 2u * V * 8u, 16);
   L.bars = o;        o = o + (2u * stages + 3u * (uint32_t)slots) * 8u;
   L.total = o;
   return L;
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 1)
+template <int kScore, int kAlt>
+__global__ void __launch_bounds__(kWarp * (1 + FusedCfg<kScore, kAlt>::kD + FusedCfg<kScore, kAlt>::kR), 1)
 score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__ proj, const uint8_t* __restrict__ valid,
                         int64_t n_frames, int V, int J, int H, int HW, int stride, int stages, int slots, int n_iters, double eps,
                         uint64_t seed, int64_t frame_offset, int32_t* __restrict__ out_xy, double* __restrict__ out_xyz,
                         double* __restrict__ out_reproj, int32_t* __restrict__ out_inliers, double* __restrict__ out_metric,
-                        int32_t* __restrict__ out_inlier_count) {
+                        int32_t* __restrict__ out_inlier_count, float* __restrict__ out_map_score) {
+  constexpr int kFusedDecodeWarps = FusedCfg<kScore, kAlt>::kD;
+  constexpr int kFusedRansacWarps = FusedCfg<kScore, kAlt>::kR;
   extern __shared__ __align__(128) unsigned char smem[];
-  const FusedSmem L = fused_layout(V, J, HW, stages, slots);
+  const FusedSmem L = fused_layout(V, J, HW, stages, slots, kFusedRansacWarps);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty = full + stages;
   uint64_t* kp_ready = empty + stages;
@@ -143,16 +167,26 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
         const int st = (int)(c % stages);
         const uint32_t kf = (uint32_t)(c / stages);
         if (!mbar_wait(&full[st], kf & 1u, g_fused_abort, 4, i, st)) return;
-        const float4* __restrict__ p = reinterpret_cast<const float4*>(smem + L.ring + (uint32_t)st * L.stage_bytes);
+        float* stage = reinterpret_cast<float*>(smem + L.ring + (uint32_t)st * L.stage_bytes);
+        const float4* p = reinterpret_cast<const float4*>(stage);
         const uint32_t idx = warp_argmax_map<8, true>([&](int q) { return p[q]; }, hw4, lane, nullptr);
+        const bool ok = valid == nullptr || valid[frame * J + m % J] != 0;
         if (lane == 0) {
-          mbar_arrive(&empty[st]);  // every lane's loads were consumed by the reductions above
-          const int j = m % J;
+          // every lane's loads were consumed by the reductions above
+          if (kScore == MVAL_MAP_SCORE_NONE) mbar_arrive(&empty[st]);
           int2 xy = make_int2((int)(idx % (uint32_t)H) * stride, (int)(idx / (uint32_t)H) * stride);
-          if (valid != nullptr && valid[frame * J + j] == 0) xy = make_int2(0, 0);  // evaluation.py:21-23
+          if (!ok) xy = make_int2(0, 0);  // evaluation.py:21-23
           kp_all[sl * VJ + m] = xy;
           if (out_xy) reinterpret_cast<int2*>(out_xy)[frame * VJ + m] = xy;
-          mbar_arrive(&kp_ready[sl]);
+          mbar_arrive(&kp_ready[sl]);  // the RANSAC warps may start on this key-point while the score is evaluated
+        }
+        if constexpr (kScore != MVAL_MAP_SCORE_NONE) {
+          using Op = typename FusedCfg<kScore, kAlt>::Op;
+          __syncwarp();
+          Op::run(stage, frame * VJ + m, ok, lane, typename Op::Args{out_map_score}, nullptr, typename Op::Pre{});
+          if (Op::kWritesSmem) fence_proxy_async_smem();  // BSB rewrote the stage; order that before the TMA refill
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[st]);
         }
       }
     }
@@ -262,15 +296,18 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
 }
 
 // Returns MVAL_ERR_UNSUPPORTED (without setting an error) when the shape does not fit the fused kernel; the caller
-// then takes the three-launch path.
-int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
-                            int H, int W, int stride, const mval_ransac_params& prm, int32_t* out_xy, double* out_xyz,
-                            double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
-                            cudaStream_t stream) {
+// then takes the multi-launch path.
+template <int kScore, int kAlt>
+static int launch_fused_variant(const float* hm, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
+                                int H, int W, int stride, const mval_ransac_params& prm, int32_t* out_xy, double* out_xyz,
+                                double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
+                                float* out_map_score, cudaStream_t stream) {
+  constexpr int kD = FusedCfg<kScore, kAlt>::kD, kR = FusedCfg<kScore, kAlt>::kR;
   const int HW = H * W;
   if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(hm) & 15) != 0 || (reinterpret_cast<uintptr_t>(proj) & 15) != 0 ||
       prm.pairs != nullptr)
     return MVAL_ERR_UNSUPPORTED;
+  if (kScore != MVAL_MAP_SCORE_NONE && (H != kMapDim || W != kMapDim)) return MVAL_ERR_UNSUPPORTED;  // Ops are 64 x 64 only
   int dev = 0, max_smem = 0;
   MVAL_CUDA(cudaGetDevice(&dev));
   MVAL_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -281,19 +318,18 @@ int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* 
   // joints, 2 slots / 12 stages at 20 x 42 (4 slots would leave 6 stages and the stream latency-bound).
   int stages = 0, slots = 0;
   for (int sl = kMaxFrameSlots; sl >= 2; --sl) {
-    int st = kMaxStages / kFusedDecodeWarps * kFusedDecodeWarps;
-    while (st >= kFusedDecodeWarps && fused_layout(V, J, HW, st, sl).total > (uint32_t)max_smem) st -= kFusedDecodeWarps;
+    int st = kMaxStages / kD * kD;
+    while (st >= kD && fused_layout(V, J, HW, st, sl, kR).total > (uint32_t)max_smem) st -= kD;
     if (st > stages) { stages = st; slots = sl; }
   }
-  if (stages < kFusedDecodeWarps) return MVAL_ERR_UNSUPPORTED;
-  const FusedSmem L = fused_layout(V, J, HW, stages, slots);
-  MVAL_CUDA(cudaFuncSetAttribute(score_pool_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  if (stages < kD) return MVAL_ERR_UNSUPPORTED;
+  const FusedSmem L = fused_layout(V, J, HW, stages, slots, kR);
+  MVAL_CUDA(cudaFuncSetAttribute(score_pool_fused_kernel<kScore, kAlt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   const int64_t sms = num_sms();
   const int grid = (int)(n_frames < sms ? n_frames : sms);
-  score_pool_fused_kernel<<<grid, kFusedThreads, L.total, stream>>>(hm, proj, valid, n_frames, V, J, H, HW, stride, stages, slots,
-                                                                  prm.n_iters, prm.epsilon, prm.pair_seed, prm.frame_offset,
-                                                                  out_xy, out_xyz, out_reproj, out_inliers, out_metric,
-                                                                  out_inlier_count);
+  score_pool_fused_kernel<kScore, kAlt><<<grid, kWarp * (1 + kD + kR), L.total, stream>>>(
+      hm, proj, valid, n_frames, V, J, H, HW, stride, stages, slots, prm.n_iters, prm.epsilon, prm.pair_seed, prm.frame_offset,
+      out_xy, out_xyz, out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score);
   MVAL_LAUNCH_CHECK("score_pool_fused");
   static const bool debug_sync = getenv("MVAL_DEBUG_SYNC") != nullptr;
   if (debug_sync) {
@@ -309,6 +345,31 @@ int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* 
     }
   }
   return MVAL_OK;
+}
+
+int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
+                            int H, int W, int stride, const mval_ransac_params& prm, int map_score, int32_t* out_xy,
+                            double* out_xyz, double* out_reproj, int32_t* out_inliers, double* out_metric,
+                            int32_t* out_inlier_count, float* out_map_score, cudaStream_t stream) {
+  const char* alt_env = getenv("MVAL_FUSED_ALT");  // A/B measurements and tests only; read on every call
+  const bool alt = alt_env != nullptr && alt_env[0] == '1';
+#define MVAL_FUSED_CASE(K)                                                                                               \
+  case K:                                                                                                                \
+    return alt ? launch_fused_variant<K, 1>(hm, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz,         \
+                                            out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score, stream) \
+               : launch_fused_variant<K, 0>(hm, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz,         \
+                                            out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score, stream)
+  switch (map_score) {
+    case MVAL_MAP_SCORE_NONE:
+      return launch_fused_variant<MVAL_MAP_SCORE_NONE, 0>(hm, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz,
+                                                          out_reproj, out_inliers, out_metric, out_inlier_count, nullptr, stream);
+    MVAL_FUSED_CASE(MVAL_MAP_SCORE_HP);
+    MVAL_FUSED_CASE(MVAL_MAP_SCORE_MPE);
+    MVAL_FUSED_CASE(MVAL_MAP_SCORE_BSB);
+    default:
+      return MVAL_ERR_UNSUPPORTED;
+  }
+#undef MVAL_FUSED_CASE
 }
 
 }  // namespace mval

@@ -1,0 +1,435 @@
+// Per-map heat-map score evaluators ("Ops") shared by the persistent kernels: map_stream_kernel (mapstream.cu) runs
+// one Op per map on its own; score_pool_fused_kernel (fused.cu) runs HP / MPE / BSB in its decode warps right after the
+// arg-max, so that a strategy that needs both the triangulation and a per-map score reads every heat map ONCE.
+//
+// An Op evaluates one 64 x 64 float32 map that already sits in shared memory, with one warp:
+//   Op::run(map, m, ok, lane, args, scratch, pre)   m = global map index of the output, ok = joint is valid
+//   Op::kWritesSmem                                 the Op rewrites the stage (the caller must fence before the refill)
+//   Op::prefetch(m, args)                           per-map inputs fetched one map ahead (XE only)
+#pragma once
+#include "tma.cuh"
+
+namespace mval {
+
+constexpr int kMapDim = 64;
+constexpr int kMapFloats = kMapDim * kMapDim;
+constexpr uint32_t kMapBytes = kMapFloats * 4u;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {  // one FMNMX3 (sm_100+)
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float y;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// soft-arg-max: softmax over the whole map, expectation of the pixel grid, times stride (kornia
+// spatial_soft_argmax2d(normalized_coordinates=False)).  Two passes over shared memory: the map maximum, then
+// w = 2^(x log2e - M log2e) (one FFMA + one MUFU per pixel; the rounding of M log2e scales every weight alike and
+// cancels in the ratio).  With W = 64 a lane's float4 column is fixed (4 * (lane % 16)) and its row is 2u + lane / 16,
+// so per vector only sum(w), sum(k w_k) and row * sum(w) are accumulated -- in float32 over 8 vectors, in float64
+// across them and across lanes.
+// ---------------------------------------------------------------------------------------------------------------
+struct NoPrefetch {};
+
+struct SoftArgmaxOp {
+  struct Args {
+    float stride;
+    float* out_xy;
+  };
+  using Pre = NoPrefetch;
+  static constexpr bool kWritesSmem = false;
+  __device__ static __forceinline__ Pre prefetch(int64_t, const Args&) { return {}; }
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*, const Pre&) {
+    (void)ok;
+    const float4* __restrict__ p = reinterpret_cast<const float4*>(map) + lane;
+    float mx = -INFINITY;
+#pragma unroll 8
+    for (int u = 0; u < 32; ++u) {
+      const float4 t = p[u * 32];
+      mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float nml = -mx * kLog2e;
+    const float half = (float)(lane >> 4);
+    double S = 0.0, X = 0.0, Y = 0.0;
+#pragma unroll 1
+    for (int blk = 0; blk < 4; ++blk) {
+      float s32 = 0.f, x32 = 0.f, y32 = 0.f;
+#pragma unroll
+      for (int uu = 0; uu < 8; ++uu) {
+        const int u = blk * 8 + uu;
+        const float4 t = p[u * 32];
+        const float w0 = ex2_approx(fmaf(t.x, kLog2e, nml)), w1 = ex2_approx(fmaf(t.y, kLog2e, nml));
+        const float w2 = ex2_approx(fmaf(t.z, kLog2e, nml)), w3 = ex2_approx(fmaf(t.w, kLog2e, nml));
+        const float ws = (w0 + w1) + (w2 + w3);
+        s32 += ws;
+        x32 += fmaf(3.0f, w3, fmaf(2.0f, w2, w1));
+        y32 = fmaf((float)(2 * u) + half, ws, y32);
+      }
+      S += (double)s32;
+      X += (double)x32;
+      Y += (double)y32;
+    }
+    X = fma((double)((lane & 15) * 4), S, X);
+    S = warp_sum(S);
+    X = warp_sum(X);
+    Y = warp_sum(Y);
+    if (lane == 0)  // the reference multiplies the float32 expectation by stride in float32 (:193-197)
+      reinterpret_cast<float2*>(a.out_xy)[m] = make_float2((float)(X / S) * a.stride, (float)(Y / S) * a.stride);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// HP (strategy.py:1185-1186): 1 - max over the map of softmax(row); the row maximum of softmax(row) is 1 / S_r with
+// S_r = sum_c exp(x_rc - max_r), so the score is 1 - 1 / min_r S_r.  One LDS.128 covers two rows (16 lanes each); row
+// max / row sum are 16-lane butterflies; exp = ex2.approx of the exactly formed difference times log2e (the maximum
+// itself contributes exactly 1).  A NaN row (a NaN, an infinity or an all -inf row) poisons the map like torch's softmax.
+// ---------------------------------------------------------------------------------------------------------------
+struct HpOp {
+  struct Args {
+    float* out;
+  };
+  using Pre = NoPrefetch;
+  static constexpr bool kWritesSmem = false;
+  __device__ static __forceinline__ Pre prefetch(int64_t, const Args&) { return {}; }
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*, const Pre&) {
+    if (!ok) {
+      if (lane == 0) a.out[m] = __int_as_float(0x7fc00000);
+      return;
+    }
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float4* __restrict__ p = reinterpret_cast<const float4*>(map) + lane;
+    float min_s = INFINITY;
+    bool bad = false;
+#pragma unroll 8
+    for (int t = 0; t < 32; ++t) {
+      const float4 x = p[t * 32];
+      float rm = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(kFull, rm, o));
+      float rs = (ex2_approx((x.x - rm) * kLog2e) + ex2_approx((x.y - rm) * kLog2e)) +
+                 (ex2_approx((x.z - rm) * kLog2e) + ex2_approx((x.w - rm) * kLog2e));
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(kFull, rs, o);
+      bad |= (rs != rs);
+      min_s = fminf(min_s, rs);
+    }
+    min_s = fminf(min_s, __shfl_xor_sync(kFull, min_s, 16));
+    bad = __any_sync(kFull, bad);
+    if (lane == 0) a.out[m] = bad ? __int_as_float(0x7fc00000) : 1.0f - 1.0f / min_s;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// MPE (kMode 0) / BSB (kMode 1): local peaks as skimage.feature.peak_local_max(map, min_distance=2) defines them
+// (equal to the maximum of their 5 x 5 window, strictly above the map minimum, 2 pixels off the border).
+//
+// Scan layout: lane = (half, l16): float4 column block 4 * l16 .. 4 * l16 + 3 of row stream `half` -- half 0 walks rows
+// 0..33 and tests rows 2..31, half 1 walks rows 30..63 and tests rows 32..61 -- so one LDS.128 per lane feeds two rows
+// per warp instruction.  Horizontal 5-max: four 16-lane shuffles bring the two neighbouring values on each side (or
+// their pair maxima), three-input FMNMX does the rest; vertical 5-max: a register window of the last five horizontal
+// maxima, two FMNMX3 per pixel.  A pixel equal to its window maximum sets one bit in a per-column mask (30 tested rows
+// per stream), nothing else happens inside the scan: peaks are frequent on noisy maps (one per ~25 pixels), so any
+// per-peak work in the scan would run, diverged, on almost every row.  Afterwards each lane walks its own set bits,
+// one bit of each of its four column masks per trip (about 2-3 trips), with the map still in shared memory:
+//   MPE = entropy of softmax over the peak values = log S - T / S with S = sum e^(v - c), T = sum (v - c) e^(v - c);
+//         the shift c is the maximum of the whole map (known from the scan, >= every peak), so one pass suffices; should
+//         every term underflow (a border pixel ~100 above every peak) a second pass shifts by the largest peak instead;
+//   BSB = |p0 - p1| of the two highest peaks.
+// Warp-wide minima / maxima / counts go through REDUX on monotone integer keys (one instruction instead of a five-step
+// shuffle butterfly); only the two float sums of MPE use a butterfly.
+// Equal neighbouring maxima (a plateau above the map minimum) all count as peaks; skimage's ensure_spacing would keep
+// a subset of them that depends on an unstable argsort -- see DESIGN.md section 2.
+// BSB works on the ROW-softmaxed map (F.softmax without dim on a 2-D tensor), so a first pass rewrites the stage in
+// place, p = exp(x - rowmax) / rowsum.  That pass runs with lane = row (rows l and l + 32): a lane holds its whole row in
+// 64 registers, so the row statistics need no shuffles at all; the float4 column blocks are visited in the rotated
+// order (k + lane) % 16, which keeps every quarter-warp on eight distinct 16-byte bank groups (conflict-free LDS.128 /
+// STS.128).  exp = ex2.approx of the exactly formed difference times log2e (the row maximum contributes exactly 1), the
+// quotient is e * (1/s) corrected by one residual step.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t order_key(float x) {  // monotone float -> uint (no NaN handling needed here)
+  const uint32_t u = __float_as_uint(x);
+  return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float order_key_inv(uint32_t k) {
+  return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu));
+}
+__device__ __forceinline__ float warp_min_f(float v) { return order_key_inv(__reduce_min_sync(kFull, order_key(v))); }
+__device__ __forceinline__ float warp_max_f(float v) { return order_key_inv(__reduce_max_sync(kFull, order_key(v))); }
+
+template <int kMode>
+struct PeaksOp {
+  struct Args {
+    float* out;
+  };
+  using Pre = NoPrefetch;
+  static constexpr bool kWritesSmem = (kMode == 1);
+  __device__ static __forceinline__ Pre prefetch(int64_t, const Args&) { return {}; }
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*, const Pre&) {
+    if (!ok) {
+      if (lane == 0) a.out[m] = __int_as_float(0x7fc00000);
+      return;
+    }
+    const int half = lane >> 4, l16 = lane & 15;
+    float4* p4 = reinterpret_cast<float4*>(map);
+    float gmin = INFINITY, gmax = -INFINITY;
+    if (kMode == 1) {
+      constexpr float kLog2e = 1.4426950408889634f;
+#pragma unroll 1
+      for (int rr = 0; rr < 2; ++rr) {
+        float4* row = p4 + (lane + 32 * rr) * 16;
+        float4 x[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = row[(k + lane) & 15];
+        float rm = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2)
+          rm = max3(rm, max3(x[k].x, x[k].y, x[k].z), max3(x[k].w, x[k + 1].x, max3(x[k + 1].y, x[k + 1].z, x[k + 1].w)));
+        // packed float32x2 arithmetic (FADD2 / FMUL2 / FFMA2, sm_100): half the issue slots of the scalar forms
+        const float2 nrm = make_float2(-rm, -rm), l2e = make_float2(kLog2e, kLog2e);
+        float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float2 ta = __fmul2_rn(__fadd2_rn(make_float2(x[k].x, x[k].y), nrm), l2e);
+          const float2 tb = __fmul2_rn(__fadd2_rn(make_float2(x[k].z, x[k].w), nrm), l2e);
+          x[k].x = ex2_approx(ta.x);
+          x[k].y = ex2_approx(ta.y);
+          x[k].z = ex2_approx(tb.x);
+          x[k].w = ex2_approx(tb.y);
+          sa = __fadd2_rn(sa, make_float2(x[k].x, x[k].y));
+          sb = __fadd2_rn(sb, make_float2(x[k].z, x[k].w));
+        }
+        const float s = (sa.x + sa.y) + (sb.x + sb.y);
+        const float r = __frcp_rn(s);
+        const float2 r2 = make_float2(r, r), ns2 = make_float2(-s, -s);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float2 ea = make_float2(x[k].x, x[k].y), eb = make_float2(x[k].z, x[k].w);
+          float2 qa = __fmul2_rn(ea, r2), qb = __fmul2_rn(eb, r2);
+          qa = __ffma2_rn(__ffma2_rn(qa, ns2, ea), r2, qa);  // q + (e - q s) / s: one residual correction step
+          qb = __ffma2_rn(__ffma2_rn(qb, ns2, eb), r2, qb);
+          gmin = min3(min3(qa.x, qa.y, qb.x), qb.y, gmin);
+          row[(k + lane) & 15] = make_float4(qa.x, qa.y, qb.x, qb.y);
+        }
+      }
+      __syncwarp();
+    }
+    const int rbase = half * 30;
+    float h[4][5], xs[4][3];
+    uint32_t bits[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int t = 0; t < 34; ++t) {
+      const float4 x = p4[(rbase + t) * 16 + l16];
+      const float m01 = fmaxf(x.x, x.y), m23 = fmaxf(x.z, x.w);
+      if (kMode == 0) {
+        gmin = min3(min3(x.x, x.y, x.z), x.w, gmin);
+        gmax = max3(m01, m23, gmax);
+      }
+      // neighbours inside the 16-lane row segment; the edge lanes get their own values back, which only ever reach the
+      // windows of border columns (masked below) or are members of the window anyway
+      const float Lm = __shfl_up_sync(kFull, m23, 1, 16), Lc3 = __shfl_up_sync(kFull, x.w, 1, 16);
+      const float Rc0 = __shfl_down_sync(kFull, x.x, 1, 16), Rm = __shfl_down_sync(kFull, m01, 1, 16);
+      const int s5 = t % 5, s3 = t % 3;
+      h[0][s5] = max3(Lm, m01, x.z);
+      h[1][s5] = max3(Lc3, m01, m23);
+      h[2][s5] = max3(m01, m23, Rc0);
+      h[3][s5] = max3(x.y, m23, Rm);
+      xs[0][s3] = x.x; xs[1][s3] = x.y; xs[2][s3] = x.z; xs[3][s3] = x.w;
+      if (t >= 4) {  // row rbase + t - 2 now has its five window rows in the ring
+        const int c3 = (t - 2) % 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float w = max3(max3(h[k][0], h[k][1], h[k][2]), h[k][3], h[k][4]);
+          if (xs[k][c3] == w) bits[k] |= 1u << (t - 4);
+        }
+      }
+    }
+    if (l16 == 0) bits[0] = bits[1] = 0u;   // columns 0, 1
+    if (l16 == 15) bits[2] = bits[3] = 0u;  // columns 62, 63
+    gmin = warp_min_f(gmin);
+    const float* col = map + (rbase + 2) * kMapDim + l16 * 4;  // bit i of bits[k] <-> col[i * 64 + k]
+    if (kMode == 0) {
+      constexpr float kLog2e = 1.4426950408889634f;
+      gmax = warp_max_f(gmax);
+      float S = 0.f, T = 0.f, M = -INFINITY;
+      int n = 0;
+      uint32_t b0 = bits[0], b1 = bits[1], b2 = bits[2], b3 = bits[3];
+      while (b0 | b1 | b2 | b3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t& b = (k == 0) ? b0 : (k == 1) ? b1 : (k == 2) ? b2 : b3;
+          if (b) {
+            const int i = __ffs(b) - 1;
+            b &= b - 1;
+            const float v = col[i * kMapDim + k];
+            if (v > gmin) {  // image > image.min(): peaks sitting at the map minimum are not peaks
+              const float d = v - gmax;
+              const float w = ex2_approx(d * kLog2e);
+              S += w;
+              T = fmaf(d, w, T);
+              M = fmaxf(M, v);
+              ++n;
+            }
+          }
+        }
+      }
+      n = __reduce_add_sync(kFull, n);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(kFull, S, o);
+        T += __shfl_xor_sync(kFull, T, o);
+      }
+      if (n > 0 && !(S >= 1e-30f)) {  // every term underflowed: shift by the largest peak instead (never on real maps)
+        M = warp_max_f(M);
+        S = 0.f;
+        T = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t b = bits[k];
+          while (b) {
+            const int i = __ffs(b) - 1;
+            b &= b - 1;
+            const float v = col[i * kMapDim + k];
+            if (v > gmin) {
+              const float d = v - M;
+              const float w = expf(d);
+              S += w;
+              T = fmaf(d, w, T);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          S += __shfl_xor_sync(kFull, S, o);
+          T += __shfl_xor_sync(kFull, T, o);
+        }
+      }
+      // H = -sum p log p with p = e^(v - c) / S  =  log S - T / S ; no peak: the reference sums an empty list
+      if (lane == 0) a.out[m] = (n > 0) ? logf(S) - T / S : 0.f;
+    } else {
+      float t1 = -INFINITY, t2 = -INFINITY;
+      int n = 0;
+      uint32_t b0 = bits[0], b1 = bits[1], b2 = bits[2], b3 = bits[3];
+      while (b0 | b1 | b2 | b3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t& b = (k == 0) ? b0 : (k == 1) ? b1 : (k == 2) ? b2 : b3;
+          if (b) {
+            const int i = __ffs(b) - 1;
+            b &= b - 1;
+            const float v = col[i * kMapDim + k];
+            if (v > gmin) {
+              ++n;
+              t2 = fmaxf(t2, fminf(t1, v));  // (t1, t2) = the two largest of {t1, t2, v}
+              t1 = fmaxf(t1, v);
+            }
+          }
+        }
+      }
+      n = __reduce_add_sync(kFull, n);
+      // two largest values over all lanes: the maximum, then either the maximum again (held by two lanes, or twice by
+      // one lane: then that lane's t2 equals it) or the largest remaining value
+      const float top = warp_max_f(t1);
+      const bool mine = (t1 == top);
+      const int owners = __popc(__ballot_sync(kFull, mine));
+      float second = warp_max_f(mine ? t2 : t1);
+      if (owners >= 2) second = top;
+      // fewer than two peaks: the reference raises IndexError (strategy.py:1208); NaN here, raised by the host wrapper
+      if (lane == 0) a.out[m] = (n >= 2) ? fabsf(top - second) : __int_as_float(0x7fc00000);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Reprojection-XE term of one map (utils/triangulation.py:236-257): sum((heatmap - render)^2) / (H W) with
+// render[y][x] = exp(-((x - u)^2 + (y - v)^2) / (2 sigma^2)) in float64, (u, v) the reprojection of the triangulated
+// joint in IMAGE pixels (the reference compares it with the heat-map pixel grid as is).  The Gaussian is separable:
+// the warp forms gx[0..63], gy[0..63] (4 double exponentials per lane) in its scratch, a lane keeps the gx of its four
+// columns in registers and a pixel costs one conversion and two DFMA (r = h - gx gy; acc += r r).
+// ---------------------------------------------------------------------------------------------------------------
+struct XeOp {
+  struct Args {
+    const double* proj;
+    const double* xyz;
+    int V, J;
+    double inv_two_sigma2;
+    double* out_map;
+  };
+  // The projection matrix row block and the 3-D joint of a map come from global memory; they are fetched one map ahead
+  // (while the warp still waits for / works on the current stage) so that their latency never sits between the
+  // arrival of a map and its evaluation.
+  struct Pre {
+    double P[12], X[3];
+  };
+  static constexpr bool kWritesSmem = false;
+  __device__ static __forceinline__ Pre prefetch(int64_t m, const Args& a) {
+    Pre q;
+    const int j = (int)(m % a.J);
+    const int64_t fv = m / a.J;
+    const double* __restrict__ P = a.proj + fv * 12;
+    const double* __restrict__ X = a.xyz + ((fv / a.V) * a.J + j) * 3;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) q.P[i] = __ldg(P + i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) q.X[i] = __ldg(X + i);
+    return q;
+  }
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char* scratch,
+                                             const Pre& q) {
+    (void)ok;
+    double* gx = reinterpret_cast<double*>(scratch);
+    double* gy = gx + kMapDim;
+    const double* P = q.P;
+    const double x = q.X[0], y = q.X[1], z = q.X[2];
+    // [X, 1] @ P^T (:476), then dehomogenise with w == 0 -> 1 (:397-399)
+    const double pu = ((x * P[0] + y * P[1]) + z * P[2]) + P[3];
+    const double pv = ((x * P[4] + y * P[5]) + z * P[6]) + P[7];
+    double pw = ((x * P[8] + y * P[9]) + z * P[10]) + P[11];
+    if (pw == 0.0) pw = 1.0;
+    const double u = pu / pw, v = pv / pw;
+    __syncwarp();
+#pragma unroll
+    for (int i = lane; i < kMapDim; i += 32) {
+      const double dx = (double)i - u, dy = (double)i - v;
+      gx[i] = exp(-(dx * dx) * a.inv_two_sigma2);
+      gy[i] = exp(-(dy * dy) * a.inv_two_sigma2);
+    }
+    __syncwarp();
+    const int half = lane >> 4, l16 = lane & 15;
+    const double2 ga = reinterpret_cast<const double2*>(gx)[l16 * 2], gb = reinterpret_cast<const double2*>(gx)[l16 * 2 + 1];
+    const float4* __restrict__ p = reinterpret_cast<const float4*>(map) + lane;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll 8
+    for (int t = 0; t < 32; ++t) {
+      const float4 h = p[t * 32];
+      const double g = gy[2 * t + half];
+      const double r0 = fma(-ga.x, g, (double)h.x), r1 = fma(-ga.y, g, (double)h.y);
+      const double r2 = fma(-gb.x, g, (double)h.z), r3 = fma(-gb.y, g, (double)h.w);
+      acc0 = fma(r0, r0, acc0);
+      acc1 = fma(r1, r1, acc1);
+      acc2 = fma(r2, r2, acc2);
+      acc3 = fma(r3, r3, acc3);
+    }
+    const double acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
+    if (lane == 0) a.out_map[m] = acc * (1.0 / (double)kMapFloats);
+  }
+};
+
+}  // namespace mval

@@ -62,7 +62,71 @@ sal_key_kernel(const float* __restrict__ sal_metric, const float* __restrict__ i
   key[i] = keep ? (-(double)m + 0.0) : __longlong_as_double(0x7ff8000000000000ll);
 }
 
+// strategy.py:981-985: cluster_id = self.kmeans.predict([kp])[0] with kp the root-relative pose of the frame (float64
+// differences of the float32 predictions, x_0..x_{J-1}, y.., z..), one sklearn call per candidate in the reference.
+// sklearn's predict is argmin_c (|c|^2 - 2 x.c) in float64, first centre on ties (lloyd_iter_chunked_dense with
+// update_centers=False).  One thread per frame; the dot product is a sequential float64 fma chain, so it can differ
+// from sklearn's GEMM by rounding only: the margin to the runner-up is returned as well and the host re-asks sklearn
+// for the frames whose margin is within rounding distance.
+__global__ void __launch_bounds__(128)
+kmeans_assign_kernel(const float* __restrict__ pred, int64_t n, int J, int root, const double* __restrict__ centres,
+                     const double* __restrict__ centre_sq, int k, int32_t* __restrict__ label, double* __restrict__ margin) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const float* p = pred + f * J * 3;
+  const double rx = (double)p[root * 3], ry = (double)p[root * 3 + 1], rz = (double)p[root * 3 + 2];
+  double best = INFINITY, second = INFINITY;
+  int arg = 0;
+  for (int c = 0; c < k; ++c) {
+    const double* cc = centres + (int64_t)c * 3 * J;
+    double dot = 0.0;
+    for (int j = 0; j < J; ++j) dot = fma((double)p[j * 3] - rx, __ldg(cc + j), dot);
+    for (int j = 0; j < J; ++j) dot = fma((double)p[j * 3 + 1] - ry, __ldg(cc + J + j), dot);
+    for (int j = 0; j < J; ++j) dot = fma((double)p[j * 3 + 2] - rz, __ldg(cc + 2 * J + j), dot);
+    const double s = fma(-2.0, dot, __ldg(centre_sq + c));
+    if (s < best) {
+      second = best;
+      best = s;
+      arg = c;
+    } else if (s < second) {
+      second = s;
+    }
+  }
+  label[f] = arg;
+  if (margin) margin[f] = second - best;  // +inf with a single centre, NaN when the scores are not comparable
+}
+
+__global__ void __launch_bounds__(128) centre_sq_kernel(const double* __restrict__ centres, int k, int d, double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k) return;
+  double s = 0.0;
+  for (int i = 0; i < d; ++i) s = fma(centres[(int64_t)c * d + i], centres[(int64_t)c * d + i], s);
+  out[c] = s;
+}
+
 }  // namespace mval
+
+extern "C" int mval_kmeans_assign(const float* pred, int64_t n_frames, int J, int root, const double* centres, int k,
+                                  int32_t* out_label, double* out_margin, void* stream_) {
+  using namespace mval;
+  if (int rc = require_device()) return rc;
+  MVAL_REQUIRE(n_frames >= 0 && J > 0 && root >= 0 && root < J && k > 0, "mval_kmeans_assign: bad shape, root joint or k");
+  if (n_frames == 0) return MVAL_OK;
+  MVAL_REQUIRE(pred && centres && out_label, "mval_kmeans_assign: null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  double* sq = nullptr;
+  MVAL_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sq), sizeof(double) * k, stream));
+  centre_sq_kernel<<<(unsigned)((k + 127) / 128), 128, 0, stream>>>(centres, k, 3 * J, sq);
+  kmeans_assign_kernel<<<(unsigned)((n_frames + 127) / 128), 128, 0, stream>>>(pred, n_frames, J, root, centres, sq, k, out_label,
+                                                                              out_margin);
+  count_launch(2);
+  int rc = MVAL_OK;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) rc = cuda_fail(e, "launch kmeans_assign");
+  e = cudaFreeAsync(sq, stream);
+  if (rc == MVAL_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");
+  return rc;
+}
 
 extern "C" int mval_pose_features(const void* xyz, int xyz_is_double, int64_t n_frames, int J, int root, float* out_features,
                                   void* stream) {

@@ -152,8 +152,12 @@ def triangulate_ransac(keypoints_2d, proj, valid=None, n_iters=DEFAULT_N_ITERS, 
 
 
 def score_pool(heatmaps, proj, stride, valid=None, n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0,
-               frame_offset=0, return_keypoints_2d=True):
-    """Device-resident pool scoring: decode (arg-max) + RANSAC triangulation + per-frame uncertainty."""
+               frame_offset=0, return_keypoints_2d=True, map_score=None):
+    """Device-resident pool scoring: decode (arg-max) + RANSAC triangulation + per-frame uncertainty.
+    map_score "HP" / "MPE" / "BSB" additionally returns out["map_score"] float32 [N, V, J] -- the per-map score of
+    score_hp / score_peaks, evaluated in the same pass over the heat maps (mval_score_pool_scored)."""
+    if map_score not in _lib.MAP_SCORE:
+        raise ValueError("map_score must be None, 'HP', 'MPE' or 'BSB'")
     hm = _cuda(heatmaps, torch.float32, "heatmaps")
     N, V, J, H, W = hm.shape
     P = _cuda(proj.to(hm.device) if not proj.is_cuda else proj, torch.float64, "proj")
@@ -163,12 +167,16 @@ def score_pool(heatmaps, proj, stride, valid=None, n_iters=DEFAULT_N_ITERS, epsi
     out = _alloc_tri_outputs(N, J, hm.device)
     xy = torch.empty((N, V, J, 2), dtype=torch.int32, device=hm.device) if return_keypoints_2d else None
     prm = ransac_params(n_iters, epsilon, pair_seed, frame_offset)
+    per_map = torch.empty((N, V, J), dtype=torch.float32, device=hm.device) if map_score is not None else None
     with torch.cuda.device(hm.device):
-        check(_lib.load().mval_score_pool(_ptr(hm), _ptr(P), _ptr(v), N, V, J, H, W, int(stride), C.byref(prm), _ptr(xy),
-                                          _ptr(out["keypoints_3d"]), _ptr(out["reproj_mean"]), _ptr(out["inliers"]),
-                                          _ptr(out["metric"]), _ptr(out["inlier_count"]), _stream()))
+        check(_lib.load().mval_score_pool_scored(_ptr(hm), _ptr(P), _ptr(v), N, V, J, H, W, int(stride), C.byref(prm),
+                                                 _lib.MAP_SCORE[map_score], _ptr(xy), _ptr(out["keypoints_3d"]),
+                                                 _ptr(out["reproj_mean"]), _ptr(out["inliers"]), _ptr(out["metric"]),
+                                                 _ptr(out["inlier_count"]), _ptr(per_map), _stream()))
     if xy is not None:
         out["keypoints_2d"] = xy
+    if per_map is not None:
+        out["map_score"] = per_map
     return out
 
 
@@ -265,6 +273,23 @@ def mkpe(pred, gt, valid):
     with torch.cuda.device(p.device):
         check(_lib.load().mval_mkpe(_ptr(p), _ptr(g), _ptr(v), N, J, int(g.shape[1]), _ptr(out), _stream()))
     return out
+
+
+def kmeans_assign(pred, centres, root):
+    """strategy.py:981-985 for a whole pool: pred float32 CUDA [N, J, 3] (sal_dict["pred_3d_keypoints"]), centres float64
+    [k, 3 J] (kmeans.cluster_centers_) -> (label int32 [N], margin float64 [N]); see include/mval_b200.h."""
+    p = _cuda(pred, torch.float32, "pred")
+    N, J, _ = p.shape
+    c = _cuda(centres if torch.is_tensor(centres) and centres.is_cuda else torch.as_tensor(np.asarray(centres)).to(p.device),
+              torch.float64, "centres")
+    if c.dim() != 2 or c.shape[1] != 3 * J:
+        raise ValueError("centres has shape %s, expected [k, %d]" % (tuple(c.shape), 3 * J))
+    label = torch.empty((N,), dtype=torch.int32, device=p.device)
+    margin = torch.empty((N,), dtype=torch.float64, device=p.device)
+    with torch.cuda.device(p.device):
+        check(_lib.load().mval_kmeans_assign(_ptr(p), N, J, int(root), _ptr(c), int(c.shape[0]), _ptr(label), _ptr(margin),
+                                             _stream()))
+    return label, margin
 
 
 def pose_features(keypoints_3d, root):

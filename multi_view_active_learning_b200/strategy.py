@@ -81,12 +81,11 @@ class ScoringSelectionMixin:
             sal_guids = self._sal_candidates(sal_dict, al_guids, train_dataset.pseudo_label_guids, cfg.SAL.INLIER_THRESHOLD,
                                              None if clustered else 2 * pseudo_num_frames)
             if clustered:
+                # reference :976-992: walk the candidates in order, every cluster takes its first per_cluster_count
+                cluster_ids = self._cluster_ids(sal_dict["pred_3d_keypoints"], sal_guids)
                 counter = [0 for _ in range(cfg.SAL.NUM_CLUSTERS)]
                 per_cluster_count = pseudo_num_frames // cfg.SAL.NUM_CLUSTERS
-                for guid in sal_guids:
-                    kp = np.array(sal_dict["pred_3d_keypoints"][guid]).T
-                    kp = (kp[0:3, :] - kp[0:3, self.joint_root_index:self.joint_root_index + 1]).flatten()
-                    cluster_id = self.kmeans.predict([kp])[0]
+                for guid, cluster_id in zip(sal_guids, cluster_ids):
                     if counter[cluster_id] < per_cluster_count:
                         counter[cluster_id] += 1
                         sal_sampled_guids.append(guid)
@@ -94,6 +93,25 @@ class ScoringSelectionMixin:
                 sal_sampled_guids = random.sample(sal_guids[:2 * pseudo_num_frames], pseudo_num_frames)
             train_dataset.pseudo_label_by_frame_guids(sal_sampled_guids, sal_dict["pred_3d_keypoints"])
         return train_dataset, al_guids, sal_sampled_guids, sal_dict
+
+    def _cluster_ids(self, pred_3d_keypoints, guids, margin_rtol=1e-9):
+        """strategy.py:981-985 ``self.kmeans.predict([kp])[0]`` for every candidate at once (mval_kmeans_assign).  The
+        device evaluates sklearn's predict rule in float64; a frame whose two best centres are closer than rounding
+        could separate (relative margin <= margin_rtol; also NaN) is handed to sklearn itself, literally as the
+        reference does, so the labels are the reference's."""
+        if not guids:
+            return []
+        pred = torch.tensor([pred_3d_keypoints[g] for g in guids], dtype=torch.float32).cuda()
+        centres = np.asarray(self.kmeans.cluster_centers_, dtype=np.float64)
+        label, margin = ops.kmeans_assign(pred, centres, self.joint_root_index)
+        label, margin = label.cpu().numpy(), margin.cpu().numpy()
+        cmax = float(np.abs(centres).max())
+        scale = cmax * max(cmax, 2.0 * float(pred.abs().max())) * centres.shape[1] + 1.0  # bound on |x||c| d
+        for i in np.nonzero(~(margin > margin_rtol * scale))[0].tolist():
+            kp = np.array(pred_3d_keypoints[guids[i]]).T
+            kp = (kp[0:3, :] - kp[0:3, self.joint_root_index:self.joint_root_index + 1]).flatten()
+            label[i] = self.kmeans.predict([kp])[0]
+        return label.tolist()
 
     @staticmethod
     def _sal_candidates(sal_dict, al_guids, pseudo_label_guids, inlier_threshold, limit=None):
@@ -145,19 +163,21 @@ class ScoringSelectionMixin:
             return np.zeros(B), False
         if cfg.STRATEGY in ("HP", "MPE", "BSB"):
             config = {"HP": cfg.HP_CONFIG, "MPE": cfg.MPE_CONFIG, "BSB": cfg.BSB_CONFIG}[cfg.STRATEGY]
-            vals = self._compute_map_score_batch(cfg.STRATEGY, config, heatmaps, joint_valid)
+            # tri["map_score"]: the per-map scores the fused pass already produced next to the triangulation
+            vals = self._compute_map_score_batch(cfg.STRATEGY, config, heatmaps, joint_valid, tri.get("map_score"))
             return np.asarray(vals, dtype=np.float64), config == "STD"
         raise NotImplementedError()
 
     @staticmethod
-    def _compute_map_score_batch(kind, config, heatmaps, joint_valid):
+    def _compute_map_score_batch(kind, config, heatmaps, joint_valid, per_map=None):
         """strategy.py:1149-1215 for a batch: the per-map score (HP / MPE / BSB) on the device, then AVG (Python float
-        sum / len, like the reference's sum(x)/len(x)) or STD (np.std) over (view, valid joint) on the host."""
+        sum / len, like the reference's sum(x)/len(x)) or STD (np.std) over (view, valid joint) on the host.
+        per_map: float32 [B, V, J] scores that were already computed (ops.score_pool(..., map_score=kind))."""
         valid = (torch.as_tensor(joint_valid) != 0)
-        if kind == "HP":
-            per_map = ops.score_hp(heatmaps, valid)
-        else:
-            per_map = ops.score_peaks(heatmaps, kind, valid)
+        if valid.dim() == 1:
+            valid = valid.unsqueeze(0).expand(heatmaps.shape[0], -1)
+        if per_map is None:
+            per_map = ops.score_hp(heatmaps, valid) if kind == "HP" else ops.score_peaks(heatmaps, kind, valid)
         per_map = per_map.cpu().numpy().astype(np.float64)  # [B, V, J], NaN for invalid joints
         v = valid.cpu().numpy()
         out = []
@@ -212,7 +232,8 @@ class ScoringSelectionMixin:
                     heatmaps, dp["proj_matrices"], cfg.POSE_ESTIMATOR.STRIDE, joint_valid,
                     use_soft_argmax=cfg.AL.USE_SOFTARGMAX, pair_seed=getattr(cfg, "RANDOM_SEED", 0),
                     frame_offset=rank_base + n_done, use_reprojection_xe=cfg.AL.USE_REPROJECTION_XE,
-                    sigma=cfg.AL.REPROJECTION_SIGMA)
+                    sigma=cfg.AL.REPROJECTION_SIGMA,
+                    map_score=cfg.AL.STRATEGY if cfg.AL.STRATEGY in ("HP", "MPE", "BSB") else None)
                 n_done += B
                 al, al_is_f64 = self._frame_al_metric(heatmaps, joint_valid, tri)
                 acc["sal"].append(tri["metric"].float())  # torch.Tensor([metric]) -> float32 (:1061)

@@ -522,6 +522,90 @@ def test_kcenter_sharded_loop_bit_exact(ops):
     assert sel2.cpu().tolist() == exp_sel
 
 
+# ------------------------------------------------------------------------------------------------ fused pass with AL scores
+def _with_env(name, value, fn):
+    import os
+
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("N,V,J,vp", [(1500, 8, 19, 1.0), (700, 5, 19, 0.8), (300, 20, 42, 0.8), (200, 31, 19, 1.0),
+                                      (333, 2, 3, 0.7), (5, 8, 19, 0.9)])
+@pytest.mark.parametrize("alt", ["0", "1"])
+def test_fused_scored_pass_equals_separate_passes(ops, N, V, J, vp, alt):
+    """mval_score_pool_scored: the decode warps of the fused kernel evaluate HP / MPE / BSB on the staged map right after
+    its arg-max (one pass over the pool instead of two).  Every triangulation output must be bit-identical to the
+    unscored fused pass and the per-map scores must equal those of mval_score_hp / mval_score_peaks (same device code:
+    bit-identical), for both warp budgets (MVAL_FUSED_ALT), several ring rounds per SM, invalid joints, 2 and 4 frame
+    slots, and C(V,2) > 64."""
+    pool = S.make_pool(N, V, J, seed=N + V, valid_prob=vp, p_outlier=0.15)
+    hm = ops.synth_heatmaps(_cuda(pool["centres"]), noise=0.05, seed=11)
+    P, valid = _cuda(pool["P"]), torch.from_numpy(pool["valid"])
+    v = np.broadcast_to(pool["valid"][:, None, :], (N, V, J))
+    plain = ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345)
+    for kind in ("HP", "MPE", "BSB"):
+        both = _with_env("MVAL_FUSED_ALT", alt, lambda: ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345,
+                                                                       map_score=kind))
+        for k in ("keypoints_2d", "keypoints_3d", "inliers", "inlier_count"):
+            assert torch.equal(both[k], plain[k]), (kind, k)
+        for k in ("metric", "reproj_mean"):
+            assert torch.equal(torch.nan_to_num(both[k], nan=-1.0), torch.nan_to_num(plain[k], nan=-1.0)), (kind, k)
+        sep = (ops.score_hp(hm, valid) if kind == "HP" else ops.score_peaks(hm, kind, valid)).cpu().numpy()
+        got = both["map_score"].cpu().numpy()
+        assert got.shape == (N, V, J)
+        assert np.isnan(got[~v]).all() and np.array_equal(np.isnan(got), np.isnan(sep)), kind
+        assert np.array_equal(got[v], sep[v]), (kind, np.nanmax(np.abs(got[v] - sep[v])))
+
+
+def test_fused_scored_pass_edge_cases(ops):
+    """NaN / infinity / constant maps, maps with fewer than two peaks, zero frames and a shape the fused kernel does not
+    take (48 x 48: the entry point then runs the two passes back to back) through mval_score_pool_scored."""
+    rng = np.random.default_rng(2)
+    hm = rng.normal(size=(3, 2, 6, 64, 64)).astype(np.float32)
+    hm[0, :, 1, 10, 10] = np.nan
+    hm[0, :, 2, 5, 5] = np.inf
+    hm[1, :, 3, 7, :] = -np.inf
+    hm[1, :, 4] = 3.0
+    hm[2, 0, 5] = -1.0
+    hm[2, 0, 5, 20, 20] = 0.5  # one peak only: BSB is NaN there
+    P = _cuda(S.make_pool(3, 2, 6, seed=4)["P"])
+    valid = torch.ones(3, 6, dtype=torch.bool)
+    valid[2, 0] = False
+    g = _cuda(hm)
+    plain = ops.score_pool(g, P, 4, valid)
+    for kind in ("HP", "MPE", "BSB"):
+        both = ops.score_pool(g, P, 4, valid, map_score=kind)
+        assert torch.equal(both["keypoints_2d"], plain["keypoints_2d"]), kind
+        assert torch.equal(both["inlier_count"], plain["inlier_count"]), kind
+        assert torch.equal(torch.nan_to_num(both["keypoints_3d"], nan=-1.0), torch.nan_to_num(plain["keypoints_3d"], nan=-1.0)), kind
+        sep = (ops.score_hp(g, valid) if kind == "HP" else ops.score_peaks(g, kind, valid)).cpu().numpy()
+        got = both["map_score"].cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(sep)), kind
+        assert np.array_equal(got[~np.isnan(got)], sep[~np.isnan(sep)]), kind
+        assert np.isnan(got[2, :, 0]).all()  # invalid joint
+        if kind != "MPE":
+            assert np.isnan(got[0, :, 1]).all() and np.isnan(got[0, :, 2]).all()
+        empty = ops.score_pool(g[:0], P[:0], 4, map_score=kind)
+        assert empty["map_score"].shape == (0, 2, 6) and empty["metric"].numel() == 0
+    small = _cuda(rng.normal(size=(7, 3, 4, 48, 48)).astype(np.float32))
+    Ps = _cuda(S.make_pool(7, 3, 4, seed=5)["P"])
+    for kind in ("HP", "MPE", "BSB"):
+        both = ops.score_pool(small, Ps, 4, map_score=kind)
+        sep = ops.score_hp(small) if kind == "HP" else ops.score_peaks(small, kind)
+        assert torch.equal(torch.nan_to_num(both["map_score"], nan=-9.0), torch.nan_to_num(sep, nan=-9.0)), kind
+        assert torch.equal(both["keypoints_2d"], ops.decode_argmax(small, 4))
+    with pytest.raises(ValueError):
+        ops.score_pool(g, P, 4, map_score="XE")
+
+
 # ------------------------------------------------------------------------------------------------ map-stream kernels
 def _legacy(fn):
     """Runs fn with the persistent TMA-ring kernels (csrc/mapstream.cu) switched off -> one-warp-per-map kernels."""

@@ -208,6 +208,38 @@ def test_sal_rank_mkpe_and_pose_features_kernels():
     assert np.array_equal(ops.pose_features(torch.from_numpy(xyz.astype(np.float32)).cuda(), 2).cpu().numpy(), exp)
 
 
+def test_kmeans_assign_matches_sklearn_predict():
+    """mval_kmeans_assign against the reference's per-candidate call self.kmeans.predict([kp])[0] (strategy.py:981-985):
+    identical labels, margins >= 0, duplicated centres resolve to the first one."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from sklearn.cluster import KMeans
+
+    from multi_view_active_learning_b200 import ops
+
+    rng = np.random.default_rng(3)
+    for J, root, k, n in ((19, 2, 7, 600), (42, 21, 4, 150)):
+        train = rng.normal(size=(300, 3 * J)) * 250
+        km = KMeans(k, random_state=0, n_init=2).fit(train)
+        pred32 = (rng.normal(size=(n, J, 3)) * 300).astype(np.float32)
+        label, margin = ops.kmeans_assign(torch.from_numpy(pred32).cuda(), km.cluster_centers_, root)
+        exp = []
+        for i in range(n):
+            kp = np.array(pred32[i].tolist()).T  # what sal_dict["pred_3d_keypoints"][guid] holds
+            kp = (kp[0:3, :] - kp[0:3, root:root + 1]).flatten()
+            exp.append(int(km.predict([kp])[0]))
+        assert label.cpu().tolist() == exp
+        m = margin.cpu().numpy()
+        assert (m >= 0).all() and np.isfinite(m).all()
+        dup = np.concatenate([km.cluster_centers_[:1], km.cluster_centers_])  # centre 0 twice
+        l2, m2 = ops.kmeans_assign(torch.from_numpy(pred32).cuda(), dup, root)
+        l2 = l2.cpu().numpy()
+        assert np.array_equal(np.where(l2 == 0, 0, l2 - 1), np.asarray(exp)) and not (l2 == 1).any()
+        assert (m2.cpu().numpy()[l2 == 0] == 0).all()
+    empty, _ = ops.kmeans_assign(torch.zeros(0, 19, 3).cuda(), np.zeros((3, 57)), 2)
+    assert empty.numel() == 0
+
+
 def test_sal_cluster_balanced_pseudo_labels(tmp_path):
     """SAL with SAL.CLUSTER_FILE_PATH (reference strategy.py:37-52, 976-992): k-means over the cluster file's
     root-relative poses, then the ascending sal_metric order (device filter + sort) is walked and every cluster takes at
