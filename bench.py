@@ -199,6 +199,39 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
+def gpu_numa_info(index):
+    """NUMA placement of GPU `index` and of this process (context for the host-buffer e2e number)."""
+    info = {}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:  # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bdf = bdf[4:]
+        base = "/sys/bus/pci/devices/" + bdf
+        info["gpu_numa_node"] = int(open(base + "/numa_node").read())
+        info["gpu_local_cpulist"] = open(base + "/local_cpulist").read().strip()
+    except Exception as e:  # informational only
+        info["error"] = repr(e)[:120]
+    try:
+        info["process_cpu_count"] = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    return info
+
+
+def parse_cpulist(text):
+    cpus = set()
+    for part in (text or "").split(","):
+        if part.strip():
+            a, _, b = part.strip().partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
 # ----------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -331,7 +364,24 @@ def run_ours(args):
     # timed region; max over ranks per step, median over steps
     E = min(args.e2e_frames if n_gpus < 4 else min(args.e2e_frames, 2048), R)
     pin = lambda t: t.cpu().pin_memory()
+    # pinned pages are placed by first touch: allocate them from the CPUs next to this rank's GPU when the process is
+    # allowed to run there, so that the H2D stream does not cross the socket interconnect
+    numa = gpu_numa_info(local_rank)
+    allowed = os.sched_getaffinity(0)
+    near = allowed & parse_cpulist(numa.get("gpu_local_cpulist"))
+    if near:
+        os.sched_setaffinity(0, near)
     h_hm, h_P = pin(hm[:E]), pin(P[:E])
+    if near:
+        os.sched_setaffinity(0, allowed)
+    numa["pinned_from_gpu_local_cpus"] = bool(near)
+    # the raw link: one cudaMemcpyAsync of the same pinned heat maps, CUDA events (what e2e can reach at most)
+    probe_dst = torch.empty_like(hm[: min(E, 512)])
+    probe_src = h_hm[: probe_dst.shape[0]]
+    probe_dst.copy_(probe_src, non_blocking=True)
+    link_ms = time_ms(lambda: probe_dst.copy_(probe_src, non_blocking=True), 3)
+    link_gbs = probe_src.numel() * 4 / (link_ms * 1e-3) / 1e9
+    del probe_dst
     outs = None
     e2e_times = []
     for it in range(1 + args.e2e_steps):
@@ -354,6 +404,9 @@ def run_ours(args):
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * n_gpus, "d2h_bytes_per_step": d2h * n_gpus,
            "frames_per_step": E * n_gpus, "steps": args.e2e_steps, "aggregate": "max over ranks per step, median over steps",
            "step_ms": [round(1e3 * t, 2) for t in e2e_times],
+           "h2d_gbs": h2d / float(np.median(e2e_times)) / 1e9, "link_h2d_gbs_measured": link_gbs,
+           "link_note": "link_h2d_gbs_measured = one cudaMemcpyAsync of the same pinned heat maps on this rank (CUDA events): "
+                        "the bound of any end-to-end number whose inputs start in host memory", "numa": numa,
            "call": "mval_score_pool_host (pinned host heat maps -> chunked H2D on 2 streams -> fused kernel -> D2H) + "
                    "mval_topk_desc + ranking merge, on every rank concurrently"}
     del h_hm
@@ -730,12 +783,15 @@ def run_scores(args):
         "score_pool_fused_kernel (a1+a4..a7)": lambda: ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False),
     }
     # the fused pass with the AL score of the same maps evaluated by its decode warps (one read of the pool instead of
-    # two: compare with the sum of the fused line and the map_stream line of that score); alt = the 10 + 5 warp budget
+    # two: compare with the sum of the fused line and the map_stream line of that score); alt1 / alt2 = the other warp
+    # budgets of csrc/fused.cu (10 + 5 and 12 + 3 warps at 128 registers; default 12 + 6 at 96)
     for kind in ("HP", "MPE", "BSB"):
-        for alt in ("0", "1"):
-            kernels["score_pool_fused_kernel<%s>%s (a1+a4..a8)" % (kind, " alt" if alt == "1" else "")] = (
+        for alt in ("0", "1", "2"):
+            kernels["score_pool_fused_kernel<%s>%s (a1+a4..a8)" % (kind, " alt" + alt if alt != "0" else "")] = (
                 lambda kind=kind, alt=alt: (os.environ.__setitem__("MVAL_FUSED_ALT", alt),
                                             ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False, map_score=kind)))
+    if args.scores_only:
+        kernels = {k: f for k, f in kernels.items() if args.scores_only in k}
     out = {}
     for name, fn in kernels.items():
         for _ in range(3):
@@ -825,6 +881,7 @@ def main():
     ap.add_argument("--coreset-path", default="auto", choices=["auto", "ffma", "tc"])
     ap.add_argument("--coreset-data", default="gaussian", choices=["gaussian", "clustered"])
     ap.add_argument("--coreset-cpu-rows", type=int, default=50000)
+    ap.add_argument("--scores-only", default="", help="scores workload: only the kernels whose name contains this string")
     ap.add_argument("--backbone-frames", type=int, default=16, help="backbone workload: frames (x views images) per batch")
     ap.add_argument("--verify", action="store_true", help="hybrid: gather the pose features and check the sharded coreset "
                     "selection against the single-device loop on rank 0")

@@ -38,17 +38,17 @@
 namespace mval {
 
 // Warp budget and per-map evaluator of each variant.  The register file is split per scheduler (16 384 registers
-// each), so 17-20 warps per CTA cap a thread at 96 registers and 13-16 warps at 128.  kAlt picks between the two
-// budgets for the scored variants: 0 = 12 decode + 6 RANSAC warps at 96 registers (one decode warp per ring stage, as
-// in map_stream_kernel; ptxas spills a few loop-invariant addresses, none of the float64 Jacobi state), 1 = 10 + 5
-// warps at 128 registers (MVAL_FUSED_ALT=1, A/B measurements).
+// each), so 17-20 warps per CTA cap a thread at 96 registers and 13-16 warps at 128.  kAlt picks the budget of the
+// scored variants (MVAL_FUSED_ALT, A/B measurements): 0 = 12 decode + 6 RANSAC warps at 96 registers (one decode warp
+// per ring stage, as in map_stream_kernel; ptxas spills a few loop-invariant addresses, none of the float64 Jacobi
+// state), 1 = 10 + 5 warps and 2 = 12 + 3 warps, both at 128 registers.
 template <int kScore> struct FusedOp;
 template <> struct FusedOp<MVAL_MAP_SCORE_NONE> { using Op = void; };
 template <> struct FusedOp<MVAL_MAP_SCORE_HP> { using Op = HpOp; };
 template <> struct FusedOp<MVAL_MAP_SCORE_MPE> { using Op = PeaksOp<0>; };
 template <> struct FusedOp<MVAL_MAP_SCORE_BSB> { using Op = PeaksOp<1>; };
 template <int kScore, int kAlt> struct FusedCfg : FusedOp<kScore> {
-  static constexpr int kD = kAlt ? 10 : 12, kR = kAlt ? 5 : 6;  // 512 / 608 threads
+  static constexpr int kD = kAlt == 1 ? 10 : 12, kR = kAlt == 0 ? 6 : (kAlt == 1 ? 5 : 3);  // 608 / 512 / 512 threads
 };
 template <int kAlt> struct FusedCfg<MVAL_MAP_SCORE_NONE, kAlt> : FusedOp<MVAL_MAP_SCORE_NONE> {
   static constexpr int kD = 6, kR = 8;  // 480 threads
@@ -352,13 +352,15 @@ int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* 
                             double* out_xyz, double* out_reproj, int32_t* out_inliers, double* out_metric,
                             int32_t* out_inlier_count, float* out_map_score, cudaStream_t stream) {
   const char* alt_env = getenv("MVAL_FUSED_ALT");  // A/B measurements and tests only; read on every call
-  const bool alt = alt_env != nullptr && alt_env[0] == '1';
-#define MVAL_FUSED_CASE(K)                                                                                               \
-  case K:                                                                                                                \
-    return alt ? launch_fused_variant<K, 1>(hm, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz,         \
-                                            out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score, stream) \
-               : launch_fused_variant<K, 0>(hm, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz,         \
-                                            out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score, stream)
+  const int alt = (alt_env != nullptr && (alt_env[0] == '1' || alt_env[0] == '2')) ? alt_env[0] - '0' : 0;
+#define MVAL_FUSED_ARGS                                                                                               \
+  hm, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz, out_reproj, out_inliers, out_metric,           \
+      out_inlier_count, out_map_score, stream
+#define MVAL_FUSED_CASE(K)                                                 \
+  case K:                                                                  \
+    return alt == 1   ? launch_fused_variant<K, 1>(MVAL_FUSED_ARGS)        \
+           : alt == 2 ? launch_fused_variant<K, 2>(MVAL_FUSED_ARGS)        \
+                      : launch_fused_variant<K, 0>(MVAL_FUSED_ARGS)
   switch (map_score) {
     case MVAL_MAP_SCORE_NONE:
       return launch_fused_variant<MVAL_MAP_SCORE_NONE, 0>(hm, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz,
@@ -370,6 +372,7 @@ int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* 
       return MVAL_ERR_UNSUPPORTED;
   }
 #undef MVAL_FUSED_CASE
+#undef MVAL_FUSED_ARGS
 }
 
 }  // namespace mval

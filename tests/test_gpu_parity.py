@@ -539,12 +539,12 @@ def _with_env(name, value, fn):
 
 @pytest.mark.parametrize("N,V,J,vp", [(1500, 8, 19, 1.0), (700, 5, 19, 0.8), (300, 20, 42, 0.8), (200, 31, 19, 1.0),
                                       (333, 2, 3, 0.7), (5, 8, 19, 0.9)])
-@pytest.mark.parametrize("alt", ["0", "1"])
+@pytest.mark.parametrize("alt", ["0", "1", "2"])
 def test_fused_scored_pass_equals_separate_passes(ops, N, V, J, vp, alt):
     """mval_score_pool_scored: the decode warps of the fused kernel evaluate HP / MPE / BSB on the staged map right after
     its arg-max (one pass over the pool instead of two).  Every triangulation output must be bit-identical to the
     unscored fused pass and the per-map scores must equal those of mval_score_hp / mval_score_peaks (same device code:
-    bit-identical), for both warp budgets (MVAL_FUSED_ALT), several ring rounds per SM, invalid joints, 2 and 4 frame
+    bit-identical), for all three warp budgets (MVAL_FUSED_ALT), several ring rounds per SM, invalid joints, 2 and 4 frame
     slots, and C(V,2) > 64."""
     pool = S.make_pool(N, V, J, seed=N + V, valid_prob=vp, p_outlier=0.15)
     hm = ops.synth_heatmaps(_cuda(pool["centres"]), noise=0.05, seed=11)
