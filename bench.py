@@ -783,13 +783,13 @@ def run_scores(args):
         "score_pool_fused_kernel (a1+a4..a7)": lambda: ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False),
     }
     # the fused pass with the AL score of the same maps evaluated by its decode warps (one read of the pool instead of
-    # two: compare with the sum of the fused line and the map_stream line of that score); alt1 / alt2 = the other warp
-    # budgets of csrc/fused.cu (10 + 5 and 12 + 3 warps at 128 registers; default 12 + 6 at 96)
+    # two: compare with the sum of the fused line and the map_stream line of that score)
     for kind in ("HP", "MPE", "BSB"):
-        for alt in ("0", "1", "2"):
-            kernels["score_pool_fused_kernel<%s>%s (a1+a4..a8)" % (kind, " alt" + alt if alt != "0" else "")] = (
-                lambda kind=kind, alt=alt: (os.environ.__setitem__("MVAL_FUSED_ALT", alt),
-                                            ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False, map_score=kind)))
+        kernels["score_pool_fused_kernel<%s> (a1+a4..a8)" % kind] = (
+            lambda kind=kind: ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False, map_score=kind))
+    kernels["score_pool_fused_kernel, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = (
+        lambda: (os.environ.__setitem__("MVAL_ROW_ARGMAX", "0"), ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False),
+                 os.environ.__setitem__("MVAL_ROW_ARGMAX", "1")))
     if args.scores_only:
         kernels = {k: f for k, f in kernels.items() if args.scores_only in k}
     out = {}
@@ -798,7 +798,6 @@ def run_scores(args):
             fn()
         ms, _ = _timed(fn, 5)
         out[name] = {"avg_launch_ms": ms, "achieved": algo / (ms * 1e-3) / 1e9, "frac": algo / (ms * 1e-3) / 1e9 / hbm_peak}
-    os.environ["MVAL_FUSED_ALT"] = "0"
     print(json.dumps({"metric": "per-map heat-map kernels: algorithmic GB/s", "unit": "GB/s", "n_gpus": 1,
                       "config": {"workload": "%d frames x %d views x %d joints x %dx%d float32 heat maps resident (%.1f GB), "
                                  "one launch each" % (n, V, J, H, W, algo / 1e9)},

@@ -202,7 +202,7 @@ int mval_topk_desc(const double* scores, int64_t n, int64_t index_offset, int32_
 int mval_sal_rank(const float* sal_metric, const float* inlier_count, const uint8_t* excluded, int64_t n,
                   float inlier_threshold, int32_t k, int64_t* out_idx, int32_t* out_count, void* stream);
 
-/* Replaces the per-candidate self.kmeans.predict([kp])[0] of the cluster-balanced pseudo-label walk (strategy.py:981-985)
+/* Replaces the per-candidate self.kmeans.predict([kp])[0] of the cluster-balanced pseudo-label walk (strategy.py:981-989)
  * for a whole pool: kp = root-relative pose (pose^T[0:3, :] - pose^T[0:3, root]).flatten() in float64 from the float32
  * predictions of sal_dict["pred_3d_keypoints"], label = argmin_c (|c|^2 - 2 kp.c), first centre on ties -- sklearn
  * KMeans.predict.  pred float32 device [n_frames][J][3]; centres float64 device [k][3 J] (kmeans.cluster_centers_).

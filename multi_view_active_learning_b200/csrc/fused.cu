@@ -38,21 +38,16 @@
 namespace mval {
 
 // Warp budget and per-map evaluator of each variant.  The register file is split per scheduler (16 384 registers
-// each), so 17-20 warps per CTA cap a thread at 96 registers and 13-16 warps at 128.  kAlt picks the budget of the
-// scored variants (MVAL_FUSED_ALT, A/B measurements): 0 = 12 decode + 6 RANSAC warps at 96 registers (one decode warp
-// per ring stage, as in map_stream_kernel; ptxas spills a few loop-invariant addresses, none of the float64 Jacobi
-// state), 1 = 10 + 5 warps and 2 = 12 + 3 warps, both at 128 registers.
-template <int kScore> struct FusedOp;
-template <> struct FusedOp<MVAL_MAP_SCORE_NONE> { using Op = void; };
-template <> struct FusedOp<MVAL_MAP_SCORE_HP> { using Op = HpOp; };
-template <> struct FusedOp<MVAL_MAP_SCORE_MPE> { using Op = PeaksOp<0>; };
-template <> struct FusedOp<MVAL_MAP_SCORE_BSB> { using Op = PeaksOp<1>; };
-template <int kScore, int kAlt> struct FusedCfg : FusedOp<kScore> {
-  static constexpr int kD = kAlt == 1 ? 10 : 12, kR = kAlt == 0 ? 6 : (kAlt == 1 ? 5 : 3);  // 608 / 512 / 512 threads
-};
-template <int kAlt> struct FusedCfg<MVAL_MAP_SCORE_NONE, kAlt> : FusedOp<MVAL_MAP_SCORE_NONE> {
-  static constexpr int kD = 6, kR = 8;  // 480 threads
-};
+// each), so 17-20 warps per CTA cap a thread at 96 registers and 13-16 warps at 128.  Measured on 16 384 frames
+// (profiles/r1f_summary.md): 12 decode + 6 RANSAC warps at 96 registers (ptxas spills) 10.1 / 11.0 / 18.5 ms for HP /
+// MPE / BSB, 10 + 5 warps at 128 registers 9.4 / 10.6 / 13.9 ms, 12 + 3 warps at 128 registers 8.9 / 10.2 / 13.1 ms:
+// the scored variants are bound by the decode warps, and three RANSAC warps keep up with the float64 work of a pass
+// that takes 1.5-2x as long as the unscored one.
+template <int kScore> struct FusedCfg;
+template <> struct FusedCfg<MVAL_MAP_SCORE_NONE> { static constexpr int kD = 6, kR = 8; using Op = void; };       // 480 threads
+template <> struct FusedCfg<MVAL_MAP_SCORE_HP> { static constexpr int kD = 12, kR = 3; using Op = HpOp; };        // 512 threads
+template <> struct FusedCfg<MVAL_MAP_SCORE_MPE> { static constexpr int kD = 12, kR = 3; using Op = PeaksOp<0>; };
+template <> struct FusedCfg<MVAL_MAP_SCORE_BSB> { static constexpr int kD = 12, kR = 3; using Op = PeaksOp<1>; };
 constexpr int kMaxFrameSlots = 4;  // frame slots per CTA: 4 when they are small, fewer when V * J is large (see launcher)
 constexpr int kMaxStages = 64;
 
@@ -88,15 +83,17 @@ __host__ __device__ inline FusedSmem fused_layout(int V, int J, int HW, int stag
   return L;
 }
 
-template <int kScore, int kAlt>
-__global__ void __launch_bounds__(kWarp * (1 + FusedCfg<kScore, kAlt>::kD + FusedCfg<kScore, kAlt>::kR), 1)
+// kRowArgmax: 64 x 64 maps are arg-maxed by the lane = row sweep of mapops.cuh (warp_argmax_map64) instead of the
+// generic per-vector scan; both are the same function of the map.
+template <int kScore, bool kRowArgmax>
+__global__ void __launch_bounds__(kWarp * (1 + FusedCfg<kScore>::kD + FusedCfg<kScore>::kR), 1)
 score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__ proj, const uint8_t* __restrict__ valid,
                         int64_t n_frames, int V, int J, int H, int HW, int stride, int stages, int slots, int n_iters, double eps,
                         uint64_t seed, int64_t frame_offset, int32_t* __restrict__ out_xy, double* __restrict__ out_xyz,
                         double* __restrict__ out_reproj, int32_t* __restrict__ out_inliers, double* __restrict__ out_metric,
                         int32_t* __restrict__ out_inlier_count, float* __restrict__ out_map_score) {
-  constexpr int kFusedDecodeWarps = FusedCfg<kScore, kAlt>::kD;
-  constexpr int kFusedRansacWarps = FusedCfg<kScore, kAlt>::kR;
+  constexpr int kFusedDecodeWarps = FusedCfg<kScore>::kD;
+  constexpr int kFusedRansacWarps = FusedCfg<kScore>::kR;
   extern __shared__ __align__(128) unsigned char smem[];
   const FusedSmem L = fused_layout(V, J, HW, stages, slots, kFusedRansacWarps);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -169,19 +166,31 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
         if (!mbar_wait(&full[st], kf & 1u, g_fused_abort, 4, i, st)) return;
         float* stage = reinterpret_cast<float*>(smem + L.ring + (uint32_t)st * L.stage_bytes);
         const float4* p = reinterpret_cast<const float4*>(stage);
-        const uint32_t idx = warp_argmax_map<8, true>([&](int q) { return p[q]; }, hw4, lane, nullptr);
         const bool ok = valid == nullptr || valid[frame * J + m % J] != 0;
+        uint32_t idx = 0u;
+        if constexpr (kScore == MVAL_MAP_SCORE_HP) {
+          // HP's row sweep knows every row maximum: score and arg-max come out of one pass over the stage
+          if (ok)
+            idx = HpOp::eval<true>(stage, frame * VJ + m, lane, HpOp::Args{out_map_score});
+          else if (lane == 0)
+            out_map_score[frame * VJ + m] = __int_as_float(0x7fc00000);
+        } else if constexpr (kRowArgmax) {
+          idx = warp_argmax_map64(stage, lane);
+        } else {
+          idx = warp_argmax_map<8, true>([&](int q) { return p[q]; }, hw4, lane, nullptr);
+        }
+        constexpr bool kScoreAfter = kScore == MVAL_MAP_SCORE_MPE || kScore == MVAL_MAP_SCORE_BSB;
         if (lane == 0) {
           // every lane's loads were consumed by the reductions above
-          if (kScore == MVAL_MAP_SCORE_NONE) mbar_arrive(&empty[st]);
+          if (!kScoreAfter) mbar_arrive(&empty[st]);
           int2 xy = make_int2((int)(idx % (uint32_t)H) * stride, (int)(idx / (uint32_t)H) * stride);
           if (!ok) xy = make_int2(0, 0);  // evaluation.py:21-23
           kp_all[sl * VJ + m] = xy;
           if (out_xy) reinterpret_cast<int2*>(out_xy)[frame * VJ + m] = xy;
           mbar_arrive(&kp_ready[sl]);  // the RANSAC warps may start on this key-point while the score is evaluated
         }
-        if constexpr (kScore != MVAL_MAP_SCORE_NONE) {
-          using Op = typename FusedCfg<kScore, kAlt>::Op;
+        if constexpr (kScoreAfter) {
+          using Op = typename FusedCfg<kScore>::Op;
           __syncwarp();
           Op::run(stage, frame * VJ + m, ok, lane, typename Op::Args{out_map_score}, nullptr, typename Op::Pre{});
           if (Op::kWritesSmem) fence_proxy_async_smem();  // BSB rewrote the stage; order that before the TMA refill
@@ -297,12 +306,12 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
 
 // Returns MVAL_ERR_UNSUPPORTED (without setting an error) when the shape does not fit the fused kernel; the caller
 // then takes the multi-launch path.
-template <int kScore, int kAlt>
+template <int kScore, bool kRowArgmax>
 static int launch_fused_variant(const float* hm, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
                                 int H, int W, int stride, const mval_ransac_params& prm, int32_t* out_xy, double* out_xyz,
                                 double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
                                 float* out_map_score, cudaStream_t stream) {
-  constexpr int kD = FusedCfg<kScore, kAlt>::kD, kR = FusedCfg<kScore, kAlt>::kR;
+  constexpr int kD = FusedCfg<kScore>::kD, kR = FusedCfg<kScore>::kR;
   const int HW = H * W;
   if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(hm) & 15) != 0 || (reinterpret_cast<uintptr_t>(proj) & 15) != 0 ||
       prm.pairs != nullptr)
@@ -324,10 +333,10 @@ static int launch_fused_variant(const float* hm, const double* proj, const uint8
   }
   if (stages < kD) return MVAL_ERR_UNSUPPORTED;
   const FusedSmem L = fused_layout(V, J, HW, stages, slots, kR);
-  MVAL_CUDA(cudaFuncSetAttribute(score_pool_fused_kernel<kScore, kAlt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  MVAL_CUDA(cudaFuncSetAttribute(score_pool_fused_kernel<kScore, kRowArgmax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   const int64_t sms = num_sms();
   const int grid = (int)(n_frames < sms ? n_frames : sms);
-  score_pool_fused_kernel<kScore, kAlt><<<grid, kWarp * (1 + kD + kR), L.total, stream>>>(
+  score_pool_fused_kernel<kScore, kRowArgmax><<<grid, kWarp * (1 + kD + kR), L.total, stream>>>(
       hm, proj, valid, n_frames, V, J, H, HW, stride, stages, slots, prm.n_iters, prm.epsilon, prm.pair_seed, prm.frame_offset,
       out_xy, out_xyz, out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score);
   MVAL_LAUNCH_CHECK("score_pool_fused");
@@ -351,27 +360,26 @@ int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* 
                             int H, int W, int stride, const mval_ransac_params& prm, int map_score, int32_t* out_xy,
                             double* out_xyz, double* out_reproj, int32_t* out_inliers, double* out_metric,
                             int32_t* out_inlier_count, float* out_map_score, cudaStream_t stream) {
-  const char* alt_env = getenv("MVAL_FUSED_ALT");  // A/B measurements and tests only; read on every call
-  const int alt = (alt_env != nullptr && (alt_env[0] == '1' || alt_env[0] == '2')) ? alt_env[0] - '0' : 0;
 #define MVAL_FUSED_ARGS                                                                                               \
   hm, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz, out_reproj, out_inliers, out_metric,           \
       out_inlier_count, out_map_score, stream
-#define MVAL_FUSED_CASE(K)                                                 \
-  case K:                                                                  \
-    return alt == 1   ? launch_fused_variant<K, 1>(MVAL_FUSED_ARGS)        \
-           : alt == 2 ? launch_fused_variant<K, 2>(MVAL_FUSED_ARGS)        \
-                      : launch_fused_variant<K, 0>(MVAL_FUSED_ARGS)
   switch (map_score) {
-    case MVAL_MAP_SCORE_NONE:
-      return launch_fused_variant<MVAL_MAP_SCORE_NONE, 0>(hm, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz,
-                                                          out_reproj, out_inliers, out_metric, out_inlier_count, nullptr, stream);
-    MVAL_FUSED_CASE(MVAL_MAP_SCORE_HP);
-    MVAL_FUSED_CASE(MVAL_MAP_SCORE_MPE);
-    MVAL_FUSED_CASE(MVAL_MAP_SCORE_BSB);
+    case MVAL_MAP_SCORE_NONE: {
+      out_map_score = nullptr;
+      const char* off = getenv("MVAL_ROW_ARGMAX");  // "0": generic arg-max scan on 64 x 64 maps too (A/B, tests); read per call
+      if (H == kMapDim && W == kMapDim && !(off != nullptr && off[0] == '0'))
+        return launch_fused_variant<MVAL_MAP_SCORE_NONE, true>(MVAL_FUSED_ARGS);
+      return launch_fused_variant<MVAL_MAP_SCORE_NONE, false>(MVAL_FUSED_ARGS);
+    }
+    case MVAL_MAP_SCORE_HP:
+      return launch_fused_variant<MVAL_MAP_SCORE_HP, true>(MVAL_FUSED_ARGS);
+    case MVAL_MAP_SCORE_MPE:
+      return launch_fused_variant<MVAL_MAP_SCORE_MPE, true>(MVAL_FUSED_ARGS);
+    case MVAL_MAP_SCORE_BSB:
+      return launch_fused_variant<MVAL_MAP_SCORE_BSB, true>(MVAL_FUSED_ARGS);
     default:
       return MVAL_ERR_UNSUPPORTED;
   }
-#undef MVAL_FUSED_CASE
 #undef MVAL_FUSED_ARGS
 }
 

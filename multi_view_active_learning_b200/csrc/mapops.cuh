@@ -35,6 +35,71 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
+__device__ __forceinline__ uint32_t order_key(float x) {  // monotone float -> uint (no NaN handling needed here)
+  const uint32_t u = __float_as_uint(x);
+  return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float order_key_inv(uint32_t k) {
+  return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu));
+}
+__device__ __forceinline__ float warp_min_f(float v) { return order_key_inv(__reduce_min_sync(kFull, order_key(v))); }
+__device__ __forceinline__ float warp_max_f(float v) { return order_key_inv(__reduce_max_sync(kFull, order_key(v))); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-wise sweeps of a 64 x 64 map in shared memory with lane = row (rows `lane` and `lane + 32`): a lane pulls its
+// whole row into 64 registers, float4 column blocks in the rotated order (k + lane) % 16, which keeps every quarter-warp
+// on eight distinct 16-byte bank groups (conflict-free LDS.128).  Row statistics then need no shuffles at all.
+//
+// Arg-max on top of the row maxima (torch.argmax semantics: first index of the maximum, NaN is the maximum, -0.0 ==
+// +0.0): every lane keeps (largest row maximum, first row attaining it); afterwards one REDUX pair picks the first such
+// row of the map and half a warp re-reads that single row to find the first column.  0.75 instructions per element
+// (FMNMX3 pairs + a packed-add NaN / infinity sentinel) against 2.75 for the per-vector compare-and-select scan of
+// warp_argmax_map; a map whose sentinel fires (NaN, +-inf, or a sum that overflows) is re-scanned by warp_argmax_map
+// with its exact monotone-key compare, so the result is the same function of the map in every case.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_row_rotated(const float4* p4, int row, int lane, float4 (&x)[16]) {
+  const float4* rp = p4 + row * 16;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = rp[(k + lane) & 15];
+}
+__device__ __forceinline__ float row_max(const float4 (&x)[16]) {
+  float rm = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 16; k += 2)
+    rm = max3(rm, max3(x[k].x, x[k].y, x[k].z), max3(x[k].w, x[k + 1].x, max3(x[k + 1].y, x[k + 1].z, x[k + 1].w)));
+  return rm;
+}
+// (best, best_row) of every lane -> flat index of the first maximum of the map.  Only valid when the map holds no NaN.
+__device__ __forceinline__ uint32_t argmax_from_row_maxima(const float4* p4, int lane, float best, int best_row) {
+  const float top = warp_max_f(best + 0.0f);  // + 0.0f: -0.0 and +0.0 are the same maximum
+  const uint32_t row = __reduce_min_sync(kFull, best == top ? (uint32_t)best_row : 0xffffffffu);
+  const float4 w = p4[row * 16 + (lane & 15)];
+  const uint32_t c = w.x == top ? 0u : (w.y == top ? 1u : (w.z == top ? 2u : (w.w == top ? 3u : 0xffffu)));
+  const uint32_t col = __reduce_min_sync(kFull, c == 0xffffu ? 0xffffffffu : (uint32_t)(lane & 15) * 4u + c);
+  return row * (uint32_t)kMapDim + col;
+}
+__device__ __forceinline__ uint32_t warp_argmax_map64(const float* map, int lane) {
+  const float4* p4 = reinterpret_cast<const float4*>(map);
+  float best = -INFINITY;
+  int best_row = lane;
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int rr = 0; rr < 2; ++rr) {
+    const int row = lane + 32 * rr;
+    float4 x[16];
+    load_row_rotated(p4, row, lane, x);
+    const float rm = row_max(x);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = __fadd2_rn(acc, __fadd2_rn(make_float2(x[k].x, x[k].y), make_float2(x[k].z, x[k].w)));
+    const bool gt = rm > best;  // strict: the lower row is kept on ties
+    best = gt ? rm : best;
+    best_row = gt ? row : best_row;
+  }
+  const float sentinel = (acc.x + acc.y) * 0.0f;  // NaN as soon as the lane saw a NaN or an infinity
+  if (__any_sync(kFull, sentinel != sentinel))
+    return warp_argmax_map<8, true>([&](int q) { return p4[q]; }, kMapFloats / 4, lane, nullptr);
+  return argmax_from_row_maxima(p4, lane, best, best_row);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // soft-arg-max: softmax over the whole map, expectation of the pixel grid, times stride (kornia
@@ -98,9 +163,12 @@ struct SoftArgmaxOp {
 
 // ---------------------------------------------------------------------------------------------------------------
 // HP (strategy.py:1185-1186): 1 - max over the map of softmax(row); the row maximum of softmax(row) is 1 / S_r with
-// S_r = sum_c exp(x_rc - max_r), so the score is 1 - 1 / min_r S_r.  One LDS.128 covers two rows (16 lanes each); row
-// max / row sum are 16-lane butterflies; exp = ex2.approx of the exactly formed difference times log2e (the maximum
-// itself contributes exactly 1).  A NaN row (a NaN, an infinity or an all -inf row) poisons the map like torch's softmax.
+// S_r = sum_c exp(x_rc - max_r), so the score is 1 - 1 / min_r S_r.  Lane = row (see above): a row's maximum and its
+// S_r are formed in registers without a shuffle, in packed float32x2 arithmetic; exp = ex2.approx of the exactly formed
+// difference times log2e (the maximum itself contributes exactly 1); 3.5 instructions per pixel against 10 for the
+// 16-lanes-per-row butterflies of round 1e.  A NaN row (a NaN, an infinity or an all -inf row) poisons the map like
+// torch's softmax.  eval<true> also returns the arg-max of the map (the row maxima are already there), which is what
+// the decode warps of score_pool_fused_kernel<HP> use instead of a separate arg-max sweep.
 // ---------------------------------------------------------------------------------------------------------------
 struct HpOp {
   struct Args {
@@ -109,31 +177,51 @@ struct HpOp {
   using Pre = NoPrefetch;
   static constexpr bool kWritesSmem = false;
   __device__ static __forceinline__ Pre prefetch(int64_t, const Args&) { return {}; }
+  template <bool kArgmax>
+  __device__ static __forceinline__ uint32_t eval(const float* map, int64_t m, int lane, const Args& a) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float4* p4 = reinterpret_cast<const float4*>(map);
+    float min_s = INFINITY, best = -INFINITY;
+    int best_row = lane;
+    bool bad = false;
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = lane + 32 * rr;
+      float4 x[16];
+      load_row_rotated(p4, row, lane, x);
+      const float rm = row_max(x);
+      const float2 nrm = make_float2(-rm, -rm), l2e = make_float2(kLog2e, kLog2e);
+      float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float2 ta = __fmul2_rn(__fadd2_rn(make_float2(x[k].x, x[k].y), nrm), l2e);
+        const float2 tb = __fmul2_rn(__fadd2_rn(make_float2(x[k].z, x[k].w), nrm), l2e);
+        sa = __fadd2_rn(sa, make_float2(ex2_approx(ta.x), ex2_approx(ta.y)));
+        sb = __fadd2_rn(sb, make_float2(ex2_approx(tb.x), ex2_approx(tb.y)));
+      }
+      const float s = (sa.x + sa.y) + (sb.x + sb.y);
+      bad |= (s != s);
+      min_s = fminf(min_s, s);
+      if (kArgmax) {
+        const bool gt = rm > best;
+        best = gt ? rm : best;
+        best_row = gt ? row : best_row;
+      }
+    }
+    min_s = warp_min_f(min_s);
+    bad = __any_sync(kFull, bad);
+    if (lane == 0) a.out[m] = bad ? __int_as_float(0x7fc00000) : 1.0f - 1.0f / min_s;
+    if (!kArgmax) return 0u;
+    if (bad)  // warp-uniform; the map holds a NaN, an infinity or an all -inf row: exact monotone-key scan
+      return warp_argmax_map<8, true>([&](int q) { return p4[q]; }, kMapFloats / 4, lane, nullptr);
+    return argmax_from_row_maxima(p4, lane, best, best_row);
+  }
   __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*, const Pre&) {
     if (!ok) {
       if (lane == 0) a.out[m] = __int_as_float(0x7fc00000);
       return;
     }
-    constexpr float kLog2e = 1.4426950408889634f;
-    const float4* __restrict__ p = reinterpret_cast<const float4*>(map) + lane;
-    float min_s = INFINITY;
-    bool bad = false;
-#pragma unroll 8
-    for (int t = 0; t < 32; ++t) {
-      const float4 x = p[t * 32];
-      float rm = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(kFull, rm, o));
-      float rs = (ex2_approx((x.x - rm) * kLog2e) + ex2_approx((x.y - rm) * kLog2e)) +
-                 (ex2_approx((x.z - rm) * kLog2e) + ex2_approx((x.w - rm) * kLog2e));
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(kFull, rs, o);
-      bad |= (rs != rs);
-      min_s = fminf(min_s, rs);
-    }
-    min_s = fminf(min_s, __shfl_xor_sync(kFull, min_s, 16));
-    bad = __any_sync(kFull, bad);
-    if (lane == 0) a.out[m] = bad ? __int_as_float(0x7fc00000) : 1.0f - 1.0f / min_s;
+    eval<false>(map, m, lane, a);
   }
 };
 
@@ -164,16 +252,6 @@ struct HpOp {
 // STS.128).  exp = ex2.approx of the exactly formed difference times log2e (the row maximum contributes exactly 1), the
 // quotient is e * (1/s) corrected by one residual step.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t order_key(float x) {  // monotone float -> uint (no NaN handling needed here)
-  const uint32_t u = __float_as_uint(x);
-  return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
-}
-__device__ __forceinline__ float order_key_inv(uint32_t k) {
-  return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu));
-}
-__device__ __forceinline__ float warp_min_f(float v) { return order_key_inv(__reduce_min_sync(kFull, order_key(v))); }
-__device__ __forceinline__ float warp_max_f(float v) { return order_key_inv(__reduce_max_sync(kFull, order_key(v))); }
-
 template <int kMode>
 struct PeaksOp {
   struct Args {

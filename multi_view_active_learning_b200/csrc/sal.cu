@@ -62,7 +62,7 @@ sal_key_kernel(const float* __restrict__ sal_metric, const float* __restrict__ i
   key[i] = keep ? (-(double)m + 0.0) : __longlong_as_double(0x7ff8000000000000ll);
 }
 
-// strategy.py:981-985: cluster_id = self.kmeans.predict([kp])[0] with kp the root-relative pose of the frame (float64
+// strategy.py:981-989: cluster_id = self.kmeans.predict([kp])[0] with kp the root-relative pose of the frame (float64
 // differences of the float32 predictions, x_0..x_{J-1}, y.., z..), one sklearn call per candidate in the reference.
 // sklearn's predict is argmin_c (|c|^2 - 2 x.c) in float64, first centre on ties (lloyd_iter_chunked_dense with
 // update_centers=False).  One thread per frame; the dot product is a sequential float64 fma chain, so it can differ

@@ -276,7 +276,7 @@ def mkpe(pred, gt, valid):
 
 
 def kmeans_assign(pred, centres, root):
-    """strategy.py:981-985 for a whole pool: pred float32 CUDA [N, J, 3] (sal_dict["pred_3d_keypoints"]), centres float64
+    """strategy.py:981-989 for a whole pool: pred float32 CUDA [N, J, 3] (sal_dict["pred_3d_keypoints"]), centres float64
     [k, 3 J] (kmeans.cluster_centers_) -> (label int32 [N], margin float64 [N]); see include/mval_b200.h."""
     p = _cuda(pred, torch.float32, "pred")
     N, J, _ = p.shape

@@ -95,7 +95,7 @@ class ScoringSelectionMixin:
         return train_dataset, al_guids, sal_sampled_guids, sal_dict
 
     def _cluster_ids(self, pred_3d_keypoints, guids, margin_rtol=1e-9):
-        """strategy.py:981-985 ``self.kmeans.predict([kp])[0]`` for every candidate at once (mval_kmeans_assign).  The
+        """strategy.py:981-989 ``self.kmeans.predict([kp])[0]`` for every candidate at once (mval_kmeans_assign).  The
         device evaluates sklearn's predict rule in float64; a frame whose two best centres are closer than rounding
         could separate (relative margin <= margin_rtol; also NaN) is handed to sklearn itself, literally as the
         reference does, so the labels are the reference's."""
@@ -165,7 +165,8 @@ class ScoringSelectionMixin:
             config = {"HP": cfg.HP_CONFIG, "MPE": cfg.MPE_CONFIG, "BSB": cfg.BSB_CONFIG}[cfg.STRATEGY]
             # tri["map_score"]: the per-map scores the fused pass already produced next to the triangulation
             vals = self._compute_map_score_batch(cfg.STRATEGY, config, heatmaps, joint_valid, tri.get("map_score"))
-            return np.asarray(vals, dtype=np.float64), config == "STD"
+            # torch.tensor(...) of the reference: float64 only for HP's np.std of Python floats (:1081-1085)
+            return np.asarray(vals, dtype=np.float64), config == "STD" and cfg.STRATEGY == "HP"
         raise NotImplementedError()
 
     @staticmethod
@@ -178,19 +179,23 @@ class ScoringSelectionMixin:
             valid = valid.unsqueeze(0).expand(heatmaps.shape[0], -1)
         if per_map is None:
             per_map = ops.score_hp(heatmaps, valid) if kind == "HP" else ops.score_peaks(heatmaps, kind, valid)
-        per_map = per_map.cpu().numpy().astype(np.float64)  # [B, V, J], NaN for invalid joints
+        per_map = per_map.cpu().numpy()  # float32 [B, V, J], NaN for invalid joints
         v = valid.cpu().numpy()
         out = []
         for b in range(per_map.shape[0]):
-            vals = per_map[b][:, v[b]].reshape(-1)
-            if config == "AVG":
-                out.append(sum(vals.tolist()) / len(vals))
-            elif config == "STD":
-                out.append(np.std(vals))
-            elif kind == "MPE":
-                raise NotImplementedError("AL.MPE_CONFIG should be either AVG or STD.")  # reference :1157-1158
-            else:
+            vals = per_map[b][:, v[b]].reshape(-1)  # view-major, like the reference's loops
+            if config not in ("AVG", "STD"):
+                if kind == "MPE":
+                    raise NotImplementedError("AL.MPE_CONFIG should be either AVG or STD.")  # reference :1157-1158
                 out.append(None)  # the reference falls off the end of _compute_hp / _compute_bsb and returns None
+            elif kind == "HP":
+                # :1186-1193: the per-map values are Python floats (.item()): double sum / len, np.std of float64
+                vals = vals.astype(np.float64)
+                out.append(sum(vals.tolist()) / len(vals) if config == "AVG" else np.std(vals))
+            else:
+                # :1151-1158, :1210-1215: np.float32 scalars: Python sum() adds them one by one in float32; np.std of a
+                # float32 array is a float32 (NumPy >= 2 promotion)
+                out.append(sum(list(vals)) / len(vals) if config == "AVG" else np.std(vals))
         return out
 
     def _one_frame(self, kind, config, heatmaps, joint_valid):

@@ -166,6 +166,51 @@ def case_hp(st):
     print("hp_scores", res)
 
 
+def case_peaks(st):
+    """_compute_mpe / _compute_mpes / _compute_bsb of the unmodified reference (strategy.py:1149-1176, 1195-1215) with the
+    one call it makes into scikit-image -- peak_local_max(map, min_distance=2, indices=True[, num_peaks=2]), skimage <= 0.19,
+    not installable here -- served by the restatement in oracle/scores_oracle.py.  This pins everything the reference
+    itself does around the peaks (which values are read, the float32 softmax over them, math.log, the order of the two
+    best peaks, AVG / STD, the joint_valid skip); the peak finder alone stays "parity unpinned"."""
+    from oracle import scores_oracle as SO
+
+    rng = np.random.default_rng(15)
+    V, J = 2, 4
+    centres = rng.uniform(6, 58, size=(V, J, 2)).astype(np.float32)
+    hm = S.render_heatmaps(centres, noise=0.05, seed=16) * np.float32(3.0)
+    second = S.render_heatmaps(rng.uniform(6, 58, size=(V, J, 2)).astype(np.float32), noise=0.0, seed=0) * np.float32(1.5)
+    hm = (hm + second).astype(np.float32)  # two bumps per map + noise: several local peaks everywhere
+    valid = np.array([1, 0, 1, 1], dtype=np.float32)
+
+    def served_peaks(image, min_distance=1, indices=True, num_peaks=np.inf, **kw):
+        assert indices is True and not kw
+        return SO.peak_local_max(image, min_distance=min_distance, num_peaks=num_peaks)
+
+    st.peak_local_max = served_peaks
+
+    class NS:
+        pass
+
+    self_ = NS()
+    self_.al_cfg = NS()
+    self_.al_cfg.AL = NS()
+    self_._compute_mpes = lambda h, v: st.ActiveLearningStrategy._compute_mpes(self_, h, v)
+    import warnings
+
+    res = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ents = st.ActiveLearningStrategy._compute_mpes(self_, torch.from_numpy(hm), torch.from_numpy(valid))
+        for cfg in ("AVG", "STD"):
+            self_.al_cfg.AL.MPE_CONFIG = self_.al_cfg.AL.BSB_CONFIG = cfg
+            res["mpe_" + cfg] = st.ActiveLearningStrategy._compute_mpe(self_, torch.from_numpy(hm), torch.from_numpy(valid))
+            res["bsb_" + cfg] = st.ActiveLearningStrategy._compute_bsb(self_, torch.from_numpy(hm), torch.from_numpy(valid))
+    np.savez_compressed(os.path.join(OUT, "peak_scores.npz"), heatmaps=hm, valid=valid,
+                        mpe_per_map=np.array(ents, dtype=np.float64), numpy_version=np.__version__,
+                        **{k: np.float64(v) for k, v in res.items()})
+    print("peak_scores", res, "n maps", len(ents))
+
+
 def case_coreset(cs):
     import uuid
 
@@ -230,6 +275,7 @@ def main():
     case_huber(tri)
     case_decode(ev)
     case_hp(st)
+    case_peaks(st)
     case_coreset(cs)
     case_xe(tri)
 

@@ -92,27 +92,31 @@ def peak_local_max(image, min_distance=2, num_peaks=np.inf):
 
 
 def mpe_scores(heatmaps):
-    """[..., H, W] float32 -> float32 [...]: entropy of softmax over the local-peak values (strategy.py:1168-1175);
-    a map without peaks scores 0 (sum over an empty list)."""
+    """[..., H, W] float32 -> float32 [...]: entropy of softmax over the local-peak values, with the reference's own
+    arithmetic (strategy.py:1168-1175): peaks in peak_local_max order (descending intensity), np.exp of the float32
+    values without a shift, Python sum() over float32 elements (sequential float32 adds), math.log in double, the
+    products and their sum in float32 again (NumPy >= 2 promotion: np.float32 * Python float stays float32).  A map
+    without peaks scores 0 (sum over an empty list).  Pinned against the reference in tests/golden/peak_scores.npz."""
     hm = np.asarray(heatmaps, dtype=np.float32)
     out = np.zeros(hm.shape[:-2], dtype=np.float32)
     for idx in np.ndindex(*hm.shape[:-2]):
         pk = peak_local_max(hm[idx], min_distance=2)
-        if len(pk) == 0:
-            continue
-        v = hm[idx][pk[:, 0], pk[:, 1]].astype(np.float64)
-        p = np.exp(v - v.max())
-        p /= p.sum()
-        out[idx] = np.float32(-(p * np.log(p)).sum())
+        peaks = [hm[idx][c[0]][c[1]] for c in pk]
+        with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+            e = np.exp(np.asarray(peaks, dtype=np.float32))
+            probs = e / sum(e)
+        out[idx] = sum(-p * math.log(p) for p in probs)
     return out
 
 
 def bsb_scores(heatmaps):
     """[..., H, W] float32 -> float32 [...]: |p0 - p1| of the two highest local peaks of the ROW-softmaxed map
-    (strategy.py:1202-1208); NaN where the map has fewer than two peaks (the reference raises IndexError there)."""
-    hm = np.asarray(heatmaps, dtype=np.float32)
-    e = np.exp(hm - hm.max(axis=-1, keepdims=True))
-    sm = (e / e.sum(axis=-1, keepdims=True, dtype=np.float32)).astype(np.float32)
+    (strategy.py:1202-1208; F.softmax without dim on a 2-D tensor = dim 1, evaluated with torch like the reference);
+    NaN where the map has fewer than two peaks (the reference raises IndexError there)."""
+    import torch
+
+    hm = np.ascontiguousarray(np.asarray(heatmaps, dtype=np.float32))
+    sm = torch.softmax(torch.from_numpy(hm), dim=-1).numpy()
     out = np.full(hm.shape[:-2], np.nan, dtype=np.float32)
     for idx in np.ndindex(*hm.shape[:-2]):
         pk = peak_local_max(sm[idx], min_distance=2, num_peaks=2)
@@ -121,10 +125,16 @@ def bsb_scores(heatmaps):
     return out
 
 
-def reduce_frame_score(per_map, joint_valid, config="AVG"):
-    """per_map [V, J] -> AVG (Python float sum / len) or STD (np.std) over (view, valid joint), reference
-    :1151-1158, :1188-1193, :1210-1215."""
-    vals = [float(per_map[v, k]) for v in range(per_map.shape[0]) for k in range(per_map.shape[1]) if joint_valid[k]]
+def reduce_frame_score(per_map, joint_valid, config="AVG", kind="HP"):
+    """per_map [V, J] -> the frame score over (view, valid joint), view-major, as the reference forms it:
+      HP       the per-map values are Python floats (.item()): AVG = sum(x) / len(x) in double, STD = np.std of a float64
+               array (:1188-1193);
+      MPE/BSB  the per-map values are np.float32 scalars: AVG = Python sum() = sequential float32 adds, / len in float32;
+               STD = np.std of a float32 array, a float32 (:1151-1158, :1210-1215; NumPy >= 2 promotion rules)."""
+    if kind == "HP":
+        vals = [float(per_map[v, k]) for v in range(per_map.shape[0]) for k in range(per_map.shape[1]) if joint_valid[k]]
+    else:
+        vals = [np.float32(per_map[v, k]) for v in range(per_map.shape[0]) for k in range(per_map.shape[1]) if joint_valid[k]]
     if config == "AVG":
         return sum(vals) / len(vals)
     if config == "STD":

@@ -106,6 +106,22 @@ def test_hp_scores(ops, golden):
     np.testing.assert_allclose(ops.score_hp(_cuda(hm)).cpu().numpy(), SO.hp_scores(hm), rtol=0, atol=2e-6)
 
 
+def test_mpe_bsb_scores_vs_reference_golden(ops, golden):
+    """Kernels against what the unmodified reference's _compute_mpes / _compute_bsb returned for tests/golden/
+    peak_scores.npz (skimage's peak finder served by the restatement, everything else the reference's own code)."""
+    g = golden("peak_scores")
+    hm, valid = g["heatmaps"], g["valid"].astype(bool)
+    V, J = hm.shape[:2]
+    mpe = ops.score_peaks(_cuda(hm[None]), "MPE", torch.from_numpy(valid)).cpu().numpy()[0]
+    got = np.array([mpe[v, k] for v in range(V) for k in range(J) if valid[k]], dtype=np.float64)
+    np.testing.assert_allclose(got, g["mpe_per_map"], rtol=0, atol=2e-5)
+    assert np.isnan(mpe[:, ~valid]).all()
+    bsb = ops.score_peaks(_cuda(hm[None]), "BSB", torch.from_numpy(valid)).cpu().numpy()[0]
+    for cfg, tol in (("AVG", 2e-6), ("STD", 2e-6)):
+        assert abs(float(SO.reduce_frame_score(bsb, valid, cfg, "BSB")) - float(g["bsb_" + cfg])) <= tol
+        assert abs(float(SO.reduce_frame_score(mpe, valid, cfg, "MPE")) - float(g["mpe_" + cfg])) <= 2e-5
+
+
 def test_mpe_bsb_scores_vs_restatement(ops):
     """MPE / BSB against the scipy restatement of skimage.peak_local_max (parity unpinned: skimage is not installed).
     Tolerance: float32 softmax / entropy of ~130 peak values -> 2e-5 absolute."""
@@ -539,21 +555,22 @@ def _with_env(name, value, fn):
 
 @pytest.mark.parametrize("N,V,J,vp", [(1500, 8, 19, 1.0), (700, 5, 19, 0.8), (300, 20, 42, 0.8), (200, 31, 19, 1.0),
                                       (333, 2, 3, 0.7), (5, 8, 19, 0.9)])
-@pytest.mark.parametrize("alt", ["0", "1", "2"])
-def test_fused_scored_pass_equals_separate_passes(ops, N, V, J, vp, alt):
+def test_fused_scored_pass_equals_separate_passes(ops, N, V, J, vp):
     """mval_score_pool_scored: the decode warps of the fused kernel evaluate HP / MPE / BSB on the staged map right after
     its arg-max (one pass over the pool instead of two).  Every triangulation output must be bit-identical to the
     unscored fused pass and the per-map scores must equal those of mval_score_hp / mval_score_peaks (same device code:
-    bit-identical), for all three warp budgets (MVAL_FUSED_ALT), several ring rounds per SM, invalid joints, 2 and 4 frame
-    slots, and C(V,2) > 64."""
+    bit-identical), over several ring rounds per SM, invalid joints, 2 and 4 frame slots, and C(V,2) > 64.  The
+    unscored pass is also run with the generic arg-max scan (MVAL_ROW_ARGMAX=0) in place of the lane = row sweep."""
     pool = S.make_pool(N, V, J, seed=N + V, valid_prob=vp, p_outlier=0.15)
     hm = ops.synth_heatmaps(_cuda(pool["centres"]), noise=0.05, seed=11)
     P, valid = _cuda(pool["P"]), torch.from_numpy(pool["valid"])
     v = np.broadcast_to(pool["valid"][:, None, :], (N, V, J))
     plain = ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345)
+    scan = _with_env("MVAL_ROW_ARGMAX", "0", lambda: ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345))
+    assert torch.equal(plain["keypoints_2d"], scan["keypoints_2d"]) and torch.equal(plain["keypoints_3d"], scan["keypoints_3d"])
+    assert torch.equal(plain["keypoints_2d"], ops.decode_argmax(hm, 4, valid))
     for kind in ("HP", "MPE", "BSB"):
-        both = _with_env("MVAL_FUSED_ALT", alt, lambda: ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345,
-                                                                       map_score=kind))
+        both = ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345, map_score=kind)
         for k in ("keypoints_2d", "keypoints_3d", "inliers", "inlier_count"):
             assert torch.equal(both[k], plain[k]), (kind, k)
         for k in ("metric", "reproj_mean"):
@@ -563,6 +580,34 @@ def test_fused_scored_pass_equals_separate_passes(ops, N, V, J, vp, alt):
         assert got.shape == (N, V, J)
         assert np.isnan(got[~v]).all() and np.array_equal(np.isnan(got), np.isnan(sep)), kind
         assert np.array_equal(got[v], sep[v]), (kind, np.nanmax(np.abs(got[v] - sep[v])))
+
+
+def test_fused_argmax_on_reference_decode_edge_cases(ops, golden):
+    """The arg-max of the fused pass (lane = row sweep; HP variant: row maxima of the softmax sweep) on the maps of
+    tests/golden/decode_edge_cases.npz -- ties (first index wins), NaN (counts as the maximum), +-inf, -0.0 vs +0.0,
+    invalid joints -- against what the unmodified reference's get_scaled_pred_corrdinates returned."""
+    g = golden("decode_edge_cases")
+    hm = _cuda(np.stack([g["heatmaps"], g["heatmaps"][::-1]]))  # [2 frames, 3 views, 5 joints, 64, 64]
+    P = _cuda(S.make_pool(2, 3, 5, seed=9)["P"])
+    exp = np.stack([g["scaled"], g["scaled"][::-1]])
+    exp_all = np.stack([g["scaled_all_valid"], g["scaled_all_valid"][::-1]])
+    valid = torch.from_numpy(g["valid"])
+    for kind in (None, "HP", "MPE", "BSB"):
+        assert np.array_equal(ops.score_pool(hm, P, int(g["stride"]), valid, map_score=kind)["keypoints_2d"].cpu().numpy(), exp), kind
+        assert np.array_equal(ops.score_pool(hm, P, int(g["stride"]), None, map_score=kind)["keypoints_2d"].cpu().numpy(), exp_all), kind
+    # ties across the two rows of one lane (rows r and r + 32), across lanes, and inside one row; -0.0 before +0.0
+    t = np.full((1, 2, 4, 64, 64), -1.0, dtype=np.float32)
+    t[0, :, 0, 40, 7] = t[0, :, 0, 8, 9] = t[0, :, 0, 8, 50] = 2.0    # rows 8 and 40 belong to lane 8: first is (8, 9)
+    t[0, :, 1, 63, 63] = t[0, :, 1, 31, 0] = 5.0                       # lanes 31 (row 63) and 31 (row 31): row 31 first
+    t[0, :, 2] = -0.0
+    t[0, :, 2, 3, 3] = 0.0                                             # all zeros of either sign: index 0 wins
+    t[0, :, 3, 0, 1] = t[0, :, 3, 0, 0] = 7.0
+    Pt = _cuda(S.make_pool(1, 2, 4, seed=10)["P"])
+    want = np.array([[9, 8], [0, 31], [0, 0], [0, 0]]) * 4
+    for kind in (None, "HP", "MPE", "BSB"):
+        got = ops.score_pool(_cuda(t), Pt, 4, None, map_score=kind)["keypoints_2d"].cpu().numpy()
+        assert np.array_equal(got[0, 0], want) and np.array_equal(got[0, 1], want), kind
+    assert np.array_equal(ops.decode_argmax(_cuda(t), 4).cpu().numpy()[0, 0], want)
 
 
 def test_fused_scored_pass_edge_cases(ops):
@@ -581,6 +626,10 @@ def test_fused_scored_pass_edge_cases(ops):
     valid[2, 0] = False
     g = _cuda(hm)
     plain = ops.score_pool(g, P, 4, valid)
+    # the lane = row arg-max sweep falls back to the exact scan on maps with NaN / infinities: same key-points as the
+    # stand-alone decode kernel and as the generic scan
+    assert torch.equal(plain["keypoints_2d"], ops.decode_argmax(g, 4, valid))
+    assert torch.equal(plain["keypoints_2d"], _with_env("MVAL_ROW_ARGMAX", "0", lambda: ops.score_pool(g, P, 4, valid))["keypoints_2d"])
     for kind in ("HP", "MPE", "BSB"):
         both = ops.score_pool(g, P, 4, valid, map_score=kind)
         assert torch.equal(both["keypoints_2d"], plain["keypoints_2d"]), kind
@@ -591,7 +640,7 @@ def test_fused_scored_pass_edge_cases(ops):
         assert np.array_equal(np.isnan(got), np.isnan(sep)), kind
         assert np.array_equal(got[~np.isnan(got)], sep[~np.isnan(sep)]), kind
         assert np.isnan(got[2, :, 0]).all()  # invalid joint
-        if kind != "MPE":
+        if kind == "HP":  # a NaN / an infinity poisons every row softmax it takes part in
             assert np.isnan(got[0, :, 1]).all() and np.isnan(got[0, :, 2]).all()
         empty = ops.score_pool(g[:0], P[:0], 4, map_score=kind)
         assert empty["map_score"].shape == (0, 2, 6) and empty["metric"].numel() == 0

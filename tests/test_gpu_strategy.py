@@ -89,7 +89,7 @@ def reference_emulation(ds, cfg):
         elif cfg.AL.STRATEGY in ("MPE", "BSB"):
             per_map = (SO.mpe_scores if cfg.AL.STRATEGY == "MPE" else SO.bsb_scores)(ds.hm[i])
             config = cfg.AL.MPE_CONFIG if cfg.AL.STRATEGY == "MPE" else cfg.AL.BSB_CONFIG
-            m = SO.reduce_frame_score(per_map, ds.pool["valid"][i], config)
+            m = SO.reduce_frame_score(per_map, ds.pool["valid"][i], config, cfg.AL.STRATEGY)
             sal["al_metric"][guid] = float(np.float32(m)) if config == "AVG" else float(m)
         else:
             sal["al_metric"][guid] = 0.0
@@ -209,7 +209,7 @@ def test_sal_rank_mkpe_and_pose_features_kernels():
 
 
 def test_kmeans_assign_matches_sklearn_predict():
-    """mval_kmeans_assign against the reference's per-candidate call self.kmeans.predict([kp])[0] (strategy.py:981-985):
+    """mval_kmeans_assign against the reference's per-candidate call self.kmeans.predict([kp])[0] (strategy.py:981-989):
     identical labels, margins >= 0, duplicated centres resolve to the first one."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")

@@ -76,6 +76,22 @@ def test_hp_scores(golden):
     np.testing.assert_allclose(SC.hp_metric(g["heatmaps"], g["valid"], "STD"), float(g["hp_std"]), atol=2e-6)
 
 
+def test_peak_scores_match_reference(golden):
+    """MPE / BSB: the oracle against the unmodified reference's _compute_mpes / _compute_mpe / _compute_bsb
+    (strategy.py:1149-1176, 1195-1215) run with the restated peak finder standing in for skimage (oracle/make_golden.py:
+    case_peaks) -- bit for bit, per map and per frame, AVG and STD."""
+    g = golden("peak_scores")
+    hm, valid = g["heatmaps"], g["valid"].astype(bool)
+    mpe, bsb = SC.mpe_scores(hm), SC.bsb_scores(hm)
+    ents = [mpe[v, k] for v in range(hm.shape[0]) for k in range(hm.shape[1]) if valid[k]]
+    assert np.array_equal(np.asarray(ents, dtype=np.float64), g["mpe_per_map"])
+    assert len(ents) == 6 and min(ents) > 1.0  # several peaks per map: the entropy is far from 0
+    for cfg in ("AVG", "STD"):
+        assert float(SC.reduce_frame_score(mpe, valid, cfg, "MPE")) == float(g["mpe_" + cfg])
+        assert float(SC.reduce_frame_score(bsb, valid, cfg, "BSB")) == float(g["bsb_" + cfg])
+    assert isinstance(SC.reduce_frame_score(mpe, valid, "AVG", "MPE"), np.float32)
+
+
 def test_coreset_matches_reference(golden):
     g = golden("coreset_random")
     F = C.stacked_features(g["sal_poses"], g["al_poses"], int(g["root"]))

@@ -62,3 +62,35 @@ def test_al_experiment_writes_no_sal_guid_file(tmp_path):
     open(os.path.join(run, "SAMPLED-GUID-ITER-0"), "w").write(json.dumps(["160422-0"]))
     st.restore_dataset(ds, 2)
     assert ds.pseudo_label_guids == [] and len(ds.labeled_data) == 2
+
+
+def test_frame_aggregation_of_precomputed_map_scores():
+    """_compute_map_score_batch with the per-map scores the fused pass already produced (no kernel call): AVG is the
+    reference's Python sum(x) / len(x) and STD its np.std over (view, valid joint), view-major (strategy.py:1151-1158,
+    1188-1193, 1210-1215); a [J] validity vector applies to every frame."""
+    import numpy as np
+    import pytest
+    import torch
+
+    from multi_view_active_learning_b200.strategy import ScoringSelectionMixin as M
+    from oracle import scores_oracle as SO
+
+    rng = np.random.default_rng(5)
+    B, V, J = 4, 5, 7
+    scores = rng.random((B, V, J)).astype(np.float32)
+    valid = rng.random((B, J)) < 0.7
+    valid[:, 0] = True
+    per_map = torch.from_numpy(np.where(valid[:, None, :], scores, np.nan).astype(np.float32))
+    hm = torch.zeros(B, V, J, 1, 1)  # only its batch size is looked at when per_map is given
+    for kind in ("HP", "MPE", "BSB"):
+        for config in ("AVG", "STD"):
+            got = M._compute_map_score_batch(kind, config, hm, torch.from_numpy(valid), per_map)
+            exp = [SO.reduce_frame_score(scores[b], valid[b], config, kind) for b in range(B)]
+            assert [float(g) for g in got] == [float(e) for e in exp]
+            # HP aggregates Python floats in double; MPE / BSB aggregate np.float32 scalars in float32 (NumPy >= 2)
+            assert all(isinstance(g, np.float32) for g in got) == (kind != "HP")
+    one = M._compute_map_score_batch("BSB", "AVG", hm, torch.from_numpy(valid[0]), torch.from_numpy(scores))
+    assert [float(g) for g in one] == [float(SO.reduce_frame_score(scores[b], valid[0], "AVG", "BSB")) for b in range(B)]
+    assert M._compute_map_score_batch("HP", "MEDIAN", hm, torch.from_numpy(valid), per_map) == [None] * B
+    with pytest.raises(NotImplementedError):
+        M._compute_map_score_batch("MPE", "MEDIAN", hm, torch.from_numpy(valid), per_map)
