@@ -787,9 +787,19 @@ def run_scores(args):
     for kind in ("HP", "MPE", "BSB"):
         kernels["score_pool_fused_kernel<%s> (a1+a4..a8)" % kind] = (
             lambda kind=kind: ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False, map_score=kind))
-    kernels["score_pool_fused_kernel, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = (
-        lambda: (os.environ.__setitem__("MVAL_ROW_ARGMAX", "0"), ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False),
-                 os.environ.__setitem__("MVAL_ROW_ARGMAX", "1")))
+    # arg-max flavour A/B (csrc/fused.cu: launch_score_pool_fused): the non-default flavour of each variant
+    def flavoured(value, kind):
+        def run():
+            os.environ["MVAL_ROW_ARGMAX"] = value
+            try:
+                return ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False, map_score=kind)
+            finally:
+                del os.environ["MVAL_ROW_ARGMAX"]
+        return run
+
+    kernels["score_pool_fused_kernel, lane=row arg-max (MVAL_ROW_ARGMAX=1)"] = flavoured("1", None)
+    kernels["score_pool_fused_kernel<MPE>, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = flavoured("0", "MPE")
+    kernels["score_pool_fused_kernel<BSB>, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = flavoured("0", "BSB")
     if args.scores_only:
         kernels = {k: f for k, f in kernels.items() if args.scores_only in k}
     out = {}

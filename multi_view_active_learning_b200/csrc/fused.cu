@@ -363,19 +363,25 @@ int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* 
 #define MVAL_FUSED_ARGS                                                                                               \
   hm, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz, out_reproj, out_inliers, out_metric,           \
       out_inlier_count, out_map_score, stream
+  // Arg-max flavour on 64 x 64 maps.  Measured (profiles/r1f_summary.md): the unscored pass is faster with the generic
+  // per-vector scan (5.78 against 6.06 ms per 16 384 frames: its six decode warps are latency-, not issue-bound), the
+  // MPE / BSB passes are issue-bound and take the lane = row sweep (170 instead of 400 instructions per map).
+  // MVAL_ROW_ARGMAX = 0 / 1 forces one flavour everywhere (A/B measurements and tests; read on every call).
+  const char* env = getenv("MVAL_ROW_ARGMAX");
+  const int force = (env != nullptr && (env[0] == '0' || env[0] == '1')) ? env[0] - '0' : -1;
+  const bool is64 = H == kMapDim && W == kMapDim;
   switch (map_score) {
-    case MVAL_MAP_SCORE_NONE: {
+    case MVAL_MAP_SCORE_NONE:
       out_map_score = nullptr;
-      const char* off = getenv("MVAL_ROW_ARGMAX");  // "0": generic arg-max scan on 64 x 64 maps too (A/B, tests); read per call
-      if (H == kMapDim && W == kMapDim && !(off != nullptr && off[0] == '0'))
-        return launch_fused_variant<MVAL_MAP_SCORE_NONE, true>(MVAL_FUSED_ARGS);
+      if (is64 && force == 1) return launch_fused_variant<MVAL_MAP_SCORE_NONE, true>(MVAL_FUSED_ARGS);
       return launch_fused_variant<MVAL_MAP_SCORE_NONE, false>(MVAL_FUSED_ARGS);
-    }
-    case MVAL_MAP_SCORE_HP:
+    case MVAL_MAP_SCORE_HP:  // the arg-max is a by-product of HP's own row sweep
       return launch_fused_variant<MVAL_MAP_SCORE_HP, true>(MVAL_FUSED_ARGS);
     case MVAL_MAP_SCORE_MPE:
+      if (force == 0) return launch_fused_variant<MVAL_MAP_SCORE_MPE, false>(MVAL_FUSED_ARGS);
       return launch_fused_variant<MVAL_MAP_SCORE_MPE, true>(MVAL_FUSED_ARGS);
     case MVAL_MAP_SCORE_BSB:
+      if (force == 0) return launch_fused_variant<MVAL_MAP_SCORE_BSB, false>(MVAL_FUSED_ARGS);
       return launch_fused_variant<MVAL_MAP_SCORE_BSB, true>(MVAL_FUSED_ARGS);
     default:
       return MVAL_ERR_UNSUPPORTED;

@@ -560,17 +560,18 @@ def test_fused_scored_pass_equals_separate_passes(ops, N, V, J, vp):
     its arg-max (one pass over the pool instead of two).  Every triangulation output must be bit-identical to the
     unscored fused pass and the per-map scores must equal those of mval_score_hp / mval_score_peaks (same device code:
     bit-identical), over several ring rounds per SM, invalid joints, 2 and 4 frame slots, and C(V,2) > 64.  The
-    unscored pass is also run with the generic arg-max scan (MVAL_ROW_ARGMAX=0) in place of the lane = row sweep."""
+    passes are run with both arg-max flavours (MVAL_ROW_ARGMAX: generic per-vector scan / lane = row sweep)."""
     pool = S.make_pool(N, V, J, seed=N + V, valid_prob=vp, p_outlier=0.15)
     hm = ops.synth_heatmaps(_cuda(pool["centres"]), noise=0.05, seed=11)
     P, valid = _cuda(pool["P"]), torch.from_numpy(pool["valid"])
     v = np.broadcast_to(pool["valid"][:, None, :], (N, V, J))
     plain = ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345)
-    scan = _with_env("MVAL_ROW_ARGMAX", "0", lambda: ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345))
-    assert torch.equal(plain["keypoints_2d"], scan["keypoints_2d"]) and torch.equal(plain["keypoints_3d"], scan["keypoints_3d"])
+    rows = _with_env("MVAL_ROW_ARGMAX", "1", lambda: ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345))
+    assert torch.equal(plain["keypoints_2d"], rows["keypoints_2d"]) and torch.equal(plain["keypoints_3d"], rows["keypoints_3d"])
     assert torch.equal(plain["keypoints_2d"], ops.decode_argmax(hm, 4, valid))
-    for kind in ("HP", "MPE", "BSB"):
-        both = ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345, map_score=kind)
+    for kind, flavour in (("HP", "1"), ("MPE", "0"), ("MPE", "1"), ("BSB", "0"), ("BSB", "1")):
+        both = _with_env("MVAL_ROW_ARGMAX", flavour, lambda: ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345,
+                                                                            map_score=kind))
         for k in ("keypoints_2d", "keypoints_3d", "inliers", "inlier_count"):
             assert torch.equal(both[k], plain[k]), (kind, k)
         for k in ("metric", "reproj_mean"):
@@ -592,9 +593,10 @@ def test_fused_argmax_on_reference_decode_edge_cases(ops, golden):
     exp = np.stack([g["scaled"], g["scaled"][::-1]])
     exp_all = np.stack([g["scaled_all_valid"], g["scaled_all_valid"][::-1]])
     valid = torch.from_numpy(g["valid"])
-    for kind in (None, "HP", "MPE", "BSB"):
-        assert np.array_equal(ops.score_pool(hm, P, int(g["stride"]), valid, map_score=kind)["keypoints_2d"].cpu().numpy(), exp), kind
-        assert np.array_equal(ops.score_pool(hm, P, int(g["stride"]), None, map_score=kind)["keypoints_2d"].cpu().numpy(), exp_all), kind
+    for kind, flavour in ((None, "0"), (None, "1"), ("HP", "1"), ("MPE", "0"), ("MPE", "1"), ("BSB", "0"), ("BSB", "1")):
+        run = lambda v: _with_env("MVAL_ROW_ARGMAX", flavour, lambda: ops.score_pool(hm, P, int(g["stride"]), v, map_score=kind))
+        assert np.array_equal(run(valid)["keypoints_2d"].cpu().numpy(), exp), (kind, flavour)
+        assert np.array_equal(run(None)["keypoints_2d"].cpu().numpy(), exp_all), (kind, flavour)
     # ties across the two rows of one lane (rows r and r + 32), across lanes, and inside one row; -0.0 before +0.0
     t = np.full((1, 2, 4, 64, 64), -1.0, dtype=np.float32)
     t[0, :, 0, 40, 7] = t[0, :, 0, 8, 9] = t[0, :, 0, 8, 50] = 2.0    # rows 8 and 40 belong to lane 8: first is (8, 9)
@@ -604,9 +606,10 @@ def test_fused_argmax_on_reference_decode_edge_cases(ops, golden):
     t[0, :, 3, 0, 1] = t[0, :, 3, 0, 0] = 7.0
     Pt = _cuda(S.make_pool(1, 2, 4, seed=10)["P"])
     want = np.array([[9, 8], [0, 31], [0, 0], [0, 0]]) * 4
-    for kind in (None, "HP", "MPE", "BSB"):
-        got = ops.score_pool(_cuda(t), Pt, 4, None, map_score=kind)["keypoints_2d"].cpu().numpy()
-        assert np.array_equal(got[0, 0], want) and np.array_equal(got[0, 1], want), kind
+    for kind, flavour in ((None, "0"), (None, "1"), ("HP", "1"), ("MPE", "1"), ("BSB", "1")):
+        got = _with_env("MVAL_ROW_ARGMAX", flavour, lambda: ops.score_pool(_cuda(t), Pt, 4, None, map_score=kind))
+        got = got["keypoints_2d"].cpu().numpy()
+        assert np.array_equal(got[0, 0], want) and np.array_equal(got[0, 1], want), (kind, flavour)
     assert np.array_equal(ops.decode_argmax(_cuda(t), 4).cpu().numpy()[0, 0], want)
 
 
@@ -629,7 +632,7 @@ def test_fused_scored_pass_edge_cases(ops):
     # the lane = row arg-max sweep falls back to the exact scan on maps with NaN / infinities: same key-points as the
     # stand-alone decode kernel and as the generic scan
     assert torch.equal(plain["keypoints_2d"], ops.decode_argmax(g, 4, valid))
-    assert torch.equal(plain["keypoints_2d"], _with_env("MVAL_ROW_ARGMAX", "0", lambda: ops.score_pool(g, P, 4, valid))["keypoints_2d"])
+    assert torch.equal(plain["keypoints_2d"], _with_env("MVAL_ROW_ARGMAX", "1", lambda: ops.score_pool(g, P, 4, valid))["keypoints_2d"])
     for kind in ("HP", "MPE", "BSB"):
         both = ops.score_pool(g, P, 4, valid, map_score=kind)
         assert torch.equal(both["keypoints_2d"], plain["keypoints_2d"]), kind
