@@ -346,8 +346,9 @@ def run_ours(args):
         "achieved": pool_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pool_gbs / hbm_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel over 4096 frames
         # (profiles/r1b_summary.md: 10.2046 GB + 8.55 MB), scaled to the frames of one launch here
-        "traffic": (10.2046e9 + 8.55e6) / 4096.0 * R if (fused and (V, J) == (8, 19)) else None,
-        "traffic_source": "ncu capture of 4096 frames (profiles/r1b_ncu_full_raw_fused.csv), scaled per frame",
+        "traffic": (10.204355e9 + 7.094e6) / 4096.0 * R if (fused and (V, J) == (8, 19)) else None,
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture over 4096 frames "
+                          "(profiles/r1f_ncu_full_raw_fused_plain.csv), scaled per frame",
         "peak_source": peak_src, "algorithmic_bytes_per_launch": pool_bytes,
         "algorithmic_bytes_per_frame": FRAME_ALGO_BYTES, "frames_per_launch": R, "avg_launch_ms": pool_ms,
         "share_of_step": pool_ms * (pool_frames / R) / ms_per_step,

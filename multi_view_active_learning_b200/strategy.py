@@ -30,6 +30,67 @@ def _item32(x):
     return float(np.float32(x))
 
 
+# builtin sum() over Python floats is Neumaier-compensated since Python 3.12 and a plain left-to-right sum before; the
+# reference's ``sum(hps) / len(hps)`` (strategy.py:1188-1190) inherits whichever the interpreter does, and so do we
+_SUM_IS_COMPENSATED = sum([1e16, 1.0, -1e16]) == 1.0
+
+
+def _python_float_sums(xt):
+    """xt float64 [m, n] (one COLUMN per sequence) -> float64 [n]: what ``sum(column.tolist())`` returns for every
+    column, evaluated for all of them at once (m vector steps instead of n Python-level sums).  Mirrors builtin sum():
+    start 0, left to right; on Python >= 3.12 with the Neumaier compensation term of Python/bltinmodule.c."""
+    s = np.zeros(xt.shape[1], dtype=np.float64)
+    c = np.zeros(xt.shape[1], dtype=np.float64)
+    with np.errstate(invalid="ignore", over="ignore"):
+        for row in xt:
+            nxt = s + row
+            if _SUM_IS_COMPENSATED:
+                c += np.where(np.abs(s) >= np.abs(row), (s - nxt) + row, (row - nxt) + s)
+            s = nxt
+        if _SUM_IS_COMPENSATED:
+            s = np.where((c != 0) & np.isfinite(c), s + c, s)
+    return s
+
+
+def _aggregate_map_scores(kind, config, per_map, valid):
+    """per_map float32 [B, V, J], valid bool [B, J] -> the frame scores of strategy.py:1151-1158 / 1188-1193 / 1210-1215
+    for all B frames, with the reference's own arithmetic (values taken view-major over the valid joints):
+      HP       per-map values are Python floats (.item()): AVG = builtin sum() / len in double, STD = np.std of a float64
+               array  -> float64 [B];
+      MPE/BSB  per-map values are np.float32 scalars: AVG = builtin sum() = one float32 add after the other, / len in
+               float32; STD = np.std of a float32 array (NumPy >= 2 promotion)  -> float32 [B].
+    Frames are grouped by their NUMBER of valid joints (at most J + 1 groups): both the left-to-right sums and NumPy's
+    pairwise reduction depend on the values and their count only, so a group is one dense [n, m] array, summed value by
+    value (AVG) or reduced with np.std(axis=1), which runs the pairwise summation per row exactly like the 1-D call."""
+    B, V, J = per_map.shape
+    dtype = np.float64 if kind == "HP" else np.float32
+    out = np.empty(B, dtype=dtype)
+    counts = valid.sum(axis=1)
+    for c in np.unique(counts).tolist():
+        rows = slice(None) if bool((counts == c).all()) else np.nonzero(counts == c)[0]
+        x, v = per_map[rows], valid[rows]
+        n = x.shape[0]
+        if c != J:  # compact every frame's valid entries (row-major = view-major, joints ascending)
+            x = x[np.broadcast_to(v[:, None, :], x.shape)]
+        x = x.reshape(n, V * c)
+        m = x.shape[1]
+        if config == "AVG":
+            if m == 0:
+                raise ZeroDivisionError("division by zero")  # sum([]) / len([]) in the reference
+            xt = np.ascontiguousarray(x.T, dtype=dtype)
+            if kind == "HP":
+                out[rows] = _python_float_sums(xt) / m
+            else:
+                acc = np.zeros(n, dtype=np.float32)
+                with np.errstate(invalid="ignore", over="ignore"):
+                    for row in xt:
+                        acc = acc + row
+                out[rows] = acc / np.float32(m)
+        else:
+            out[rows] = np.std(x.astype(dtype, copy=False), axis=1)
+    return out
+
+
 class ScoringSelectionMixin:
     # ------------------------------------------------------------------------------------------ entry point
     def sample_next_batch(self, train_dataset, al_num_frames, sal_num_frames, pose_estimator, iteration, rank=-1):
@@ -171,32 +232,19 @@ class ScoringSelectionMixin:
 
     @staticmethod
     def _compute_map_score_batch(kind, config, heatmaps, joint_valid, per_map=None):
-        """strategy.py:1149-1215 for a batch: the per-map score (HP / MPE / BSB) on the device, then AVG (Python float
-        sum / len, like the reference's sum(x)/len(x)) or STD (np.std) over (view, valid joint) on the host.
+        """strategy.py:1149-1215 for a batch: the per-map score (HP / MPE / BSB) on the device, then the reference's AVG /
+        STD over (view, valid joint) for every frame at once (``_aggregate_map_scores``).
         per_map: float32 [B, V, J] scores that were already computed (ops.score_pool(..., map_score=kind))."""
         valid = (torch.as_tensor(joint_valid) != 0)
         if valid.dim() == 1:
             valid = valid.unsqueeze(0).expand(heatmaps.shape[0], -1)
         if per_map is None:
             per_map = ops.score_hp(heatmaps, valid) if kind == "HP" else ops.score_peaks(heatmaps, kind, valid)
-        per_map = per_map.cpu().numpy()  # float32 [B, V, J], NaN for invalid joints
-        v = valid.cpu().numpy()
-        out = []
-        for b in range(per_map.shape[0]):
-            vals = per_map[b][:, v[b]].reshape(-1)  # view-major, like the reference's loops
-            if config not in ("AVG", "STD"):
-                if kind == "MPE":
-                    raise NotImplementedError("AL.MPE_CONFIG should be either AVG or STD.")  # reference :1157-1158
-                out.append(None)  # the reference falls off the end of _compute_hp / _compute_bsb and returns None
-            elif kind == "HP":
-                # :1186-1193: the per-map values are Python floats (.item()): double sum / len, np.std of float64
-                vals = vals.astype(np.float64)
-                out.append(sum(vals.tolist()) / len(vals) if config == "AVG" else np.std(vals))
-            else:
-                # :1151-1158, :1210-1215: np.float32 scalars: Python sum() adds them one by one in float32; np.std of a
-                # float32 array is a float32 (NumPy >= 2 promotion; SURVEY.md 8a row a8)
-                out.append(sum(list(vals)) / len(vals) if config == "AVG" else np.std(vals))
-        return out
+        if config not in ("AVG", "STD"):
+            if kind == "MPE":
+                raise NotImplementedError("AL.MPE_CONFIG should be either AVG or STD.")  # reference :1157-1158
+            return [None] * per_map.shape[0]  # the reference falls off the end of _compute_hp / _compute_bsb: None
+        return _aggregate_map_scores(kind, config, per_map.cpu().numpy(), valid.cpu().numpy())
 
     def _one_frame(self, kind, config, heatmaps, joint_valid):
         hm = heatmaps if heatmaps.is_cuda else heatmaps.cuda()
@@ -283,13 +331,11 @@ class ScoringSelectionMixin:
         al = f["al"].cpu().numpy()
         al = al.tolist() if al_is_f64 else al.astype(np.float32).astype(np.float64).tolist()
         pred = f["pred"].cpu().numpy().tolist()
-        for i in range(n):
-            guid = "%s-%s" % (poses[i], frames[i])
-            sal_dict["sal_metric"][guid] = sal[i]
-            sal_dict["inlier_count"][guid] = inl[i]
-            sal_dict["pred_3d_keypoints"][guid] = pred[i]
-            sal_dict["al_metric"][guid] = al[i]
-            sal_dict["mkpe"][guid] = mkpe[i]
+        # one pass per dict at C speed: the reference inserts guid by guid (:1115-1133), same order, same values
+        guids = ["%s-%s" % pf for pf in zip(poses, frames)]
+        for name, values in (("sal_metric", sal), ("inlier_count", inl), ("pred_3d_keypoints", pred), ("al_metric", al),
+                             ("mkpe", mkpe)):
+            sal_dict[name].update(zip(guids, values))
         return sal_dict
 
 

@@ -94,3 +94,34 @@ def test_frame_aggregation_of_precomputed_map_scores():
     assert M._compute_map_score_batch("HP", "MEDIAN", hm, torch.from_numpy(valid), per_map) == [None] * B
     with pytest.raises(NotImplementedError):
         M._compute_map_score_batch("MPE", "MEDIAN", hm, torch.from_numpy(valid), per_map)
+
+
+def test_vectorised_frame_aggregation_is_the_reference_arithmetic():
+    """_aggregate_map_scores evaluates all frames of a batch at once; it must return, bit for bit, what the reference's
+    per-frame expressions return: builtin sum() of Python floats (Neumaier-compensated on Python >= 3.12) / len and
+    np.std of a float64 array for HP; float32 left-to-right sums and float32 np.std for MPE / BSB -- for ragged validity
+    patterns, 8 x 19 and 20 x 42 maps per frame, and values that expose the summation order."""
+    import numpy as np
+    import pytest
+
+    from multi_view_active_learning_b200 import strategy as ST
+    from oracle import scores_oracle as SO
+
+    rng = np.random.default_rng(9)
+    wide = (rng.random((64, 300)) * rng.choice([1e-8, 1.0, 1e8], size=(64, 300))).astype(np.float32).astype(np.float64)
+    assert np.array_equal(ST._python_float_sums(np.ascontiguousarray(wide.T)), np.array([sum(r.tolist()) for r in wide]))
+    assert ST._python_float_sums(np.zeros((0, 3))).tolist() == [0.0, 0.0, 0.0]
+    for B, V, J in ((37, 8, 19), (9, 20, 42), (5, 2, 3)):
+        scores = (rng.random((B, V, J)) * rng.choice([1e-4, 1.0, 50.0], size=(B, V, J))).astype(np.float32)
+        valid = rng.random((B, J)) < 0.8
+        valid[:, 0] = True
+        valid[B // 2:] = valid[B // 2]  # several frames share a pattern, others are unique
+        for kind in ("HP", "MPE", "BSB"):
+            for config in ("AVG", "STD"):
+                got = ST._aggregate_map_scores(kind, config, scores, valid)
+                exp = [SO.reduce_frame_score(scores[b], valid[b], config, kind) for b in range(B)]
+                assert got.dtype == (np.float64 if kind == "HP" else np.float32)
+                assert [float(g) for g in got] == [float(e) for e in exp], (kind, config, B)
+    none_valid = np.zeros((2, 3), dtype=bool)
+    with pytest.raises(ZeroDivisionError):
+        ST._aggregate_map_scores("HP", "AVG", np.ones((2, 2, 3), np.float32), none_valid)
