@@ -212,23 +212,32 @@ class ScoringSelectionMixin:
         images = data["images"].cuda()
         return pose_estimator(images.reshape([-1, images.shape[2], images.shape[3], images.shape[4]]))
 
-    def _frame_al_metric(self, heatmaps, joint_valid, tri):
-        """AL metric of every frame of the batch as (numpy values, is_float64) -- strategy.py:1072-1094."""
-        cfg = self.al_cfg.AL
-        B = heatmaps.shape[0]
-        if cfg.STRATEGY == "RANDOM":
-            return np.array([_item32(torch.rand(1).item()) for _ in range(B)]), False
-        if cfg.STRATEGY == "TRIANGULATION":
-            return tri["metric"].cpu().numpy(), True
-        if cfg.STRATEGY == "CORESET":
-            return np.zeros(B), False
-        if cfg.STRATEGY in ("HP", "MPE", "BSB"):
-            config = {"HP": cfg.HP_CONFIG, "MPE": cfg.MPE_CONFIG, "BSB": cfg.BSB_CONFIG}[cfg.STRATEGY]
-            # tri["map_score"]: the per-map scores the fused pass already produced next to the triangulation
-            vals = self._compute_map_score_batch(cfg.STRATEGY, config, heatmaps, joint_valid, tri.get("map_score"))
-            # torch.tensor(...) of the reference: float64 only for HP's np.std of Python floats (:1081-1085)
-            return np.asarray(vals, dtype=np.float64), config == "STD" and cfg.STRATEGY == "HP"
+    def _batch_al_metric(self, B, tri):
+        """What strategy.py:1072-1094 contributes for the B frames of one batch, WITHOUT synchronising with the device:
+        ("al", float64 CUDA [B]) for the strategies whose metric is final per frame, or ("map", float32 CUDA [B, V, J])
+        for HP / MPE / BSB, whose per-map scores (from the same fused pass as the triangulation) are reduced to frame
+        scores once per pool in ``_pool_al_metric``."""
+        strategy = self.al_cfg.AL.STRATEGY
+        if strategy == "RANDOM":
+            # torch.rand(1).cuda() per frame in the reference: same draws from the global generator, float32 values
+            draws = [torch.rand(1) for _ in range(B)]
+            return "al", (torch.cat(draws) if draws else torch.zeros(0)).double().cuda()
+        if strategy == "TRIANGULATION":
+            return "al", tri["metric"]
+        if strategy == "CORESET":
+            return "al", torch.zeros(B, dtype=torch.float64, device=tri["metric"].device)
+        if strategy in ("HP", "MPE", "BSB"):
+            return "map", tri["map_score"]
         raise NotImplementedError()
+
+    def _pool_al_metric(self, per_map, valid):
+        """HP / MPE / BSB: per-map scores float32 CUDA [N, V, J] + validity float CUDA [N, J] of this rank's frames -> (frame
+        scores float64 CUDA [N], whether the reference's tensor is float64) -- strategy.py:1076-1090 for the whole pool."""
+        cfg = self.al_cfg.AL
+        config = {"HP": cfg.HP_CONFIG, "MPE": cfg.MPE_CONFIG, "BSB": cfg.BSB_CONFIG}[cfg.STRATEGY]
+        vals = self._compute_map_score_batch(cfg.STRATEGY, config, per_map, valid, per_map)
+        # torch.tensor(...) of the reference: float64 only for HP's np.std of Python floats (:1081-1085)
+        return torch.from_numpy(np.asarray(vals, dtype=np.float64)).to(per_map.device), config == "STD" and cfg.STRATEGY == "HP"
 
     @staticmethod
     def _compute_map_score_batch(kind, config, heatmaps, joint_valid, per_map=None):
@@ -266,10 +275,12 @@ class ScoringSelectionMixin:
         return self._one_frame("BSB", self.al_cfg.AL.BSB_CONFIG, heatmaps, joint_valid)
 
     def _compute_sal_dict(self, data_loader, pose_estimator):
-        """Reference strategy.py:1004-1147, batched (see module docstring)."""
+        """Reference strategy.py:1004-1147, batched (see module docstring).  Nothing in the loop waits for the device:
+        every batch enqueues its forward and ONE fused scoring launch and keeps the results as CUDA tensors, so the
+        kernels of batch k run while the loader collates and uploads batch k + 1; the frame scores of HP / MPE / BSB, the
+        MKPE and the dicts are formed once per pool."""
         cfg = self.al_cfg
-        acc = {k: [] for k in ("sal", "inl", "al", "pred", "gt", "valid", "pose", "frame")}
-        al_is_f64 = False
+        acc = {k: [] for k in ("sal", "inl", "al", "map", "pred", "gt", "valid", "pose", "frame")}
         n_done = 0
         rank_base = 0
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -288,16 +299,20 @@ class ScoringSelectionMixin:
                     sigma=cfg.AL.REPROJECTION_SIGMA,
                     map_score=cfg.AL.STRATEGY if cfg.AL.STRATEGY in ("HP", "MPE", "BSB") else None)
                 n_done += B
-                al, al_is_f64 = self._frame_al_metric(heatmaps, joint_valid, tri)
+                field, value = self._batch_al_metric(B, tri)
+                acc[field].append(value)
                 acc["sal"].append(tri["metric"].float())  # torch.Tensor([metric]) -> float32 (:1061)
                 acc["inl"].append(tri["inlier_count"].float())
-                acc["al"].append(torch.from_numpy(np.asarray(al, dtype=np.float64)).cuda())
                 acc["pred"].append(tri["keypoints_3d"].float())  # torch.Tensor(keypoints_3d) -> float32 (:1046)
-                acc["gt"].append(dp["3d_keypoints"].cuda().float())
-                acc["valid"].append(torch.as_tensor(joint_valid).cuda().float())
-                acc["pose"].append(torch.as_tensor(dp["pose"]).reshape(-1).cuda().long())
-                acc["frame"].append(torch.as_tensor(dp["frame_id"]).reshape(-1).cuda().long())
+                acc["gt"].append(dp["3d_keypoints"].cuda(non_blocking=True).float())
+                acc["valid"].append(torch.as_tensor(joint_valid).cuda(non_blocking=True).float())
+                acc["pose"].append(torch.as_tensor(dp["pose"]).reshape(-1).cuda(non_blocking=True).long())
+                acc["frame"].append(torch.as_tensor(dp["frame_id"]).reshape(-1).cuda(non_blocking=True).long())
         fields = {k: (torch.cat(v) if v else torch.zeros(0).cuda()) for k, v in acc.items()}
+        al_is_f64 = cfg.AL.STRATEGY == "TRIANGULATION"
+        per_map = fields.pop("map")
+        if acc["map"]:
+            fields["al"], al_is_f64 = self._pool_al_metric(per_map, fields["valid"])
         fields = self._gather_interleaved(fields)
         return self._build_sal_dict(fields, al_is_f64)
 

@@ -125,3 +125,69 @@ def test_vectorised_frame_aggregation_is_the_reference_arithmetic():
     none_valid = np.zeros((2, 3), dtype=bool)
     with pytest.raises(ZeroDivisionError):
         ST._aggregate_map_scores("HP", "AVG", np.ones((2, 2, 3), np.float32), none_valid)
+
+
+def test_compute_sal_dict_host_flow_without_device(monkeypatch):
+    """The host side of _compute_sal_dict (reference strategy.py:1004-1147) with the device calls stubbed out: per-batch
+    results are only accumulated, the HP / MPE / BSB frame scores are formed once per pool from the per-map scores of
+    the fused pass, dicts come out in loader order with the reference's roundings (float32 for everything except
+    TRIANGULATION's metric and HP's STD)."""
+    import numpy as np
+    import torch
+
+    from multi_view_active_learning_b200 import ops, strategy as ST
+    from oracle import scores_oracle as SO
+
+    V, J, B, n_batches = 2, 5, 4, 3
+    rng = np.random.default_rng(21)
+    maps = rng.random((n_batches, B, V, J)).astype(np.float32)
+    valid = rng.random((n_batches, B, J)) < 0.7
+    valid[..., 0] = True
+    seen = []
+
+    def fake_triangulation_batch(hm, P, stride, joint_valid, **kw):
+        k = len(seen)
+        seen.append(kw)
+        out = {"metric": torch.arange(B, dtype=torch.float64) + k + 1.0 / 3.0,
+               "inlier_count": torch.full((B,), 8, dtype=torch.int32),
+               "keypoints_3d": torch.full((B, J, 3), 0.1, dtype=torch.float64) * (k + 1)}
+        if kw.get("map_score"):
+            out["map_score"] = torch.from_numpy(np.where(valid[k][:, None, :], maps[k], np.nan).astype(np.float32))
+        return out
+
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(ops, "mkpe", lambda p, g, v: torch.zeros(p.shape[0]))
+    monkeypatch.setattr(ST.triangulation, "triangulation_batch", fake_triangulation_batch)
+
+    def loader():
+        for k in range(n_batches):
+            yield {"images": torch.zeros(B, V, J, 8, 8), "proj_matrices": torch.zeros(B, V, 3, 4, dtype=torch.float64),
+                   "joint_valid": torch.from_numpy(valid[k].astype(np.float32)), "3d_keypoints": torch.zeros(B, 4, J),
+                   "pose": torch.full((B,), 160422), "frame_id": torch.arange(B) + 10 * k}
+
+    for strategy, config in (("TRIANGULATION", "AVG"), ("HP", "AVG"), ("HP", "STD"), ("MPE", "AVG"), ("BSB", "STD"), ("CORESET", "AVG")):
+        del seen[:]
+        cfg = _cfg("/tmp")
+        cfg.POSE_ESTIMATOR = NS(STRIDE=4)
+        cfg.AL = NS(STRATEGY=strategy, USE_SOFTARGMAX=False, USE_REPROJECTION_XE=False, REPROJECTION_SIGMA=1.0,
+                    HP_CONFIG=config, MPE_CONFIG=config, BSB_CONFIG=config)
+        st = ActiveLearningStrategy(cfg)
+        st._compute_batch_heatmap = lambda pe, d: d["images"].reshape(-1, J, 8, 8)
+        sal = st._compute_sal_dict(loader(), None)
+        guids = ["160422-%d" % (10 * k + i) for k in range(n_batches) for i in range(B)]
+        assert all(list(sal[name]) == guids for name in sal)
+        assert [kw["frame_offset"] for kw in seen] == [0, B, 2 * B]
+        assert all(kw["map_score"] == (strategy if strategy in ("HP", "MPE", "BSB") else None) for kw in seen)
+        assert sal["sal_metric"]["160422-11"] == float(np.float32(1 + 1 + 1.0 / 3.0))  # torch.Tensor([metric]) is float32
+        assert sal["pred_3d_keypoints"]["160422-20"][0][0] == float(np.float32(0.1 * 3))
+        for k in range(n_batches):
+            for i in range(B):
+                got = sal["al_metric"]["160422-%d" % (10 * k + i)]
+                if strategy == "TRIANGULATION":
+                    assert got == i + k + 1.0 / 3.0  # the float64 metric itself (:1074-1075)
+                elif strategy == "CORESET":
+                    assert got == 0.0
+                else:
+                    exp = SO.reduce_frame_score(maps[k, i], valid[k, i], config, strategy)
+                    exact = strategy == "HP" and config == "STD"  # the only float64 tensor among them (:1081-1085)
+                    assert got == (float(exp) if exact else float(np.float32(exp))), (strategy, config, k, i)
