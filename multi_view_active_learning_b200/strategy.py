@@ -7,7 +7,9 @@ stand-alone form used by the tests.  Training, evaluation, checkpoints and Tenso
 with the reference -- they are outside SURVEY.md section 8.
 
 What changes relative to the reference's ``_compute_sal_dict`` (strategy.py:1004-1147):
-  * one batched kernel pass per data-loader batch instead of a Python loop over frames, joints and view pairs;
+  * one batched kernel pass per data-loader batch instead of a Python loop over frames, joints and view pairs -- for the
+    HP / MPE / BSB strategies the same pass also yields the per-map scores (mval_score_pool_scored), and nothing in the
+    loop waits for the device;
   * no per-frame collectives: every rank accumulates its frames on the device and the 8 per-frame all_gathers
     (:1106-1114) become one all_gather per field at the end;
   * the guid-keyed OrderedDicts are built once, in the order the reference would have inserted them (for each
