@@ -211,6 +211,33 @@ def case_peaks(st):
     print("peak_scores", res, "n maps", len(ents))
 
 
+def case_softargmax(tri):
+    """triangulation(..., use_soft_argmax=True) of the unmodified reference (utils/triangulation.py:191-200).  kornia is
+    not installable here, but `transformers` ships a verbatim copy of kornia's `spatial_expectation2d` and
+    `create_meshgrid` ("Copied from kornia library: kornia/geometry/subpix/dsnt.py:76", transformers/models/efficientloftr/
+    modeling_efficientloftr.py); kornia.spatial_soft_argmax2d(x, temperature=1, normalized_coordinates) is
+    spatial_expectation2d(spatial_softmax2d(x, temperature), normalized_coordinates) with spatial_softmax2d =
+    F.softmax(x.view(B, C, -1) * temperature, dim=-1).view_as(x) (dsnt.py), served to the reference's `kornia` name that way.
+    Pins the key-points (float32), the 3-D joints and the metric of the soft-arg-max path."""
+    import torch.nn.functional as F
+    from transformers.models.efficientloftr.modeling_efficientloftr import spatial_expectation2d
+
+    def spatial_soft_argmax2d(input, temperature=torch.tensor(1.0), normalized_coordinates=True):
+        b, c, h, w = input.shape
+        soft = F.softmax(input.view(b, c, -1) * temperature.to(input.dtype), dim=-1).view(b, c, h, w)
+        return spatial_expectation2d(soft, normalized_coordinates)
+
+    tri.kornia.spatial_soft_argmax2d = spatial_soft_argmax2d
+    N, V, J = 4, 5, 6
+    pool = S.make_pool(N, V, J, seed=401, valid_prob=0.85, p_outlier=0.1)
+    hm = S.render_heatmaps(pool["centres"], noise=0.05, seed=402) * np.float32(8.0)
+    out = run_reference_triangulation(tri, hm, pool["P"], S.STRIDE, pool["valid"], 0, use_soft_argmax=True)
+    assert out["keypoints_2d"].dtype == np.float32
+    np.savez_compressed(os.path.join(OUT, "softargmax_v5_j6.npz"), P=pool["P"], valid=pool["valid"], stride=S.STRIDE,
+                        centres=pool["centres"], heatmap_seed=402, noise=0.05, gain=8.0, **out)
+    print("softargmax kp[0,0,:2]", out["keypoints_2d"][0, 0, :2], "metric", out["metric"])
+
+
 def case_coreset(cs):
     import uuid
 
@@ -276,6 +303,7 @@ def main():
     case_decode(ev)
     case_hp(st)
     case_peaks(st)
+    case_softargmax(tri)
     case_coreset(cs)
     case_xe(tri)
 

@@ -114,7 +114,9 @@ def decode_argmax(heatmaps, stride, valid=None):
 
 
 def decode_softargmax(heatmaps, stride):
-    """[..., H, W] float32 -> float32 [..., 2] (x, y) * stride.  parity unpinned (kornia not installed).
+    """[..., H, W] float32 -> float32 [..., 2] (x, y) * stride.  kornia itself is not installable here; pinned against
+    the reference run with kornia's spatial_expectation2d / create_meshgrid as vendored verbatim by `transformers`
+    (tests/golden/softargmax_v5_j6.npz, oracle/make_golden.py:case_softargmax) to float32 rounding (4.6e-5 px).
 
     kornia.spatial_soft_argmax2d(hm, temperature=1, normalized_coordinates=False): softmax over the
     flattened H*W map, then the expectation of the pixel grid (x = column 0..W-1, y = row 0..H-1);

@@ -94,6 +94,28 @@ def test_softargmax_vs_oracle(ops):
     np.testing.assert_allclose(got, exp, rtol=0, atol=2e-4)
 
 
+def test_softargmax_path_vs_reference_golden(ops, golden):
+    """Soft-arg-max decode + triangulation against the unmodified reference run with kornia's vendored expectation code
+    (tests/golden/softargmax_v5_j6.npz): key-points within 2e-4 px, inlier counts equal, 3-D joints within 1e-3 rel /
+    1e-2 mm, metric within 1e-4 px -- through the batched entry and through the reference's per-frame signature."""
+    from multi_view_active_learning_b200.utils import triangulation as T
+
+    g = golden("softargmax_v5_j6")
+    hm = S.render_heatmaps(g["centres"], noise=float(g["noise"]), seed=int(g["heatmap_seed"])) * np.float32(g["gain"])
+    stride = int(g["stride"])
+    kp = ops.decode_softargmax(_cuda(hm), stride).cpu().numpy()
+    np.testing.assert_allclose(kp, g["keypoints_2d"], rtol=0, atol=2e-4)
+    out = T.triangulation_batch(_cuda(hm), _cuda(g["P"]), stride, torch.from_numpy(g["valid"]), use_soft_argmax=True)
+    assert np.array_equal(out["inlier_count"].cpu().numpy(), g["inlier_count"])
+    np.testing.assert_allclose(out["keypoints_3d"].cpu().numpy(), g["keypoints_3d"], rtol=XYZ_RTOL, atol=XYZ_ATOL_MM)
+    np.testing.assert_allclose(out["metric"].cpu().numpy(), g["metric"], rtol=0, atol=REPROJ_ATOL_PX)
+    one = T.triangulation(torch.from_numpy(hm[1]), torch.from_numpy(g["P"][1]), stride, torch.from_numpy(g["valid"][1]),
+                          use_soft_argmax=True)
+    assert one["keypoints_2d"].dtype == np.float32 and int(one["inlier_count"]) == int(g["inlier_count"][1])
+    np.testing.assert_allclose(one["keypoints_3d"], g["keypoints_3d"][1], rtol=XYZ_RTOL, atol=XYZ_ATOL_MM)
+    assert abs(float(one["metric"]) - float(g["metric"][1])) <= REPROJ_ATOL_PX
+
+
 def test_hp_scores(ops, golden):
     g = golden("hp_scores")
     valid = g["valid"] != 0

@@ -76,6 +76,26 @@ def test_hp_scores(golden):
     np.testing.assert_allclose(SC.hp_metric(g["heatmaps"], g["valid"], "STD"), float(g["hp_std"]), atol=2e-6)
 
 
+def test_softargmax_matches_reference_with_vendored_kornia(golden):
+    """Soft-arg-max path: the unmodified reference's triangulation(use_soft_argmax=True) with kornia's
+    spatial_expectation2d / create_meshgrid as vendored verbatim by `transformers` standing in for the missing package
+    (oracle/make_golden.py:case_softargmax).  The float64 restatement agrees with the reference's float32 key-points to
+    float32 rounding; from the reference's own key-points the RANSAC restatement reproduces 3-D joints, metric and
+    inlier counts."""
+    g = golden("softargmax_v5_j6")
+    hm = S.render_heatmaps(g["centres"], noise=float(g["noise"]), seed=int(g["heatmap_seed"])) * np.float32(g["gain"])
+    kp = O.decode_softargmax(hm, int(g["stride"]))
+    assert kp.dtype == np.float32 and g["keypoints_2d"].dtype == np.float32
+    np.testing.assert_allclose(kp, g["keypoints_2d"], rtol=0, atol=1e-4)  # px; observed 4.6e-5
+    out = O.triangulate_pool(None, g["P"], int(g["stride"]), g["valid"], keypoints_2d=g["keypoints_2d"])
+    assert np.array_equal(out["inlier_count"], g["inlier_count"])
+    np.testing.assert_allclose(out["keypoints_3d"], g["keypoints_3d"], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(out["metric"], g["metric"], rtol=1e-12)
+    own = O.triangulate_pool(hm, g["P"], int(g["stride"]), g["valid"], use_soft_argmax=True)
+    assert np.array_equal(own["inlier_count"], g["inlier_count"])
+    np.testing.assert_allclose(own["keypoints_3d"], g["keypoints_3d"], rtol=1e-3, atol=1e-2)
+
+
 def test_peak_scores_match_reference(golden):
     """MPE / BSB: the oracle against the unmodified reference's _compute_mpes / _compute_mpe / _compute_bsb
     (strategy.py:1149-1176, 1195-1215) run with the restated peak finder standing in for skimage (oracle/make_golden.py:
