@@ -80,3 +80,69 @@ def test_distributed_topk_and_gather_world2():
         assert sel_idx == exp  # every rank ends with the same selection, equal to the single-process nlargest
         assert sel_val == [float(scores[i]) for i in exp]
         assert gx == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0] and gy == gx
+
+
+def _sal_worker(rank, world, port, n_frames, out_q):
+    """One rank of _compute_sal_dict with the device calls stubbed (CPU tensors, gloo): frames are dealt round-robin like
+    the reference's DistributedSampler (strategy.py:753), every rank must end with the same dicts in the order the
+    reference's per-frame all_gathers insert them (frame 0, 1, 2, ...: local position t of rank r = global t * world + r)."""
+    from types import SimpleNamespace as NS
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from multi_view_active_learning_b200 import ops, strategy as ST
+
+        V, J, B = 2, 4, 3
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        ops.mkpe = lambda p, g, v: p[:, 0, 0].float()
+
+        def fake_triangulation_batch(hm, P, stride, joint_valid, **kw):
+            ids = hm[:, 0, 0, 0, 0].double()  # the frame id travels in the first heat-map pixel
+            scores = ids[:, None, None].float() + torch.arange(V * J, dtype=torch.float32).reshape(1, V, J) / 8
+            return {"metric": ids + 0.25, "inlier_count": torch.full((len(ids),), 8, dtype=torch.int32),
+                    "keypoints_3d": ids[:, None, None].expand(-1, J, 3).clone(), "map_score": scores}
+
+        ST.triangulation.triangulation_batch = fake_triangulation_batch
+        mine = list(range(rank, n_frames, world))
+
+        def loader():
+            for s in range(0, len(mine), B):
+                ids = torch.tensor(mine[s:s + B])
+                hm = torch.zeros(len(ids), V, J, 4, 4)
+                hm[:, 0, 0, 0, 0] = ids.float()
+                yield {"images": hm, "proj_matrices": torch.zeros(len(ids), V, 3, 4, dtype=torch.float64),
+                       "joint_valid": torch.ones(len(ids), J), "3d_keypoints": torch.zeros(len(ids), 4, J),
+                       "pose": torch.full((len(ids),), 7), "frame_id": ids}
+
+        cfg = NS(EXPR_TYPE="AL", RANDOM_SEED=1, DATA=NS(NUM_JOINTS=J, TYPE="panoptic"), POSE_ESTIMATOR=NS(STRIDE=4),
+                 SAL=NS(INLIER_THRESHOLD=4, CLUSTER_FILE_PATH="", NUM_CLUSTERS=2),
+                 AL=NS(STRATEGY="HP", USE_SOFTARGMAX=False, USE_REPROJECTION_XE=False, REPROJECTION_SIGMA=1.0, HP_CONFIG="AVG",
+                       MPE_CONFIG="AVG", BSB_CONFIG="AVG"))
+        st = ST.ActiveLearningStrategy(cfg)
+        st._compute_batch_heatmap = lambda pe, d: d["images"].reshape(-1, J, 4, 4)
+        sal = st._compute_sal_dict(loader(), None)
+        out_q.put((rank, list(sal["al_metric"].items()), list(sal["sal_metric"].items()), list(sal["mkpe"].values())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_compute_sal_dict_world2_order_and_values():
+    n_frames, world = 12, 2  # 6 frames per rank, batches of 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sal_worker, args=(r, world, port, n_frames, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    mean_offset = sum(i / 8 for i in range(8)) / 8  # HP AVG of the stub's per-map scores = frame id + mean(0 .. 7) / 8
+    for rank, al, sal, mkpe in results:
+        assert [g for g, _ in al] == ["7-%d" % i for i in range(n_frames)] == [g for g, _ in sal]
+        assert [v for _, v in sal] == [i + 0.25 for i in range(n_frames)]
+        assert [v for _, v in al] == [float(np.float32(i + mean_offset)) for i in range(n_frames)]
+        assert mkpe == [float(i) for i in range(n_frames)]
