@@ -747,6 +747,189 @@ def run_hybrid(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# the north-star target THROUGH THE REPOSITORY'S OWN API: ActiveLearningStrategy.sample_next_batch (reference
+# strategy.py:54-135 -> _sal_pseudo_labeling :915-1002 -> _compute_sal_dict :1004-1147 -> nlargest / CoreSet
+# utils/coreset.py:13-95) over a pool whose heat maps are on the device (what the pose estimator's forward leaves there)
+# ----------------------------------------------------------------------------------------------------------------
+def similarity_proj(P_res, n, R, seed, dev):
+    """Distinct cameras for every pool frame although the resident heat maps repeat every R frames: frame f uses
+    P_res[f % R] @ M_f with M_f a similarity transform of the world, which leaves every reprojection error unchanged
+    and rotates / scales / shifts the triangulated pose (so the coreset sees n different poses)."""
+    import torch
+
+    g = torch.Generator(device=dev).manual_seed(seed)
+    q = torch.randn((n, 4), generator=g, device=dev, dtype=torch.float64)
+    q = q / q.norm(dim=1, keepdim=True)
+    w_, x_, y_, z_ = q.unbind(1)
+    Rm = torch.stack([1 - 2 * (y_ * y_ + z_ * z_), 2 * (x_ * y_ - z_ * w_), 2 * (x_ * z_ + y_ * w_),
+                      2 * (x_ * y_ + z_ * w_), 1 - 2 * (x_ * x_ + z_ * z_), 2 * (y_ * z_ - x_ * w_),
+                      2 * (x_ * z_ - y_ * w_), 2 * (y_ * z_ + x_ * w_), 1 - 2 * (x_ * x_ + y_ * y_)], dim=1).reshape(n, 3, 3)
+    sc = 0.5 + torch.rand((n, 1, 1), generator=g, device=dev, dtype=torch.float64)
+    M = torch.zeros((n, 4, 4), dtype=torch.float64, device=dev)
+    M[:, :3, :3] = Rm * sc
+    M[:, :3, 3] = torch.randn((n, 3), generator=g, device=dev, dtype=torch.float64) * 100
+    M[:, 3, 3] = 1.0
+    idx = torch.arange(n, device=dev) % R
+    return torch.matmul(P_res[idx], M[:, None])  # [n, V, 3, 4]
+
+
+class DevicePoolDataset:
+    """The surface of dataset/dataset.py's ActiveLearningDataset that the selection path touches (:47-74, 98-110), over a
+    synthetic pool whose heat maps are resident on the device.  Rank r owns the frames r, r + G, r + 2G, ... (the
+    DistributedSampler's deal without its shuffle), so the gathered table is in global frame order."""
+
+    POSE_ID = 160422
+
+    def __init__(self, hm, P_pool, n_local, rank, world, batch, n_labeled, joints, dev):
+        import torch
+
+        self.hm, self.P, self.n_local, self.rank, self.world, self.batch, self.dev = hm, P_pool, n_local, rank, world, batch, dev
+        self.R = hm.shape[0]
+        gl = torch.Generator().manual_seed(7)
+        lab = torch.randn((n_labeled, 4, joints), generator=gl, dtype=torch.float64) * 300.0
+        self.labeled_data = [{"3d_keypoints": lab[i].numpy()} for i in range(n_labeled)]
+        self.pseudo_label_guids, self.pseudo_labeled_data, self.labeled_guids = [], [], []
+        self.valid = torch.ones((batch, joints), dtype=torch.float32, device=dev)
+        self.gt = torch.zeros((batch, 4, joints), dtype=torch.float32, device=dev)
+        self.frame_ids = torch.arange(n_local, device=dev, dtype=torch.int64) * world + rank
+        self.pose_ids = torch.full((n_local,), self.POSE_ID, device=dev, dtype=torch.int64)
+
+    # dataset/dataset.py:98-102, 47-51, 61-74
+    def resample_unlabeled_data(self):
+        pass
+
+    def get_al_dict_for_coreset(self):
+        return {i: np.array(self.labeled_data[i]["3d_keypoints"]).transpose([1, 0]) for i in range(len(self.labeled_data))}
+
+    def label_by_frame_guids(self, guids):
+        self.labeled_guids = list(guids)
+
+    def pseudo_label_by_frame_guids(self, guids, pseudo_labels):
+        self.pseudo_label_guids = guids
+        self.pseudo_labeled_data = [{"pseudo_3d_keypoints": np.array(pseudo_labels[g]).transpose([1, 0])} for g in guids]
+
+    def loader(self):
+        """What DataLoader(dataset, batch_size, sampler=DistributedSampler(dataset)) yields (dataset/dataset.py:142-155)
+        when the backbone's output is already on the device: "images" carries the heat maps and the pose estimator is the
+        identity (the forward is timed separately, north star)."""
+        for o in range(0, self.n_local, self.batch):
+            m = min(self.batch, self.n_local - o)
+            r0 = o % self.R
+            if r0 + m > self.R:
+                r0 = 0
+            yield {"images": self.hm[r0:r0 + m], "proj_matrices": self.P[o:o + m], "joint_valid": self.valid[:m],
+                   "3d_keypoints": self.gt[:m], "pose": self.pose_ids[o:o + m], "frame_id": self.frame_ids[o:o + m]}
+
+
+def api_cfg(strategy, expr, batch, joints):
+    from types import SimpleNamespace as NS
+
+    return NS(EXPR_TYPE=expr, RANDOM_SEED=1307, DATA=NS(NUM_JOINTS=joints, TYPE="panoptic"), POSE_ESTIMATOR=NS(STRIDE=STRIDE),
+              SAL=NS(INLIER_THRESHOLD=4, CLUSTER_FILE_PATH="", NUM_CLUSTERS=10),
+              AL=NS(STRATEGY=strategy, USE_SOFTARGMAX=False, USE_REPROJECTION_XE=False, REPROJECTION_SIGMA=1.0, HP_CONFIG="AVG",
+                    MPE_CONFIG="AVG", BSB_CONFIG="AVG", INFERENCE=NS(BATCH_SIZE=batch, NUM_WORKERS=0)))
+
+
+def api_selection(ctx, hm, P_res, n_local, batch, budget, n_labeled, pseudo, reps, variants=None):
+    """Times ActiveLearningStrategy.sample_next_batch(iteration >= 1) end to end (wall clock between a barrier +
+    synchronize on both sides, max over ranks, median over `reps` calls after one warm-up call) for the given
+    (strategy, EXPR_TYPE) variants.  Returns {variant: record}."""
+    import random
+
+    import torch
+    import torch.distributed as dist
+
+    from multi_view_active_learning_b200 import _lib
+    from multi_view_active_learning_b200.strategy import ActiveLearningStrategy
+
+    world, rank, dev = ctx["world"], ctx["rank"], ctx["dev"]
+    P_pool = similarity_proj(P_res, n_local, hm.shape[0], 77 + rank, dev)
+    out = {}
+    for strategy, expr in (variants or (("TRIANGULATION", "AL"), ("CORESET", "AL"), ("TRIANGULATION", "SAL"))):
+        cfg = api_cfg(strategy, expr, batch, J)
+        st = ActiveLearningStrategy(cfg)
+        times, sel, launches = [], None, 0
+        for it in range(1 + reps):
+            ds = DevicePoolDataset(hm, P_pool, n_local, rank, world, batch, n_labeled, J, dev)
+            st._get_dataloader = lambda d, bs, nw, ds=ds: ds.loader()
+            random.seed(5)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            l0 = _lib.launch_count()
+            t0 = time.perf_counter()
+            st.sample_next_batch(ds, budget, pseudo, torch.nn.Identity(), iteration=1, rank=rank)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            launches = _lib.launch_count() - l0
+            if world > 1:
+                tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            if it > 0:
+                times.append(dt)
+            sel = (st.last_al_guids, st.last_sal_guids)
+        same = None
+        if world > 1:  # every rank must end with the same selection (strategy.py:945-950)
+            import hashlib
+
+            h = int(hashlib.sha1(json.dumps(sel).encode()).hexdigest()[:15], 16)
+            hs = torch.tensor([h], dtype=torch.int64, device=dev)
+            all_h = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(all_h, hs)
+            same = bool((all_h == all_h[0]).all().item())
+        ms = 1e3 * float(np.median(times))
+        out["%s/%s" % (strategy, expr)] = {
+            "ms_per_call": ms, "call_ms": [round(1e3 * t, 2) for t in times], "value": n_local * world / (ms * 1e-3), "unit": UNIT,
+            "frames_total": n_local * world, "al_num_frames": budget, "sal_num_frames": pseudo if expr == "SAL" else 0,
+            "labeled": n_labeled, "al_guids_head": sel[0][:3], "n_al_guids": len(sel[0]), "n_sal_guids": len(sel[1]),
+            "same_selection_on_every_rank": same, "gpu_launches": int(launches),
+            "call": "ActiveLearningStrategy.sample_next_batch(train_dataset, al_num_frames, sal_num_frames, pose_estimator, "
+                    "iteration=1, rank) -- strategy.py:54; heat maps on the device (identity pose estimator, batches of %d "
+                    "frames), device-resident sal_dict (table.py)" % batch}
+    return out
+
+
+def run_api(args):
+    """--workload api: the north-star target through sample_next_batch: `pool_frames` frames per GPU (default for this
+    workload: 125 000 = 1M over 8 GPUs), 8 views, 19 joints."""
+    import torch
+    import torch.distributed as dist
+
+    from multi_view_active_learning_b200 import ops
+    from multi_view_active_learning_b200 import synthetic as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    R = args.resident_frames
+    host_pool = S.make_pool(R, V, J, seed=1234 + rank, p_outlier=0.1)
+    hm = ops.synth_heatmaps(torch.from_numpy(host_pool["centres"]).to(dev), H, W, 1.0, 0.05, 1234 + rank)
+    P_res = torch.from_numpy(host_pool["P"]).to(dev)
+    ctx = {"world": world, "rank": rank, "dev": dev}
+    n_local = args.pool_frames
+    rec = api_selection(ctx, hm, P_res, n_local, args.api_batch, args.coreset_budget, args.coreset_labeled, args.api_pseudo,
+                        args.steps)
+    if rank == 0:
+        head = rec["CORESET/AL"]
+        print(json.dumps({
+            "metric": "selection through sample_next_batch: pool frames scored + selected / sec", "value": head["value"],
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "ms_per_step": head["ms_per_call"], "higher_is_better": True,
+            "scaling": "weak", "dtype": "f64 (triangulation) / f32 (coreset)", "data": "synthetic",
+            "config": {"workload": "north-star target through the API: %d frames per GPU x %d GPU(s), %d views, %d joints, "
+                                   "sample_next_batch (strategy.py:54) with device heat maps" % (n_local, world, V, J),
+                       "resident_frames": R, "batch": args.api_batch}, "variants": rec}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # secondary workload: the per-map heat-map kernels (soft-arg-max, HP, MPE, BSB, XE) on a resident chunk
 # ----------------------------------------------------------------------------------------------------------------
 def run_scores(args):
@@ -877,17 +1060,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pool-frames", type=int, default=POOL_FRAMES_PER_GPU)
+    ap.add_argument("--pool-frames", type=int, default=None, help="frames per GPU (default 100000; api / hybrid: 125000)")
     ap.add_argument("--resident-frames", type=int, default=16384)
     ap.add_argument("--e2e-frames", type=int, default=4096)
     ap.add_argument("--e2e-steps", type=int, default=9)
     ap.add_argument("--cpu-frames", type=int, default=4096)
     ap.add_argument("--ref-frames-per-core", type=int, default=128)
-    ap.add_argument("--workload", default="scoring", choices=["scoring", "coreset", "scores", "hybrid", "backbone"])
+    ap.add_argument("--workload", default="scoring", choices=["scoring", "coreset", "scores", "hybrid", "backbone", "api"])
+    ap.add_argument("--api-batch", type=int, default=8192, help="api workload: frames per loader batch")
+    ap.add_argument("--api-pseudo", type=int, default=1000, help="api workload: sal_num_frames of the SAL variant")
     ap.add_argument("--coreset-rows", type=int, default=1_000_000)
     ap.add_argument("--coreset-dim", type=int, default=2048)
-    ap.add_argument("--coreset-labeled", type=int, default=64)
-    ap.add_argument("--coreset-budget", type=int, default=2048)
+    ap.add_argument("--coreset-labeled", type=int, default=None, help="labeled centres (coreset: 64; api / hybrid: 1000)")
+    ap.add_argument("--coreset-budget", type=int, default=None, help="picks (coreset: 2048; api / hybrid: 10000)")
     ap.add_argument("--coreset-path", default="auto", choices=["auto", "ffma", "tc"])
     ap.add_argument("--coreset-data", default="gaussian", choices=["gaussian", "clustered"])
     ap.add_argument("--coreset-cpu-rows", type=int, default=50000)
@@ -901,6 +1086,13 @@ def main():
     ap.add_argument("--views", type=int, default=V, help="camera views per frame (C2: 8; C3: 20; C5: 31)")
     ap.add_argument("--joints", type=int, default=J, help="joints per frame (Panoptic 19; InterHand 42)")
     args = ap.parse_args()
+    big = args.workload in ("api", "hybrid")
+    if args.pool_frames is None:
+        args.pool_frames = 125_000 if big else POOL_FRAMES_PER_GPU
+    if args.coreset_labeled is None:
+        args.coreset_labeled = 1000 if big else 64
+    if args.coreset_budget is None:
+        args.coreset_budget = 10_000 if big else 2048
     if (args.views, args.joints) != (V, J):  # other BASELINE.json shapes (C3 / C5): same code path, different rig
         g = globals()
         g["V"], g["J"] = args.views, args.joints
@@ -917,6 +1109,8 @@ def main():
         return run_hybrid(args)
     if args.workload == "backbone":
         return run_backbone(args)
+    if args.workload == "api":
+        return run_api(args)
     return run_ours(args)
 
 

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MVAL_ABI_VERSION 4
+#define MVAL_ABI_VERSION 5
 #define MVAL_MAX_VIEWS 32
 
 enum mval_status {
@@ -51,6 +51,19 @@ int mval_version(void);
 const char* mval_last_error(void);
 /* Number of kernel launches issued through this library by the calling process so far (bench bookkeeping). */
 uint64_t mval_launch_count(void);
+
+/* The persistent kernels (mval_score_pool*, the 64 x 64 forms of mval_decode_softargmax / mval_score_hp /
+ * mval_score_peaks / mval_score_xe) guard every mbarrier wait with a watchdog: a wait that exceeds ~5 s of SM clocks
+ * makes all roles drain and leaves a record in pinned host memory.  Because the entry points are asynchronous the
+ * failure is reported by the NEXT call into the library that launches such a kernel, or by mval_check_async, as
+ * MVAL_ERR_CUDA (mval_last_error() names the wait); the record is cleared by that report and later launches run
+ * normally.  mval_check_async synchronises `stream` and returns the status of everything launched on it so far --
+ * call it before consuming results on the host (the Python layer does so at its own synchronisation points).
+ * The reference has no counterpart: its per-frame calls are synchronous and raise in place. */
+int mval_check_async(void* stream);
+/* Test hook: time-out of the watchdog in SM clocks (0 = default) and, with stall != 0, producers that issue no copies
+ * (every consumer wait then times out).  Affects the current device until called again with (0, 0). */
+int mval_debug_watchdog(uint64_t timeout_cycles, int stall);
 
 /* ------------------------------------------------------------------------------------------------------
  * (1) heat-map decode
@@ -96,7 +109,8 @@ int mval_score_peaks(const float* heatmaps, int64_t n_frames, int V, int J, int 
  *   pairs != NULL : uint8 device [n_frames][J][n_iters][2], the pairs to visit, in order, for every
  *                   (frame, joint)  (the per-frame drop-in wrapper draws them with Python's random.shuffle
  *                   exactly like the reference and passes them here);
- *   pairs == NULL : counter-based subset keyed by (pair_seed, frame_offset + frame, joint), see
+ *   pairs == NULL : counter-based subset keyed by (pair_seed, frame key, joint) with frame key = frame_keys[frame] when
+ *                   given and frame_offset + frame otherwise, see
  *                   oracle/triangulation_oracle.py:pair_subset_indices for the exact arithmetic.
  * When C(V,2) <= n_iters both are ignored and all pairs are visited in lexicographic order. */
 typedef struct mval_ransac_params {
@@ -105,6 +119,9 @@ typedef struct mval_ransac_params {
   uint64_t pair_seed;
   int64_t frame_offset;  /* global index of frame 0 of this call (pool sharding / chunking) */
   const uint8_t* pairs;  /* optional explicit pair table, see above */
+  const int64_t* frame_keys; /* optional, int64 device [n_frames]: the key of every frame in the counter-based subset
+                                (instead of frame_offset + frame), e.g. pose * 2^32 + frame_id of its guid, so that the
+                                subsets do not depend on how the pool is sharded or ordered */
 } mval_ransac_params;
 
 /* Replaces utils/triangulation.py:205-232 for a whole batch of frames: per valid (frame, joint)
@@ -187,11 +204,30 @@ int mval_score_xe(const float* heatmaps, const double* proj, const double* xyz, 
  * ---------------------------------------------------------------------------------------------------- */
 
 /* Replaces strategy.py:932-949: drop NaN scores, then heapq.nlargest(k, ...) = descending by score, ties by
- * ascending pool index.  Writes min(k, #non-NaN) entries; *out_count (device int32) receives that number.
+ * ascending pool index.  Writes min(k, #non-NaN) entries; *out_count (device int32) receives that number; the
+ * remaining slots of out_idx / out_val are set to -1 / NaN.
  * scores float64 device [n]; out_idx int64 device [k] (global index = index_offset + local);
  * out_val float64 device [k]. */
 int mval_topk_desc(const double* scores, int64_t n, int64_t index_offset, int32_t k, int64_t* out_idx,
                    double* out_val, int32_t* out_count, void* stream);
+
+/* The cross-rank half of the same ranking: every rank's mval_topk_desc output (scores descending, GLOBAL indices, unused
+ * slots NaN / -1) is all-gathered rank after rank; this call merges the n = world * k candidates on the device into the
+ * global top-k.  With contiguous frame sharding "rank-major, then local order" is ascending pool order among equal scores,
+ * so the stable sort reproduces nlargest's tie-break.  out_idx[i] = indices[position of the i-th best candidate]. */
+int mval_topk_merge(const double* scores, const int64_t* indices, int64_t n, int32_t k, int64_t* out_idx, double* out_val,
+                    int32_t* out_count, void* stream);
+
+/* Dict-insertion semantics of the guid-keyed tables strategy.py:1115-1133 builds (sal_dict[...][guid] = value, guid =
+ * "%s-%s" % (pose, frame_id)) for rows that stay on the device: a guid that occurs in several rows (DistributedSampler
+ * pads the last batch by repeating frames, strategy.py:753) keeps the position of its FIRST row and the value of its LAST.
+ * pose / frame int64 device [n], both in [0, 2^32).
+ * out_keep   uint8 device [n]  1 = first row of its guid
+ * out_src    int32 device [n]  for kept rows: the last row with the same guid (take the values from there); -1 otherwise
+ * out_unique int32 device [1]  number of distinct guids, or -1 when a pose / frame id does not fit 32 bits (the caller
+ *                              then falls back to building the dict on the host). */
+int mval_first_occurrence(const int64_t* pose, const int64_t* frame, int64_t n, uint8_t* out_keep, int32_t* out_src,
+                          int32_t* out_unique, void* stream);
 
 /* Replaces strategy.py:957-975 (the pseudo-label candidate filter and its sort): frames with a non-NaN sal_metric,
  * inlier_count > inlier_threshold (SAL.INLIER_THRESHOLD) and excluded[i] == 0 (the caller marks frames already picked by

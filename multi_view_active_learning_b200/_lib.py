@@ -12,7 +12,7 @@ MVAL_ERR_CUDA = -3
 MVAL_ERR_NO_DEVICE = -4
 MVAL_ERR_OUT_OF_MEMORY = -5
 MAX_VIEWS = 32
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAP_SCORE = {None: 0, "HP": 1, "MPE": 2, "BSB": 3}  # MVAL_MAP_SCORE_*
 
 
@@ -24,7 +24,7 @@ class MvalError(RuntimeError):
 
 class RansacParams(C.Structure):
     _fields_ = [("n_iters", C.c_int32), ("epsilon", C.c_double), ("pair_seed", C.c_uint64),
-                ("frame_offset", C.c_int64), ("pairs", C.c_void_p)]
+                ("frame_offset", C.c_int64), ("pairs", C.c_void_p), ("frame_keys", C.c_void_p)]
 
 
 _p, _i, _i64, _f, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
@@ -33,6 +33,8 @@ PROTOTYPES = {
     "mval_version": (C.c_int, []),
     "mval_last_error": (C.c_char_p, []),
     "mval_launch_count": (C.c_uint64, []),
+    "mval_check_async": (C.c_int, [_p]),
+    "mval_debug_watchdog": (C.c_int, [_u64, _i]),
     "mval_decode_argmax": (C.c_int, [_p, _i64, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "mval_decode_softargmax": (C.c_int, [_p, _i64, _i, _i, _i, _i, _f, _p, _p]),
     "mval_score_hp": (C.c_int, [_p, _i64, _i, _i, _i, _i, _p, _p, _p]),
@@ -44,6 +46,8 @@ PROTOTYPES = {
     "mval_score_pool_host": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _i64, _p, _p, _p, _p, _p, _p]),
     "mval_score_xe": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _d, _p, _p, _p]),
     "mval_topk_desc": (C.c_int, [_p, _i64, _i64, C.c_int32, _p, _p, _p, _p]),
+    "mval_topk_merge": (C.c_int, [_p, _p, _i64, C.c_int32, _p, _p, _p, _p]),
+    "mval_first_occurrence": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p]),
     "mval_sal_rank": (C.c_int, [_p, _p, _p, _i64, _f, C.c_int32, _p, _p, _p]),
     "mval_mkpe": (C.c_int, [_p, _p, _p, _i64, _i, _i, _p, _p]),
     "mval_kmeans_assign": (C.c_int, [_p, _i64, _i, _i, _p, _i, _p, _p, _p]),
@@ -68,10 +72,19 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.isfile(LIB_PATH) or os.environ.get("MVAL_REBUILD") == "1":
-        from . import build as _build
+    from . import build as _build
 
-        _build.build()
+    stale = False
+    try:
+        stale = _build.needs_build()  # missing, or a source / header is newer than the library (never load a stale ABI)
+    except OSError:
+        pass
+    if stale or os.environ.get("MVAL_REBUILD") == "1":
+        try:
+            _build.build(force=os.environ.get("MVAL_REBUILD") == "1")
+        except Exception:
+            if not os.path.isfile(LIB_PATH):
+                raise
     if not os.path.isfile(LIB_PATH):
         raise MvalError(MVAL_ERR_NO_DEVICE, "libmval_b200.so is missing and could not be built; there is no CPU fallback")
     lib = C.CDLL(LIB_PATH)

@@ -41,15 +41,19 @@ int require_device() {
     // Keep stream-ordered scratch (cudaMallocAsync) cached in the default pool: with the default release threshold
     // of 0 every synchronisation hands the memory back to the OS and the next call pays a fresh cudaMalloc
     // (measured: 5.6 ms median, up to 800 ms, per mval_topk_desc call).
-    for (int d = 0; d < n; ++d) {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
+    cached = 0;
+  }
+  // only the device the caller works on, once per device (not a process-wide side effect on every visible GPU)
+  static bool tuned[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !tuned[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     (void)cudaGetLastError();
-    cached = 0;
+    tuned[dev] = true;
   }
   return cached;
 }
@@ -59,6 +63,11 @@ int num_sms() {
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return sms;
 }
+
+int fused_watchdog_poll();
+int fused_watchdog_debug(unsigned long long timeout_cycles, int stall);
+int stream_watchdog_poll();
+int stream_watchdog_debug(unsigned long long timeout_cycles, int stall);
 
 int launch_decode_argmax(const float* hm, int64_t n_frames, int V, int J, int H, int W, int stride,
                          const uint8_t* valid, int32_t* out_xy, float* out_peak, cudaStream_t stream);
@@ -203,6 +212,7 @@ int score_pool_host(const float* heatmaps, const double* proj, const uint8_t* va
     mval_ransac_params p = *params;
     p.frame_offset = params->frame_offset + f0;
     if (p.pairs) p.pairs = nullptr;  // explicit pair tables are a device-pointer feature; validated by the caller below
+    if (p.frame_keys) p.frame_keys = params->frame_keys + f0;  // a DEVICE array over the whole pool
     rc = score_pool(s.hm, s.proj, valid ? s.valid : nullptr, n, V, J, H, W, stride, &p, MVAL_MAP_SCORE_NONE, s.xy, s.xyz,
                     s.reproj, s.inliers, s.metric, s.inlier_count, nullptr, s.stream);
     if (rc != MVAL_OK) return fail(rc);
@@ -226,6 +236,19 @@ extern "C" {
 int mval_version(void) { return MVAL_ABI_VERSION; }
 const char* mval_last_error(void) { return mval::g_error; }
 uint64_t mval_launch_count(void) { return mval::g_launches.load(std::memory_order_relaxed); }
+
+int mval_check_async(void* stream) {
+  if (int rc = mval::require_device()) return rc;
+  MVAL_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  if (int rc = mval::fused_watchdog_poll()) return rc;
+  return mval::stream_watchdog_poll();
+}
+
+int mval_debug_watchdog(uint64_t timeout_cycles, int stall) {
+  if (int rc = mval::require_device()) return rc;
+  if (int rc = mval::fused_watchdog_debug(timeout_cycles, stall)) return rc;
+  return mval::stream_watchdog_debug(timeout_cycles, stall);
+}
 
 int mval_score_pool(const float* heatmaps, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
                     int H, int W, int stride, const mval_ransac_params* params, int32_t* out_xy, double* out_xyz,

@@ -52,7 +52,14 @@ constexpr int kMaxFrameSlots = 4;  // frame slots per CTA: 4 when they are small
 constexpr int kMaxStages = 64;
 
 // Abort record of the mbarrier watchdog (tma.cuh): [0] flag, [1] code, [2] block, [3] warp, [4] frame iter, [5] index
-__device__ unsigned long long g_fused_abort[8];
+__device__ unsigned long long g_fused_abort[kWdWords];
+static WatchdogHost g_fused_watchdog;
+
+int fused_watchdog_poll() { return g_fused_watchdog.poll(g_fused_abort, "score_pool_fused"); }
+int fused_watchdog_debug(unsigned long long timeout_cycles, int stall) {
+  if (int rc = g_fused_watchdog.prepare(g_fused_abort, "score_pool_fused")) return rc;
+  return g_fused_watchdog.debug_set(g_fused_abort, timeout_cycles, stall);
+}
 
 struct FusedSmem {  // byte offsets into dynamic shared memory
   uint32_t ring, proj, kp, mask, red_reproj, red_inl, pair, perm, pxy, bars, total;
@@ -89,7 +96,8 @@ template <int kScore, bool kRowArgmax>
 __global__ void __launch_bounds__(kWarp * (1 + FusedCfg<kScore>::kD + FusedCfg<kScore>::kR), 1)
 score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__ proj, const uint8_t* __restrict__ valid,
                         int64_t n_frames, int V, int J, int H, int HW, int stride, int stages, int slots, int n_iters, double eps,
-                        uint64_t seed, int64_t frame_offset, int32_t* __restrict__ out_xy, double* __restrict__ out_xyz,
+                        uint64_t seed, int64_t frame_offset, const int64_t* __restrict__ frame_keys, int32_t* __restrict__ out_xy,
+                        double* __restrict__ out_xyz,
                         double* __restrict__ out_reproj, int32_t* __restrict__ out_inliers, double* __restrict__ out_metric,
                         int32_t* __restrict__ out_inlier_count, float* __restrict__ out_map_score) {
   constexpr int kFusedDecodeWarps = FusedCfg<kScore>::kD;
@@ -125,7 +133,7 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------- producer
-    if (lane == 0) {
+    if (lane == 0 && !watchdog_stalled(g_fused_abort)) {
       int64_t c = 0;
       for (int64_t i = 0; i < nf; ++i) {
         const int64_t frame = blockIdx.x + i * (int64_t)gridDim.x;
@@ -231,7 +239,7 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
             px[v] = (double)q.x;
             py[v] = (double)q.y;
           }
-          if (subset) draw_pair_subset(perm, n_all, n_iters, seed, frame_offset + frame, j, lane);
+          if (subset) draw_pair_subset(perm, n_all, n_iters, seed, frame_keys ? frame_keys[frame] : frame_offset + frame, j, lane);
           __syncwarp();
           mask = ransac_vote_warp(
               P, px, py, V, n_pairs, eps,
@@ -336,23 +344,12 @@ static int launch_fused_variant(const float* hm, const double* proj, const uint8
   MVAL_CUDA(cudaFuncSetAttribute(score_pool_fused_kernel<kScore, kRowArgmax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   const int64_t sms = num_sms();
   const int grid = (int)(n_frames < sms ? n_frames : sms);
+  // a watchdog trip of an EARLIER launch surfaces here (or in mval_check_async), never silently
+  if (int rc = g_fused_watchdog.prepare(g_fused_abort, "score_pool_fused")) return rc;
   score_pool_fused_kernel<kScore, kRowArgmax><<<grid, kWarp * (1 + kD + kR), L.total, stream>>>(
       hm, proj, valid, n_frames, V, J, H, HW, stride, stages, slots, prm.n_iters, prm.epsilon, prm.pair_seed, prm.frame_offset,
-      out_xy, out_xyz, out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score);
+      prm.frame_keys, out_xy, out_xyz, out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score);
   MVAL_LAUNCH_CHECK("score_pool_fused");
-  static const bool debug_sync = getenv("MVAL_DEBUG_SYNC") != nullptr;
-  if (debug_sync) {
-    MVAL_CUDA(cudaStreamSynchronize(stream));
-    unsigned long long rec[8] = {0};
-    MVAL_CUDA(cudaMemcpyFromSymbol(rec, g_fused_abort, sizeof(rec)));
-    if (rec[0] != 0ull) {
-      unsigned long long zero[8] = {0};
-      cudaMemcpyToSymbol(g_fused_abort, zero, sizeof(zero));
-      set_error("score_pool_fused watchdog: wait code %llu timed out (block %llu warp %llu frame-iter %llu index %llu)", rec[1],
-                rec[2], rec[3], rec[4], rec[5]);
-      return MVAL_ERR_CUDA;
-    }
-  }
   return MVAL_OK;
 }
 

@@ -28,7 +28,14 @@ constexpr int kStreamThreads = kWarp * (1 + kStreamWarps);  // 416
 constexpr uint32_t kScratchPerWarp = 1024;  // XE: two tables of 64 doubles
 constexpr uint32_t kStreamSmem = kStreamStages * kMapBytes + 2u * kStreamStages * 8u + kStreamWarps * kScratchPerWarp;
 
-__device__ unsigned long long g_stream_abort[8];
+__device__ unsigned long long g_stream_abort[kWdWords];
+static WatchdogHost g_stream_watchdog;
+
+int stream_watchdog_poll() { return g_stream_watchdog.poll(g_stream_abort, "map_stream"); }
+int stream_watchdog_debug(unsigned long long timeout_cycles, int stall) {
+  if (int rc = g_stream_watchdog.prepare(g_stream_abort, "map_stream")) return rc;
+  return g_stream_watchdog.debug_set(g_stream_abort, timeout_cycles, stall);
+}
 
 template <class Op>
 __global__ void __launch_bounds__(kStreamThreads, 1)
@@ -51,7 +58,7 @@ map_stream_kernel(const float* __restrict__ hm, int64_t n_maps, const uint8_t* _
   const int64_t nm = (n_maps > (int64_t)blockIdx.x) ? (n_maps - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   const int64_t VJ = (int64_t)V * J;
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && !watchdog_stalled(g_stream_abort)) {
       for (int64_t c = 0; c < nm; ++c) {
         const int64_t m = blockIdx.x + c * (int64_t)gridDim.x;
         const int st = (int)(c % kStreamStages);
@@ -98,23 +105,11 @@ static int launch_map_stream(const char* name, const float* hm, int64_t n_maps, 
   MVAL_CUDA(cudaFuncSetAttribute(map_stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmem));
   const int64_t sms = num_sms();
   const int grid = (int)(n_maps < sms ? n_maps : sms);
+  if (int rc = g_stream_watchdog.prepare(g_stream_abort, name)) return rc;
   map_stream_kernel<Op><<<grid, kStreamThreads, kStreamSmem, stream>>>(hm, n_maps, valid, V, J, args);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, name);
-  static const bool debug_sync = getenv("MVAL_DEBUG_SYNC") != nullptr;
-  if (debug_sync) {
-    MVAL_CUDA(cudaStreamSynchronize(stream));
-    unsigned long long rec[8] = {0};
-    MVAL_CUDA(cudaMemcpyFromSymbol(rec, g_stream_abort, sizeof(rec)));
-    if (rec[0] != 0ull) {
-      unsigned long long zero[8] = {0};
-      cudaMemcpyToSymbol(g_stream_abort, zero, sizeof(zero));
-      set_error("%s watchdog: wait code %llu timed out (block %llu warp %llu iter %llu index %llu)", name, rec[1], rec[2],
-                rec[3], rec[4], rec[5]);
-      return MVAL_ERR_CUDA;
-    }
-  }
   return MVAL_OK;
 }
 

@@ -233,7 +233,7 @@ __device__ __forceinline__ void draw_pair_subset(uint16_t* perm, int n_all, int 
   for (int i = lane; i < n_all; i += kWarp) perm[i] = (uint16_t)i;
   __syncwarp();
   if (lane == 0) {
-    uint64_t state = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(global_frame * 64 + joint + 1);
+    uint64_t state = seed + 0x9E3779B97F4A7C15ull * ((uint64_t)global_frame * 64ull + (uint64_t)(joint + 1));
     for (int i = 0; i < n_iters; ++i) {
       const uint64_t z = splitmix64(state);
       const int r = i + (int)(((z >> 32) * (uint64_t)(n_all - i)) >> 32);

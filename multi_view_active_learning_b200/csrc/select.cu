@@ -146,50 +146,50 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
 
 __global__ void __launch_bounds__(256)
 topk_gather_kernel(const double* __restrict__ scores, const uint32_t* __restrict__ sorted_idx,
-                   const int32_t* __restrict__ n_valid, int32_t k, int64_t index_offset, int64_t* __restrict__ out_idx,
-                   double* __restrict__ out_val, int32_t* __restrict__ out_count) {
+                   const int32_t* __restrict__ n_valid, int32_t k, int64_t index_offset, const int64_t* __restrict__ index_map,
+                   int64_t* __restrict__ out_idx, double* __restrict__ out_val, int32_t* __restrict__ out_count) {
   const int take = min(k, *n_valid);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && out_count) *out_count = take;
   if (i < take) {
     const uint32_t s = sorted_idx[i];
-    out_idx[i] = index_offset + (int64_t)s;
+    out_idx[i] = index_map ? index_map[s] : index_offset + (int64_t)s;
     if (out_val) out_val[i] = scores[s];
+  } else if (i < k) {
+    out_idx[i] = -1;  // slots beyond the count are defined: -1 / NaN (fixed-size exchange buffers rely on it)
+    if (out_val) out_val[i] = __longlong_as_double(0x7ff8000000000000ll);
   }
 }
 
-}  // namespace mval
+// Workspace of one stable LSD radix sort of n (uint64 key, uint32 payload) pairs, carved out of one stream-ordered
+// allocation; sort() leaves the result in keys[cur] / idx[cur].
+struct RadixSort {
+  char* ws = nullptr;
+  uint64_t* keys[2] = {nullptr, nullptr};
+  uint32_t* idx[2] = {nullptr, nullptr};
+  uint32_t* counts = nullptr;
+  int32_t* scalar = nullptr;  // 64 spare bytes for the caller (counters)
+  int n_blocks = 0;
+  int cur = 0;
 
-extern "C" int mval_topk_desc(const double* scores, int64_t n, int64_t index_offset, int32_t k, int64_t* out_idx,
-                              double* out_val, int32_t* out_count, void* stream_) {
-  using namespace mval;
-  if (int rc = require_device()) return rc;
-  MVAL_REQUIRE(n >= 0 && k >= 0, "mval_topk_desc: bad sizes");
-  MVAL_REQUIRE(n < (1ll << 32), "mval_topk_desc: more than 2^32 scores in one call");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (n == 0 || k == 0) {
-    if (out_count) MVAL_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int32_t), stream));
+  int alloc(int64_t n, cudaStream_t stream) {
+    n_blocks = (int)((n + kSortTile - 1) / kSortTile);
+    const size_t sz_keys = (sizeof(uint64_t) * n + 255) & ~size_t(255);
+    const size_t sz_idx = (sizeof(uint32_t) * n + 255) & ~size_t(255);
+    const size_t sz_counts = (sizeof(uint32_t) * 256 * (size_t)n_blocks + 255) & ~size_t(255);
+    MVAL_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), 2 * sz_keys + 2 * sz_idx + sz_counts + 256, stream));
+    keys[0] = reinterpret_cast<uint64_t*>(ws);
+    keys[1] = reinterpret_cast<uint64_t*>(ws + sz_keys);
+    idx[0] = reinterpret_cast<uint32_t*>(ws + 2 * sz_keys);
+    idx[1] = reinterpret_cast<uint32_t*>(ws + 2 * sz_keys + sz_idx);
+    counts = reinterpret_cast<uint32_t*>(ws + 2 * sz_keys + 2 * sz_idx);
+    scalar = reinterpret_cast<int32_t*>(ws + 2 * sz_keys + 2 * sz_idx + sz_counts);
     return MVAL_OK;
   }
-  MVAL_REQUIRE(scores && out_idx, "mval_topk_desc: null pointer");
-  const int n_blocks = (int)((n + kSortTile - 1) / kSortTile);
-  const size_t sz_keys = (sizeof(uint64_t) * n + 255) & ~size_t(255);
-  const size_t sz_idx = (sizeof(uint32_t) * n + 255) & ~size_t(255);
-  const size_t sz_counts = (sizeof(uint32_t) * 256 * (size_t)n_blocks + 255) & ~size_t(255);
-  char* ws = nullptr;
-  MVAL_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), 2 * sz_keys + 2 * sz_idx + sz_counts + 256, stream));
-  uint64_t* keys[2] = {reinterpret_cast<uint64_t*>(ws), reinterpret_cast<uint64_t*>(ws + sz_keys)};
-  uint32_t* idx[2] = {reinterpret_cast<uint32_t*>(ws + 2 * sz_keys), reinterpret_cast<uint32_t*>(ws + 2 * sz_keys + sz_idx)};
-  uint32_t* counts = reinterpret_cast<uint32_t*>(ws + 2 * sz_keys + 2 * sz_idx);
-  int32_t* n_valid = reinterpret_cast<int32_t*>(ws + 2 * sz_keys + 2 * sz_idx + sz_counts);
-  int rc = MVAL_OK;
-  auto run = [&]() -> int {
-    MVAL_CUDA(cudaMemsetAsync(n_valid, 0, sizeof(int32_t), stream));
-    topk_make_keys_kernel<<<(unsigned)((n + kSortThreads - 1) / kSortThreads), kSortThreads, 0, stream>>>(scores, n, keys[0],
-                                                                                                        idx[0], n_valid);
-    MVAL_LAUNCH_CHECK("topk_make_keys");
-    int cur = 0;
-    for (int pass = 0; pass < 8; ++pass) {
+  // keys[0] / idx[0] hold the input; first_pass..last_pass-1 are the 8-bit digits to sort on (LSD)
+  int sort(int64_t n, cudaStream_t stream, int first_pass = 0, int last_pass = 8) {
+    cur = 0;
+    for (int pass = first_pass; pass < last_pass; ++pass) {
       const int shift = pass * 8;
       radix_hist_kernel<<<n_blocks, kSortThreads, 0, stream>>>(keys[cur], n, shift, n_blocks, counts);
       MVAL_LAUNCH_CHECK("radix_hist");
@@ -200,14 +200,128 @@ extern "C" int mval_topk_desc(const double* scores, int64_t n, int64_t index_off
       MVAL_LAUNCH_CHECK("radix_scatter");
       cur ^= 1;
     }
-    const int64_t kk = k < n ? k : n;
-    topk_gather_kernel<<<(unsigned)((kk + 255) / 256), 256, 0, stream>>>(scores, idx[cur], n_valid, k, index_offset, out_idx,
-                                                                       out_val, out_count);
+    return MVAL_OK;
+  }
+  int release(cudaStream_t stream, int rc) {
+    if (ws == nullptr) return rc;
+    cudaError_t e = cudaFreeAsync(ws, stream);
+    ws = nullptr;
+    if (rc == MVAL_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");
+    return rc;
+  }
+};
+
+// ---- dict-insertion semantics for the guid-keyed tables of strategy.py:1115-1133 ----------------------------------
+// Row i carries the key (pose_i, frame_i) = the guid "%s-%s" % (pose, frame).  Inserting the rows in order into an
+// OrderedDict keeps a key at the position of its FIRST row and with the value of its LAST row.
+__global__ void __launch_bounds__(256)
+guid_keys_kernel(const int64_t* __restrict__ pose, const int64_t* __restrict__ frame, int64_t n, uint64_t* __restrict__ keys,
+                 uint32_t* __restrict__ idx, int32_t* __restrict__ bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t p = (uint64_t)pose[i], f = (uint64_t)frame[i];
+  if ((p >> 32) != 0ull || (f >> 32) != 0ull) *bad = 1;  // does not fit the packed 64-bit key
+  keys[i] = (p << 32) | (f & 0xffffffffull);
+  idx[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+guid_groups_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idx, int64_t n, uint8_t* __restrict__ keep,
+                   int32_t* __restrict__ src, int32_t* __restrict__ n_unique) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool first = false;
+  if (p < n) {
+    const uint64_t k = keys[p];
+    first = (p == 0) || keys[p - 1] != k;
+    const uint32_t row = idx[p];
+    if (first) {
+      int64_t q = p;  // the sort is stable: rows of one key are in ascending order, the last one carries the value
+      while (q + 1 < n && keys[q + 1] == k) ++q;
+      keep[row] = 1;
+      src[row] = (int32_t)idx[q];
+    } else {
+      keep[row] = 0;
+      src[row] = -1;
+    }
+  }
+  const int c = __syncthreads_count(first);
+  if (threadIdx.x == 0 && c) atomicAdd(n_unique, c);
+}
+
+__global__ void guid_finish_kernel(const int32_t* __restrict__ scalar, int32_t* __restrict__ out_unique) {
+  // scalar[0] = number of unique keys, scalar[1] = a key did not fit 32 + 32 bits
+  *out_unique = scalar[1] ? -1 : scalar[0];
+}
+
+}  // namespace mval
+
+static int topk_impl(const double* scores, int64_t n, int64_t index_offset, const int64_t* index_map, int32_t k,
+                     int64_t* out_idx, double* out_val, int32_t* out_count, cudaStream_t stream, const char* who) {
+  using namespace mval;
+  MVAL_REQUIRE(n >= 0 && k >= 0, "%s: bad sizes", who);
+  MVAL_REQUIRE(n < (1ll << 32), "%s: more than 2^32 scores in one call", who);
+  if (n == 0 || k == 0) {
+    if (out_count) MVAL_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int32_t), stream));
+    if (k > 0 && out_idx) MVAL_CUDA(cudaMemsetAsync(out_idx, 0xff, sizeof(int64_t) * k, stream));
+    if (k > 0 && out_val) MVAL_CUDA(cudaMemsetAsync(out_val, 0xff, sizeof(double) * k, stream));  // all ones = NaN
+    return MVAL_OK;
+  }
+  MVAL_REQUIRE(scores && out_idx, "%s: null pointer", who);
+  RadixSort rs;
+  if (int rc = rs.alloc(n, stream)) return rc;
+  auto run = [&]() -> int {
+    MVAL_CUDA(cudaMemsetAsync(rs.scalar, 0, sizeof(int32_t), stream));
+    topk_make_keys_kernel<<<(unsigned)((n + kSortThreads - 1) / kSortThreads), kSortThreads, 0, stream>>>(scores, n, rs.keys[0],
+                                                                                                        rs.idx[0], rs.scalar);
+    MVAL_LAUNCH_CHECK("topk_make_keys");
+    if (int rc = rs.sort(n, stream)) return rc;
+    topk_gather_kernel<<<(unsigned)((k + 255) / 256), 256, 0, stream>>>(scores, rs.idx[rs.cur], rs.scalar, k, index_offset,
+                                                                      index_map, out_idx, out_val, out_count);
     MVAL_LAUNCH_CHECK("topk_gather");
     return MVAL_OK;
   };
-  rc = run();
-  cudaError_t e = cudaFreeAsync(ws, stream);
-  if (rc == MVAL_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");
-  return rc;
+  return rs.release(stream, run());
+}
+
+extern "C" int mval_topk_desc(const double* scores, int64_t n, int64_t index_offset, int32_t k, int64_t* out_idx,
+                              double* out_val, int32_t* out_count, void* stream) {
+  if (int rc = mval::require_device()) return rc;
+  return topk_impl(scores, n, index_offset, nullptr, k, out_idx, out_val, out_count, static_cast<cudaStream_t>(stream),
+                   "mval_topk_desc");
+}
+
+extern "C" int mval_topk_merge(const double* scores, const int64_t* indices, int64_t n, int32_t k, int64_t* out_idx,
+                               double* out_val, int32_t* out_count, void* stream) {
+  if (int rc = mval::require_device()) return rc;
+  MVAL_REQUIRE(n == 0 || indices != nullptr, "mval_topk_merge: null pointer");
+  return topk_impl(scores, n, 0, indices, k, out_idx, out_val, out_count, static_cast<cudaStream_t>(stream), "mval_topk_merge");
+}
+
+extern "C" int mval_first_occurrence(const int64_t* pose, const int64_t* frame, int64_t n, uint8_t* out_keep, int32_t* out_src,
+                                     int32_t* out_unique, void* stream_) {
+  using namespace mval;
+  if (int rc = require_device()) return rc;
+  MVAL_REQUIRE(n >= 0 && n < (1ll << 31), "mval_first_occurrence: bad size");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MVAL_REQUIRE(out_unique != nullptr, "mval_first_occurrence: null pointer");
+  if (n == 0) {
+    MVAL_CUDA(cudaMemsetAsync(out_unique, 0, sizeof(int32_t), stream));
+    return MVAL_OK;
+  }
+  MVAL_REQUIRE(pose && frame && out_keep && out_src, "mval_first_occurrence: null pointer");
+  RadixSort rs;
+  if (int rc = rs.alloc(n, stream)) return rc;
+  auto run = [&]() -> int {
+    MVAL_CUDA(cudaMemsetAsync(rs.scalar, 0, 2 * sizeof(int32_t), stream));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    guid_keys_kernel<<<blocks, 256, 0, stream>>>(pose, frame, n, rs.keys[0], rs.idx[0], rs.scalar + 1);
+    MVAL_LAUNCH_CHECK("guid_keys");
+    if (int rc = rs.sort(n, stream)) return rc;
+    guid_groups_kernel<<<blocks, 256, 0, stream>>>(rs.keys[rs.cur], rs.idx[rs.cur], n, out_keep, out_src, rs.scalar);
+    MVAL_LAUNCH_CHECK("guid_groups");
+    guid_finish_kernel<<<1, 1, 0, stream>>>(rs.scalar, out_unique);
+    MVAL_LAUNCH_CHECK("guid_finish");
+    return MVAL_OK;
+  };
+  return rs.release(stream, run());
 }

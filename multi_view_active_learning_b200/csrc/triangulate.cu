@@ -30,7 +30,8 @@ template <typename PT>
 __global__ void __launch_bounds__(kVoteThreads)
 ransac_vote_kernel(const PT* __restrict__ xy, const double* __restrict__ proj, const uint8_t* __restrict__ valid,
                    int64_t n_tasks, int V, int J, int n_iters, double eps, uint64_t seed, int64_t frame_offset,
-                   const uint8_t* __restrict__ pairs_explicit, uint32_t* __restrict__ out_mask) {
+                   const int64_t* __restrict__ frame_keys, const uint8_t* __restrict__ pairs_explicit,
+                   uint32_t* __restrict__ out_mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n_all = V * (V - 1) / 2;
   const bool subset = n_all > n_iters;
@@ -65,7 +66,7 @@ ransac_vote_kernel(const PT* __restrict__ xy, const double* __restrict__ proj, c
   }
   uint16_t* perm = sPerm + warp * n_all;
   if (subset && pairs_explicit == nullptr)
-    draw_pair_subset(perm, n_all, n_iters, seed, frame_offset + frame, joint, lane);
+    draw_pair_subset(perm, n_all, n_iters, seed, frame_keys ? frame_keys[frame] : frame_offset + frame, joint, lane);
   __syncwarp();
   const uint8_t* explicit_row = pairs_explicit ? pairs_explicit + (int64_t)task * n_iters * 2 : nullptr;
   const uint32_t mask = ransac_vote_warp(
@@ -167,7 +168,7 @@ static int launch_ransac(const PT* xy, const double* proj, const uint8_t* valid,
   }
   const size_t smem = vote_smem_bytes(V);
   ransac_vote_kernel<PT><<<(unsigned)vote_blocks, kVoteThreads, smem, stream>>>(
-      xy, proj, valid, n_tasks, V, J, prm.n_iters, prm.epsilon, prm.pair_seed, prm.frame_offset, prm.pairs, mask);
+      xy, proj, valid, n_tasks, V, J, prm.n_iters, prm.epsilon, prm.pair_seed, prm.frame_offset, prm.frame_keys, prm.pairs, mask);
   MVAL_LAUNCH_CHECK("ransac_vote");
   ransac_final_kernel<PT><<<(unsigned)((n_tasks + 127) / 128), 128, 0, stream>>>(xy, proj, valid, mask, n_tasks, V, J,
                                                                                 out_xyz, out_reproj, out_inliers);

@@ -47,14 +47,24 @@ def _valid_u8(valid, n_frames, J, device):
     return v.to(device).contiguous()
 
 
-def ransac_params(n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0, frame_offset=0, pairs=None):
+def ransac_params(n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0, frame_offset=0, pairs=None, frame_keys=None):
     p = RansacParams()
     p.n_iters = int(n_iters)
     p.epsilon = float(epsilon)
     p.pair_seed = int(pair_seed) & ((1 << 64) - 1)
     p.frame_offset = int(frame_offset)
     p.pairs = None if pairs is None else pairs.data_ptr()
+    p.frame_keys = None if frame_keys is None else frame_keys.data_ptr()
     return p
+
+
+def _frame_keys(frame_keys, n_frames, device):
+    if frame_keys is None:
+        return None
+    k = torch.as_tensor(frame_keys).to(device=device, dtype=torch.int64).contiguous().reshape(-1)
+    if k.numel() != n_frames:
+        raise ValueError("frame_keys must hold one int64 per frame")
+    return k
 
 
 def decode_argmax(heatmaps, stride, valid=None, return_peak=False):
@@ -114,7 +124,7 @@ def _alloc_tri_outputs(N, J, device):
 
 
 def triangulate_ransac(keypoints_2d, proj, valid=None, n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0,
-                       frame_offset=0, pairs=None, direct_optimization=False):
+                       frame_offset=0, pairs=None, direct_optimization=False, frame_keys=None):
     """keypoints_2d [N, V, J, 2] int32/float32 CUDA, proj [N, V, 3, 4] -> dict of CUDA tensors
     (utils/triangulation.py:205-232 for N frames at once).  direct_optimization=True adds the Huber refinement of
     :319-336 on the inlier views (keypoints_3d, reproj_mean and metric are then those of the refined points;
@@ -135,7 +145,8 @@ def triangulate_ransac(keypoints_2d, proj, valid=None, n_iters=DEFAULT_N_ITERS, 
             raise ValueError("pairs must be uint8 [N, J, n_iters, 2]")
     out = _alloc_tri_outputs(N, J, kp.device)
     out["inlier_mask"] = torch.empty((N, J), dtype=torch.int32, device=kp.device)
-    prm = ransac_params(n_iters, epsilon, pair_seed, frame_offset, pairs)
+    fk = _frame_keys(frame_keys, N, kp.device)
+    prm = ransac_params(n_iters, epsilon, pair_seed, frame_offset, pairs, fk)
     with torch.cuda.device(kp.device):
         check(_lib.load().mval_triangulate_ransac(_ptr(kp), int(is_float), _ptr(P), _ptr(v), N, V, J, C.byref(prm),
                                                   _ptr(out["keypoints_3d"]), _ptr(out["reproj_mean"]),
@@ -152,7 +163,7 @@ def triangulate_ransac(keypoints_2d, proj, valid=None, n_iters=DEFAULT_N_ITERS, 
 
 
 def score_pool(heatmaps, proj, stride, valid=None, n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0,
-               frame_offset=0, return_keypoints_2d=True, map_score=None):
+               frame_offset=0, return_keypoints_2d=True, map_score=None, frame_keys=None):
     """Device-resident pool scoring: decode (arg-max) + RANSAC triangulation + per-frame uncertainty.
     map_score "HP" / "MPE" / "BSB" additionally returns out["map_score"] float32 [N, V, J] -- the per-map score of
     score_hp / score_peaks, evaluated in the same pass over the heat maps (mval_score_pool_scored)."""
@@ -166,7 +177,8 @@ def score_pool(heatmaps, proj, stride, valid=None, n_iters=DEFAULT_N_ITERS, epsi
     v = _valid_u8(valid, N, J, hm.device)
     out = _alloc_tri_outputs(N, J, hm.device)
     xy = torch.empty((N, V, J, 2), dtype=torch.int32, device=hm.device) if return_keypoints_2d else None
-    prm = ransac_params(n_iters, epsilon, pair_seed, frame_offset)
+    fk = _frame_keys(frame_keys, N, hm.device)
+    prm = ransac_params(n_iters, epsilon, pair_seed, frame_offset, frame_keys=fk)
     per_map = torch.empty((N, V, J), dtype=torch.float32, device=hm.device) if map_score is not None else None
     with torch.cuda.device(hm.device):
         check(_lib.load().mval_score_pool_scored(_ptr(hm), _ptr(P), _ptr(v), N, V, J, H, W, int(stride), C.byref(prm),
@@ -231,19 +243,62 @@ def score_xe(heatmaps, proj, keypoints_3d, sigma, return_per_map=False):
     return (out, per_map) if return_per_map else out
 
 
-def topk_desc(scores, k, index_offset=0):
+def check_async():
+    """Synchronises the current stream and raises if a persistent kernel launched on it tripped its mbarrier watchdog
+    (include/mval_b200.h: mval_check_async).  Call before results are consumed on the host."""
+    check(_lib.load().mval_check_async(_stream()))
+
+
+def topk_desc(scores, k, index_offset=0, fixed=False, out=None):
     """scores float64 CUDA [n] -> (idx int64 [m], val float64 [m]), m = min(k, #non-NaN): descending score, ties by
-    ascending index, NaN dropped (strategy.py:932-949)."""
+    ascending index, NaN dropped (strategy.py:932-949).
+    fixed=True: no host synchronisation -- returns (idx [k], val [k], count int32 [1]) with the slots beyond the count set
+    to -1 / NaN, the form the cross-rank merge (topk_merge) consumes.  ``out`` = (idx, val, count) buffers to reuse."""
     s = _cuda(scores, torch.float64, "scores").reshape(-1)
     n = s.numel()
-    k = int(min(k, n))
-    idx = torch.empty((max(k, 1),), dtype=torch.int64, device=s.device)
-    val = torch.empty((max(k, 1),), dtype=torch.float64, device=s.device)
-    cnt = torch.zeros((1,), dtype=torch.int32, device=s.device)
+    k = int(k) if fixed else int(min(k, n))
+    if out is None:
+        out = (torch.empty((max(k, 1),), dtype=torch.int64, device=s.device),
+               torch.empty((max(k, 1),), dtype=torch.float64, device=s.device),
+               torch.empty((1,), dtype=torch.int32, device=s.device))
+    idx, val, cnt = out
     with torch.cuda.device(s.device):
         check(_lib.load().mval_topk_desc(_ptr(s), n, int(index_offset), k, _ptr(idx), _ptr(val), _ptr(cnt), _stream()))
+    if fixed:
+        return idx, val, cnt
     m = int(cnt.item())
     return idx[:m], val[:m]
+
+
+def topk_merge(scores, indices, k, out=None):
+    """Candidates of all ranks (scores float64 [n] with NaN in unused slots, indices int64 [n] global pool indices, gathered
+    rank after rank) -> (idx int64 [k], val float64 [k], count int32 [1]) on the device: the global top-k in the
+    reference's order (strategy.py:945-949); no host synchronisation."""
+    s = _cuda(scores, torch.float64, "scores").reshape(-1)
+    g = _cuda(indices, torch.int64, "indices").reshape(-1)
+    assert s.numel() == g.numel()
+    k = int(k)
+    if out is None:
+        out = (torch.empty((max(k, 1),), dtype=torch.int64, device=s.device),
+               torch.empty((max(k, 1),), dtype=torch.float64, device=s.device),
+               torch.empty((1,), dtype=torch.int32, device=s.device))
+    with torch.cuda.device(s.device):
+        check(_lib.load().mval_topk_merge(_ptr(s), _ptr(g), s.numel(), k, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream()))
+    return out
+
+
+def first_occurrence(pose, frame):
+    """Dict-insertion semantics for rows keyed by guid = (pose, frame) (include/mval_b200.h: mval_first_occurrence):
+    -> (keep uint8 [n], src int32 [n], unique int32 [1]) CUDA tensors."""
+    p = _cuda(pose, torch.int64, "pose").reshape(-1)
+    f = _cuda(frame, torch.int64, "frame").reshape(-1)
+    n = p.numel()
+    keep = torch.empty((n,), dtype=torch.uint8, device=p.device)
+    src = torch.empty((n,), dtype=torch.int32, device=p.device)
+    unique = torch.empty((1,), dtype=torch.int32, device=p.device)
+    with torch.cuda.device(p.device):
+        check(_lib.load().mval_first_occurrence(_ptr(p), _ptr(f), n, _ptr(keep), _ptr(src), _ptr(unique), _stream()))
+    return keep, src, unique
 
 
 def sal_rank(sal_metric, inlier_count, excluded, inlier_threshold, k):

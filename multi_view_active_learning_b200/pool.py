@@ -48,6 +48,41 @@ def distributed_topk(local_topk, k, group=None):
     return merge_topk(torch.cat(all_val).cpu().numpy(), torch.cat(all_idx).cpu().numpy(), k)
 
 
+class RankingExchange:
+    """Cross-rank top-k without the host: every rank's fixed-size local top-k (ops.topk_desc(..., fixed=True): global
+    indices, unused slots -1 / NaN) is packed into ONE int64 buffer, exchanged with ONE all_gather_into_tensor and merged
+    on the device by mval_topk_merge; the selection stays on the device until the caller reads it.  Buffers are allocated
+    once per (k, device)."""
+
+    def __init__(self, k, device, group=None):
+        from . import ops  # noqa: F401
+
+        self.k, self.group = int(k), group
+        self.multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.multi else 1
+        self.local = (torch.empty(self.k, dtype=torch.int64, device=device), torch.empty(self.k, dtype=torch.float64, device=device),
+                      torch.empty(1, dtype=torch.int32, device=device))
+        self.send = torch.empty(2 * self.k, dtype=torch.int64, device=device)
+        self.recv = torch.empty(self.world * 2 * self.k, dtype=torch.int64, device=device)
+        self.out = (torch.empty(self.k, dtype=torch.int64, device=device), torch.empty(self.k, dtype=torch.float64, device=device),
+                    torch.empty(1, dtype=torch.int32, device=device))
+
+    def __call__(self, scores, index_offset):
+        """scores float64 CUDA [n_local] of this rank's contiguous shard starting at global index ``index_offset`` ->
+        (idx int64 [k], val float64 [k], count int32 [1]) CUDA, identical on every rank."""
+        from . import ops
+
+        idx, val, cnt = ops.topk_desc(scores, self.k, index_offset=index_offset, fixed=True, out=self.local)
+        if not self.multi:
+            return idx, val, cnt
+        self.send[: self.k].copy_(idx)
+        self.send[self.k:].copy_(val.view(torch.int64))
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        r = self.recv.view(self.world, 2, self.k)
+        return ops.topk_merge(r[:, 1].contiguous().view(torch.float64).reshape(-1), r[:, 0].contiguous().reshape(-1), self.k,
+                              out=self.out)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # coreset k-center greedy over row-sharded features (utils/coreset.py:71-95 across ranks)
 # ----------------------------------------------------------------------------------------------------------------

@@ -12,8 +12,10 @@ What changes relative to the reference's ``_compute_sal_dict`` (strategy.py:1004
     loop waits for the device;
   * no per-frame collectives: every rank accumulates its frames on the device and the 8 per-frame all_gathers
     (:1106-1114) become one all_gather per field at the end;
-  * the guid-keyed OrderedDicts are built once, in the order the reference would have inserted them (for each
-    local position, rank 0..G-1), with the reference's float32 / float64 roundings.
+  * the five guid-keyed dicts are views (table.py) of one device-resident table whose rows are in the order the
+    reference would have inserted them (for each local position, rank 0..G-1; a repeated guid keeps its first position
+    and its last value) and whose values carry the reference's float32 / float64 roundings; Python
+    objects are only made for what is looked at -- the selected guids, or everything when SAL-DICT-ITER-k is written.
 """
 import json
 import math
@@ -25,6 +27,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .table import LazyColumn, PoolTable, SalDict, dumps
 from .utils import coreset, triangulation
 
 
@@ -121,7 +124,9 @@ class ScoringSelectionMixin:
 
     # ------------------------------------------------------------------------------------------ selection
     def _sal_pseudo_labeling(self, train_dataset, al_num_frames, pseudo_num_frames, pose_estimator):
-        """Reference strategy.py:915-1002."""
+        """Reference strategy.py:915-1002.  ``sal_dict`` is the device-resident table of ``_compute_sal_dict`` (table.py):
+        ranking, coreset features, the pseudo-label filter and the cluster ids are all computed from its CUDA columns and
+        only the selected rows are turned into guid strings -- nothing here is O(pool) in Python."""
         cfg = self.al_cfg
         if cfg.AL.STRATEGY == "RANDOM" and cfg.EXPR_TYPE == "AL":
             train_dataset, al_guids = self._random_sample_frames(train_dataset, al_num_frames, seed=cfg.RANDOM_SEED)
@@ -154,7 +159,10 @@ class ScoringSelectionMixin:
                         sal_sampled_guids.append(guid)
             else:
                 sal_sampled_guids = random.sample(sal_guids[:2 * pseudo_num_frames], pseudo_num_frames)
-            train_dataset.pseudo_label_by_frame_guids(sal_sampled_guids, sal_dict["pred_3d_keypoints"])
+            pseudo_labels = sal_dict["pred_3d_keypoints"]
+            if isinstance(pseudo_labels, LazyColumn):
+                pseudo_labels.prefetch(sal_sampled_guids)  # one device gather for the rows the dataset reads (:998-1000)
+            train_dataset.pseudo_label_by_frame_guids(sal_sampled_guids, pseudo_labels)
         return train_dataset, al_guids, sal_sampled_guids, sal_dict
 
     def _cluster_ids(self, pred_3d_keypoints, guids, margin_rtol=1e-9):
@@ -164,13 +172,21 @@ class ScoringSelectionMixin:
         reference does, so the labels are the reference's."""
         if not guids:
             return []
-        pred = torch.tensor([pred_3d_keypoints[g] for g in guids], dtype=torch.float32).cuda()
+        if isinstance(pred_3d_keypoints, LazyColumn):
+            dev = pred_3d_keypoints.device_values
+            rows = torch.as_tensor(pred_3d_keypoints.table.rows_of(guids), dtype=torch.int64, device=dev.device)
+            pred = dev[rows]
+        else:
+            pred = torch.tensor([pred_3d_keypoints[g] for g in guids], dtype=torch.float32).cuda()
         centres = np.asarray(self.kmeans.cluster_centers_, dtype=np.float64)
         label, margin = ops.kmeans_assign(pred, centres, self.joint_root_index)
         label, margin = label.cpu().numpy(), margin.cpu().numpy()
         cmax = float(np.abs(centres).max())
         scale = cmax * max(cmax, 2.0 * float(pred.abs().max())) * centres.shape[1] + 1.0  # bound on |x||c| d
-        for i in np.nonzero(~(margin > margin_rtol * scale))[0].tolist():
+        close = np.nonzero(~(margin > margin_rtol * scale))[0].tolist()
+        if close and isinstance(pred_3d_keypoints, LazyColumn):
+            pred_3d_keypoints.prefetch([guids[i] for i in close])
+        for i in close:
             kp = np.array(pred_3d_keypoints[guids[i]]).T
             kp = (kp[0:3, :] - kp[0:3, self.joint_root_index:self.joint_root_index + 1]).flatten()
             label[i] = self.kmeans.predict([kp])[0]
@@ -180,6 +196,17 @@ class ScoringSelectionMixin:
     def _sal_candidates(sal_dict, al_guids, pseudo_label_guids, inlier_threshold, limit=None):
         """strategy.py:957-975: guids with a non-NaN sal_metric and inlier_count > threshold that were neither picked by
         the AL step nor pseudo-labelled before, by ascending sal_metric (ties in dict order); the first ``limit``."""
+        table = getattr(sal_dict, "table", None)
+        if table is not None:
+            if table.n == 0:
+                return []
+            metric, inliers = table.values["sal_metric"], table.values["inlier_count"]
+            excluded = torch.zeros(table.n, dtype=torch.uint8, device=metric.device)
+            rows = table.rows_of(list(al_guids) + list(pseudo_label_guids), missing_ok=True)
+            if rows:
+                excluded[torch.as_tensor(rows, dtype=torch.int64, device=metric.device)] = 1
+            idx = ops.sal_rank(metric, inliers, excluded, float(inlier_threshold), table.n if limit is None else int(limit))
+            return table.guid_at(idx)
         keys = list(sal_dict["sal_metric"].keys())
         if not keys:
             return []
@@ -193,10 +220,13 @@ class ScoringSelectionMixin:
     @staticmethod
     def _rank_nlargest(al_metric, n):
         """strategy.py:932-949 (NaN filter + heapq.nlargest) as a device top-k: descending score, ties by dict
-        insertion order."""
-        keys = list(al_metric.keys())
-        if not keys or n <= 0:
+        insertion order.  A LazyColumn is ranked straight from its CUDA column."""
+        if n <= 0 or len(al_metric) == 0:
             return []
+        if isinstance(al_metric, LazyColumn):
+            idx, _ = ops.topk_desc(al_metric.device_values, n)
+            return al_metric.table.guid_at(idx)
+        keys = list(al_metric.keys())
         scores = torch.tensor(list(al_metric.values()), dtype=torch.float64).cuda()
         idx, _ = ops.topk_desc(scores, n)
         return [keys[i] for i in idx.cpu().tolist()]
@@ -279,14 +309,11 @@ class ScoringSelectionMixin:
     def _compute_sal_dict(self, data_loader, pose_estimator):
         """Reference strategy.py:1004-1147, batched (see module docstring).  Nothing in the loop waits for the device:
         every batch enqueues its forward and ONE fused scoring launch and keeps the results as CUDA tensors, so the
-        kernels of batch k run while the loader collates and uploads batch k + 1; the frame scores of HP / MPE / BSB, the
-        MKPE and the dicts are formed once per pool."""
+        kernels of batch k run while the loader collates and uploads batch k + 1; the frame scores of HP / MPE / BSB and
+        the MKPE are formed once per pool, the ranks exchange two packed tensors, and the result is the device-resident
+        table of table.py viewed through the reference's five guid-keyed dicts."""
         cfg = self.al_cfg
         acc = {k: [] for k in ("sal", "inl", "al", "map", "pred", "gt", "valid", "pose", "frame")}
-        n_done = 0
-        rank_base = 0
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            rank_base = torch.distributed.get_rank() << 32  # distinct pair-subset streams per rank (V >= 12 only)
         for dp in data_loader:
             with torch.no_grad():
                 heatmaps = self._compute_batch_heatmap(pose_estimator, dp)
@@ -294,13 +321,17 @@ class ScoringSelectionMixin:
                 B = dp["proj_matrices"].shape[0]
                 heatmaps = heatmaps.reshape([B, -1, kp, w, h]).float()
                 joint_valid = dp["joint_valid"]
+                pose = torch.as_tensor(dp["pose"]).reshape(-1).cuda(non_blocking=True).long()
+                frame = torch.as_tensor(dp["frame_id"]).reshape(-1).cuda(non_blocking=True).long()
+                n_views = heatmaps.shape[1]
+                # more than 64 view pairs (utils/triangulation.py:279-282): the pair subsets are keyed by the frame's guid,
+                # not by its position, so that the result does not depend on world size, rank or loader order
+                keys = (pose << 32) + frame if n_views * (n_views - 1) // 2 > 64 else None
                 tri = triangulation.triangulation_batch(
                     heatmaps, dp["proj_matrices"], cfg.POSE_ESTIMATOR.STRIDE, joint_valid,
                     use_soft_argmax=cfg.AL.USE_SOFTARGMAX, pair_seed=getattr(cfg, "RANDOM_SEED", 0),
-                    frame_offset=rank_base + n_done, use_reprojection_xe=cfg.AL.USE_REPROJECTION_XE,
-                    sigma=cfg.AL.REPROJECTION_SIGMA,
+                    frame_keys=keys, use_reprojection_xe=cfg.AL.USE_REPROJECTION_XE, sigma=cfg.AL.REPROJECTION_SIGMA,
                     map_score=cfg.AL.STRATEGY if cfg.AL.STRATEGY in ("HP", "MPE", "BSB") else None)
-                n_done += B
                 field, value = self._batch_al_metric(B, tri)
                 acc[field].append(value)
                 acc["sal"].append(tri["metric"].float())  # torch.Tensor([metric]) -> float32 (:1061)
@@ -308,52 +339,114 @@ class ScoringSelectionMixin:
                 acc["pred"].append(tri["keypoints_3d"].float())  # torch.Tensor(keypoints_3d) -> float32 (:1046)
                 acc["gt"].append(dp["3d_keypoints"].cuda(non_blocking=True).float())
                 acc["valid"].append(torch.as_tensor(joint_valid).cuda(non_blocking=True).float())
-                acc["pose"].append(torch.as_tensor(dp["pose"]).reshape(-1).cuda(non_blocking=True).long())
-                acc["frame"].append(torch.as_tensor(dp["frame_id"]).reshape(-1).cuda(non_blocking=True).long())
+                acc["pose"].append(pose)
+                acc["frame"].append(frame)
         fields = {k: (torch.cat(v) if v else torch.zeros(0).cuda()) for k, v in acc.items()}
         al_is_f64 = cfg.AL.STRATEGY == "TRIANGULATION"
         per_map = fields.pop("map")
+        if getattr(ops, "check_async", None) is not None and fields["sal"].is_cuda:
+            ops.check_async()  # a tripped watchdog of any launch above raises here, before the scores are used
+        if acc["sal"]:
+            self._raise_reference_errors(fields["valid"], per_map if acc["map"] else None)
         if acc["map"]:
             fields["al"], al_is_f64 = self._pool_al_metric(per_map, fields["valid"])
-        fields = self._gather_interleaved(fields)
-        return self._build_sal_dict(fields, al_is_f64)
+        return self._build_table(fields, al_is_f64).as_sal_dict()
+
+    def _raise_reference_errors(self, valid, per_map):
+        """The batched pass cannot raise in the middle of a frame; the reference's per-frame errors are raised here, once
+        per pool: a frame without a valid joint is np.min([]) in triangulation() (utils/triangulation.py:231), and a BSB map
+        with fewer than two peaks is probs[1] of a one-element list (strategy.py:1208)."""
+        flags = [(valid.sum(dim=1) == 0).any()]
+        if per_map is not None and self.al_cfg.AL.STRATEGY == "BSB":
+            flags.append((torch.isnan(per_map) & (valid != 0)[:, None, :]).any())
+        flags = torch.stack(flags).cpu().tolist()
+        if flags[0]:
+            raise ValueError("zero-size array to reduction operation minimum which has no identity")
+        if len(flags) > 1 and flags[1]:
+            raise IndexError("list index out of range")
 
     @staticmethod
-    def _gather_interleaved(fields):
-        """One all_gather per field; result ordered as the reference's per-frame gathers would have inserted them:
-        local position t of rank r lands at t * world + r (strategy.py:1106-1133)."""
+    def _gather_rows(packs):
+        """packs: tensors [n_local, ...] of this rank's rows (loader order).  Returns them for ALL ranks in the order the
+        reference's per-frame all_gathers insert rows into its dicts: local position t of rank r lands at t * world + r
+        (strategy.py:1106-1133).  One all_gather_into_tensor per pack (the reference: 8 list all_gathers per FRAME)."""
         import torch.distributed as dist
 
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return fields
+            return packs
         world = dist.get_world_size()
-        out = {}
-        for k, t in fields.items():
-            parts = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(parts, t.contiguous())
-            out[k] = torch.stack(parts, dim=1).reshape((-1,) + tuple(t.shape[1:]))
+        n = int(packs[0].shape[0])
+        sizes = torch.empty(world, dtype=torch.int64, device=packs[0].device)
+        dist.all_gather_into_tensor(sizes, torch.tensor([n], dtype=torch.int64, device=packs[0].device))
+        sizes = sizes.cpu().tolist()
+        n_max = max(sizes)
+        out = []
+        for t in packs:
+            t = t.contiguous()
+            if n < n_max:  # a loader without the DistributedSampler's padding: pad, gather, drop the padding below
+                pad = torch.zeros((n_max - n,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                t = torch.cat([t, pad])
+            g = torch.empty((world * n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(g, t)
+            g = g.reshape((world, n_max) + tuple(t.shape[1:])).transpose(0, 1).reshape((n_max * world,) + tuple(t.shape[1:]))
+            out.append(g)
+        if min(sizes) < n_max:
+            dev = out[0].device
+            live = (torch.arange(n_max, device=dev)[:, None] < torch.tensor(sizes, device=dev)[None, :]).reshape(-1)
+            out = [g[live] for g in out]
         return out
 
     @staticmethod
-    def _build_sal_dict(f, al_is_f64):
-        sal_dict = {k: OrderedDict() for k in ("al_metric", "sal_metric", "inlier_count", "pred_3d_keypoints", "mkpe")}
-        n = f["sal"].shape[0]
-        if n == 0:
-            return sal_dict
-        # utils/evaluation.py:198-208 compute_mkpe([pred], [gt], [valid]) per frame, float32 (mval_mkpe)
-        mkpe = ops.mkpe(f["pred"], f["gt"], f["valid"]).cpu().tolist()
-        poses, frames = f["pose"].cpu().tolist(), f["frame"].cpu().tolist()
-        sal = f["sal"].cpu().tolist()
-        inl = f["inl"].cpu().tolist()
-        al = f["al"].cpu().numpy()
-        al = al.tolist() if al_is_f64 else al.astype(np.float32).astype(np.float64).tolist()
-        pred = f["pred"].cpu().numpy().tolist()
-        # one pass per dict at C speed: the reference inserts guid by guid (:1115-1133), same order, same values
-        guids = ["%s-%s" % pf for pf in zip(poses, frames)]
-        for name, values in (("sal_metric", sal), ("inlier_count", inl), ("pred_3d_keypoints", pred), ("al_metric", al),
-                             ("mkpe", mkpe)):
-            sal_dict[name].update(zip(guids, values))
-        return sal_dict
+    def _gather_interleaved(fields):
+        """Dict form of ``_gather_rows`` (kept for callers of the round-1 name)."""
+        names = list(fields)
+        return dict(zip(names, ScoringSelectionMixin._gather_rows([fields[k] for k in names])))
+
+    def _build_table(self, f, al_is_f64):
+        """Local rows -> MKPE (utils/evaluation.py:198-208, on the device, before the exchange: the reference gathers the
+        ground truth of every frame to every rank only to compute it there) -> two packed exchanges -> dict-insertion
+        semantics for repeated guids (mval_first_occurrence) -> PoolTable."""
+        n, J = f["sal"].shape[0], (f["pred"].shape[1] if f["pred"].dim() == 3 else 0)
+        dev = f["sal"].device
+        if n:
+            mkpe = ops.mkpe(f["pred"], f["gt"], f["valid"])
+            al = f["al"].double()
+            if not al_is_f64:
+                al = al.float().double()  # torch.tensor(python float) of the reference is float32 (:1077-1090)
+            pack32 = torch.cat([f["sal"].reshape(n, 1), f["inl"].reshape(n, 1), mkpe.reshape(n, 1), f["pred"].reshape(n, -1)], dim=1)
+            pack64 = torch.stack([f["pose"], f["frame"], al.view(torch.int64)], dim=1)
+        else:
+            pack32 = torch.zeros((0, 3 + 3 * J), dtype=torch.float32, device=dev)
+            pack64 = torch.zeros((0, 3), dtype=torch.int64, device=dev)
+        pack32, pack64 = self._gather_rows([pack32, pack64])
+        if pack64.shape[0]:
+            pose, frame = pack64[:, 0].contiguous(), pack64[:, 1].contiguous()
+            keep, src, unique = ops.first_occurrence(pose, frame)
+            unique = int(unique.cpu().item())
+            if unique < 0:
+                src = self._first_occurrence_host(pose, frame)  # ids beyond 32 bits: dict semantics on the host
+                rows = torch.nonzero(src >= 0).reshape(-1)
+                pack32, pack64 = pack32[src[rows].long()], torch.cat([pack64[rows, :2], pack64[src[rows].long(), 2:]], dim=1)
+            elif unique != pack64.shape[0]:
+                rows = torch.nonzero(keep).reshape(-1)
+                last = src[rows].long()
+                pack32, pack64 = pack32[last], torch.cat([pack64[rows, :2], pack64[last, 2:]], dim=1)
+        N = pack64.shape[0]
+        return PoolTable(pose=pack64[:, 0].contiguous(), frame=pack64[:, 1].contiguous(),
+                         al=pack64[:, 2].contiguous().view(torch.float64), sal=pack32[:, 0].contiguous(),
+                         inl=pack32[:, 1].contiguous(), mkpe=pack32[:, 2].contiguous(),
+                         pred=pack32[:, 3:].contiguous().reshape(N, J, 3))
+
+    @staticmethod
+    def _first_occurrence_host(pose, frame):
+        first, last = {}, {}
+        for i, key in enumerate(zip(pose.cpu().tolist(), frame.cpu().tolist())):
+            first.setdefault(key, i)
+            last[key] = i
+        src = torch.full((pose.shape[0],), -1, dtype=torch.int32)
+        for key, i in first.items():
+            src[i] = last[key]
+        return src.to(pose.device)
 
 
 class SelectionLogMixin:
@@ -381,7 +474,7 @@ class SelectionLogMixin:
                 with self._open(self._log_path("SAL-GUID-ITER-%d" % iteration), "w") as f:
                     f.write(json.dumps(sal_guids))
             with self._open(self._log_path("SAL-DICT-ITER-%d" % iteration), "w") as f:
-                f.write(json.dumps(sal_dict))
+                f.write(dumps(sal_dict))  # json.dumps of the five dicts the LazyColumns stand for
         with self._open(self._log_path("SAMPLED-GUID-ITER-%d" % iteration), "w") as f:
             f.write(json.dumps(al_guids))
 

@@ -77,24 +77,26 @@ def triangulation(
 
 def triangulation_batch(heatmaps, proj_matricies, stride, valid_joints, use_soft_argmax=False, n_iters=64,
                         reprojection_error_epsilon=5, pair_seed=0, frame_offset=0, use_reprojection_xe=False, sigma=None,
-                        direct_optimization=False, map_score=None):
+                        direct_optimization=False, map_score=None, frame_keys=None):
     """Pool-level entry: heatmaps [N, V, J, H, W] (CUDA), proj_matricies [N, V, 3, 4], valid_joints [N, J] or [J].
     Returns a dict of CUDA tensors (keypoints_3d [N,J,3] f64, keypoints_2d, metric [N] f64, inlier_count [N] i32,
     reproj_mean [N,J], inliers [N,J]).  For C(V,2) > n_iters the view-pair subsets are the counter-based ones keyed
-    by (pair_seed, frame_offset + frame, joint) -- see include/mval_b200.h.
+    by (pair_seed, frame key, joint), frame key = frame_keys[frame] (int64 [N], e.g. derived from the guid, so that the
+    subsets do not depend on sharding) or frame_offset + frame -- see include/mval_b200.h.
     map_score "HP" / "MPE" / "BSB": also return "map_score" float32 [N, V, J], the per-map AL score of strategy.py:1149-1215;
     on the arg-max path it comes out of the same pass over the heat maps as the triangulation."""
     if use_soft_argmax or direct_optimization:
         # the refinement (utils/triangulation.py:319-336) needs the inlier masks, which only the unfused path keeps
         kp = ops.decode_softargmax(heatmaps, stride) if use_soft_argmax else ops.decode_argmax(heatmaps, stride, valid_joints)
         out = ops.triangulate_ransac(kp, proj_matricies, valid_joints, n_iters, float(reprojection_error_epsilon),
-                                     pair_seed, frame_offset, direct_optimization=bool(direct_optimization))
+                                     pair_seed, frame_offset, direct_optimization=bool(direct_optimization),
+                                     frame_keys=frame_keys)
         if map_score is not None:
             out["map_score"] = (ops.score_hp(heatmaps, valid_joints) if map_score == "HP"
                                 else ops.score_peaks(heatmaps, map_score, valid_joints))
     else:
         out = ops.score_pool(heatmaps, proj_matricies, stride, valid_joints, n_iters, float(reprojection_error_epsilon),
-                             pair_seed, frame_offset, map_score=map_score)
+                             pair_seed, frame_offset, map_score=map_score, frame_keys=frame_keys)
     if use_reprojection_xe:
         # utils/triangulation.py:223-224: metric = _compute_xe(...) replaces the mean reprojection error
         out["reproj_metric"] = out["metric"]

@@ -264,7 +264,7 @@ def ransac_pool(P, pts, valid, pairs, eps=5.0, direct_optimization=False):
 
 
 def triangulate_pool(heatmaps, P, stride, valid, n_iters=64, eps=5.0, pair_seed=0, frame_offset=0,
-                     use_soft_argmax=False, keypoints_2d=None, chunk=256, direct_optimization=False):
+                     use_soft_argmax=False, keypoints_2d=None, chunk=256, direct_optimization=False, frame_keys=None):
     """Pool-level restatement of reference utils/triangulation.py:168-233 (use_reprojection_xe=False;
     direct_optimization=True adds the Huber refinement of :319-336 through scipy, exactly as the reference does).
 
@@ -296,7 +296,8 @@ def triangulate_pool(heatmaps, P, stride, valid, n_iters=64, eps=5.0, pair_seed=
             for n in range(s, e):
                 for j in range(J):
                     if valid[n, j]:
-                        pairs[n - s, j] = allp[pair_subset_indices(n_all, n_iters, pair_seed, frame_offset + n, j)]
+                        pairs[n - s, j] = allp[pair_subset_indices(
+                            n_all, n_iters, pair_seed, frame_offset + n if frame_keys is None else int(frame_keys[n]), j)]
         r = ransac_pool(P[s:e], keypoints_2d[s:e], valid[s:e], pairs, eps, direct_optimization)
         for o, x in zip(outs, r):
             o.append(x)

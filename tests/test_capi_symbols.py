@@ -54,8 +54,9 @@ def test_no_cpu_fallback_without_device():
 
 def test_ransac_params_layout_matches_header():
     p = _lib.RansacParams()
-    assert ctypes.sizeof(p) == 40
+    assert ctypes.sizeof(p) == 48
     assert _lib.RansacParams.epsilon.offset == 8 and _lib.RansacParams.pairs.offset == 32
+    assert _lib.RansacParams.frame_keys.offset == 40
 
 
 def test_header_is_plain_c(tmp_path):

@@ -82,7 +82,22 @@ def test_distributed_topk_and_gather_world2():
         assert gx == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0] and gy == gx
 
 
-def _sal_worker(rank, world, port, n_frames, out_q):
+def _first_occurrence_numpy(pose, frame):
+    """Test stand-in for mval_first_occurrence (the device call is stubbed on CPU): OrderedDict insertion semantics."""
+    keys = list(zip(pose.tolist(), frame.tolist()))
+    first, last = {}, {}
+    for i, k in enumerate(keys):
+        first.setdefault(k, i)
+        last[k] = i
+    keep = torch.zeros(len(keys), dtype=torch.uint8)
+    src = torch.full((len(keys),), -1, dtype=torch.int32)
+    for k, i in first.items():
+        keep[i] = 1
+        src[i] = last[k]
+    return keep, src, torch.tensor([len(first)], dtype=torch.int32)
+
+
+def _sal_worker(rank, world, port, n_frames, out_q, mode="even"):
     """One rank of _compute_sal_dict with the device calls stubbed (CPU tensors, gloo): frames are dealt round-robin like
     the reference's DistributedSampler (strategy.py:753), every rank must end with the same dicts in the order the
     reference's per-frame all_gathers insert them (frame 0, 1, 2, ...: local position t of rank r = global t * world + r)."""
@@ -97,6 +112,7 @@ def _sal_worker(rank, world, port, n_frames, out_q):
         V, J, B = 2, 4, 3
         torch.Tensor.cuda = lambda self, *a, **k: self
         ops.mkpe = lambda p, g, v: p[:, 0, 0].float()
+        ops.first_occurrence = _first_occurrence_numpy
 
         def fake_triangulation_batch(hm, P, stride, joint_valid, **kw):
             ids = hm[:, 0, 0, 0, 0].double()  # the frame id travels in the first heat-map pixel
@@ -106,6 +122,8 @@ def _sal_worker(rank, world, port, n_frames, out_q):
 
         ST.triangulation.triangulation_batch = fake_triangulation_batch
         mine = list(range(rank, n_frames, world))
+        if mode == "sampler_padding" and len(mine) < -(-n_frames // world):
+            mine.append(rank - (n_frames % world))  # DistributedSampler repeats the head of the index list (strategy.py:753)
 
         def loader():
             for s in range(0, len(mine), B):
@@ -128,15 +146,22 @@ def _sal_worker(rank, world, port, n_frames, out_q):
         dist.destroy_process_group()
 
 
-def test_compute_sal_dict_world2_order_and_values():
-    n_frames, world = 12, 2  # 6 frames per rank, batches of 3
+import pytest
+
+
+@pytest.mark.parametrize("n_frames,mode", [(12, "even"), (11, "uneven"), (11, "sampler_padding")])
+def test_compute_sal_dict_world2_order_and_values(n_frames, mode):
+    """even: 6 frames per rank, batches of 3.  uneven: a loader that gives rank 1 one frame less (rows are padded for the
+    exchange and dropped again).  sampler_padding: the DistributedSampler's repeat of frame 0 on rank 1 -- the guid keeps
+    its first position and appears once, exactly like the reference's dict insertion."""
+    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_sal_worker, args=(r, world, port, n_frames, q)) for r in range(world)]
+    procs = [ctx.Process(target=_sal_worker, args=(r, world, port, n_frames, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=180) for _ in range(world)]
+    results = [q.get(timeout=120) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -272,3 +272,157 @@ def test_sal_cluster_balanced_pseudo_labels(tmp_path):
             exp.append(g)
     assert sal_guids == exp and 0 < len(exp) <= 9
     assert ds.pseudo_label_guids == exp
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# round 2: the device-resident sal_dict (table.py) against the dict path on a 10k-frame pool
+# --------------------------------------------------------------------------------------------------------------------
+class DevicePool:
+    """Loader + dataset surface over device-resident heat maps (identity pose estimator)."""
+
+    def __init__(self, n, V=8, J=19, seed=3, batch=2048, n_labeled=50, dup_tail=0):
+        from multi_view_active_learning_b200 import ops
+
+        pool = S.make_pool(n, V, J, seed=seed, p_outlier=0.15, valid_prob=0.97)
+        self.n, self.batch = n, batch
+        self.hm = ops.synth_heatmaps(torch.from_numpy(pool["centres"]).cuda(), 64, 64, 1.0, 0.05, seed)
+        self.P = torch.from_numpy(pool["P"]).cuda()
+        self.valid = torch.from_numpy(pool["valid"].astype(np.float32)).cuda()
+        self.gt = torch.from_numpy(np.concatenate([pool["X"].transpose(0, 2, 1), np.ones((n, 1, J))], axis=1).astype(np.float32)).cuda()
+        self.frame = torch.arange(n, dtype=torch.int64).cuda() * 2 + 5
+        self.pose = (160000 + torch.arange(n, dtype=torch.int64) % 7).cuda()
+        self.order = list(range(n)) + list(range(dup_tail))  # DistributedSampler-style repeat of the head
+        rng = np.random.default_rng(seed + 1)
+        self.labeled_data = [{"3d_keypoints": rng.normal(size=(4, J)) * 300} for _ in range(n_labeled)]
+        self.pseudo_label_guids, self.labeled, self.pseudo_seen = [], [], None
+
+    def resample_unlabeled_data(self):
+        pass
+
+    def get_al_dict_for_coreset(self):
+        return {i: np.array(d["3d_keypoints"]).transpose([1, 0]) for i, d in enumerate(self.labeled_data)}
+
+    def label_by_frame_guids(self, guids):
+        self.labeled = list(guids)
+
+    def pseudo_label_by_frame_guids(self, guids, pseudo_labels):
+        self.pseudo_label_guids = guids
+        self.pseudo_seen = [np.array(pseudo_labels[g]).transpose([1, 0]) for g in guids]
+
+    def loader(self):
+        for o in range(0, len(self.order), self.batch):
+            idx = torch.as_tensor(self.order[o:o + self.batch]).cuda()
+            yield {"images": self.hm[idx], "proj_matrices": self.P[idx], "joint_valid": self.valid[idx],
+                   "3d_keypoints": self.gt[idx], "pose": self.pose[idx], "frame_id": self.frame[idx]}
+
+
+@pytest.mark.parametrize("strategy,expr", [("TRIANGULATION", "AL"), ("TRIANGULATION", "SAL"), ("CORESET", "AL"), ("HP", "SAL")])
+def test_device_table_selection_equals_dict_path(strategy, expr):
+    """_sal_pseudo_labeling over the device-resident table must select exactly what the same code selects from the
+    materialised reference-style dicts (the round-1 path), on a 10 000-frame pool, incl. the sampler's repeated frames."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import random
+
+    from multi_view_active_learning_b200 import utils as U
+    from multi_view_active_learning_b200.table import LazyColumn, SalDict
+
+    cfg = make_cfg(strategy, expr=expr)
+    st = make_strategy(cfg)
+    ds = DevicePool(10_000, dup_tail=3)
+    st._get_dataloader = lambda d, bs, nw: ds.loader()
+    random.seed(11)
+    _, al_guids, sal_guids, sal = st._sal_pseudo_labeling(ds, 300, 40, torch.nn.Identity())
+    assert isinstance(sal, SalDict) and isinstance(sal["al_metric"], LazyColumn)
+    assert len(sal["al_metric"]) == 10_000 and sal.table.n == 10_000  # the 3 repeated frames were folded into their guids
+    plain = sal.to_plain()
+    assert list(plain["al_metric"])[:3] == ["160000-5", "160001-7", "160002-9"]
+    # the same selection from plain dicts
+    if strategy == "CORESET":
+        exp_al = U.coreset.CoreSet(plain["pred_3d_keypoints"], ds.get_al_dict_for_coreset(), 2).select_batch(300)
+    else:
+        exp_al = st._rank_nlargest(plain["al_metric"], 300)
+        finite = {g: v for g, v in plain["al_metric"].items() if not math.isnan(v)}
+        assert exp_al == SO.rank_nlargest(finite, 300)
+    assert al_guids == exp_al and ds.labeled == exp_al and len(set(al_guids)) == 300
+    if expr == "SAL":
+        cand = st._sal_candidates(plain, al_guids, [], cfg.SAL.INLIER_THRESHOLD, 80)
+        assert cand == st._sal_candidates(sal, al_guids, [], cfg.SAL.INLIER_THRESHOLD, 80)
+        lit = {g: m for g, m in plain["sal_metric"].items()
+               if g not in al_guids and not math.isnan(m) and plain["inlier_count"][g] > cfg.SAL.INLIER_THRESHOLD}
+        assert cand == sorted(lit, key=lit.get)[:80]
+        random.seed(11)
+        assert sal_guids == random.sample(cand, 40)
+        assert all(np.array_equal(a, np.array(plain["pred_3d_keypoints"][g]).T) for a, g in zip(ds.pseudo_seen, sal_guids))
+        # a long exclusion list (pseudo labels of earlier iterations) goes through the vectorised guid lookup
+        old = list(plain["sal_metric"])[100:700]
+        assert st._sal_candidates(sal, al_guids, old, cfg.SAL.INLIER_THRESHOLD, 50) == st._sal_candidates(
+            plain, al_guids, old, cfg.SAL.INLIER_THRESHOLD, 50)
+
+
+def test_first_occurrence_and_topk_merge_kernels():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from multi_view_active_learning_b200 import ops
+
+    rng = np.random.default_rng(5)
+    n = 20_000
+    pose = rng.integers(0, 5, size=n)
+    frame = rng.integers(0, 9000, size=n)  # plenty of repeated guids
+    keep, src, unique = ops.first_occurrence(torch.from_numpy(pose).cuda(), torch.from_numpy(frame).cuda())
+    first, last = {}, {}
+    for i, k in enumerate(zip(pose.tolist(), frame.tolist())):
+        first.setdefault(k, i)
+        last[k] = i
+    assert int(unique.item()) == len(first)
+    keep, src = keep.cpu().numpy(), src.cpu().numpy()
+    assert sorted(np.nonzero(keep)[0].tolist()) == sorted(first.values())
+    assert all(src[i] == last[k] for k, i in first.items()) and (src[keep == 0] == -1).all()
+    _, _, u = ops.first_occurrence(torch.tensor([1 << 40, 3]).cuda(), torch.tensor([1, 2]).cuda())
+    assert int(u.item()) == -1  # does not fit the packed key: the caller falls back to the host
+    # cross-rank merge: 4 "ranks" with contiguous shards, ties across ranks, NaN padding
+    scores = rng.normal(size=4000).round(1)
+    scores[rng.integers(0, 4000, 50)] = np.nan
+    k = 64
+    idxs, vals = [], []
+    for r in range(4):
+        i, v, c = ops.topk_desc(torch.from_numpy(scores[r * 1000:(r + 1) * 1000]).cuda(), k, index_offset=r * 1000, fixed=True)
+        assert int(c.item()) == k and i.shape[0] == k
+        idxs.append(i)
+        vals.append(v)
+    mi, mv, mc = ops.topk_merge(torch.cat(vals), torch.cat(idxs), k)
+    exp = SO.rank_nlargest({i: float(s) for i, s in enumerate(scores) if not math.isnan(s)}, k)
+    assert int(mc.item()) == k and mi.cpu().tolist() == exp and mv.cpu().tolist() == [float(scores[i]) for i in exp]
+    # fewer candidates than k: the tail is -1 / NaN
+    i, v, c = ops.topk_desc(torch.tensor([1.0, float("nan"), 3.0], dtype=torch.float64).cuda(), 5, fixed=True)
+    assert int(c.item()) == 2 and i.cpu().tolist() == [2, 0, -1, -1, -1] and np.isnan(v.cpu().numpy()[2:]).all()
+
+
+def test_watchdog_is_reported_and_recovers():
+    """A persistent kernel whose producer never issues (test hook) must not return garbage silently: the time-out is
+    reported as MVAL_ERR_CUDA by mval_check_async / the next launch, the record is cleared and later launches work."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from multi_view_active_learning_b200 import _lib, ops
+
+    pool = S.make_pool(64, 8, 19, seed=2)
+    hm = ops.synth_heatmaps(torch.from_numpy(pool["centres"]).cuda(), 64, 64, 1.0, 0.05, 2)
+    P = torch.from_numpy(pool["P"]).cuda()
+    good = ops.score_pool(hm, P, 4)
+    ops.check_async()
+    lib = _lib.load()
+    try:
+        _lib.check(lib.mval_debug_watchdog(2_000_000, 1))  # ~1 ms time-out, producers stalled
+        ops.score_pool(hm, P, 4)
+        with pytest.raises(_lib.MvalError, match="watchdog"):
+            ops.check_async()
+        ops.score_hp(hm)
+        torch.cuda.synchronize()
+        with pytest.raises(_lib.MvalError, match="watchdog"):
+            ops.score_hp(hm)  # reported by the NEXT launch as well
+    finally:
+        _lib.check(lib.mval_debug_watchdog(0, 0))
+    ops.check_async()  # the record was cleared by the reports
+    again = ops.score_pool(hm, P, 4)
+    ops.check_async()
+    assert torch.equal(again["metric"], good["metric"]) and torch.equal(again["inlier_count"], good["inlier_count"])
