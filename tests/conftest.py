@@ -22,3 +22,21 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+def first_occurrence_numpy(pose, frame):
+    """Stand-in for the device call mval_first_occurrence in the CPU tests that stub the kernels out: the dict-insertion
+    semantics of strategy.py:1115-1133 (a repeated guid keeps its first position and its last value)."""
+    import torch
+
+    keys = list(zip(pose.tolist(), frame.tolist()))
+    first, last = {}, {}
+    for i, k in enumerate(keys):
+        first.setdefault(k, i)
+        last[k] = i
+    keep = torch.zeros(len(keys), dtype=torch.uint8)
+    src = torch.full((len(keys),), -1, dtype=torch.int32)
+    for k, i in first.items():
+        keep[i] = 1
+        src[i] = last[k]
+    return keep, src, torch.tensor([len(first)], dtype=torch.int32)

@@ -82,21 +82,6 @@ def test_distributed_topk_and_gather_world2():
         assert gx == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0] and gy == gx
 
 
-def _first_occurrence_numpy(pose, frame):
-    """Test stand-in for mval_first_occurrence (the device call is stubbed on CPU): OrderedDict insertion semantics."""
-    keys = list(zip(pose.tolist(), frame.tolist()))
-    first, last = {}, {}
-    for i, k in enumerate(keys):
-        first.setdefault(k, i)
-        last[k] = i
-    keep = torch.zeros(len(keys), dtype=torch.uint8)
-    src = torch.full((len(keys),), -1, dtype=torch.int32)
-    for k, i in first.items():
-        keep[i] = 1
-        src[i] = last[k]
-    return keep, src, torch.tensor([len(first)], dtype=torch.int32)
-
-
 def _sal_worker(rank, world, port, n_frames, out_q, mode="even"):
     """One rank of _compute_sal_dict with the device calls stubbed (CPU tensors, gloo): frames are dealt round-robin like
     the reference's DistributedSampler (strategy.py:753), every rank must end with the same dicts in the order the
@@ -112,7 +97,9 @@ def _sal_worker(rank, world, port, n_frames, out_q, mode="even"):
         V, J, B = 2, 4, 3
         torch.Tensor.cuda = lambda self, *a, **k: self
         ops.mkpe = lambda p, g, v: p[:, 0, 0].float()
-        ops.first_occurrence = _first_occurrence_numpy
+        from conftest import first_occurrence_numpy
+
+        ops.first_occurrence = first_occurrence_numpy
 
         def fake_triangulation_batch(hm, P, stride, joint_valid, **kw):
             ids = hm[:, 0, 0, 0, 0].double()  # the frame id travels in the first heat-map pixel

@@ -157,6 +157,9 @@ def test_compute_sal_dict_host_flow_without_device(monkeypatch):
 
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     monkeypatch.setattr(ops, "mkpe", lambda p, g, v: torch.zeros(p.shape[0]))
+    from conftest import first_occurrence_numpy
+
+    monkeypatch.setattr(ops, "first_occurrence", first_occurrence_numpy)
     monkeypatch.setattr(ST.triangulation, "triangulation_batch", fake_triangulation_batch)
 
     def loader():
@@ -176,7 +179,7 @@ def test_compute_sal_dict_host_flow_without_device(monkeypatch):
         sal = st._compute_sal_dict(loader(), None)
         guids = ["160422-%d" % (10 * k + i) for k in range(n_batches) for i in range(B)]
         assert all(list(sal[name]) == guids for name in sal)
-        assert [kw["frame_offset"] for kw in seen] == [0, B, 2 * B]
+        assert all(kw["frame_keys"] is None for kw in seen)  # 1 view pair: no subset to key (V >= 12 passes the guid keys)
         assert all(kw["map_score"] == (strategy if strategy in ("HP", "MPE", "BSB") else None) for kw in seen)
         assert sal["sal_metric"]["160422-11"] == float(np.float32(1 + 1 + 1.0 / 3.0))  # torch.Tensor([metric]) is float32
         assert sal["pred_3d_keypoints"]["160422-20"][0][0] == float(np.float32(0.1 * 3))
