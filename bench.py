@@ -46,7 +46,8 @@ def workload_config(args, n_gpus):
         "n_iters": 64, "epsilon_px": 5.0,
         "cache": "inputs (resident buffer %.1f GB) far larger than the 126 MB L2; no flush needed"
                  % (args.resident_frames * FRAME_HEATMAP_BYTES / 1e9),
-        "sharding": "contiguous frames per rank, no data-path collective; ranking = 1 all_gather of k (idx, score)",
+        "sharding": "contiguous frames per rank, no data-path collective; ranking = 1 all_gather of k (idx, score) + device merge",
+        "launches": "one persistent fused launch per step over the whole shard (chunk passes over the resident buffer as segments)",
     }
 
 
@@ -264,22 +265,30 @@ def run_ours(args):
     ops.synth_heatmaps(centres, H, W, 1.0, 0.05, seed, out=hm)
     torch.cuda.synchronize()
 
-    chunks = []
-    done = 0
+    # the shard as chunk passes over the resident buffer, scored by ONE persistent launch (mval_score_pool_segments): frame f
+    # of the shard reads heat maps of resident frame f % R, with its own projection matrices / outputs
+    seg_list, done = [], 0
     while done < pool_frames:
         n = min(R, pool_frames - done)
-        chunks.append((done, n))
+        seg_list.append(hm[:n])
         done += n
+    assert len(seg_list) <= _lib.MAX_SEGMENTS, "raise --resident-frames: more than %d chunk passes per shard" % _lib.MAX_SEGMENTS
+    P_shard = torch.cat([P[: t.shape[0]] for t in seg_list])
+    exchange = poolmod.RankingExchange(TOPK, dev)
+    sel_host = torch.empty(TOPK, dtype=torch.int64).pin_memory()
+    work = {"out": None}
+    k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
-    def step():
-        metrics = []
-        for off, n in chunks:
-            out = ops.score_pool(hm[:n], P[:n], STRIDE, None, pair_seed=0, frame_offset=shard_start + off,
-                                 return_keypoints_2d=False)
-            metrics.append(out["metric"])
-        metric = torch.cat(metrics)
-        local = ops.topk_desc(metric, TOPK, index_offset=shard_start)
-        return poolmod.distributed_topk(local, TOPK)
+    def step(ev=None):
+        if ev is not None:
+            ev[0].record()
+        work["out"] = ops.score_pool_segments(seg_list, P_shard, STRIDE, None, pair_seed=0, frame_offset=shard_start,
+                                              out=work["out"])
+        if ev is not None:
+            ev[1].record()
+        idx, val, cnt = exchange(work["out"]["metric"], shard_start)  # local top-k, one all_gather, device-side merge
+        sel_host.copy_(idx, non_blocking=True)  # the selection lands in pinned host memory, no synchronisation here
+        return idx
 
     def barrier():
         if world > 1:
@@ -287,8 +296,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        sel = step()
+        step()
     barrier()
+    ops.check_async()
     sampler = ClockSampler(local_rank)
     if rank == 0 and not args.no_clocks:
         sampler.start()
@@ -297,13 +307,16 @@ def run_ours(args):
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev0.record()
     for k in range(args.steps):
-        sel = step()
+        step(k_events[k])
         marks[k].record()
     ev1.record()
     barrier()
+    ops.check_async()  # a tripped mbarrier watchdog would have left incomplete outputs: fail loudly instead
     launches = _lib.launch_count() - launches0
     elapsed_ms = ev0.elapsed_time(ev1)
     step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([ev0] + marks[:-1], marks)]
+    fused_ms = float(np.mean([a.elapsed_time(b) for a, b in k_events]))  # the dominant kernel, live, inside the timed region
+    sel = [sel_host.tolist()]
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
@@ -334,24 +347,30 @@ def run_ours(args):
     xy = ops.decode_argmax(hm, STRIDE)
     dec_ms = time_ms(lambda: ops.decode_argmax(hm, STRIDE), 5)
     tri_ms = time_ms(lambda: ops.triangulate_ransac(xy, P), 5)
-    pool_ms = time_ms(lambda: ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False), 5)
-    fused = os.environ.get("MVAL_FUSED", "1") != "0"
+    del xy
     dec_gbs = R * FRAME_HEATMAP_BYTES / (dec_ms * 1e-3) / 1e9
-    pool_bytes = R * FRAME_ALGO_BYTES
-    pool_gbs = pool_bytes / (pool_ms * 1e-3) / 1e9
-    # dominant kernel: the fused persistent kernel does the whole scoring pass of a chunk in one launch
+    pool_bytes = pool_frames * FRAME_ALGO_BYTES
+    pool_gbs = pool_bytes / (fused_ms * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel from the tracked ncu capture (tools/ncu_traffic.py writes profiles/traffic.json from
+    # the `ncu --set full` report: dram__bytes_read.sum + dram__bytes_write.sum per launch and the frames of that launch)
+    traffic, traffic_src = None, "no ncu capture for this shape in profiles/traffic.json"
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("score_pool_fused_kernel_v%d_j%d" % (V, J))
+        if rec:
+            traffic = float(rec["dram_bytes"]) / float(rec["frames"]) * pool_frames
+            traffic_src = "%s: %.0f B over %d frames, scaled per frame to this launch" % (rec["source"], rec["dram_bytes"], rec["frames"])
+    except Exception:
+        pass
+    # dominant kernel: ONE persistent launch of the fused kernel scores the whole shard; its duration is measured live inside
+    # the timed region with CUDA events on the launching stream
     roofline = {
-        "bound": "hbm",
-        "kernel": "score_pool_fused_kernel" if fused else "decode_argmax_kernel + ransac_vote/final/frame_reduce",
+        "bound": "hbm", "kernel": "score_pool_fused_kernel (mval_score_pool_segments: one launch per step over the shard)",
         "achieved": pool_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pool_gbs / hbm_peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel over 4096 frames
-        # (profiles/r1b_summary.md: 10.2046 GB + 8.55 MB), scaled to the frames of one launch here
-        "traffic": (10.204355e9 + 7.094e6) / 4096.0 * R if (fused and (V, J) == (8, 19)) else None,
-        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture over 4096 frames "
-                          "(profiles/r1f_ncu_full_raw_fused_plain.csv), scaled per frame",
+        "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": pool_bytes,
-        "algorithmic_bytes_per_frame": FRAME_ALGO_BYTES, "frames_per_launch": R, "avg_launch_ms": pool_ms,
-        "share_of_step": pool_ms * (pool_frames / R) / ms_per_step,
+        "algorithmic_bytes_per_frame": FRAME_ALGO_BYTES, "frames_per_launch": pool_frames, "avg_launch_ms": fused_ms,
+        "launch_timing": "CUDA events around the launch in every timed step (mean of %d)" % args.steps,
+        "share_of_step": fused_ms / ms_per_step,
         "other_kernels": {
             "decode_argmax_kernel": {"achieved": dec_gbs, "frac": dec_gbs / hbm_peak, "avg_launch_ms": dec_ms,
                                      "algorithmic_bytes_per_launch": R * FRAME_HEATMAP_BYTES},
@@ -362,8 +381,8 @@ def run_ours(args):
 
     # ---- end-to-end through the host-buffer entry (every rank, concurrently): the H2D copy of the step's inputs
     # from pinned host memory, the kernels, the D2H copy of the results and the ranking exchange are all inside the
-    # timed region; max over ranks per step, median over steps
-    E = min(args.e2e_frames if n_gpus < 4 else min(args.e2e_frames, 2048), R)
+    # timed region; max over ranks per step, median over steps.  Same sample size at every N.
+    E = min(args.e2e_frames, R)
     pin = lambda t: t.cpu().pin_memory()
     # pinned pages are placed by first touch: allocate them from the CPUs next to this rank's GPU when the process is
     # allowed to run there, so that the H2D stream does not cross the socket interconnect
@@ -376,40 +395,68 @@ def run_ours(args):
     if near:
         os.sched_setaffinity(0, allowed)
     numa["pinned_from_gpu_local_cpus"] = bool(near)
-    # the raw link: one cudaMemcpyAsync of the same pinned heat maps, CUDA events (what e2e can reach at most)
-    probe_dst = torch.empty_like(hm[: min(E, 512)])
+    # the raw link: one cudaMemcpyAsync of the same pinned heat maps, CUDA events (what e2e can reach at most), first on
+    # this rank ALONE (ranks take turns), then on all ranks at once -- the second is what a shared PCIe uplink leaves
+    probe_dst = torch.empty_like(hm[: min(E, 1024)])
     probe_src = h_hm[: probe_dst.shape[0]]
     probe_dst.copy_(probe_src, non_blocking=True)
-    link_ms = time_ms(lambda: probe_dst.copy_(probe_src, non_blocking=True), 3)
-    link_gbs = probe_src.numel() * 4 / (link_ms * 1e-3) / 1e9
+    link_alone = None
+    for r in range(world):
+        barrier()
+        if r == rank:
+            link_alone = probe_src.numel() * 4 / (time_ms(lambda: probe_dst.copy_(probe_src, non_blocking=True), 3) * 1e-3) / 1e9
+    barrier()
+    link_gbs = probe_src.numel() * 4 / (time_ms(lambda: probe_dst.copy_(probe_src, non_blocking=True), 3) * 1e-3) / 1e9
     del probe_dst
+    pipe = ops.HostPipeline(V, J, H, W, chunk_frames=args.e2e_chunk, n_slots=3, device=dev)
+    e2e_exchange = poolmod.RankingExchange(TOPK, dev)
     outs = None
-    e2e_times = []
-    for it in range(1 + args.e2e_steps):
+    e2e_times, own_times = [], []
+    for it in range(2 + args.e2e_steps):
         barrier()
         t0 = time.perf_counter()
-        outs = ops.score_pool_host(h_hm, h_P, STRIDE, None, frame_offset=shard_start, out=outs)
-        local = ops.topk_desc(outs["metric"].to(dev, non_blocking=True), TOPK, index_offset=shard_start)
-        sel_e2e = poolmod.distributed_topk(local, TOPK)  # ends with the selected indices on the host
-        torch.cuda.synchronize()
+        outs = pipe.score_pool(h_hm, h_P, STRIDE, None, frame_offset=shard_start, out=outs)
+        idx, _, _ = e2e_exchange(outs["metric"].to(dev, non_blocking=True), shard_start)
+        sel_e2e = idx.cpu()  # the step ends with the selected indices on the host
         dt = time.perf_counter() - t0
+        own = dt
         if world > 1:
             tt = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-        if it > 0:
+        if it > 1:
             e2e_times.append(dt)
+            own_times.append(own)
+    pipe.close()
     e2e_val = E * n_gpus / float(np.median(e2e_times))
     h2d = E * (FRAME_HEATMAP_BYTES + V * 96)
-    d2h = sum(t.numel() * t.element_size() for t in outs.values()) + len(sel_e2e[0]) * 16
+    d2h = sum(t.numel() * t.element_size() for t in outs.values()) + sel_e2e.numel() * 8
+    per_rank = [h2d / float(np.median(own_times)) / 1e9, link_alone, link_gbs]
+    if world > 1:
+        g = torch.empty(world * 3, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(g, torch.tensor(per_rank, dtype=torch.float64, device=dev))
+        per_rank = g.view(world, 3).cpu().tolist()
+    else:
+        per_rank = [per_rank]
+    topo = None
+    if rank == 0 and world > 1:
+        try:
+            topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout[:6000]
+        except Exception:
+            pass
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * n_gpus, "d2h_bytes_per_step": d2h * n_gpus,
            "frames_per_step": E * n_gpus, "steps": args.e2e_steps, "aggregate": "max over ranks per step, median over steps",
            "step_ms": [round(1e3 * t, 2) for t in e2e_times],
            "h2d_gbs": h2d / float(np.median(e2e_times)) / 1e9, "link_h2d_gbs_measured": link_gbs,
-           "link_note": "link_h2d_gbs_measured = one cudaMemcpyAsync of the same pinned heat maps on this rank (CUDA events): "
-                        "the bound of any end-to-end number whose inputs start in host memory", "numa": numa,
-           "call": "mval_score_pool_host (pinned host heat maps -> chunked H2D on 2 streams -> fused kernel -> D2H) + "
-                   "mval_topk_desc + ranking merge, on every rank concurrently"}
+           "per_rank": {"columns": ["e2e_h2d_gbs (own step time)", "link_h2d_gbs, this rank copying alone",
+                                    "link_h2d_gbs, all ranks copying at once"], "rows": per_rank},
+           "link_note": "link_* = one cudaMemcpyAsync of the same pinned heat maps (CUDA events): the bound of any end-to-end "
+                        "number whose inputs start in host memory; when the all-ranks figure is below the alone figure the "
+                        "ranks share a PCIe uplink / host memory controller and e2e cannot scale past it", "numa": numa,
+           "nvidia_smi_topo": topo,
+           "call": "ops.HostPipeline.score_pool = mval_pipeline_score_pool (pinned host heat maps -> chunked H2D over 3 "
+                   "persistent staging slots / streams -> fused kernel -> D2H; nothing allocated per call) + mval_topk_desc + "
+                   "all_gather + mval_topk_merge, on every rank concurrently"}
     del h_hm
     # Variant at the reference's own boundary: triangulation() receives the heat maps as CUDA tensors straight from
     # the backbone (strategy.py:1027-1045) and only the projection matrices / validity masks live on the host.  Per step:
@@ -422,9 +469,9 @@ def run_ours(args):
         t0 = time.perf_counter()
         dP = h_P_all.to(dev, non_blocking=True)
         out_dv = ops.score_pool(hm, dP, STRIDE, None, frame_offset=shard_start, return_keypoints_2d=True)
-        local = ops.topk_desc(out_dv["metric"], TOPK, index_offset=shard_start)
+        idx_dv, _, _ = e2e_exchange(out_dv["metric"], shard_start)
         res_host = {k: v.to("cpu", non_blocking=True) for k, v in out_dv.items()}
-        sel_dv = poolmod.distributed_topk(local, TOPK)
+        sel_dv = (idx_dv.cpu(),)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -441,6 +488,11 @@ def run_ours(args):
         "call": "ops.score_pool on CUDA heat maps (the reference's triangulation() boundary: heat maps come from the "
                 "backbone on the device, strategy.py:1027-1045) with P copied from pinned host memory and all results "
                 "copied back, + mval_topk_desc + ranking merge"}
+
+    # ---- the other BASELINE.json configurations, measured in the same run so that they reach the driver's records
+    extra = None
+    if not args.no_extra:
+        extra = extra_records({"world": world, "rank": rank, "dev": dev}, args, hm, P, hbm_peak, peak_src, time_ms)
 
     line = None
     if rank == 0:
@@ -461,15 +513,77 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": dict(workload_config(args, n_gpus), seed=1234),
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_gpus), "seed": 1234,
             "step_ms": step_ms, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "selected_head": [int(i) for i in sel[0][:5]],
+            "selected_head": [int(i) for i in sel[0][:5]], "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def rig_record(dev, views, joints, frames, hbm_peak, peak_src, time_ms, label):
+    """The fused scoring kernel on another rig (BASELINE.json configs[2] / [4]): one launch over `frames` resident frames."""
+    import torch
+
+    from multi_view_active_learning_b200 import ops
+    from multi_view_active_learning_b200 import synthetic as S
+
+    pool = S.make_pool(min(frames, 256), views, joints, seed=4321, p_outlier=0.1, box=100.0 if joints == 42 else 400.0,
+                       radius=500.0 if joints == 42 else 3000.0)
+    reps = -(-frames // pool["centres"].shape[0])
+    centres = torch.from_numpy(np.tile(pool["centres"], (reps, 1, 1, 1))[:frames]).to(dev)
+    Pr = torch.from_numpy(np.tile(pool["P"], (reps, 1, 1, 1))[:frames]).to(dev)
+    hm_r = ops.synth_heatmaps(centres, H, W, 1.0, 0.05, 99)  # distinct noise per frame: nothing repeats in the buffer
+    out = {"out": None}
+
+    def run():
+        out["out"] = ops.score_pool_segments([hm_r], Pr, STRIDE, None, pair_seed=1234, out=out["out"])
+
+    run()
+    ms = time_ms(run, 3)
+    ops.check_async()
+    frame_bytes = views * joints * H * W * 4 + views * 96 + joints + joints * 24 + 16
+    gbs = frames * frame_bytes / (ms * 1e-3) / 1e9
+    rec = {"workload": label, "views": views, "joints": joints, "frames_per_launch": frames, "avg_launch_ms": ms,
+           "value": frames / (ms * 1e-3), "unit": UNIT,
+           "roofline": {"bound": "hbm", "kernel": "score_pool_fused_kernel", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_frame": frame_bytes, "algorithmic_bytes_per_launch": frames * frame_bytes},
+           "view_pairs": "64 of %d per joint (counter-based subsets, utils/triangulation.py:279-282)" % (views * (views - 1) // 2),
+           "metric_mean": float(out["out"]["metric"].mean().item())}
+    del hm_r, out
+    torch.cuda.empty_cache()
+    return rec
+
+
+def extra_records(ctx, args, hm, P_res, hbm_peak, peak_src, time_ms):
+    """Sub-records of the default line for the configurations BASELINE.json names besides C2: the north-star target through
+    the API (T), the coreset (C4, strong scaling over the ranks of this run), and the fused kernel on the C3 / C5 rigs."""
+    import torch
+
+    world, rank = ctx["world"], ctx["rank"]
+    extra = {}
+    api = api_selection(ctx, hm, P_res, args.extra_api_frames, 8192, 10_000, 1000, 1000, 2)
+    if rank == 0:
+        extra["T_api_sample_next_batch"] = {
+            "workload": "north-star target through the API: %d frames per GPU x %d GPU(s) = %d frames, 8 views, 19 joints; "
+                        "ActiveLearningStrategy.sample_next_batch with device heat maps" % (args.extra_api_frames, world,
+                                                                                              args.extra_api_frames * world),
+            "variants": api}
+    c4 = coreset_record(ctx, args.coreset_rows, args.coreset_dim, 1000, 10_000, with_cpu=False)
+    if rank == 0:
+        extra["C4_coreset"] = c4
+    if rank == 0:  # kernel-level records of the other rigs: one GPU's worth, measured on rank 0
+        extra["C3_interhand_20v_42j"] = rig_record(ctx["dev"], 20, 42, 1536, hbm_peak, peak_src, time_ms,
+                                                   "C3 rig: InterHand 42 joints, 20 views (fused decode + RANSAC + uncertainty)")
+        extra["C5_panoptic_31v_19j"] = rig_record(ctx["dev"], 31, 19, 2048, hbm_peak, peak_src, time_ms,
+                                                  "C5 rig: Panoptic 19 joints, 31 views (fused decode + RANSAC + uncertainty)")
+    if world > 1:
+        torch.distributed.barrier()
+    return extra if rank == 0 else None
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -488,32 +602,25 @@ def _timed(fn, iters=1):
     return a.elapsed_time(b) / iters, out
 
 
-def run_coreset(args):
-    """C4-style workload: k-center greedy over n x d float32 features sharded by rows.  Reports the whole selection
-    (norms + labeled fold-in + budget picks in exact rounds) and the roofline of its dominant kernel (the batched
-    update: tcgen05 TF32 screening GEMM when applicable, register-tiled FFMA pass otherwise)."""
-    import numpy as np
+def coreset_record(ctx, n_total, d, L, budget, path="auto", data="gaussian", kslots=0, cpu_rows=50000, with_cpu=True):
+    """C4-style workload: k-center greedy over n_total x d float32 features sharded by rows over the ranks (STRONG scaling:
+    the total is fixed).  Returns (on rank 0) the record of the whole selection (norms + labeled fold-in + budget picks in
+    exact rounds, device-timed, max over ranks) with two rooflines: the tensor-pipe fraction of the tcgen05 screening GEMM
+    that dominates the batched update, and the HBM fraction of the single-centre step the reference's loop is made of."""
     import torch
     import torch.distributed as dist
 
     from multi_view_active_learning_b200 import _lib, ops, pool as poolmod
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    n_total, d, L, budget = args.coreset_rows, args.coreset_dim, args.coreset_labeled, args.coreset_budget
-    flags = {"auto": 0, "ffma": 1, "tc": 2}[args.coreset_path]
+    world, rank, dev = ctx["world"], ctx["rank"], ctx["dev"]
+    flags = {"auto": 0, "ffma": 1, "tc": 2}[path]
     lo, hi = poolmod.shard_range(n_total, world, rank)
     n = hi - lo
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     feat = torch.randn((n, d), generator=g, device=dev, dtype=torch.float32)
     gl = torch.Generator(device=dev).manual_seed(7)
     labeled = torch.randn((L, d), generator=gl, device=dev, dtype=torch.float32)
-    if args.coreset_data == "clustered":  # 64 tight clusters: a pick collapses the minima of its whole cluster
+    if data == "clustered":  # 64 tight clusters: a pick collapses the minima of its whole cluster
         gc = torch.Generator(device=dev).manual_seed(5)
         cent = torch.randn((64, d), generator=gc, device=dev, dtype=torch.float32) * 4.0
         feat = feat * 0.25 + cent[torch.randint(0, 64, (n,), generator=g, device=dev)]
@@ -524,6 +631,10 @@ def run_coreset(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # tcgen05 kind::tf32 runs at half the dense bf16 rate; the measured bf16 figure (a cuBLAS GEMM) halved is the peak
+    tf32_peak = float(peaks.get("bf16_tflops", 2250.0)) / 2.0
+    tf32_src = ("MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 issues at half the bf16 rate)" if "bf16_tflops" in peaks
+                else "fallback: nominal 2250 dense bf16 TFLOP/s / 2")
 
     # ---- kernels timed alone on this rank's shard (CUDA events on the launching stream, after a warm-up call)
     norms = ops.kcenter_norms(feat)
@@ -536,26 +647,35 @@ def run_coreset(args):
     cidx = torch.randint(0, n, (T,), generator=g, device=dev)
     cent_rows, cent_norms = feat[cidx].contiguous(), norms[cidx].contiguous()
     poolmod.kcenter_fold_centres([{"feat": feat, "norms": norms, "min": min_d, "off": lo}], labeled, lab_norms, flags=1)
-    ops.kcenter_update_batch(feat, norms, cent_rows, cent_norms, min_d.clone(), 1)
-    ffma_ms, _ = _timed(lambda: ops.kcenter_update_batch(feat, norms, cent_rows, cent_norms, min_d.clone(), 1), 2)
+    scratch = min_d.clone()
+
+    def update(fl):
+        scratch.copy_(min_d)
+        ops.kcenter_update_batch(feat, norms, cent_rows, cent_norms, scratch, fl)
+
+    update(1)
+    ffma_ms, _ = _timed(lambda: update(1), 2)
     auto_ms, tc_survivors, tc_capacity = None, None, None
     if flags != 1:
-        ops.kcenter_update_batch(feat, norms, cent_rows, cent_norms, min_d.clone(), flags)
-        auto_ms, _ = _timed(lambda: ops.kcenter_update_batch(feat, norms, cent_rows, cent_norms, min_d.clone(), flags), 3)
+        update(flags)
+        auto_ms, _ = _timed(lambda: update(flags), 3)
         tc_survivors, tc_capacity = ops.kcenter_tc_stats()
-    clone_ms, _ = _timed(lambda: min_d.clone(), 3)
+    clone_ms, _ = _timed(lambda: scratch.copy_(min_d), 3)
     rec = ops.kcenter_select(feat, norms, min_d, lo, 256)
     select_ms, _ = _timed(lambda: ops.kcenter_select(feat, norms, min_d, lo, 256, out=rec), 5)
+    del scratch
 
-    # ---- the whole selection, device-timed, max over ranks
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    l0 = _lib.launch_count()
-    stats = []
-    total_ms, (sel, _) = _timed(lambda: poolmod.kcenter_greedy_sharded([(feat, lo)], labeled, budget, flags=flags, stats=stats,
-                                                                           k_slots=args.coreset_kslots or None))
-    launches = _lib.launch_count() - l0
+    # ---- the whole selection, device-timed, max over ranks (second of two runs: the first warms the allocator / NCCL)
+    total_ms, stats, sel, launches = None, [], None, 0
+    for _ in range(2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        stats = []
+        total_ms, (sel, _) = _timed(lambda: poolmod.kcenter_greedy_sharded([(feat, lo)], labeled, budget, flags=flags, stats=stats,
+                                                                               k_slots=kslots or None))
+        launches = _lib.launch_count() - l0
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -563,10 +683,10 @@ def run_coreset(args):
 
     # ---- CPU arm on a bounded sample (rank 0): the C oracle (same arithmetic) on all host cores
     cpu = None
-    if rank == 0 and args.cpu_frames > 0:
+    if rank == 0 and with_cpu:
         from oracle import coreset_oracle as CO
 
-        ns = min(n, args.coreset_cpu_rows)
+        ns = min(n, cpu_rows)
         Fs = np.concatenate([feat[:ns].cpu().numpy(), labeled[: min(L, 8)].cpu().numpy()])
         steps = 8
         t0 = time.perf_counter()
@@ -582,35 +702,62 @@ def run_coreset(args):
         # parity of the sample against the GPU on the same rows
         gsel, _ = ops.kcenter_greedy(torch.from_numpy(Fs).to(dev), ns, steps)
         cpu["gpu_matches_oracle_on_sample"] = bool(gsel.cpu().tolist() == cpu_sel)
+    out = None
     if rank == 0:
         upd_ms = (auto_ms if auto_ms is not None else ffma_ms) - clone_ms
         ffma_only = ffma_ms - clone_ms
         flops = 2.0 * n * T * d
         step_bytes = n * (d * 4 + 12)
+        tc_ran = auto_ms is not None and tc_survivors is not None and tc_capacity
         out = {
             "metric": "coreset k-center greedy: pool rows selected-from / sec", "value": n_total / (total_ms * 1e-3),
             "unit": "rows/s", "n_gpus": world, "ms_total": total_ms, "higher_is_better": True, "dtype": "f32",
-            "data": "synthetic (%s)" % args.coreset_data,
+            "scaling": "strong", "data": "synthetic (%s)" % data,
             "config": {"workload": "C4-style coreset: %d x %d float32 features, %d labeled centres, budget %d, rows sharded "
                                    "over %d GPU(s); exact greedy in rounds" % (n_total, d, L, budget, world),
-                       "update_path": args.coreset_path},
+                       "update_path": path},
             "rounds": {"count": len(stats), "picks_per_round_mean": float(np.mean(stats)), "picks_per_round_min": int(min(stats)),
                        "picks_per_round_max": int(max(stats))},
             "ms_per_pick": total_ms / budget,
             "equivalent_sequential_ms": (L + budget) * single_ms,
             "kernels_ms": {"norms": norms_ms, "single_centre_update": single_ms, "update_256_centres_ffma": ffma_only,
                            "update_256_centres_selected_path": upd_ms, "select_256": select_ms},
-            "roofline": {"bound": "hbm", "kernel": "kc_rowdot_kernel<1> (single-centre update, one greedy step of the reference)",
-                         "achieved": step_bytes / (single_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": step_bytes / (single_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                         "algorithmic_bytes_per_launch": step_bytes, "avg_launch_ms": single_ms,
-                         "batched_update": {"centres": T, "ffma_tflops": flops / (ffma_only * 1e-3) / 1e12,
-                                            "selected_path_tflops_equiv": flops / (upd_ms * 1e-3) / 1e12,
-                                            "selected_path_gbs": step_bytes / (upd_ms * 1e-3) / 1e9,
-                                            "tc_survivor_pairs": tc_survivors, "tc_pair_capacity": tc_capacity}},
+            "roofline": {"bound": "tensor", "kernel": "kc_screen_tc2_kernel (+ kc_recheck_kernel + the no-op FFMA guard): one "
+                         "batched update of %d centres over this rank's %d rows" % (T, n) if tc_ran else
+                         "kc_batch_kernel (FFMA; the tensor-core screen does not apply to this shape)",
+                         "achieved": flops / (upd_ms * 1e-3) / 1e12, "peak": tf32_peak if tc_ran else 72.0, "unit": "TFLOP/s",
+                         "frac": flops / (upd_ms * 1e-3) / 1e12 / (tf32_peak if tc_ran else 72.0), "traffic": None,
+                         "peak_source": tf32_src if tc_ran else "fp32 FFMA pipe: 148 SMs x 128 lanes x 2 x 1.9 GHz",
+                         "algorithmic_flops_per_launch": flops, "avg_launch_ms": upd_ms,
+                         "tc_survivor_pairs": tc_survivors, "tc_pair_capacity": tc_capacity,
+                         "ffma_tflops_same_update": flops / (ffma_only * 1e-3) / 1e12},
+            "roofline_single_step": {"bound": "hbm", "kernel": "kc_rowdot_kernel<1> (single-centre update, one greedy step of the reference)",
+                                     "achieved": step_bytes / (single_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": step_bytes / (single_ms * 1e-3) / 1e9 / hbm_peak,
+                                     "algorithmic_bytes_per_launch": step_bytes, "avg_launch_ms": single_ms},
             "gpu_launches": int(launches), "selected_head": sel[:5].cpu().tolist()}
         if cpu is not None:
             out["cpu_baseline"] = cpu
+    del feat, norms, min_d
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_coreset(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    out = coreset_record({"world": world, "rank": rank, "dev": dev}, args.coreset_rows, args.coreset_dim, args.coreset_labeled,
+                         args.coreset_budget, args.coreset_path, args.coreset_data, args.coreset_kslots, args.coreset_cpu_rows,
+                         with_cpu=args.cpu_frames > 0)
+    if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -1064,6 +1211,7 @@ def main():
     ap.add_argument("--resident-frames", type=int, default=16384)
     ap.add_argument("--e2e-frames", type=int, default=4096)
     ap.add_argument("--e2e-steps", type=int, default=9)
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="frames per staging chunk of the host pipeline (0 = ~256 MiB)")
     ap.add_argument("--cpu-frames", type=int, default=4096)
     ap.add_argument("--ref-frames-per-core", type=int, default=128)
     ap.add_argument("--workload", default="scoring", choices=["scoring", "coreset", "scores", "hybrid", "backbone", "api"])
@@ -1082,6 +1230,8 @@ def main():
                     "selection against the single-device loop on rank 0")
     ap.add_argument("--coreset-kslots", type=int, default=0, help="candidate slots per shard and round (0 = pool.py default)")
     ap.add_argument("--coreset-pad", type=int, default=0, help="hybrid: zero-pad the pose features to a multiple of this")
+    ap.add_argument("--no-extra", action="store_true", help="scoring workload: skip the extra sub-records (T / C4 / C3 / C5)")
+    ap.add_argument("--extra-api-frames", type=int, default=125_000, help="frames per GPU of the T record in `extra`")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks during the timed region")
     ap.add_argument("--views", type=int, default=V, help="camera views per frame (C2: 8; C3: 20; C5: 31)")
     ap.add_argument("--joints", type=int, default=J, help="joints per frame (Panoptic 19; InterHand 42)")

@@ -35,6 +35,7 @@ extern "C" {
 
 #define MVAL_ABI_VERSION 5
 #define MVAL_MAX_VIEWS 32
+#define MVAL_MAX_SEGMENTS 64
 
 enum mval_status {
   MVAL_OK = 0,
@@ -180,10 +181,48 @@ int mval_score_pool_scored(const float* heatmaps, const double* proj, const uint
                            int32_t* out_xy, double* out_xyz, double* out_reproj, int32_t* out_inliers,
                            double* out_metric, int32_t* out_inlier_count, float* out_map_score, void* stream);
 
-/* Same as mval_score_pool but every pointer is HOST memory (pinned recommended): the library streams the
- * pool through the device in chunks of `chunk_frames` frames (0 = choose), double-buffered on two internal
- * streams so that host->device copies overlap the kernels, and returns after the last result has landed in
- * host memory.  This is the end-to-end entry a caller with host-side heat maps uses. */
+/* mval_score_pool_scored over a pool whose heat maps are NOT one contiguous buffer: `n_segments` device buffers
+ * (1..MVAL_MAX_SEGMENTS), segment s holding seg_frames[s] whole frames, concatenated in order -- e.g. the outputs of
+ * successive pose-estimator batches (strategy.py:1024-1035), or chunk passes over a resident buffer.  seg_heatmaps /
+ * seg_frames are HOST arrays (of device pointers / frame counts) read during the call.  proj, valid and every output are
+ * contiguous over all n_frames = sum(seg_frames) frames.  ONE persistent launch covers the whole pool (no per-chunk
+ * launch tails).  64 x 64-style shapes that fit the fused kernel only; otherwise MVAL_ERR_UNSUPPORTED (call
+ * mval_score_pool_scored per segment). */
+int mval_score_pool_segments(const float* const* seg_heatmaps, const int64_t* seg_frames, int n_segments, const double* proj,
+                             const uint8_t* valid, int V, int J, int H, int W, int stride,
+                             const mval_ransac_params* params, int map_score, int32_t* out_xy, double* out_xyz,
+                             double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
+                             float* out_map_score, void* stream);
+
+/* Host-buffer pipeline: every data pointer is HOST memory (pinned recommended).  A handle owns n_slots (0 = 3, at most 4)
+ * slots, each with its own stream and device staging buffers for chunk_frames frames (0 = about 256 MiB of heat maps);
+ * mval_pipeline_score_pool streams the pool through them -- the host->device copy of one chunk overlaps the kernels of
+ * the previous one -- and returns after the last result has landed in host memory (it also reports a watchdog trip of
+ * any of its launches).  Nothing is allocated per call.  This is the end-to-end entry of a caller whose heat maps are on
+ * the host; it covers what triangulation() / _compute_sal_dict take as flags (utils/triangulation.py:168-179,
+ * strategy.py:1036-1045, 1072-1094):
+ *   map_score            MVAL_MAP_SCORE_*: HP / MPE / BSB of the same maps -> out_map_score float32 host [n][V][J]
+ *   use_soft_argmax      key-points by soft-arg-max (out_xy is then float32 [n][V][J][2], otherwise int32)
+ *   use_reprojection_xe  out_metric = the reprojection XE of utils/triangulation.py:236-257 with `sigma`
+ *   direct_optimization  Huber refinement of :319-336
+ * options == NULL: arg-max decode, no extras.  One handle serves one device and one shape; it is not re-entrant. */
+typedef struct mval_pipeline mval_pipeline;
+typedef struct mval_pipeline_options {
+  int32_t map_score;
+  int32_t use_soft_argmax;
+  int32_t use_reprojection_xe;
+  int32_t direct_optimization;
+  double sigma;
+} mval_pipeline_options;
+int mval_pipeline_create(int V, int J, int H, int W, int64_t chunk_frames, int n_slots, mval_pipeline** out);
+int mval_pipeline_destroy(mval_pipeline* pipeline);
+int mval_pipeline_score_pool(mval_pipeline* pipeline, const float* heatmaps, const double* proj, const uint8_t* valid,
+                             int64_t n_frames, int stride, const mval_ransac_params* params,
+                             const mval_pipeline_options* options, void* out_xy, double* out_xyz, double* out_reproj,
+                             int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count, float* out_map_score);
+
+/* mval_pipeline_score_pool(options = NULL) on an implicit handle that the library keeps per process (re-created only when
+ * the device, the shape or an explicit chunk_frames changes).  chunk_frames 0 = choose. */
 int mval_score_pool_host(const float* heatmaps, const double* proj, const uint8_t* valid, int64_t n_frames,
                          int V, int J, int H, int W, int stride, const mval_ransac_params* params,
                          int64_t chunk_frames, int32_t* out_xy, double* out_xyz, double* out_reproj,

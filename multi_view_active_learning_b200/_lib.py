@@ -12,6 +12,7 @@ MVAL_ERR_CUDA = -3
 MVAL_ERR_NO_DEVICE = -4
 MVAL_ERR_OUT_OF_MEMORY = -5
 MAX_VIEWS = 32
+MAX_SEGMENTS = 64
 ABI_VERSION = 5
 MAP_SCORE = {None: 0, "HP": 1, "MPE": 2, "BSB": 3}  # MVAL_MAP_SCORE_*
 
@@ -25,6 +26,11 @@ class MvalError(RuntimeError):
 class RansacParams(C.Structure):
     _fields_ = [("n_iters", C.c_int32), ("epsilon", C.c_double), ("pair_seed", C.c_uint64),
                 ("frame_offset", C.c_int64), ("pairs", C.c_void_p), ("frame_keys", C.c_void_p)]
+
+
+class PipelineOptions(C.Structure):
+    _fields_ = [("map_score", C.c_int32), ("use_soft_argmax", C.c_int32), ("use_reprojection_xe", C.c_int32),
+                ("direct_optimization", C.c_int32), ("sigma", C.c_double)]
 
 
 _p, _i, _i64, _f, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64
@@ -43,7 +49,13 @@ PROTOTYPES = {
     "mval_refine_huber": (C.c_int, [_p, _i, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p]),
     "mval_score_pool": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _p, _p, _p, _p, _p, _p, _p]),
     "mval_score_pool_scored": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "mval_score_pool_segments": (C.c_int, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _i, _p, _p, _p, _p, _p, _p,
+                                           _p, _p]),
     "mval_score_pool_host": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _i, C.POINTER(RansacParams), _i64, _p, _p, _p, _p, _p, _p]),
+    "mval_pipeline_create": (C.c_int, [_i, _i, _i, _i, _i64, _i, C.POINTER(C.c_void_p)]),
+    "mval_pipeline_destroy": (C.c_int, [_p]),
+    "mval_pipeline_score_pool": (C.c_int, [_p, _p, _p, _p, _i64, _i, C.POINTER(RansacParams), C.POINTER(PipelineOptions), _p, _p, _p,
+                                           _p, _p, _p, _p]),
     "mval_score_xe": (C.c_int, [_p, _p, _p, _i64, _i, _i, _i, _i, _d, _p, _p, _p]),
     "mval_topk_desc": (C.c_int, [_p, _i64, _i64, C.c_int32, _p, _p, _p, _p]),
     "mval_topk_merge": (C.c_int, [_p, _p, _i64, C.c_int32, _p, _p, _p, _p]),

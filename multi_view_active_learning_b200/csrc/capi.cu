@@ -81,6 +81,12 @@ int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* 
                             double* out_xyz, double* out_reproj, int32_t* out_inliers, double* out_metric,
                             int32_t* out_inlier_count, float* out_map_score, cudaStream_t stream);
 
+int launch_score_pool_fused_segments(const float* const* seg_ptr, const int64_t* seg_frames, int n_segments,
+                                     const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J, int H, int W,
+                                     int stride, const mval_ransac_params& prm, int map_score, int32_t* out_xy, double* out_xyz,
+                                     double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
+                                     float* out_map_score, cudaStream_t stream);
+
 // MVAL_FUSED=0 in the environment forces the three-launch path (A/B measurements only).
 static bool fused_enabled() {
   static int cached = -1;
@@ -138,97 +144,6 @@ int score_pool(const float* heatmaps, const double* proj, const uint8_t* valid, 
   return rc;
 }
 
-// Host-buffer pipeline: two slots, each with its own stream and device staging buffers.  Slot s processes chunks
-// s, s+2, ...: H2D of chunk k+1 (other slot's stream) overlaps the kernels of chunk k; results go back with
-// async D2H on the same stream.  Pageable host memory still works (the copies then serialise with the host).
-struct Slot {
-  cudaStream_t stream = nullptr;
-  float* hm = nullptr;
-  double* proj = nullptr;
-  uint8_t* valid = nullptr;
-  int32_t* xy = nullptr;
-  double* xyz = nullptr;
-  double* reproj = nullptr;
-  int32_t* inliers = nullptr;
-  double* metric = nullptr;
-  int32_t* inlier_count = nullptr;
-};
-
-static void free_slot(Slot& s) {
-  cudaFree(s.hm); cudaFree(s.proj); cudaFree(s.valid); cudaFree(s.xy); cudaFree(s.xyz); cudaFree(s.reproj);
-  cudaFree(s.inliers); cudaFree(s.metric); cudaFree(s.inlier_count);
-  if (s.stream) cudaStreamDestroy(s.stream);
-  s = Slot();
-}
-
-int score_pool_host(const float* heatmaps, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
-                    int H, int W, int stride, const mval_ransac_params* params, int64_t chunk_frames, int32_t* out_xy,
-                    double* out_xyz, double* out_reproj, int32_t* out_inliers, double* out_metric,
-                    int32_t* out_inlier_count) {
-  if (n_frames == 0) return MVAL_OK;
-  const size_t frame_hm = sizeof(float) * (size_t)V * J * H * W;
-  if (chunk_frames <= 0) {
-    // ~256 MiB of heat maps per chunk: large enough to amortise launches, small enough to start overlapping early
-    chunk_frames = (int64_t)((256ull << 20) / frame_hm);
-    if (chunk_frames < 1) chunk_frames = 1;
-  }
-  if (chunk_frames > n_frames) chunk_frames = n_frames;
-  const int n_slots = (n_frames > chunk_frames) ? 2 : 1;
-  Slot slots[2];
-  int rc = MVAL_OK;
-  auto fail = [&](int code) {
-    cudaDeviceSynchronize();
-    for (auto& s : slots) free_slot(s);
-    return code;
-  };
-#define SLOT_CUDA(call)                                   \
-  do {                                                    \
-    cudaError_t e__ = (call);                             \
-    if (e__ != cudaSuccess) return fail(cuda_fail(e__, #call)); \
-  } while (0)
-  const size_t c = (size_t)chunk_frames;
-  for (int i = 0; i < n_slots; ++i) {
-    Slot& s = slots[i];
-    SLOT_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    SLOT_CUDA(cudaMalloc(&s.hm, frame_hm * c));
-    SLOT_CUDA(cudaMalloc(&s.proj, sizeof(double) * 12 * V * c));
-    if (valid) SLOT_CUDA(cudaMalloc(&s.valid, (size_t)J * c));
-    SLOT_CUDA(cudaMalloc(&s.xy, sizeof(int32_t) * 2 * V * J * c));
-    SLOT_CUDA(cudaMalloc(&s.xyz, sizeof(double) * 3 * J * c));
-    SLOT_CUDA(cudaMalloc(&s.reproj, sizeof(double) * J * c));
-    SLOT_CUDA(cudaMalloc(&s.inliers, sizeof(int32_t) * J * c));
-    SLOT_CUDA(cudaMalloc(&s.metric, sizeof(double) * c));
-    SLOT_CUDA(cudaMalloc(&s.inlier_count, sizeof(int32_t) * c));
-  }
-  int k = 0;
-  for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_frames, ++k) {
-    Slot& s = slots[k % n_slots];
-    const int64_t n = (n_frames - f0 < chunk_frames) ? (n_frames - f0) : chunk_frames;
-    SLOT_CUDA(cudaMemcpyAsync(s.hm, reinterpret_cast<const char*>(heatmaps) + frame_hm * f0, frame_hm * n,
-                              cudaMemcpyHostToDevice, s.stream));
-    SLOT_CUDA(cudaMemcpyAsync(s.proj, proj + (size_t)12 * V * f0, sizeof(double) * 12 * V * n, cudaMemcpyHostToDevice,
-                              s.stream));
-    if (valid) SLOT_CUDA(cudaMemcpyAsync(s.valid, valid + (size_t)J * f0, (size_t)J * n, cudaMemcpyHostToDevice, s.stream));
-    mval_ransac_params p = *params;
-    p.frame_offset = params->frame_offset + f0;
-    if (p.pairs) p.pairs = nullptr;  // explicit pair tables are a device-pointer feature; validated by the caller below
-    if (p.frame_keys) p.frame_keys = params->frame_keys + f0;  // a DEVICE array over the whole pool
-    rc = score_pool(s.hm, s.proj, valid ? s.valid : nullptr, n, V, J, H, W, stride, &p, MVAL_MAP_SCORE_NONE, s.xy, s.xyz,
-                    s.reproj, s.inliers, s.metric, s.inlier_count, nullptr, s.stream);
-    if (rc != MVAL_OK) return fail(rc);
-    if (out_xy) SLOT_CUDA(cudaMemcpyAsync(out_xy + (size_t)2 * V * J * f0, s.xy, sizeof(int32_t) * 2 * V * J * n, cudaMemcpyDeviceToHost, s.stream));
-    SLOT_CUDA(cudaMemcpyAsync(out_xyz + (size_t)3 * J * f0, s.xyz, sizeof(double) * 3 * J * n, cudaMemcpyDeviceToHost, s.stream));
-    if (out_reproj) SLOT_CUDA(cudaMemcpyAsync(out_reproj + (size_t)J * f0, s.reproj, sizeof(double) * J * n, cudaMemcpyDeviceToHost, s.stream));
-    if (out_inliers) SLOT_CUDA(cudaMemcpyAsync(out_inliers + (size_t)J * f0, s.inliers, sizeof(int32_t) * J * n, cudaMemcpyDeviceToHost, s.stream));
-    SLOT_CUDA(cudaMemcpyAsync(out_metric + f0, s.metric, sizeof(double) * n, cudaMemcpyDeviceToHost, s.stream));
-    SLOT_CUDA(cudaMemcpyAsync(out_inlier_count + f0, s.inlier_count, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s.stream));
-  }
-  for (int i = 0; i < n_slots; ++i) SLOT_CUDA(cudaStreamSynchronize(slots[i].stream));
-  for (auto& s : slots) free_slot(s);
-#undef SLOT_CUDA
-  return MVAL_OK;
-}
-
 }  // namespace mval
 
 extern "C" {
@@ -279,17 +194,31 @@ int mval_score_pool_scored(const float* heatmaps, const double* proj, const uint
                           static_cast<cudaStream_t>(stream));
 }
 
-int mval_score_pool_host(const float* heatmaps, const double* proj, const uint8_t* valid, int64_t n_frames, int V,
-                         int J, int H, int W, int stride, const mval_ransac_params* params, int64_t chunk_frames,
-                         int32_t* out_xy, double* out_xyz, double* out_reproj, int32_t* out_inliers, double* out_metric,
-                         int32_t* out_inlier_count) {
+int mval_score_pool_segments(const float* const* seg_heatmaps, const int64_t* seg_frames, int n_segments, const double* proj,
+                             const uint8_t* valid, int V, int J, int H, int W, int stride,
+                             const mval_ransac_params* params, int map_score, int32_t* out_xy, double* out_xyz,
+                             double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
+                             float* out_map_score, void* stream) {
   if (int rc = mval::require_device()) return rc;
-  if (int rc = mval::check_pool_args("mval_score_pool_host", heatmaps, proj, n_frames, V, J, H, W, params, out_xyz,
+  MVAL_REQUIRE(seg_heatmaps && seg_frames && n_segments >= 1 && n_segments <= MVAL_MAX_SEGMENTS,
+               "mval_score_pool_segments: 1..%d segments", MVAL_MAX_SEGMENTS);
+  int64_t n_frames = 0;
+  for (int s = 0; s < n_segments; ++s) {
+    MVAL_REQUIRE(seg_frames[s] >= 0 && (seg_frames[s] == 0 || seg_heatmaps[s] != nullptr), "mval_score_pool_segments: bad segment %d", s);
+    n_frames += seg_frames[s];
+  }
+  if (int rc = mval::check_pool_args("mval_score_pool_segments", seg_heatmaps[0], proj, n_frames, V, J, H, W, params, out_xyz,
                                      out_metric, out_inlier_count))
     return rc;
-  MVAL_REQUIRE(params->pairs == nullptr, "mval_score_pool_host: explicit pair tables are not supported on the host path");
-  return mval::score_pool_host(heatmaps, proj, valid, n_frames, V, J, H, W, stride, params, chunk_frames, out_xy, out_xyz,
-                               out_reproj, out_inliers, out_metric, out_inlier_count);
+  MVAL_REQUIRE(map_score >= MVAL_MAP_SCORE_NONE && map_score <= MVAL_MAP_SCORE_BSB && (map_score == MVAL_MAP_SCORE_NONE || out_map_score),
+               "mval_score_pool_segments: bad map_score / out_map_score");
+  if (n_frames == 0) return MVAL_OK;
+  const int rc = mval::launch_score_pool_fused_segments(seg_heatmaps, seg_frames, n_segments, proj, valid, n_frames, V, J, H, W,
+                                                        stride, *params, map_score, out_xy, out_xyz, out_reproj, out_inliers,
+                                                        out_metric, out_inlier_count, out_map_score,
+                                                        static_cast<cudaStream_t>(stream));
+  if (rc == MVAL_ERR_UNSUPPORTED) mval::set_error("mval_score_pool_segments: shape / alignment / pair table not covered by the fused kernel");
+  return rc;
 }
 
 }  // extern "C"

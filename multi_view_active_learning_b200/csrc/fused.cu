@@ -48,6 +48,16 @@ template <> struct FusedCfg<MVAL_MAP_SCORE_NONE> { static constexpr int kD = 6, 
 template <> struct FusedCfg<MVAL_MAP_SCORE_HP> { static constexpr int kD = 12, kR = 3; using Op = HpOp; };        // 512 threads
 template <> struct FusedCfg<MVAL_MAP_SCORE_MPE> { static constexpr int kD = 12, kR = 3; using Op = PeaksOp<0>; };
 template <> struct FusedCfg<MVAL_MAP_SCORE_BSB> { static constexpr int kD = 12, kR = 3; using Op = PeaksOp<1>; };
+// Heat maps of one launch: up to MVAL_MAX_SEGMENTS device buffers of whole frames, frame f of the launch lives in segment
+// s with start[s] <= f < start[s + 1] at ptr[s] + (f - start[s]) * V * J * H * W (mval_score_pool_segments: a pool is
+// usually produced batch by batch by the pose estimator and need not be contiguous).  Passed by value as a
+// __grid_constant__ parameter: only the producer lane reads it, from the constant bank.
+struct SegTable {
+  const float* ptr[MVAL_MAX_SEGMENTS];
+  int64_t start[MVAL_MAX_SEGMENTS + 1];
+  int n;
+};
+
 constexpr int kMaxFrameSlots = 4;  // frame slots per CTA: 4 when they are small, fewer when V * J is large (see launcher)
 constexpr int kMaxStages = 64;
 
@@ -94,7 +104,7 @@ __host__ __device__ inline FusedSmem fused_layout(int V, int J, int HW, int stag
 // generic per-vector scan; both are the same function of the map.
 template <int kScore, bool kRowArgmax>
 __global__ void __launch_bounds__(kWarp * (1 + FusedCfg<kScore>::kD + FusedCfg<kScore>::kR), 1)
-score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__ proj, const uint8_t* __restrict__ valid,
+score_pool_fused_kernel(const __grid_constant__ SegTable segs, const double* __restrict__ proj, const uint8_t* __restrict__ valid,
                         int64_t n_frames, int V, int J, int H, int HW, int stride, int stages, int slots, int n_iters, double eps,
                         uint64_t seed, int64_t frame_offset, const int64_t* __restrict__ frame_keys, int32_t* __restrict__ out_xy,
                         double* __restrict__ out_xyz,
@@ -135,14 +145,16 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
     // ------------------------------------------------------------------------------------------- producer
     if (lane == 0 && !watchdog_stalled(g_fused_abort)) {
       int64_t c = 0;
+      int seg = 0;
       for (int64_t i = 0; i < nf; ++i) {
         const int64_t frame = blockIdx.x + i * (int64_t)gridDim.x;
+        while (seg + 1 < segs.n && frame >= segs.start[seg + 1]) ++seg;  // frames only grow
         const int sl = (int)(i % slots);
         const uint32_t ku = (uint32_t)(i / slots);
         if (!mbar_wait(&kp_free[sl], (ku & 1u) ^ 1u, g_fused_abort, 1, i, sl)) return;
         mbar_arrive_expect_tx(&kp_ready[sl], (uint32_t)V * 96u);
         bulk_g2s(smem + L.proj + sl * V * 96, proj + frame * V * 12, (uint32_t)V * 96u, &kp_ready[sl]);
-        const float* src = hm + frame * (int64_t)VJ * HW;
+        const float* src = segs.ptr[seg] + (frame - segs.start[seg]) * (int64_t)VJ * HW;
         for (int m = 0; m < VJ; ++m, ++c) {
           const int st = (int)(c % stages);
           const uint32_t kf = (uint32_t)(c / stages);
@@ -315,15 +327,15 @@ score_pool_fused_kernel(const float* __restrict__ hm, const double* __restrict__
 // Returns MVAL_ERR_UNSUPPORTED (without setting an error) when the shape does not fit the fused kernel; the caller
 // then takes the multi-launch path.
 template <int kScore, bool kRowArgmax>
-static int launch_fused_variant(const float* hm, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
+static int launch_fused_variant(const SegTable& segs, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
                                 int H, int W, int stride, const mval_ransac_params& prm, int32_t* out_xy, double* out_xyz,
                                 double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
                                 float* out_map_score, cudaStream_t stream) {
   constexpr int kD = FusedCfg<kScore>::kD, kR = FusedCfg<kScore>::kR;
   const int HW = H * W;
-  if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(hm) & 15) != 0 || (reinterpret_cast<uintptr_t>(proj) & 15) != 0 ||
-      prm.pairs != nullptr)
-    return MVAL_ERR_UNSUPPORTED;
+  if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(proj) & 15) != 0 || prm.pairs != nullptr) return MVAL_ERR_UNSUPPORTED;
+  for (int s = 0; s < segs.n; ++s)
+    if ((reinterpret_cast<uintptr_t>(segs.ptr[s]) & 15) != 0) return MVAL_ERR_UNSUPPORTED;
   if (kScore != MVAL_MAP_SCORE_NONE && (H != kMapDim || W != kMapDim)) return MVAL_ERR_UNSUPPORTED;  // Ops are 64 x 64 only
   int dev = 0, max_smem = 0;
   MVAL_CUDA(cudaGetDevice(&dev));
@@ -347,18 +359,32 @@ static int launch_fused_variant(const float* hm, const double* proj, const uint8
   // a watchdog trip of an EARLIER launch surfaces here (or in mval_check_async), never silently
   if (int rc = g_fused_watchdog.prepare(g_fused_abort, "score_pool_fused")) return rc;
   score_pool_fused_kernel<kScore, kRowArgmax><<<grid, kWarp * (1 + kD + kR), L.total, stream>>>(
-      hm, proj, valid, n_frames, V, J, H, HW, stride, stages, slots, prm.n_iters, prm.epsilon, prm.pair_seed, prm.frame_offset,
+      segs, proj, valid, n_frames, V, J, H, HW, stride, stages, slots, prm.n_iters, prm.epsilon, prm.pair_seed, prm.frame_offset,
       prm.frame_keys, out_xy, out_xyz, out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score);
   MVAL_LAUNCH_CHECK("score_pool_fused");
   return MVAL_OK;
 }
 
-int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
-                            int H, int W, int stride, const mval_ransac_params& prm, int map_score, int32_t* out_xy,
-                            double* out_xyz, double* out_reproj, int32_t* out_inliers, double* out_metric,
-                            int32_t* out_inlier_count, float* out_map_score, cudaStream_t stream) {
+int launch_score_pool_fused_segments(const float* const* seg_ptr, const int64_t* seg_frames, int n_segments,
+                                     const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J, int H, int W,
+                                     int stride, const mval_ransac_params& prm, int map_score, int32_t* out_xy, double* out_xyz,
+                                     double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
+                                     float* out_map_score, cudaStream_t stream) {
+  if (n_segments < 1 || n_segments > MVAL_MAX_SEGMENTS) return MVAL_ERR_UNSUPPORTED;
+  SegTable segs;
+  segs.n = n_segments;
+  segs.start[0] = 0;
+  for (int s = 0; s < n_segments; ++s) {
+    segs.ptr[s] = seg_ptr[s];
+    segs.start[s + 1] = segs.start[s] + seg_frames[s];
+  }
+  for (int s = n_segments; s < MVAL_MAX_SEGMENTS; ++s) {
+    segs.ptr[s] = nullptr;
+    segs.start[s + 1] = segs.start[n_segments];
+  }
+  if (segs.start[n_segments] != n_frames) return MVAL_ERR_UNSUPPORTED;
 #define MVAL_FUSED_ARGS                                                                                               \
-  hm, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz, out_reproj, out_inliers, out_metric,           \
+  segs, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz, out_reproj, out_inliers, out_metric,           \
       out_inlier_count, out_map_score, stream
   // Arg-max flavour on 64 x 64 maps.  Measured (profiles/r1f_summary.md): the unscored pass is faster with the generic
   // per-vector scan (5.78 against 6.06 ms per 16 384 frames: its six decode warps are latency-, not issue-bound), the
@@ -384,6 +410,15 @@ int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* 
       return MVAL_ERR_UNSUPPORTED;
   }
 #undef MVAL_FUSED_ARGS
+}
+
+int launch_score_pool_fused(const float* hm, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
+                            int H, int W, int stride, const mval_ransac_params& prm, int map_score, int32_t* out_xy,
+                            double* out_xyz, double* out_reproj, int32_t* out_inliers, double* out_metric,
+                            int32_t* out_inlier_count, float* out_map_score, cudaStream_t stream) {
+  return launch_score_pool_fused_segments(&hm, &n_frames, 1, proj, valid, n_frames, V, J, H, W, stride, prm, map_score, out_xy,
+                                          out_xyz, out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score,
+                                          stream);
 }
 
 }  // namespace mval

@@ -192,39 +192,136 @@ def score_pool(heatmaps, proj, stride, valid=None, n_iters=DEFAULT_N_ITERS, epsi
     return out
 
 
+def score_pool_segments(segments, proj, stride, valid=None, n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0,
+                        frame_offset=0, return_keypoints_2d=False, map_score=None, frame_keys=None, out=None):
+    """score_pool over a pool given as a LIST of CUDA heat-map buffers [n_s, V, J, H, W] (successive backbone batches, or
+    chunk passes over a resident buffer) in ONE persistent launch (mval_score_pool_segments).  proj [N, V, 3, 4] / valid /
+    the outputs cover all N = sum(n_s) frames.  ``out``: a dict from an earlier call whose tensors are reused (no
+    allocation in steady state)."""
+    if map_score not in _lib.MAP_SCORE:
+        raise ValueError("map_score must be None, 'HP', 'MPE' or 'BSB'")
+    segs = [_cuda(s, torch.float32, "segment") for s in segments]
+    if not 1 <= len(segs) <= _lib.MAX_SEGMENTS:
+        raise ValueError("1..%d segments per call" % _lib.MAX_SEGMENTS)
+    _, V, J, H, W = segs[0].shape
+    counts = [int(s.shape[0]) for s in segs]
+    N = sum(counts)
+    dev = segs[0].device
+    P = _cuda(proj.to(dev) if not proj.is_cuda else proj, torch.float64, "proj")
+    if tuple(P.shape) != (N, V, 3, 4):
+        raise ValueError("proj has shape %s, expected [%d, %d, 3, 4]" % (tuple(P.shape), N, V))
+    v = _valid_u8(valid, N, J, dev)
+    if out is None or out["metric"].shape[0] != N:
+        out = _alloc_tri_outputs(N, J, dev)
+        if return_keypoints_2d:
+            out["keypoints_2d"] = torch.empty((N, V, J, 2), dtype=torch.int32, device=dev)
+        if map_score is not None:
+            out["map_score"] = torch.empty((N, V, J), dtype=torch.float32, device=dev)
+    fk = _frame_keys(frame_keys, N, dev)
+    prm = ransac_params(n_iters, epsilon, pair_seed, frame_offset, frame_keys=fk)
+    ptrs = (C.c_void_p * len(segs))(*[s.data_ptr() for s in segs])
+    cnts = (C.c_int64 * len(segs))(*counts)
+    with torch.cuda.device(dev):
+        check(_lib.load().mval_score_pool_segments(ptrs, cnts, len(segs), _ptr(P), _ptr(v), V, J, H, W, int(stride), C.byref(prm),
+                                                   _lib.MAP_SCORE[map_score], _ptr(out.get("keypoints_2d")),
+                                                   _ptr(out["keypoints_3d"]), _ptr(out["reproj_mean"]), _ptr(out["inliers"]),
+                                                   _ptr(out["metric"]), _ptr(out["inlier_count"]), _ptr(out.get("map_score")),
+                                                   _stream()))
+    return out
+
+
+def _host_outputs(N, V, J, pin, soft, map_score):
+    out = {
+        "keypoints_2d": torch.empty((N, V, J, 2), dtype=torch.float32 if soft else torch.int32, pin_memory=pin),
+        "keypoints_3d": torch.empty((N, J, 3), dtype=torch.float64, pin_memory=pin),
+        "reproj_mean": torch.empty((N, J), dtype=torch.float64, pin_memory=pin),
+        "inliers": torch.empty((N, J), dtype=torch.int32, pin_memory=pin),
+        "metric": torch.empty((N,), dtype=torch.float64, pin_memory=pin),
+        "inlier_count": torch.empty((N,), dtype=torch.int32, pin_memory=pin),
+    }
+    if map_score is not None:
+        out["map_score"] = torch.empty((N, V, J), dtype=torch.float32, pin_memory=pin)
+    return out
+
+
+class HostPipeline:
+    """Handle of the host-buffer streaming pipeline (include/mval_b200.h: mval_pipeline_*): device staging slots and
+    streams are allocated once here and reused by every ``score_pool`` call."""
+
+    def __init__(self, V, J, H=64, W=64, chunk_frames=0, n_slots=0, device=None):
+        self.shape = (int(V), int(J), int(H), int(W))
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._h = C.c_void_p(None)
+        with torch.cuda.device(self.device):
+            check(_lib.load().mval_pipeline_create(*self.shape, int(chunk_frames), int(n_slots), C.byref(self._h)))
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            _lib.load().mval_pipeline_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def score_pool(self, heatmaps, proj, stride, valid=None, n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0,
+                   frame_offset=0, map_score=None, use_soft_argmax=False, use_reprojection_xe=False, sigma=None,
+                   direct_optimization=False, out=None):
+        """Host tensors in (heatmaps float32 [N, V, J, H, W], proj float64 [N, V, 3, 4], valid [N, J] or [J]), host tensors
+        out: H2D, kernels and D2H all inside the call (chunked, overlapped).  The keyword flags are those of
+        triangulation() / _compute_sal_dict (utils/triangulation.py:168-179, strategy.py:1072-1094)."""
+        if heatmaps.is_cuda:
+            raise RuntimeError("HostPipeline.score_pool takes host tensors; use score_pool for device-resident heat maps")
+        if map_score not in _lib.MAP_SCORE:
+            raise ValueError("map_score must be None, 'HP', 'MPE' or 'BSB'")
+        hm = heatmaps.to(torch.float32).contiguous()
+        N, V, J, H, W = hm.shape
+        if (V, J, H, W) != self.shape:
+            raise ValueError("this pipeline was created for %s, got %s" % (self.shape, (V, J, H, W)))
+        P = proj.to(torch.float64).contiguous()
+        if tuple(P.shape) != (N, V, 3, 4):
+            raise ValueError("proj has shape %s, expected [%d, %d, 3, 4]" % (tuple(P.shape), N, V))
+        v = None
+        if valid is not None:
+            v = (torch.as_tensor(valid) != 0).to(torch.uint8)
+            if v.dim() == 1:
+                v = v.unsqueeze(0).expand(N, J)
+            v = v.contiguous()
+        if out is None:
+            out = _host_outputs(N, V, J, hm.is_pinned(), use_soft_argmax, map_score)
+        opt = _lib.PipelineOptions(_lib.MAP_SCORE[map_score], int(bool(use_soft_argmax)), int(bool(use_reprojection_xe)),
+                                   int(bool(direct_optimization)), float(sigma) if sigma is not None else 0.0)
+        prm = ransac_params(n_iters, epsilon, pair_seed, frame_offset)
+        with torch.cuda.device(self.device):
+            check(_lib.load().mval_pipeline_score_pool(self._h, _ptr(hm), _ptr(P), _ptr(v), N, int(stride), C.byref(prm),
+                                                       C.byref(opt), _ptr(out.get("keypoints_2d")), _ptr(out["keypoints_3d"]),
+                                                       _ptr(out.get("reproj_mean")), _ptr(out.get("inliers")), _ptr(out["metric"]),
+                                                       _ptr(out["inlier_count"]), _ptr(out.get("map_score"))))
+        return out
+
+
+_host_pipelines = {}
+
+
 def score_pool_host(heatmaps, proj, stride, valid=None, n_iters=DEFAULT_N_ITERS, epsilon=DEFAULT_EPSILON, pair_seed=0,
-                    frame_offset=0, chunk_frames=0, out=None, device=None):
+                    frame_offset=0, chunk_frames=0, out=None, device=None, **flags):
     """End-to-end entry for HOST heat maps (CPU tensors, pinned for overlap): streams the pool through the GPU in
-    chunks (H2D, kernels, D2H all inside the call) and returns CPU tensors."""
+    chunks (H2D, kernels, D2H all inside the call) and returns CPU tensors.  ``flags``: map_score / use_soft_argmax /
+    use_reprojection_xe + sigma / direct_optimization as in HostPipeline.score_pool.  The staging buffers live in a
+    handle that is kept per (device, shape, chunk) -- nothing is allocated per call."""
     if heatmaps.is_cuda:
         raise RuntimeError("score_pool_host takes host tensors; use score_pool for device-resident heat maps")
-    hm = heatmaps.to(torch.float32).contiguous()
-    N, V, J, H, W = hm.shape
-    P = proj.to(torch.float64).contiguous()
-    v = None
-    if valid is not None:
-        v = (torch.as_tensor(valid) != 0).to(torch.uint8)
-        if v.dim() == 1:
-            v = v.unsqueeze(0).expand(N, J)
-        v = v.contiguous()
-    if out is None:
-        pin = hm.is_pinned()
-        out = {
-            "keypoints_2d": torch.empty((N, V, J, 2), dtype=torch.int32, pin_memory=pin),
-            "keypoints_3d": torch.empty((N, J, 3), dtype=torch.float64, pin_memory=pin),
-            "reproj_mean": torch.empty((N, J), dtype=torch.float64, pin_memory=pin),
-            "inliers": torch.empty((N, J), dtype=torch.int32, pin_memory=pin),
-            "metric": torch.empty((N,), dtype=torch.float64, pin_memory=pin),
-            "inlier_count": torch.empty((N,), dtype=torch.int32, pin_memory=pin),
-        }
-    prm = ransac_params(n_iters, epsilon, pair_seed, frame_offset)
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    with torch.cuda.device(dev):
-        check(_lib.load().mval_score_pool_host(_ptr(hm), _ptr(P), _ptr(v), N, V, J, H, W, int(stride), C.byref(prm),
-                                               int(chunk_frames), _ptr(out.get("keypoints_2d")), _ptr(out["keypoints_3d"]),
-                                               _ptr(out.get("reproj_mean")), _ptr(out.get("inliers")), _ptr(out["metric"]),
-                                               _ptr(out["inlier_count"])))
-    return out
+    _, V, J, H, W = heatmaps.shape
+    key = (dev.index, V, J, H, W, int(chunk_frames))
+    pipe = _host_pipelines.get(key)
+    if pipe is None:
+        for k in [k for k in _host_pipelines if k[0] == dev.index]:  # one shape at a time per device: free the old slots
+            _host_pipelines.pop(k).close()
+        pipe = _host_pipelines[key] = HostPipeline(V, J, H, W, chunk_frames, 0, dev)
+    return pipe.score_pool(heatmaps, proj, stride, valid, n_iters, epsilon, pair_seed, frame_offset, out=out, **flags)
 
 
 def score_xe(heatmaps, proj, keypoints_3d, sigma, return_per_map=False):

@@ -290,6 +290,55 @@ def test_host_pipeline_matches_device_path(ops):
     for k in ("keypoints_2d", "keypoints_3d", "inliers", "inlier_count"):
         assert np.array_equal(dev[k], host[k]), k
     np.testing.assert_array_equal(dev["metric"], host["metric"])
+    # the same handle serves the next call (no staging allocation per call) and an unpinned, ragged last chunk
+    host2 = ops.to_numpy(ops.score_pool_host(hm[:13].clone(), P[:13], 4, valid[:13], pair_seed=5, frame_offset=10, chunk_frames=8))
+    np.testing.assert_array_equal(dev["metric"][:13], host2["metric"])
+    assert len(ops._host_pipelines) == 1
+
+
+def test_host_pipeline_flags_match_triangulation_batch(ops):
+    """The host-buffer entry with the flags of triangulation() / _compute_sal_dict (utils/triangulation.py:168-179,
+    strategy.py:1072-1094): every variant equals the device-resident triangulation_batch bit for bit."""
+    from multi_view_active_learning_b200.utils.triangulation import triangulation_batch
+
+    N, V, J = 29, 5, 19
+    pool = S.make_pool(N, V, J, seed=18, valid_prob=0.9)
+    hm = torch.from_numpy(S.render_heatmaps(pool["centres"], noise=0.05, seed=5)).pin_memory()
+    P, valid = torch.from_numpy(pool["P"]), torch.from_numpy(pool["valid"])
+    pipe = ops.HostPipeline(V, J, 64, 64, chunk_frames=8, n_slots=2)
+    for flags in ({"map_score": "HP"}, {"map_score": "MPE"}, {"map_score": "BSB"}, {"use_soft_argmax": True},
+                  {"use_reprojection_xe": True, "sigma": 1.5}, {"direct_optimization": True},
+                  {"use_soft_argmax": True, "map_score": "HP", "use_reprojection_xe": True, "sigma": 2.0}):
+        host = ops.to_numpy(pipe.score_pool(hm, P, 4, valid, **flags))
+        dev = ops.to_numpy(triangulation_batch(hm.cuda(), P.cuda(), 4, valid, **flags))
+        for k in ("keypoints_2d", "keypoints_3d", "inlier_count", "metric") + (("map_score",) if "map_score" in flags else ()):
+            np.testing.assert_array_equal(dev[k], host[k], err_msg="%s %s" % (flags, k))
+    pipe.close()
+    with pytest.raises(ValueError):
+        ops.HostPipeline(8, 19).score_pool(hm, P, 4, valid)  # shape of the handle
+
+
+def test_score_pool_segments_equals_one_buffer(ops):
+    """One persistent launch over a pool given as several device buffers (mval_score_pool_segments) == the single-buffer
+    call over their concatenation, for every scored variant, with reused outputs."""
+    N, V, J = 301, 8, 19
+    pool = S.make_pool(N, V, J, seed=31, valid_prob=0.9)
+    hm = ops.synth_heatmaps(_cuda(pool["centres"]), noise=0.05, seed=6)
+    P, valid = _cuda(pool["P"]), torch.from_numpy(pool["valid"])
+    cuts = [0, 1, 150, 150, 299, 301]  # incl. an empty segment
+    segs = [hm[a:b].clone() for a, b in zip(cuts[:-1], cuts[1:])]
+    out = None
+    for ms in (None, "HP", "MPE", "BSB"):
+        one = ops.to_numpy(ops.score_pool(hm, P, 4, valid, frame_offset=7, map_score=ms))
+        out = ops.score_pool_segments(segs, P, 4, valid, frame_offset=7, map_score=ms, return_keypoints_2d=True,
+                                      out=out if ms is None else None)
+        got = ops.to_numpy(out)
+        for k in got:
+            np.testing.assert_array_equal(one[k], got[k], err_msg="%s %s" % (ms, k))
+    # the same resident buffer passed several times = chunk passes of the benchmark
+    rep = ops.to_numpy(ops.score_pool_segments([hm, hm, hm[:11]], torch.cat([P, P, P[:11]]), 4, torch.cat([valid, valid, valid[:11]])))
+    one = ops.to_numpy(ops.score_pool(hm, P, 4, valid))
+    np.testing.assert_array_equal(rep["metric"], np.concatenate([one["metric"], one["metric"], one["metric"][:11]]))
 
 
 def test_full_size_properties(ops):
