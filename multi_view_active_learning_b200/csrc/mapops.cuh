@@ -225,6 +225,66 @@ struct HpOp {
   }
 };
 
+// skimage's peak_local_max ends with ensure_spacing(coords sorted by descending intensity, spacing = min_distance,
+// p_norm = inf): a peak is dropped when an ACCEPTED peak lies at Chebyshev distance < 2 from it, i.e. in its 8-neighbourhood
+// (skimage/_shared/coord.py).  Two 5 x 5 local maxima that touch hold the same value -- a plateau -- so the rule only acts
+// among equal neighbours, in the stable order of the sort: ascending flat index.  In raster order that is the recurrence
+//     accepted(r, c) = peak(r, c) and not (accepted(r-1, c-1) or accepted(r-1, c) or accepted(r-1, c+1) or accepted(r, c-1)),
+// evaluated here on 64-bit row masks, warp-uniformly (every lane computes every row and keeps the bits of its own four
+// columns).  Only taken when some peak bits touch (never on real-valued backbone outputs; heat maps with flat regions).
+// Layout of the peak bits as in PeaksOp::run: lane = (half, l16); bit i of b[k] <-> row half * 30 + 2 + i, column 4 l16 + k.
+__device__ __forceinline__ uint64_t spread_nibbles(uint32_t x16) {  // bit l of x16 -> bit 4 l
+  uint64_t x = x16;
+  x = (x | (x << 24)) & 0x000000ff000000ffull;
+  x = (x | (x << 12)) & 0x000f000f000f000full;
+  x = (x | (x << 6)) & 0x0303030303030303ull;
+  x = (x | (x << 3)) & 0x1111111111111111ull;
+  return x;
+}
+
+static __device__ __noinline__ uint4 prune_touching_peaks(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, const float* col, float gmin,
+                                                   int lane) {
+  const int half = lane >> 4, l16 = lane & 15;
+  // image > image.min() is applied before the spacing rule (skimage: the mask is thresholded first)
+  uint32_t f[4] = {b0, b1, b2, b3};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t b = f[k], keep = 0u;
+    while (b) {
+      const int i = __ffs(b) - 1;
+      b &= b - 1;
+      if (col[i * kMapDim + k] > gmin) keep |= 1u << i;
+    }
+    f[k] = keep;
+  }
+  uint32_t out[4] = {0u, 0u, 0u, 0u};
+  uint64_t prev = 0ull;
+#pragma unroll 1
+  for (int r = 0; r < 60; ++r) {
+    const int h = r / 30, i = r - h * 30;
+    uint64_t row = 0ull;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t bal = __ballot_sync(kFull, (f[k] >> i) & 1u);
+      row |= spread_nibbles(h ? (bal >> 16) : (bal & 0xffffu)) << k;
+    }
+    const uint64_t cand = row & ~(prev | (prev << 1) | (prev >> 1));
+    uint64_t acc = cand & ~(cand << 1);  // the first pixel of every horizontal run, then every second one
+#pragma unroll 1
+    for (int it = 0; it < 32; ++it) {
+      const uint64_t nxt = acc | ((acc << 2) & cand & (cand << 1));
+      if (nxt == acc) break;
+      acc = nxt;
+    }
+    prev = acc;
+    if (h == half) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) out[k] |= (uint32_t)((acc >> (4 * l16 + k)) & 1ull) << i;
+    }
+  }
+  return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // MPE (kMode 0) / BSB (kMode 1): local peaks as skimage.feature.peak_local_max(map, min_distance=2) defines them
 // (equal to the maximum of their 5 x 5 window, strictly above the map minimum, 2 pixels off the border).
@@ -343,6 +403,32 @@ struct PeaksOp {
     if (l16 == 15) bits[2] = bits[3] = 0u;  // columns 62, 63
     gmin = warp_min_f(gmin);
     const float* col = map + (rbase + 2) * kMapDim + l16 * 4;  // bit i of bits[k] <-> col[i * 64 + k]
+    {
+      // do any two peak bits touch (8-neighbourhood)?  Inside a lane, across the neighbouring lane, across the two halves
+      // (rows 31 | 32).  Conservative: bits at the map minimum still count here, the slow path filters them first.
+      uint32_t touch = 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) touch |= bits[k] & (bits[k] << 1);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) touch |= bits[k] & (bits[k + 1] | (bits[k + 1] << 1) | (bits[k + 1] >> 1));
+      uint32_t nb = __shfl_down_sync(kFull, bits[0], 1, 16);
+      if (l16 == 15) nb = 0u;
+      touch |= bits[3] & (nb | (nb << 1) | (nb >> 1));
+      uint32_t edge[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) edge[k] = __ballot_sync(kFull, half ? (bits[k] & 1u) : ((bits[k] >> 29) & 1u));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t lo = edge[k] & 0xffffu, hi = edge[k] >> 16;  // row 31 / row 32, column 4 l + k
+        const uint32_t lo_r = (k < 3) ? (edge[k + 1] & 0xffffu) : ((edge[0] & 0xffffu) >> 1);  // column + 1
+        const uint32_t hi_r = (k < 3) ? (edge[k + 1] >> 16) : ((edge[0] >> 16) >> 1);
+        touch |= (lo & hi) | (lo & hi_r) | (hi & lo_r);
+      }
+      if (__any_sync(kFull, touch != 0u)) {
+        const uint4 q = prune_touching_peaks(bits[0], bits[1], bits[2], bits[3], col, gmin, lane);
+        bits[0] = q.x; bits[1] = q.y; bits[2] = q.z; bits[3] = q.w;
+      }
+    }
     if (kMode == 0) {
       constexpr float kLog2e = 1.4426950408889634f;
       gmax = warp_max_f(gmax);

@@ -376,8 +376,12 @@ class ScoringSelectionMixin:
             return packs
         world = dist.get_world_size()
         n = int(packs[0].shape[0])
-        sizes = torch.empty(world, dtype=torch.int64, device=packs[0].device)
-        dist.all_gather_into_tensor(sizes, torch.tensor([n], dtype=torch.int64, device=packs[0].device))
+        dev = packs[0].device
+        if dist.get_backend() == "gloo" and dev.type == "cuda":
+            # gloo (CPU tests of the multi-rank flow on one GPU) exchanges host buffers; NCCL takes the CUDA tensors as is
+            return [g.to(dev) for g in ScoringSelectionMixin._gather_rows([t.cpu() for t in packs])]
+        sizes = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, torch.tensor([n], dtype=torch.int64, device=dev))
         sizes = sizes.cpu().tolist()
         n_max = max(sizes)
         out = []

@@ -238,6 +238,28 @@ def case_softargmax(tri):
     print("softargmax kp[0,0,:2]", out["keypoints_2d"][0, 0, :2], "metric", out["metric"])
 
 
+def case_pred_coordinates_soft(ev):
+    """get_pred_coordinates(..., use_softargmax=True) of the unmodified reference (utils/evaluation.py:37-43), kornia served
+    by the same vendored expectation code as case_softargmax."""
+    import torch.nn.functional as F
+    from transformers.models.efficientloftr.modeling_efficientloftr import spatial_expectation2d
+
+    def spatial_soft_argmax2d(input, temperature=torch.tensor(1.0), normalized_coordinates=True):
+        b, c, h, w = input.shape
+        soft = F.softmax(input.view(b, c, -1) * temperature.to(input.dtype), dim=-1).view(b, c, h, w)
+        return spatial_expectation2d(soft, normalized_coordinates)
+
+    ev.kornia.spatial_soft_argmax2d = spatial_soft_argmax2d
+    B, K = 3, 5
+    pool = S.make_pool(1, B, K, seed=411)
+    hm = S.render_heatmaps(pool["centres"][0], noise=0.05, seed=412) * np.float32(6.0)  # [B, K, 64, 64]
+    boxes = np.array([[10, 20, 266, 276], [0, 0, 128, 128], [5, 7, 325, 327]], dtype=np.float32)  # square boxes (:40)
+    out = ev.get_pred_coordinates(torch.from_numpy(hm), torch.from_numpy(boxes), K, use_softargmax=True)
+    np.savez_compressed(os.path.join(OUT, "pred_coordinates_soft.npz"), centres=pool["centres"][0], heatmap_seed=412, noise=0.05,
+                        gain=6.0, boxes=boxes, coords=out.numpy())
+    print("pred_coordinates_soft", out.numpy()[0, 0], out.dtype)
+
+
 def case_coreset(cs):
     import uuid
 
@@ -304,6 +326,7 @@ def main():
     case_hp(st)
     case_peaks(st)
     case_softargmax(tri)
+    case_pred_coordinates_soft(ev)
     case_coreset(cs)
     case_xe(tri)
 

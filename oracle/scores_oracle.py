@@ -13,10 +13,13 @@ import numpy as np
 
 def hp_scores(heatmaps):
     """[..., H, W] float32 -> float32 [...]: 1 - max over the map of the row-wise softmax (float32 arithmetic)."""
-    hm = np.asarray(heatmaps, dtype=np.float32)
-    e = np.exp(hm - hm.max(axis=-1, keepdims=True))
-    p = e / e.sum(axis=-1, keepdims=True, dtype=np.float32)
-    return (np.float32(1.0) - p.max(axis=(-2, -1))).astype(np.float32)
+    import torch
+
+    # evaluated with torch itself, as the reference does (F.softmax of the 2-D map = softmax over dim 1, then 1 - max):
+    # numpy's exp and torch's vectorised exp differ in the last bit, and HP's STD is a float64 of these values
+    hm = torch.from_numpy(np.ascontiguousarray(np.asarray(heatmaps, dtype=np.float32)))
+    sm = torch.softmax(hm, dim=-1)
+    return (1 - sm.amax(dim=(-2, -1))).numpy().astype(np.float32)
 
 
 def hp_metric(heatmaps, joint_valid, config="AVG"):

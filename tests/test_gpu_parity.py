@@ -74,6 +74,19 @@ def test_decode_reference_api(ops, golden):
     np.testing.assert_allclose(pc, g["pred_coordinates"], rtol=1e-6)
 
 
+def test_pred_coordinates_softargmax_branch_vs_reference_golden(ops, golden):
+    """get_pred_coordinates(..., use_softargmax=True) (utils/evaluation.py:37-43) against the unmodified reference run with
+    kornia's vendored expectation code: bbox-scaled float32 coordinates, tensor [B, K, 2]."""
+    from multi_view_active_learning_b200.utils import evaluation
+
+    g = golden("pred_coordinates_soft")
+    hm = S.render_heatmaps(g["centres"], noise=float(g["noise"]), seed=int(g["heatmap_seed"])) * np.float32(g["gain"])
+    out = evaluation.get_pred_coordinates(torch.from_numpy(hm).cuda(), torch.from_numpy(g["boxes"]), hm.shape[1], use_softargmax=True)
+    assert torch.is_tensor(out) and tuple(out.shape) == g["coords"].shape and out.dtype == torch.float32
+    scale = (g["boxes"][:, 3] - g["boxes"][:, 1]) / 64.0
+    np.testing.assert_allclose(out.cpu().numpy(), g["coords"], rtol=0, atol=float(2e-4 * scale.max()))
+
+
 @pytest.mark.parametrize("shape", [(3, 2, 5, 64, 64), (2, 3, 4, 48, 48), (1, 2, 3, 7, 9), (2, 2, 2, 32, 64)])
 def test_decode_argmax_random_vs_oracle(ops, shape):
     rng = np.random.default_rng(sum(shape))
@@ -789,7 +802,7 @@ def test_map_stream_peak_edge_cases(ops):
         hm[0, 0, 1, r, 3 * (r - 28) + 5] = 1.0 + 0.1 * r  # one peak per seam row, far apart
     hm[0, 0, 2, 31, 31], hm[0, 0, 2, 32, 33] = 2.0, 2.5  # neighbours across the seam: only the larger survives
     hm[0, 0, 3] = 1.0
-    hm[0, 0, 3, 10:20, 10:20] = 0.5  # peaks would sit on the plateau of 1.0 = not the minimum -> all plateau pixels count
+    hm[0, 0, 3, 10:20, 10:20] = 0.5  # a plateau of 1.0 above the minimum: touching plateau pixels are pruned (ensure_spacing)
     hm[0, 0, 4] = -1.0
     hm[0, 0, 4, 20, 20], hm[0, 0, 4, 40, 40] = 0.0, 0.25
     rng = np.random.default_rng(8)
@@ -799,14 +812,62 @@ def test_map_stream_peak_edge_cases(ops):
     mpe = ops.score_peaks(_cuda(hm), "MPE").cpu().numpy()
     bsb = ops.score_peaks(_cuda(hm), "BSB").cpu().numpy()
     exp_m, exp_b = SO.mpe_scores(hm), SO.bsb_scores(hm)
-    keep = np.ones(8, dtype=bool)
-    keep[3] = False  # a plateau above the minimum: skimage prunes it with ensure_spacing, the kernel counts every pixel
+    keep = np.ones(8, dtype=bool)  # map 3 (the plateau) is part of the comparison since round 2
     np.testing.assert_allclose(mpe[0, 0, keep], exp_m[0, 0, keep], rtol=0, atol=2e-5)
     ok = keep & ~np.isnan(exp_b[0, 0])
     np.testing.assert_allclose(bsb[0, 0, ok], exp_b[0, 0, ok], rtol=0, atol=2e-6)
     assert np.array_equal(np.isnan(bsb[0, 0, keep]), np.isnan(exp_b[0, 0, keep]))
     legacy_m = _legacy(lambda: ops.score_peaks(_cuda(hm), "MPE")).cpu().numpy()
-    np.testing.assert_allclose(mpe, legacy_m, rtol=0, atol=2e-5)
+    keep[3] = False  # the generic-shape kernel (one warp streaming a map of any size) does not prune plateaus
+    np.testing.assert_allclose(mpe[0, 0, keep], legacy_m[0, 0, keep], rtol=0, atol=2e-5)
+
+
+def test_peak_plateaus_follow_ensure_spacing(ops):
+    """skimage's peak_local_max drops a peak that touches an already accepted one (ensure_spacing, Chebyshev distance < 2);
+    peaks are visited by descending value, equal values in flat-index order (strategy.py:1168-1170, 1204-1206).  Touching
+    5 x 5 maxima are always equal, so this is about plateaus: pairs, runs, blocks, across the kernel's lane boundary (columns
+    4l+3 | 4l+4) and across its two row streams (rows 31 | 32).  MPE sees the raw maps, BSB their row softmax."""
+    rng = np.random.default_rng(3)
+    M = 10
+    hm = (rng.uniform(size=(1, 1, M, 64, 64)) * 0.1).astype(np.float32)
+    hm[0, 0, 0, 20, 20] = hm[0, 0, 0, 20, 21] = 2.0          # horizontal pair + a lower peak
+    hm[0, 0, 0, 40, 40] = 1.5
+    hm[0, 0, 1, 31, 25] = hm[0, 0, 1, 32, 25] = 2.0          # vertical pair across the two row streams
+    hm[0, 0, 1, 31, 40] = hm[0, 0, 1, 32, 41] = 1.75         # diagonal pair across them
+    hm[0, 0, 1, 50, 10] = 1.25
+    hm[0, 0, 2, 12, 7] = hm[0, 0, 2, 12, 8] = 2.0            # pair across a lane boundary (columns 7 | 8)
+    hm[0, 0, 2, 13, 11] = hm[0, 0, 2, 12, 12] = 1.5          # anti-diagonal pair across one (row 12 col 12 comes first)
+    hm[0, 0, 3, 30, 30:33] = 2.0                             # run of three: first and third survive
+    hm[0, 0, 3, 45, 10:17] = 1.5                             # run of seven: every second one
+    hm[0, 0, 4, 10:12, 10:12] = 2.0                          # 2 x 2 block: only its first pixel
+    hm[0, 0, 4, 30:33, 40:43] = 1.5                          # 3 x 3 block: its four corners
+    hm[0, 0, 5, 20:26, 20] = 2.0                             # vertical run of six
+    hm[0, 0, 6, 29:35, 29:35] = 3.0                          # block over the seam rows
+    hm[0, 0, 7] = 1.0                                        # everything a plateau except a dent ...
+    hm[0, 0, 7, 5:9, 50:60] = 0.25
+    hm[0, 0, 8, 2, 2] = hm[0, 0, 8, 2, 3] = 2.0              # pair at the edge of the admissible region
+    hm[0, 0, 8, 61, 60] = hm[0, 0, 8, 61, 61] = 2.0
+    hm[0, 0, 9, 20, 20] = hm[0, 0, 9, 20, 22] = 2.0          # NOT touching (distance 2): both stay
+    mpe = ops.score_peaks(_cuda(hm), "MPE").cpu().numpy()
+    np.testing.assert_allclose(mpe[0, 0], SO.mpe_scores(hm)[0, 0], rtol=0, atol=2e-5)
+    # the same maps through the fused pool pass (decode warps evaluate the score on the staged map)
+    pool = S.make_pool(1, 2, M, seed=1)
+    hm2 = np.concatenate([hm, hm], axis=1)
+    fused = ops.score_pool(_cuda(hm2), _cuda(pool["P"]), 4, map_score="MPE")["map_score"].cpu().numpy()
+    np.testing.assert_array_equal(fused[0, 0], mpe[0, 0])
+    # BSB: equal values in one row stay equal after the row softmax; the two best SURVIVING peaks are compared
+    b = np.zeros((1, 1, 4, 64, 64), dtype=np.float32)
+    b[0, 0, 0, 20, 20] = b[0, 0, 0, 20, 21] = 6.0            # touching pair: one survives, second best is the 4.0 below
+    b[0, 0, 0, 40, 40] = 4.0
+    b[0, 0, 1, 20, 7] = b[0, 0, 1, 20, 8] = 6.0              # the same across a lane boundary
+    b[0, 0, 1, 40, 40] = 5.0
+    b[0, 0, 2, 30, 30:33] = 6.0                              # run of three: first and third survive -> difference 0
+    b[0, 0, 3, 31, 25] = b[0, 0, 3, 32, 25] = 6.0            # identical rows: vertical pair across the seam
+    b[0, 0, 3, 50, 50] = 3.0
+    bsb = ops.score_peaks(_cuda(b), "BSB").cpu().numpy()
+    exp_b = SO.bsb_scores(b)
+    np.testing.assert_allclose(bsb[0, 0], exp_b[0, 0], rtol=0, atol=2e-6)
+    assert bsb[0, 0, 2] == 0.0 and bsb[0, 0, 0] > 0.5
 
 
 # ------------------------------------------------------------------------------------------------ Huber refinement
@@ -886,3 +947,67 @@ def test_empty_inputs_and_nan_maps(ops):
     mpe = ops.score_peaks(_cuda(hm), "MPE").cpu().numpy()[0, 0]
     assert mpe[4] == 0.0  # constant map: no peak (every pixel sits at the map minimum)
     np.testing.assert_allclose(mpe[[0, 5]], SO.mpe_scores(hm[:, :, [0, 5]])[0, 0], rtol=0, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------ inlier threshold
+def _planted_threshold_pool(n_cases, V, delta, rng):
+    """Frames with one joint whose views are EXACT (integer key-points, principal points shifted so that the joint
+    projects onto them to ~1e-13 px) except one planted view whose key-point sits 2 * (5 + delta) px from the projection:
+    its half-distance reprojection error is 5 + delta for every view pair that does not contain it."""
+    base = S.ring_cameras(V, rng=rng)
+    P = np.broadcast_to(base, (n_cases,) + base.shape).copy()
+    X = rng.uniform(-300, 300, size=(n_cases, 1, 3))
+    uv = S.project(P, X)  # [n, V, 1, 2]
+    kp = np.round(uv)
+    planted = rng.integers(0, V, size=n_cases)
+    ang = rng.uniform(0, 2 * np.pi, size=n_cases)
+    want = kp.copy()  # where the joint must project to
+    for i in range(n_cases):
+        want[i, planted[i], 0] -= 2.0 * (5.0 + delta) * np.array([np.cos(ang[i]), np.sin(ang[i])])
+    shift = want - uv  # move every projection onto its target through the principal point (exact: P[0] += s * P[2])
+    P[:, :, 0, :] += shift[:, :, 0, 0:1] * P[:, :, 2, :]
+    P[:, :, 1, :] += shift[:, :, 0, 1:2] * P[:, :, 2, :]
+    return P, kp.astype(np.int32), planted
+
+
+def _single_vote(ops, P, kp, planted):
+    """One RANSAC vote per joint from an explicit view pair that does NOT contain the planted view (n_iters = 1), so the
+    planted view's membership of the final inlier set is decided by exactly that one comparison with the threshold."""
+    n, V = kp.shape[:2]
+    pairs = np.zeros((n, 1, 1, 2), dtype=np.uint8)
+    for i in range(n):
+        others = [v for v in range(V) if v != planted[i]]
+        pairs[i, 0, 0] = others[:2]
+    valid = np.ones((n, 1), dtype=bool)
+    kp3d, reproj, inliers, mask = O.ransac_pool(P, kp, valid, pairs.astype(np.int64), 5.0)
+    out = ops.to_numpy(ops.triangulate_ransac(_cuda(kp), _cuda(P), torch.from_numpy(valid), n_iters=1, pairs=_cuda(pairs)))
+    return out, {"inlier_mask": mask, "inliers": inliers, "reproj_mean": reproj}
+
+
+@pytest.mark.parametrize("delta", [1e-3, -1e-3, 1e-6, -1e-6, 1e-8, -1e-8])
+def test_inlier_votes_next_to_the_threshold(ops, delta):
+    """utils/triangulation.py:293-300 votes with  0.5 * sqrt(dx^2 + dy^2) < 5 ; the kernel votes division-free with
+    dx'^2 + dy'^2 < (10 h)^2 on the homogeneous residuals.  Planted errors of 5 + delta px: down to |delta| = 1e-8 px
+    (1e4 times the ~1e-12 px that separates LAPACK's SVD from the Jacobi solve on these rigs) every vote equals the
+    oracle's, on both sides of the threshold."""
+    rng = np.random.default_rng(int(abs(np.log10(abs(delta)))) * 7 + (delta > 0))
+    n, V = 1500, 6
+    P, kp, planted = _planted_threshold_pool(n, V, delta, rng)
+    out, ref = _single_vote(ops, P, kp, planted)
+    assert np.array_equal(out["inlier_mask"].astype(np.uint32), ref["inlier_mask"])
+    assert np.array_equal(out["inliers"], ref["inliers"])
+    inside = (ref["inlier_mask"][:, 0] >> planted) & 1
+    assert inside.all() if delta < 0 else not inside.any()  # the planted view is in (delta < 0) or out (delta > 0)
+    np.testing.assert_allclose(out["reproj_mean"], ref["reproj_mean"], rtol=0, atol=REPROJ_ATOL_PX)
+
+
+def test_inlier_votes_at_the_rounding_limit_are_counted(ops):
+    """At |delta| = 1e-12 px the two eigen-solvers legitimately disagree now and then; count it instead of
+    pretending: the disagreements must stay confined to the planted view."""
+    rng = np.random.default_rng(12)
+    n, V = 3000, 6
+    P, kp, planted = _planted_threshold_pool(n, V, 1e-12, rng)
+    out, ref = _single_vote(ops, P, kp, planted)
+    diff = out["inlier_mask"][:, 0].astype(np.uint32) ^ ref["inlier_mask"][:, 0]
+    assert ((diff & ~(1 << planted).astype(np.uint32)) == 0).all()
+    print("votes that differ from LAPACK at |delta| = 1e-12 px: %d of %d" % (int((diff != 0).sum()), n))
