@@ -602,7 +602,7 @@ def _timed(fn, iters=1):
     return a.elapsed_time(b) / iters, out
 
 
-def coreset_record(ctx, n_total, d, L, budget, path="auto", data="gaussian", kslots=0, cpu_rows=50000, with_cpu=True):
+def coreset_record(ctx, n_total, d, L, budget, path="auto", data="gaussian", kslots=0, cpu_rows=50000, with_cpu=True, pad=0):
     """C4-style workload: k-center greedy over n_total x d float32 features sharded by rows over the ranks (STRONG scaling:
     the total is fixed).  Returns (on rank 0) the record of the whole selection (norms + labeled fold-in + budget picks in
     exact rounds, device-timed, max over ranks) with two rooflines: the tensor-pipe fraction of the tcgen05 screening GEMM
@@ -620,6 +620,9 @@ def coreset_record(ctx, n_total, d, L, budget, path="auto", data="gaussian", ksl
     feat = torch.randn((n, d), generator=g, device=dev, dtype=torch.float32)
     gl = torch.Generator(device=dev).manual_seed(7)
     labeled = torch.randn((L, d), generator=gl, device=dev, dtype=torch.float32)
+    if pad:  # zero columns up to a multiple of `pad`: bit-identical distances (pool.pad_features), tensor-core screen applicable
+        feat, labeled = poolmod.pad_features(feat, pad), poolmod.pad_features(labeled, pad)
+        d = feat.shape[1]
     if data == "clustered":  # 64 tight clusters: a pick collapses the minima of its whole cluster
         gc = torch.Generator(device=dev).manual_seed(5)
         cent = torch.randn((64, d), generator=gc, device=dev, dtype=torch.float32) * 4.0
@@ -756,7 +759,7 @@ def run_coreset(args):
         dist.init_process_group("nccl", device_id=dev)
     out = coreset_record({"world": world, "rank": rank, "dev": dev}, args.coreset_rows, args.coreset_dim, args.coreset_labeled,
                          args.coreset_budget, args.coreset_path, args.coreset_data, args.coreset_kslots, args.coreset_cpu_rows,
-                         with_cpu=args.cpu_frames > 0)
+                         with_cpu=args.cpu_frames > 0, pad=args.coreset_pad)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -1229,7 +1232,7 @@ def main():
     ap.add_argument("--verify", action="store_true", help="hybrid: gather the pose features and check the sharded coreset "
                     "selection against the single-device loop on rank 0")
     ap.add_argument("--coreset-kslots", type=int, default=0, help="candidate slots per shard and round (0 = pool.py default)")
-    ap.add_argument("--coreset-pad", type=int, default=0, help="hybrid: zero-pad the pose features to a multiple of this")
+    ap.add_argument("--coreset-pad", type=int, default=0, help="coreset / hybrid: zero-pad the features to a multiple of this")
     ap.add_argument("--no-extra", action="store_true", help="scoring workload: skip the extra sub-records (T / C4 / C3 / C5)")
     ap.add_argument("--extra-api-frames", type=int, default=125_000, help="frames per GPU of the T record in `extra`")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks during the timed region")

@@ -124,6 +124,35 @@ struct TcPair {
   uint32_t row, t;
 };
 
+// Appends the surviving (row, centre) pairs of one 32-centre chunk (lane = row, v[j] = accumulator of centre t0 + j) to the
+// global list.  The survivors of the whole warp take ONE atomicAdd (round 1: one per pair, which serialised the early
+// passes where millions of pairs survive); a chunk without survivors costs the 32 compares and one vote.
+__device__ __forceinline__ void append_survivors(const float (&v)[32], const float* __restrict__ hcc, float thr, bool rok, uint32_t row,
+                                                 uint32_t t0, int lane, TcPair* __restrict__ pairs, unsigned int* __restrict__ pair_count,
+                                                 unsigned int pair_capacity) {
+  uint32_t m = 0u;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) m |= ((v[j] - hcc[j]) >= thr ? 1u : 0u) << j;
+  if (!rok) m = 0u;
+  const int cnt = __popc(m);
+  if (!__any_sync(0xffffffffu, cnt != 0)) return;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  unsigned int base = 0u;
+  if (lane == 31) base = atomicAdd(pair_count, (unsigned int)incl);
+  base = __shfl_sync(0xffffffffu, base, 31) + (unsigned int)(incl - cnt);
+  while (m) {
+    const int j = __ffs(m) - 1;
+    m &= m - 1u;
+    if (base < pair_capacity) pairs[base] = TcPair{row, t0 + (uint32_t)j};
+    ++base;
+  }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 kc_screen_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
                     const float* __restrict__ xx, const float* __restrict__ cc, const float* __restrict__ min_dist, int64_t n,
@@ -247,13 +276,7 @@ kc_screen_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const float thr = fmaxf(0.5f * ((xr - s_i) - m2), vmax - s_i);
       for (int c = 0; c < n_chunks; ++c) {
         tmem_ld32(taddr + c * 32, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (rok && (v[j] - hcc[c * 32 + j]) >= thr) {
-            const unsigned int pos = atomicAdd(pair_count, 1u);
-            if (pos < pair_capacity) pairs[pos] = TcPair{(uint32_t)row, (uint32_t)(c * 32 + j)};
-          }
-        }
+        append_survivors(v, hcc + c * 32, thr, rok, (uint32_t)row, (uint32_t)(c * 32), lane, pairs, pair_count, pair_capacity);
       }
       tc_fence_before();
       __syncwarp();
@@ -478,13 +501,7 @@ kc_screen_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       const float thr = fmaxf(0.5f * ((xr - s_i) - m2), vmax - s_i);  // see kc_screen_tc_kernel
       for (int c = 0; c < n_chunks; ++c) {
         tmem_ld32(taddr + c * 32, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (rok && (v[j] - hcc[c * 32 + j]) >= thr) {
-            const unsigned int pos = atomicAdd(pair_count, 1u);
-            if (pos < pair_capacity) pairs[pos] = TcPair{(uint32_t)row, (uint32_t)(c * 32 + j)};
-          }
-        }
+        append_survivors(v, hcc + c * 32, thr, rok, (uint32_t)row, (uint32_t)(c * 32), lane, pairs, pair_count, pair_capacity);
       }
       tc_fence_before();
       __syncwarp();

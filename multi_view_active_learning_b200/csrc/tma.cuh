@@ -29,6 +29,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // persistent kernels issue nothing: test hooks behind mval_debug_watchdog.
 constexpr int kWdWords = 16, kWdTimeout = 8, kWdMirror = 9, kWdStall = 10;
 constexpr long long kWdDefaultCycles = 10000000000ll;
+constexpr uint32_t kWaitHintNs = 20000u;  // mbarrier.try_wait suspend-time hint of the long waiters (kBackoff)
 
 __device__ __forceinline__ bool watchdog_stalled(const unsigned long long* abort_rec) {
   return *((const volatile unsigned long long*)&abort_rec[kWdStall]) != 0ull;
@@ -43,16 +44,27 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsign
   long long t0 = 0;
   uint32_t polls = 0;
   for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
+    if (kBackoff) {
+      // suspend-time hint: the hardware parks the thread until the phase completes or the hint (ns) expires, instead of
+      // returning after the short default limit -- a waiter that expects to wait long then issues almost nothing
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(smem_u32(bar)), "r"(parity), "r"(kWaitHintNs)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(smem_u32(bar)), "r"(parity)
+          : "memory");
+    }
     if (ok) return true;
-    if (kBackoff) __nanosleep(256);
-    if ((++polls & 255u) == 0u) {
+    if ((++polls & (kBackoff ? 15u : 255u)) == 0u) {
       if (*((volatile unsigned long long*)&abort_rec[0]) != 0ull) return false;
       const long long now = clock64();
       if (t0 == 0) t0 = now;
