@@ -369,6 +369,14 @@ int mval_kcenter_greedy(const float* features, int64_t n, int64_t n_unlabeled, i
 int mval_synth_heatmaps(const float* centres, int64_t n_maps, int H, int W, float sigma, float noise,
                         uint64_t seed, float* out_heatmaps, void* stream);
 
+/* Replaces dataset/dataset.py:198-207 (the ground-truth heat maps a frame is trained against, the format on the other side
+ * of the pose estimator): points float64 device [n_maps][2] = the joint's projection divided by the heat-map stride
+ * (x, y); out = exp(-((x - px)^2 + (y - py)^2) / (2 sigma^2)) on the H x W pixel grid, evaluated in float64 like the
+ * reference (a float32 grid minus a float64 label promotes to float64).  out_f64 float64 device [n_maps][H][W] and / or
+ * out_f32 (the same values rounded to float32, what the loss consumes); either may be NULL. */
+int mval_render_gt_heatmaps(const double* points, int64_t n_maps, int H, int W, double sigma, double* out_f64, float* out_f32,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

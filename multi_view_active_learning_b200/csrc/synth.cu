@@ -24,7 +24,38 @@ synth_heatmaps_kernel(const float* __restrict__ centres, int64_t n_maps, int H, 
   }
 }
 
+// dataset/dataset.py:198-207: the ground-truth heat map of a joint whose projection, divided by the heat-map stride, is
+// (px, py): exp(-((x - px)^2 + (y - py)^2) / (2 sigma^2)) on the pixel grid x = 0..W-1, y = 0..H-1.  The reference subtracts
+// a float64 label from a float32 grid, so everything from there on is float64 (torch type promotion); so is this kernel
+// (x term first, then y, like torch.sum over the last axis).
+__global__ void __launch_bounds__(256)
+render_gt_heatmaps_kernel(const double* __restrict__ pts, int64_t n_maps, int H, int W, double two_sigma2, double* __restrict__ out64,
+                          float* __restrict__ out32) {
+  const int64_t hw = (int64_t)H * W;
+  const int64_t total = n_maps * hw;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t map = e / hw;
+    const int r = (int)((e - map * hw) / W), c = (int)((e - map * hw) % W);
+    const double dx = (double)c - pts[2 * map], dy = (double)r - pts[2 * map + 1];
+    const double v = exp(-__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) / two_sigma2);
+    if (out64) out64[e] = v;
+    if (out32) out32[e] = (float)v;
+  }
+}
+
 }  // namespace mval
+
+extern "C" int mval_render_gt_heatmaps(const double* points, int64_t n_maps, int H, int W, double sigma, double* out_f64,
+                                       float* out_f32, void* stream) {
+  if (int rc = mval::require_device()) return rc;
+  MVAL_REQUIRE(n_maps >= 0 && H > 0 && W > 0 && sigma > 0, "mval_render_gt_heatmaps: bad arguments");
+  if (n_maps == 0) return MVAL_OK;
+  MVAL_REQUIRE(points && (out_f64 || out_f32), "mval_render_gt_heatmaps: null pointer");
+  mval::render_gt_heatmaps_kernel<<<mval::num_sms() * 16, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      points, n_maps, H, W, 2.0 * (sigma * sigma), out_f64, out_f32);
+  MVAL_LAUNCH_CHECK("render_gt_heatmaps");
+  return MVAL_OK;
+}
 
 extern "C" int mval_synth_heatmaps(const float* centres, int64_t n_maps, int H, int W, float sigma, float noise,
                                    uint64_t seed, float* out_heatmaps, void* stream) {

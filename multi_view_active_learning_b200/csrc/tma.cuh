@@ -29,7 +29,6 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // persistent kernels issue nothing: test hooks behind mval_debug_watchdog.
 constexpr int kWdWords = 16, kWdTimeout = 8, kWdMirror = 9, kWdStall = 10;
 constexpr long long kWdDefaultCycles = 10000000000ll;
-constexpr uint32_t kWaitHintNs = 20000u;  // mbarrier.try_wait suspend-time hint of the long waiters (kBackoff)
 
 __device__ __forceinline__ bool watchdog_stalled(const unsigned long long* abort_rec) {
   return *((const volatile unsigned long long*)&abort_rec[kWdStall]) != 0ull;
@@ -44,26 +43,18 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsign
   long long t0 = 0;
   uint32_t polls = 0;
   for (;;) {
-    if (kBackoff) {
-      // suspend-time hint: the hardware parks the thread until the phase completes or the hint (ns) expires, instead of
-      // returning after the short default limit -- a waiter that expects to wait long then issues almost nothing
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(ok)
-          : "r"(smem_u32(bar)), "r"(parity), "r"(kWaitHintNs)
-          : "memory");
-    } else {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(ok)
-          : "r"(smem_u32(bar)), "r"(parity)
-          : "memory");
-    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
     if (ok) return true;
+    // A long waiter (the RANSAC warps wait ~50 us for the key-points of a frame, with up to three frames of slack) sleeps
+    // between polls: try_wait alone comes back every ~0.1 us whatever its suspend-time hint says (measured, round 2: the poll
+    // loop was 25 % of all executed warp instructions of the fused kernel), a 2-4 us sleep cuts that by ~20x.
+    if (kBackoff) __nanosleep(polls < 2u ? 500u : 3000u);
     if ((++polls & (kBackoff ? 15u : 255u)) == 0u) {
       if (*((volatile unsigned long long*)&abort_rec[0]) != 0ull) return false;
       const long long now = clock64();

@@ -504,6 +504,18 @@ def synth_heatmaps(centres, H=64, W=64, sigma=1.0, noise=0.05, seed=0, out=None)
     return out
 
 
+def render_gt_heatmaps(points, H=64, W=64, sigma=1.0, dtype=torch.float64):
+    """dataset/dataset.py:198-207: points float64 CUDA [..., 2] (projection / stride, (x, y)) -> [..., H, W] ground-truth heat
+    maps, float64 like the reference's (dtype=torch.float32: the same values rounded once)."""
+    p = _cuda(points, torch.float64, "points")
+    n_maps = p.numel() // 2
+    out = torch.empty(tuple(p.shape[:-1]) + (H, W), dtype=dtype, device=p.device)
+    with torch.cuda.device(p.device):
+        check(_lib.load().mval_render_gt_heatmaps(_ptr(p), n_maps, H, W, float(sigma), _ptr(out if dtype == torch.float64 else None),
+                                                  _ptr(out if dtype == torch.float32 else None), _stream()))
+    return out
+
+
 def to_numpy(d):
     return {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
 
