@@ -236,7 +236,51 @@ class ScoringSelectionMixin:
         """Reference strategy.py:747-760."""
         from torch.utils.data import DataLoader, DistributedSampler
 
-        return DataLoader(dataset, batch_size=batch_size, num_workers=num_workers, sampler=DistributedSampler(dataset))
+        # pinned batches: the uploads of _device_batches are then truly asynchronous (the reference's loader is the same
+        # DataLoader + DistributedSampler without pinning, strategy.py:753-759)
+        return DataLoader(dataset, batch_size=batch_size, num_workers=num_workers, sampler=DistributedSampler(dataset),
+                          pin_memory=torch.cuda.is_available())
+
+    @staticmethod
+    def _device_batches(data_loader):
+        """the reference uploads a batch with blocking .cuda() calls, runs the forward, then scores
+        (strategy.py:1024-1035).  Here the tensors of batch k + 1 are uploaded on a COPY stream while the forward and the
+        scoring launch of batch k run on the compute stream; the compute stream waits on the upload's event only.  Batches
+        whose tensors already live on the device pass through untouched."""
+        if not torch.cuda.is_available():
+            yield from data_loader
+            return
+        copy_stream = None
+
+        def upload(dp):
+            nonlocal copy_stream
+            if not isinstance(dp, dict) or not any(torch.is_tensor(v) and not v.is_cuda for v in dp.values()):
+                return dp, None
+            if copy_stream is None:
+                copy_stream = torch.cuda.Stream()
+            with torch.cuda.stream(copy_stream):
+                out = {k: (v.cuda(non_blocking=True) if torch.is_tensor(v) and not v.is_cuda else v) for k, v in dp.items()}
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            return out, done
+
+        it = iter(data_loader)
+        try:
+            nxt = upload(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, done = nxt
+            try:
+                nxt = upload(next(it))  # enqueue the next upload before this batch's kernels are launched
+            except StopIteration:
+                nxt = None
+            if done is not None:
+                torch.cuda.current_stream().wait_event(done)
+                for v in cur.values():
+                    if torch.is_tensor(v) and v.is_cuda:
+                        v.record_stream(torch.cuda.current_stream())
+            yield cur
 
     @staticmethod
     def _compute_batch_heatmap(pose_estimator, data):
@@ -314,7 +358,7 @@ class ScoringSelectionMixin:
         table of table.py viewed through the reference's five guid-keyed dicts."""
         cfg = self.al_cfg
         acc = {k: [] for k in ("sal", "inl", "al", "map", "pred", "gt", "valid", "pose", "frame")}
-        for dp in data_loader:
+        for dp in self._device_batches(data_loader):
             with torch.no_grad():
                 heatmaps = self._compute_batch_heatmap(pose_estimator, dp)
                 _, kp, w, h = heatmaps.shape
