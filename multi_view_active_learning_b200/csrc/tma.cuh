@@ -36,25 +36,31 @@ __device__ __forceinline__ bool watchdog_stalled(const unsigned long long* abort
 
 // kBackoff: the waiter expects to wait long; it sleeps between polls so that it does not take issue slots from the
 // other warps of its scheduler.
-template <bool kBackoff = false>
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsigned long long* abort_rec, uint32_t code,
-                                          long long iter, int index) {
+// The poll loop with its watchdog is ONE out-of-line function per flavour: inlined at every wait site it was 9 KB of the
+// fused kernels' SASS (round 2), and those kernels stall on instruction fetch.
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar_addr, uint32_t parity) {
   uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok;
+}
+
+template <bool kBackoff>
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar_addr, uint32_t parity, unsigned long long* abort_rec, uint32_t code,
+                                            long long iter, int index) {
   long long t0 = 0;
   uint32_t polls = 0;
   for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) return true;
     // A long waiter (the RANSAC warps wait ~50 us for the key-points of a frame, with up to three frames of slack) sleeps
     // between polls: try_wait alone comes back every ~0.1 us whatever its suspend-time hint says (measured, round 2: the poll
     // loop was 25 % of all executed warp instructions of the fused kernel), a 2-4 us sleep cuts that by ~20x.
     if (kBackoff) __nanosleep(polls < 2u ? 500u : 3000u);
+    if (mbar_try_wait(bar_addr, parity)) return true;
     if ((++polls & (kBackoff ? 15u : 255u)) == 0u) {
       if (*((volatile unsigned long long*)&abort_rec[0]) != 0ull) return false;
       const long long now = clock64();
@@ -85,6 +91,14 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsign
       }
     }
   }
+}
+
+template <bool kBackoff = false>
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsigned long long* abort_rec, uint32_t code,
+                                          long long iter, int index) {
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait(addr, parity)) return true;
+  return mbar_wait_slow<kBackoff>(addr, parity, abort_rec, code, iter, index);
 }
 
 // Host side of the watchdog of one persistent kernel family (one instance per translation unit, next to its

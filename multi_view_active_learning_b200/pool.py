@@ -149,6 +149,8 @@ def pad_features(feat, multiple):
     tensor-core screen (csrc/kcenter_tc.cu) needs, e.g. the reference's own d = 3 J = 57 -> 64."""
     d = feat.shape[1]
     pad = (-d) % int(multiple)
+    if d + pad < 64:
+        pad = 64 - d
     if pad == 0:
         return feat
     out = torch.zeros((feat.shape[0], d + pad), dtype=feat.dtype, device=feat.device)
@@ -156,7 +158,18 @@ def pad_features(feat, multiple):
     return out
 
 
-def kcenter_greedy_sharded(shards, labeled, budget, group=None, k_slots=None, flags=0, stats=None, pad_to=None):
+def auto_pad(d):
+    """Column multiple to zero-pad d-dimensional features to so that the batched update takes the tcgen05 screen
+    (csrc/kcenter_tc.cu needs 16-byte aligned rows of at least 64 floats); 0 = leave as is.  Measured on one B200, 1M rows,
+    1000 labeled, budget 10 000 (profiles/r2_summary.md): d = 57 -> 64: 61.9 -> 30.0 ms; d = 126 -> 128: 95.3 -> 22.7 ms, same
+    picks -- the reference's own feature sizes (3 J = 57 Panoptic, 126 InterHand) were on the FFMA pass before."""
+    d = int(d)
+    if (d % 4 == 0 and d >= 64) or d <= 32:  # already eligible, or so short that the FFMA pass over d columns is cheaper
+        return 0
+    return 32
+
+
+def kcenter_greedy_sharded(shards, labeled, budget, group=None, k_slots=None, flags=0, stats=None, pad_to="auto"):
     """Greedy k-center selection over UNLABELED feature rows that are row-sharded contiguously.
 
     shards : list of (features float32 CUDA [n_s, d], global_row_offset) owned by THIS process -- one entry per
@@ -171,6 +184,8 @@ def kcenter_greedy_sharded(shards, labeled, budget, group=None, k_slots=None, fl
 
     assert len(shards) >= 1 and labeled.shape[0] >= 1, "need at least one shard and one labeled centre"
     dev = labeled.device
+    if pad_to == "auto":
+        pad_to = auto_pad(labeled.shape[1])
     if pad_to:
         labeled = pad_features(labeled.float(), pad_to)
     state = []

@@ -46,6 +46,11 @@ class CoreSet:
             self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
             self._features = np.concatenate([self._host_features(list(self.sal_dict.values())), lab]) if self._n_unl else lab
             self._feat = torch.from_numpy(np.ascontiguousarray(self._features, dtype=np.float32)).to(self._device)
+        from .. import pool
+
+        pad = pool.auto_pad(self._feat.shape[1]) if self._feat.shape[0] else 0
+        if pad:  # zero columns: bit-identical distances, and the tensor-core screen applies (pool.auto_pad)
+            self._feat = pool.pad_features(self._feat, pad)
         self._sharded = sharded
         self._norms = None
         self._min_dist = None
@@ -142,7 +147,7 @@ class CoreSet:
             import torch.distributed as dist
 
             lo, hi = pool.shard_range(self._n_unl, dist.get_world_size(), dist.get_rank())
-            sel, _ = pool.kcenter_greedy_sharded([(self._feat[lo:hi], lo)], self._feat[self._n_unl:], int(N))
+            sel, _ = pool.kcenter_greedy_sharded([(self._feat[lo:hi], lo)], self._feat[self._n_unl:], int(N), pad_to=None)
             new_batch = [int(i) for i in sel.cpu().tolist()]
         elif fresh:
             # whole selection in one C call

@@ -72,3 +72,57 @@ def test_two_rank_scoring_ranking_and_coreset():
     for r in res:
         assert r[1] == exp and r[2] == [float(metric[i]) for i in exp]
         assert r[3] == exp_c
+
+
+def _flow_worker(rank, world, port, tmpdir, q):
+    """_sal_pseudo_labeling with the mixin's own DistributedSampler loader, one NCCL rank per GPU: the packed
+    all_gather_into_tensor exchange, the dict-insertion dedupe and (CORESET) the sharded greedy rounds, against the
+    reference's world-size-2 fixtures; plus the device-side ranking exchange (RankingExchange) against the host merge."""
+    import traceback
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import sys
+
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from test_flow_golden import CASES, _run_ours
+
+        from multi_view_active_learning_b200 import ops, pool as P
+
+        os.makedirs(os.path.join(tmpdir, "r%d" % rank), exist_ok=True)
+        for case in CASES:
+            _run_ours(case, world, os.path.join(tmpdir, "r%d" % rank), None)
+        rng = np.random.default_rng(5)
+        scores = rng.normal(size=4001).round(1)
+        scores[rng.integers(0, 4001, 40)] = np.nan
+        lo, hi = P.shard_range(len(scores), world, rank)
+        ex = P.RankingExchange(64, torch.device("cuda", rank))
+        idx, val, cnt = ex(torch.from_numpy(scores[lo:hi]).cuda(), lo)
+        host_idx, host_val = P.distributed_topk(ops.topk_desc(torch.from_numpy(scores[lo:hi]).cuda(), 64, index_offset=lo), 64)
+        assert int(cnt.item()) == 64 and idx.cpu().tolist() == host_idx.tolist() and val.cpu().tolist() == host_val.tolist()
+        q.put((rank, "ok"))
+        dist.barrier()
+    except Exception:
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_flow_against_reference_fixtures(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_flow_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+    for r in range(world):
+        assert res[r] == "ok", res[r]
