@@ -568,15 +568,20 @@ kc_unpack_kernel(const char* __restrict__ recs, int n_blocks, int K, int d, size
   }
 }
 
-// One CTA replays the greedy loop on the Kc candidates (thread j = candidate j).  dt[s * Kc + j] = dist(candidate j,
-// centre = candidate s).  A pick needs the block arg-max and then, for every thread, ONE element of the winner's row of
-// dt -- a dependent L2 access (~0.5 us) if it is fetched when the winner is known.  Rows are therefore staged ahead of
-// time in shared memory: the kReplayStage rows of the candidates with the highest current values are resident (running
-// minima only decrease, so the candidates are picked roughly in descending order of their initial value), each thread
-// copies exactly the element it will read itself (cp.async, 4 B per thread = one coalesced row per block), so staged
-// data needs no block-level synchronisation at all.  A pick whose row is staged costs one barrier and a few shared-memory
-// accesses; a pick whose row is not (yet) there falls back to the global load, so the result never depends on the
-// staging.  One barrier per pick: the per-warp partials are double-buffered.
+// One CTA replays the greedy loop on the Kc <= 1024 candidates.  dt[s * Kc + j] = dist(candidate j, centre = candidate s).
+//
+// A pick is a block arg-max followed, for every candidate, by ONE element of the winner's row of dt.  Two things made the
+// round-1 kernel (1024 threads, one candidate each) cost 0.65-0.8 us per pick: every one of its 32 warps issued the whole
+// bookkeeping (~3 000 warp instructions per pick on one SM), and the row element is a dependent L2 access.  Here
+//   * 4 warps own 8 candidates per thread (candidate j = k * 128 + thread, coalesced rows): ~100 instructions per warp
+//     and pick, one barrier per pick (the per-warp partials are double-buffered);
+//   * rows are staged ahead of time in shared memory: the kReplayStage rows of the candidates with the highest initial
+//     values are resident (running minima only decrease, so candidates are picked roughly in that order) and every
+//     thread copies exactly the elements it will read itself (cp.async, 4 B each), so staged data needs no block-level
+//     synchronisation.  A winner whose row is not (yet) there is read from global memory: the result never depends on
+//     the staging.
+constexpr int kReplayThreads = 128;
+constexpr int kReplayPer = kKcMaxSlots / kReplayThreads;  // 8 candidates per thread
 constexpr int kReplayStage = 40;   // staged rows (40 x 4 KiB at Kc = 1024)
 constexpr int kReplayDepth = 8;    // cp.async groups in flight: a staged row is usable kReplayDepth picks after its issue
 
@@ -587,54 +592,66 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kN>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory"); }
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kReplayThreads)
 kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx, const float* __restrict__ dt, int Kc,
                  const float* __restrict__ tau_ptr, int max_picks, int64_t* __restrict__ selected_out,
                  int32_t* __restrict__ pick_slots, int32_t* __restrict__ n_picks_out) {
   extern __shared__ float stage[];  // [kReplayStage][Kc]
-  __shared__ uint32_t w_val[2][32];
-  __shared__ uint32_t w_rank[2][32];
+  __shared__ uint32_t w_val[2][4];
+  __shared__ uint32_t w_rank[2][4];
   __shared__ int64_t s_g[kKcMaxSlots];
   __shared__ float s_v0[kKcMaxSlots];
   __shared__ int16_t s_slot_of_rank[kKcMaxSlots];
   __shared__ int16_t s_order[kKcMaxSlots];       // candidates by (initial value desc, rank asc): the staging order
   __shared__ int16_t s_stage_slot[kKcMaxSlots];  // candidate -> stage slot holding its row, -1 = none
   __shared__ int32_t s_stage_time[kKcMaxSlots];  // pick counter at which that row was issued
-  const int j = threadIdx.x, lane = j & 31, warp = j >> 5, n_warps = (blockDim.x + 31) >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float tau = *tau_ptr;
-  float v = (j < Kc) ? val[j] : -1.0f;
-  const int64_t g = (j < Kc) ? gidx[j] : INT64_MAX;
-  if (j < kKcMaxSlots) {
-    s_g[j] = g;
-    s_v0[j] = v;
+  float v[kReplayPer];
+  uint32_t rank[kReplayPer];
+#pragma unroll
+  for (int k = 0; k < kReplayPer; ++k) {
+    const int j = k * kReplayThreads + tid;
+    v[k] = (j < Kc) ? val[j] : -1.0f;
+    s_g[j] = (j < Kc) ? gidx[j] : INT64_MAX;
+    s_v0[j] = v[k];
     s_stage_slot[j] = -1;
     s_stage_time[j] = 0;
+    rank[k] = 0xffffffffu;
   }
   __syncthreads();
-  // rank of this slot among all slots by (global index, slot): lower global index = lower rank
-  uint32_t rank = 0;
-  if (j < Kc) {
-    for (int i = 0; i < Kc; ++i) {
-      const int64_t gi = s_g[i];
-      rank += (gi < g || (gi == g && i < j)) ? 1u : 0u;
+  // rank of a slot among all slots by (global index, slot): lower global index = lower rank; and its place in the staging
+  // order by (initial value desc, rank asc)
+#pragma unroll
+  for (int k = 0; k < kReplayPer; ++k) {  // unrolled: rank[] must stay in registers
+    const int j = k * kReplayThreads + tid;
+    if (j < Kc) {
+      const int64_t g = s_g[j];
+      const float vj = s_v0[j];
+      uint32_t r = 0;
+      int ord = 0;
+      for (int i = 0; i < Kc; ++i) {
+        const int64_t gi = s_g[i];
+        const bool before = gi < g || (gi == g && i < j);
+        r += before ? 1u : 0u;
+        const float vi = s_v0[i];
+        ord += (vi > vj || (vi == vj && before)) ? 1 : 0;
+      }
+      rank[k] = r;
+      s_slot_of_rank[r] = (int16_t)j;
+      s_order[ord] = (int16_t)j;
     }
-    s_slot_of_rank[rank] = (int16_t)j;
-  }
-  __syncthreads();
-  if (j < Kc) {
-    int ord = 0;  // position in the staging order
-    for (int i = 0; i < Kc; ++i) {
-      const float vi = s_v0[i];
-      ord += (vi > v || (vi == v && (s_g[i] < g || (s_g[i] == g && i < j)))) ? 1 : 0;
-    }
-    s_order[ord] = (int16_t)j;
   }
   __syncthreads();
   const int n_stage = Kc < kReplayStage ? Kc : kReplayStage;
   for (int r = 0; r < n_stage; ++r) {
     const int c = s_order[r];
-    if (j < Kc) cp_async4(&stage[r * Kc + j], dt + (int64_t)c * Kc + j);
-    if (j == 0) {
+#pragma unroll
+    for (int k = 0; k < kReplayPer; ++k) {
+      const int j = k * kReplayThreads + tid;
+      if (j < Kc) cp_async4(&stage[r * Kc + j], dt + (int64_t)c * Kc + j);
+    }
+    if (tid == 0) {
       s_stage_slot[c] = (int16_t)r;
       s_stage_time[c] = -kReplayDepth;
     }
@@ -645,22 +662,34 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
   int next_stage = n_stage;
   int t = 0;
   for (; t < max_picks; ++t) {
-    // block arg-max of (value desc, rank asc); invalid slots (v < 0) carry key 0 and never beat a valid one
-    const uint32_t key = (v >= 0.0f) ? (__float_as_uint(v) + 1u) : 0u;
-    const uint32_t wmax = __reduce_max_sync(kFull, key);
-    const uint32_t wrank = __reduce_min_sync(kFull, key == wmax ? rank : 0xffffffffu);
+    // arg-max of (value desc, rank asc): own candidates, warp, block.  Invalid slots (v < 0) carry key 0 and never beat a
+    // valid one.
+    uint32_t bk = 0u, br = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < kReplayPer; ++k) {
+      const uint32_t key = (v[k] >= 0.0f) ? (__float_as_uint(v[k]) + 1u) : 0u;
+      const bool better = key > bk || (key == bk && rank[k] < br);
+      bk = better ? key : bk;
+      br = better ? rank[k] : br;
+    }
+    const uint32_t wmax = __reduce_max_sync(kFull, bk);
+    const uint32_t wrank = __reduce_min_sync(kFull, bk == wmax ? br : 0xffffffffu);
     const int buf = t & 1;
     if (lane == 0) { w_val[buf][warp] = wmax; w_rank[buf][warp] = wrank; }
     __syncthreads();
-    const uint32_t k2 = (lane < n_warps) ? w_val[buf][lane] : 0u;
-    const uint32_t r2 = (lane < n_warps) ? w_rank[buf][lane] : 0xffffffffu;
-    const uint32_t bmax = __reduce_max_sync(kFull, k2);
-    const uint32_t brank = __reduce_min_sync(kFull, k2 == bmax ? r2 : 0xffffffffu);
+    uint32_t bmax = w_val[buf][0], brank = w_rank[buf][0];
+#pragma unroll
+    for (int w = 1; w < kReplayThreads / 32; ++w) {
+      const uint32_t k2 = w_val[buf][w], r2 = w_rank[buf][w];
+      const bool better = k2 > bmax || (k2 == bmax && r2 < brank);
+      bmax = better ? k2 : bmax;
+      brank = better ? r2 : brank;
+    }
     if (bmax == 0u) break;  // no valid candidate at all
     const float best_v = __uint_as_float(bmax - 1u);
     if (t > 0 && !(best_v > tau)) break;
     const int s = s_slot_of_rank[brank];
-    if (j == 0) {
+    if (tid == 0) {
       selected_out[t] = s_g[s];
       pick_slots[t] = s;
     }
@@ -670,13 +699,25 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
     const bool fetch = best_v > 0.0f;
     const int slot = fetch ? (int)s_stage_slot[s] : -1;
     const bool ready = slot >= 0 && (t - s_stage_time[s]) >= kReplayDepth;
-    if (fetch && j < Kc) v = fminf(v, ready ? stage[slot * Kc + j] : __ldg(dt + (int64_t)s * Kc + j));
+    if (fetch) {
+      const float* row = ready ? (stage + slot * Kc) : nullptr;
+      const float* grow = dt + (int64_t)s * Kc;
+#pragma unroll
+      for (int k = 0; k < kReplayPer; ++k) {
+        const int j = k * kReplayThreads + tid;
+        if (j < Kc) v[k] = fminf(v[k], ready ? row[j] : __ldg(grow + j));
+      }
+    }
     // the winner's row is no longer needed: its slot takes the next row of the staging order.  (A slot whose copy is
     // still in flight is not reused -- the new copy could be overtaken by the old one -- it simply stays unused.)
     if (ready && next_stage < Kc) {
       const int c = s_order[next_stage];
-      if (j < Kc) cp_async4(&stage[slot * Kc + j], dt + (int64_t)c * Kc + j);
-      if (j == 0) {
+#pragma unroll
+      for (int k = 0; k < kReplayPer; ++k) {
+        const int j = k * kReplayThreads + tid;
+        if (j < Kc) cp_async4(&stage[slot * Kc + j], dt + (int64_t)c * Kc + j);
+      }
+      if (tid == 0) {
         s_stage_slot[c] = (int16_t)slot;
         s_stage_time[c] = t;
       }
@@ -686,7 +727,7 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
     cp_async_wait<kReplayDepth - 1>();
   }
   cp_async_wait<0>();
-  if (j == 0) *n_picks_out = t;
+  if (tid == 0) *n_picks_out = t;
 }
 
 __global__ void __launch_bounds__(128)
@@ -732,7 +773,7 @@ int kc_resolve(const void* records, int n_blocks, int K, int d, int max_picks, v
   } else {
     if (int rc = kc_pairwise_exact(rows, xx, Kc, d, dt, stream)) return rc;
   }
-  const int threads = (Kc + 31) / 32 * 32;
+  const int threads = kReplayThreads;
   const size_t replay_smem = sizeof(float) * (size_t)(Kc < kReplayStage ? Kc : kReplayStage) * Kc;
   MVAL_CUDA(cudaFuncSetAttribute(kc_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kReplayStage * kKcMaxSlots)));
   kc_replay_kernel<<<1, threads, replay_smem, stream>>>(val, gidx, dt, Kc, tau, max_picks, selected_out, pick_slots, n_picks);

@@ -539,9 +539,10 @@ kc_recheck_kernel(const float* __restrict__ X, const float* __restrict__ xx, int
     const float* xrow = X + (int64_t)pr.row * d;
     const float* crow = C + (int64_t)pr.t * d;
     float acc = 0.0f;
-    for (int k0 = 0; k0 < d; k0 += 32) {
+    float vx[32], vc[32];
+    // tile k0 of the 32 pairs: lane k of the warp reads column k0 + k of every pair's two rows (coalesced 128 B per row)
+    auto load_tile = [&](int k0) {
       const int k = k0 + lane;
-      float vx[32], vc[32];
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
         const float* xr = reinterpret_cast<const float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(xrow), r));
@@ -549,6 +550,9 @@ kc_recheck_kernel(const float* __restrict__ X, const float* __restrict__ xx, int
         vx[r] = (k < d) ? __ldg(xr + k) : 0.0f;
         vc[r] = (k < d) ? __ldg(cr + k) : 0.0f;
       }
+    };
+    load_tile(0);
+    for (int k0 = 0; k0 < d; k0 += 32) {
       __syncwarp();
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
@@ -556,6 +560,9 @@ kc_recheck_kernel(const float* __restrict__ X, const float* __restrict__ xx, int
         tc[warp][r][lane] = vc[r];
       }
       __syncwarp();
+      // the next tile's 64 loads are issued BEFORE this tile's dependent fma chain, so that the chain (the canonical order
+      // forbids splitting it) runs under their latency; round 1 issued them after it and the kernel was latency-bound
+      if (k0 + 32 < d) load_tile(k0 + 32);
       const int kk = (d - k0) < 32 ? (d - k0) : 32;
       if (kk == 32) {
 #pragma unroll
