@@ -573,15 +573,16 @@ kc_unpack_kernel(const char* __restrict__ recs, int n_blocks, int K, int d, size
 // A pick is a block arg-max followed, for every candidate, by ONE element of the winner's row of dt.  Two things made the
 // round-1 kernel (1024 threads, one candidate each) cost 0.65-0.8 us per pick: every one of its 32 warps issued the whole
 // bookkeeping (~3 000 warp instructions per pick on one SM), and the row element is a dependent L2 access.  Here
-//   * 4 warps own 8 candidates per thread (candidate j = k * 128 + thread, coalesced rows): ~100 instructions per warp
-//     and pick, one barrier per pick (the per-warp partials are double-buffered);
+//   * 16 warps own 2 candidates per thread (candidate j = k * 512 + thread, coalesced rows), one barrier per pick (the
+//     per-warp partials are double-buffered).  Measured per pick on one 125k x 2048 shard: 1024 x 1 (round 1) 0.82 us --
+//     issue-bound, every warp repeats the bookkeeping; 128 x 8: 1.1 us -- one warp per scheduler, every latency exposed;
 //   * rows are staged ahead of time in shared memory: the kReplayStage rows of the candidates with the highest initial
 //     values are resident (running minima only decrease, so candidates are picked roughly in that order) and every
 //     thread copies exactly the elements it will read itself (cp.async, 4 B each), so staged data needs no block-level
 //     synchronisation.  A winner whose row is not (yet) there is read from global memory: the result never depends on
 //     the staging.
-constexpr int kReplayThreads = 128;
-constexpr int kReplayPer = kKcMaxSlots / kReplayThreads;  // 8 candidates per thread
+constexpr int kReplayThreads = 512;
+constexpr int kReplayPer = kKcMaxSlots / kReplayThreads;  // 2 candidates per thread
 constexpr int kReplayStage = 40;   // staged rows (40 x 4 KiB at Kc = 1024)
 constexpr int kReplayDepth = 8;    // cp.async groups in flight: a staged row is usable kReplayDepth picks after its issue
 
@@ -597,8 +598,8 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
                  const float* __restrict__ tau_ptr, int max_picks, int64_t* __restrict__ selected_out,
                  int32_t* __restrict__ pick_slots, int32_t* __restrict__ n_picks_out) {
   extern __shared__ float stage[];  // [kReplayStage][Kc]
-  __shared__ uint32_t w_val[2][4];
-  __shared__ uint32_t w_rank[2][4];
+  __shared__ uint32_t w_val[2][kReplayThreads / 32];
+  __shared__ uint32_t w_rank[2][kReplayThreads / 32];
   __shared__ int64_t s_g[kKcMaxSlots];
   __shared__ float s_v0[kKcMaxSlots];
   __shared__ int16_t s_slot_of_rank[kKcMaxSlots];
@@ -677,14 +678,10 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
     const int buf = t & 1;
     if (lane == 0) { w_val[buf][warp] = wmax; w_rank[buf][warp] = wrank; }
     __syncthreads();
-    uint32_t bmax = w_val[buf][0], brank = w_rank[buf][0];
-#pragma unroll
-    for (int w = 1; w < kReplayThreads / 32; ++w) {
-      const uint32_t k2 = w_val[buf][w], r2 = w_rank[buf][w];
-      const bool better = k2 > bmax || (k2 == bmax && r2 < brank);
-      bmax = better ? k2 : bmax;
-      brank = better ? r2 : brank;
-    }
+    const uint32_t k2 = (lane < kReplayThreads / 32) ? w_val[buf][lane] : 0u;
+    const uint32_t r2 = (lane < kReplayThreads / 32) ? w_rank[buf][lane] : 0xffffffffu;
+    const uint32_t bmax = __reduce_max_sync(kFull, k2);
+    const uint32_t brank = __reduce_min_sync(kFull, k2 == bmax ? r2 : 0xffffffffu);
     if (bmax == 0u) break;  // no valid candidate at all
     const float best_v = __uint_as_float(bmax - 1u);
     if (t > 0 && !(best_v > tau)) break;

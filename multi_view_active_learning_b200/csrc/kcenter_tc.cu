@@ -517,7 +517,13 @@ kc_screen_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   }
 }
 
-// Exact canonical distance of the surviving pairs; 32 pairs per warp, coalesced through a shared-memory transpose.
+// Exact canonical distance of the surviving pairs, one pair per LANE.  The canonical dot product is one fma chain over k
+// ascending, so a pair is 2048 dependent fmas at d = 2048 whatever the mapping; what can be removed is everything around
+// the chain.  Round 1 moved the two rows of 32 pairs through a shared-memory transpose (coalesced 128 B loads, 128 pointer
+// shuffles + 64 loads + 64 stores + 64 shared loads per 32 columns): ~2.2 us per 32 columns, 0.14 ms per launch for ~50 k
+// pairs -- pure single-warp instruction latency, and 13 of the 30 ms of a 125k x 2048 shard's selection.  Here a lane
+// streams its own two rows with 128-bit loads (a 128 B line serves eight consecutive loads of the lane out of L1) and the
+// chain runs under the loads of the next columns: 2 loads + 4 fmas per 4 columns.
 //   kStore = false: min_dist[row] = min(min_dist[row], dist)
 //   kStore = true : out[(t0 + t) * ld_out + row] = dist        (candidate pairwise matrix of the replay)
 constexpr int kRcWarps = 4;
@@ -526,58 +532,49 @@ __global__ void __launch_bounds__(kRcWarps * 32)
 kc_recheck_kernel(const float* __restrict__ X, const float* __restrict__ xx, int d, const float* __restrict__ C,
                   const float* __restrict__ cc, const TcPair* __restrict__ pairs, const unsigned int* __restrict__ pair_count,
                   unsigned int pair_capacity, float* __restrict__ min_dist, int t0, int64_t ld_out) {
-  __shared__ float tx[kRcWarps][32][33];
-  __shared__ float tc[kRcWarps][32][33];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned int total = *pair_count;
   if (total > pair_capacity) total = pair_capacity;  // overflow: the FFMA fallback pass redoes everything
-  const unsigned int n_groups = (total + 31) / 32;
-  for (unsigned int g = blockIdx.x * kRcWarps + warp; g < n_groups; g += gridDim.x * kRcWarps) {
-    const unsigned int p = g * 32 + lane;
-    const bool ok = p < total;
-    const TcPair pr = ok ? pairs[p] : TcPair{0u, 0u};
+  const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  for (unsigned int p = blockIdx.x * (kRcWarps * 32) + threadIdx.x; p < total; p += gridDim.x * (kRcWarps * 32)) {
+    const TcPair pr = pairs[p];
     const float* xrow = X + (int64_t)pr.row * d;
     const float* crow = C + (int64_t)pr.t * d;
     float acc = 0.0f;
-    float vx[32], vc[32];
-    // tile k0 of the 32 pairs: lane k of the warp reads column k0 + k of every pair's two rows (coalesced 128 B per row)
-    auto load_tile = [&](int k0) {
-      const int k = k0 + lane;
+    if (vec) {
+      const float4* x4 = reinterpret_cast<const float4*>(xrow);
+      const float4* c4 = reinterpret_cast<const float4*>(crow);
+      const int n4 = d >> 2;
+      int q = 0;
+      for (; q + 8 <= n4; q += 8) {
+        float4 a[8], b[8];
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        const float* xr = reinterpret_cast<const float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(xrow), r));
-        const float* cr = reinterpret_cast<const float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(crow), r));
-        vx[r] = (k < d) ? __ldg(xr + k) : 0.0f;
-        vc[r] = (k < d) ? __ldg(cr + k) : 0.0f;
-      }
-    };
-    load_tile(0);
-    for (int k0 = 0; k0 < d; k0 += 32) {
-      __syncwarp();
+        for (int u = 0; u < 8; ++u) {
+          a[u] = __ldg(x4 + q + u);
+          b[u] = __ldg(c4 + q + u);
+        }
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        tx[warp][r][lane] = vx[r];
-        tc[warp][r][lane] = vc[r];
+        for (int u = 0; u < 8; ++u) {
+          acc = __fmaf_rn(a[u].x, b[u].x, acc);
+          acc = __fmaf_rn(a[u].y, b[u].y, acc);
+          acc = __fmaf_rn(a[u].z, b[u].z, acc);
+          acc = __fmaf_rn(a[u].w, b[u].w, acc);
+        }
       }
-      __syncwarp();
-      // the next tile's 64 loads are issued BEFORE this tile's dependent fma chain, so that the chain (the canonical order
-      // forbids splitting it) runs under their latency; round 1 issued them after it and the kernel was latency-bound
-      if (k0 + 32 < d) load_tile(k0 + 32);
-      const int kk = (d - k0) < 32 ? (d - k0) : 32;
-      if (kk == 32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc = __fmaf_rn(tx[warp][lane][j], tc[warp][lane][j], acc);
-      } else {
-        for (int j = 0; j < kk; ++j) acc = __fmaf_rn(tx[warp][lane][j], tc[warp][lane][j], acc);
+      for (; q < n4; ++q) {
+        const float4 a = __ldg(x4 + q), b = __ldg(c4 + q);
+        acc = __fmaf_rn(a.x, b.x, acc);
+        acc = __fmaf_rn(a.y, b.y, acc);
+        acc = __fmaf_rn(a.z, b.z, acc);
+        acc = __fmaf_rn(a.w, b.w, acc);
       }
+    } else {
+      for (int k = 0; k < d; ++k) acc = __fmaf_rn(__ldg(xrow + k), __ldg(crow + k), acc);
     }
-    if (ok) {
-      const float dist = kc_dist(acc, __ldg(xx + pr.row), __ldg(cc + pr.t));
-      if (kStore) {
-        min_dist[(int64_t)(t0 + (int)pr.t) * ld_out + pr.row] = dist;
-      } else if (dist < min_dist[pr.row]) {
-        atomicMin(reinterpret_cast<unsigned int*>(min_dist + pr.row), __float_as_uint(dist));
-      }
+    const float dist = kc_dist(acc, __ldg(xx + pr.row), __ldg(cc + pr.t));
+    if (kStore) {
+      min_dist[(int64_t)(t0 + (int)pr.t) * ld_out + pr.row] = dist;
+    } else if (dist < min_dist[pr.row]) {
+      atomicMin(reinterpret_cast<unsigned int*>(min_dist + pr.row), __float_as_uint(dist));
     }
   }
 }
@@ -716,7 +713,7 @@ int kc_pairwise_tc(const float* X, const float* xx, const float* val, int n, int
   for (int t0 = 0; t0 < n; t0 += kTcBlockN) {
     const int tn = (n - t0) < kTcBlockN ? (n - t0) : kTcBlockN;
     if (int rc = tc_screen(s, X, xx, n, d, X + (int64_t)t0 * d, xx + t0, tn, val, 0, stream)) return rc;
-    kc_recheck_kernel<true><<<num_sms(), kRcWarps * 32, 0, stream>>>(X, xx, d, X + (int64_t)t0 * d, xx + t0,
+    kc_recheck_kernel<true><<<num_sms() * 4, kRcWarps * 32, 0, stream>>>(X, xx, d, X + (int64_t)t0 * d, xx + t0,
                                                                      static_cast<const TcPair*>(s->tc_pairs), s->tc_count,
                                                                      (unsigned int)s->tc_pairs_capacity, out_t, t0, n);
     MVAL_LAUNCH_CHECK("kc_recheck_store");
