@@ -517,64 +517,94 @@ kc_screen_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   }
 }
 
-// Exact canonical distance of the surviving pairs, one pair per LANE.  The canonical dot product is one fma chain over k
-// ascending, so a pair is 2048 dependent fmas at d = 2048 whatever the mapping; what can be removed is everything around
-// the chain.  Round 1 moved the two rows of 32 pairs through a shared-memory transpose (coalesced 128 B loads, 128 pointer
-// shuffles + 64 loads + 64 stores + 64 shared loads per 32 columns): ~2.2 us per 32 columns, 0.14 ms per launch for ~50 k
-// pairs -- pure single-warp instruction latency, and 13 of the 30 ms of a 125k x 2048 shard's selection.  Here a lane
-// streams its own two rows with 128-bit loads (a 128 B line serves eight consecutive loads of the lane out of L1) and the
-// chain runs under the loads of the next columns: 2 loads + 4 fmas per 4 columns.
+// Exact canonical distance of the surviving pairs; 32 pairs per warp (lane = pair for the fma chain, which the canonical
+// order forbids splitting), rows moved through a shared-memory transpose so that global loads stay coalesced.
+// A steady-state launch holds only ~50 k pairs = ~1 600 warp tasks on 148 SMs, so its duration IS the latency of one
+// warp's instruction stream.  Round 1 moved 32 columns per step with scalar accesses (128 pointer shuffles + 64 LDG + 64
+// STS + 64 LDS + 32 FMA): ~2.2 us per 32 columns, 0.14 ms per launch, 13 of the 30 ms of a 125k x 2048 shard's selection.
+// (Letting every lane stream its own rows directly is no better: 32 distinct lines per load instruction, L1-throughput
+// bound, also 0.15 ms -- measured in round 2.)  Here a step moves 64 columns with 128-bit accesses (a half-warp per row) and
+// the row pointers sit in shared memory: 32 LDS.64 + 32 LDG.128 + 32 STS.128 + 32 LDS.128 + 64 FMA per 64 columns, ~4x fewer
+// instructions per column; 17 KiB of tiles per warp keeps 12 warps resident per SM, enough for one task per warp.
+// d % 4 == 0 and 16-byte aligned rows (guaranteed by kc_tc_applicable).
 //   kStore = false: min_dist[row] = min(min_dist[row], dist)
 //   kStore = true : out[(t0 + t) * ld_out + row] = dist        (candidate pairwise matrix of the replay)
 constexpr int kRcWarps = 4;
+constexpr int kRcTileK = 64, kRcStride = kRcTileK + 4;  // +4 floats: LDS.128 of 8 consecutive lanes hit 8 distinct bank groups
+constexpr uint32_t kRcSmemBytes = kRcWarps * 2 * 32 * kRcStride * 4;
 template <bool kStore>
 __global__ void __launch_bounds__(kRcWarps * 32)
 kc_recheck_kernel(const float* __restrict__ X, const float* __restrict__ xx, int d, const float* __restrict__ C,
                   const float* __restrict__ cc, const TcPair* __restrict__ pairs, const unsigned int* __restrict__ pair_count,
                   unsigned int pair_capacity, float* __restrict__ min_dist, int t0, int64_t ld_out) {
+  extern __shared__ __align__(16) float rc_smem[];
+  __shared__ const float* row_ptr[kRcWarps][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* tx = rc_smem + (size_t)warp * (2 * 32 * kRcStride);
+  float* tc = tx + 32 * kRcStride;
   unsigned int total = *pair_count;
   if (total > pair_capacity) total = pair_capacity;  // overflow: the FFMA fallback pass redoes everything
-  const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-  for (unsigned int p = blockIdx.x * (kRcWarps * 32) + threadIdx.x; p < total; p += gridDim.x * (kRcWarps * 32)) {
-    const TcPair pr = pairs[p];
-    const float* xrow = X + (int64_t)pr.row * d;
-    const float* crow = C + (int64_t)pr.t * d;
+  const unsigned int n_groups = (total + 31) / 32;
+  for (unsigned int g = blockIdx.x * kRcWarps + warp; g < n_groups; g += gridDim.x * kRcWarps) {
+    const unsigned int p = g * 32 + lane;
+    const bool ok = p < total;
+    const TcPair pr = ok ? pairs[p] : TcPair{0u, 0u};
+    __syncwarp();
+    row_ptr[warp][lane] = X + (int64_t)pr.row * d;
+    row_ptr[warp][32 + lane] = C + (int64_t)pr.t * d;
+    __syncwarp();
     float acc = 0.0f;
-    if (vec) {
-      const float4* x4 = reinterpret_cast<const float4*>(xrow);
-      const float4* c4 = reinterpret_cast<const float4*>(crow);
-      const int n4 = d >> 2;
-      int q = 0;
-      for (; q + 8 <= n4; q += 8) {
-        float4 a[8], b[8];
+    const int sub = lane >> 4, c4 = (lane & 15) * 4;  // a half-warp covers the 64 columns of one row
+    for (int k0 = 0; k0 < d; k0 += kRcTileK) {
+      const int k = k0 + c4;
+      const bool kin = k < d;
+      __syncwarp();  // the previous step's chain has finished reading the tiles
+#pragma unroll
+      for (int r0 = 0; r0 < 32; r0 += 16) {
+        float4 vx[8], vc[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          a[u] = __ldg(x4 + q + u);
-          b[u] = __ldg(c4 + q + u);
+          const int r = r0 + 2 * u + sub;
+          vx[u] = kin ? __ldg(reinterpret_cast<const float4*>(row_ptr[warp][r] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          vc[u] = kin ? __ldg(reinterpret_cast<const float4*>(row_ptr[warp][32 + r] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          acc = __fmaf_rn(a[u].x, b[u].x, acc);
-          acc = __fmaf_rn(a[u].y, b[u].y, acc);
-          acc = __fmaf_rn(a[u].z, b[u].z, acc);
-          acc = __fmaf_rn(a[u].w, b[u].w, acc);
+          const int r = r0 + 2 * u + sub;
+          *reinterpret_cast<float4*>(tx + r * kRcStride + c4) = vx[u];
+          *reinterpret_cast<float4*>(tc + r * kRcStride + c4) = vc[u];
         }
       }
-      for (; q < n4; ++q) {
-        const float4 a = __ldg(x4 + q), b = __ldg(c4 + q);
-        acc = __fmaf_rn(a.x, b.x, acc);
-        acc = __fmaf_rn(a.y, b.y, acc);
-        acc = __fmaf_rn(a.z, b.z, acc);
-        acc = __fmaf_rn(a.w, b.w, acc);
+      __syncwarp();
+      const int n4 = ((d - k0) < kRcTileK ? (d - k0) : kRcTileK) >> 2;
+      const float4* a4 = reinterpret_cast<const float4*>(tx + lane * kRcStride);
+      const float4* b4 = reinterpret_cast<const float4*>(tc + lane * kRcStride);
+      if (n4 == kRcTileK / 4) {
+#pragma unroll 8
+        for (int q = 0; q < kRcTileK / 4; ++q) {
+          const float4 a = a4[q], b = b4[q];
+          acc = __fmaf_rn(a.x, b.x, acc);
+          acc = __fmaf_rn(a.y, b.y, acc);
+          acc = __fmaf_rn(a.z, b.z, acc);
+          acc = __fmaf_rn(a.w, b.w, acc);
+        }
+      } else {
+        for (int q = 0; q < n4; ++q) {
+          const float4 a = a4[q], b = b4[q];
+          acc = __fmaf_rn(a.x, b.x, acc);
+          acc = __fmaf_rn(a.y, b.y, acc);
+          acc = __fmaf_rn(a.z, b.z, acc);
+          acc = __fmaf_rn(a.w, b.w, acc);
+        }
       }
-    } else {
-      for (int k = 0; k < d; ++k) acc = __fmaf_rn(__ldg(xrow + k), __ldg(crow + k), acc);
     }
-    const float dist = kc_dist(acc, __ldg(xx + pr.row), __ldg(cc + pr.t));
-    if (kStore) {
-      min_dist[(int64_t)(t0 + (int)pr.t) * ld_out + pr.row] = dist;
-    } else if (dist < min_dist[pr.row]) {
-      atomicMin(reinterpret_cast<unsigned int*>(min_dist + pr.row), __float_as_uint(dist));
+    if (ok) {
+      const float dist = kc_dist(acc, __ldg(xx + pr.row), __ldg(cc + pr.t));
+      if (kStore) {
+        min_dist[(int64_t)(t0 + (int)pr.t) * ld_out + pr.row] = dist;
+      } else if (dist < min_dist[pr.row]) {
+        atomicMin(reinterpret_cast<unsigned int*>(min_dist + pr.row), __float_as_uint(dist));
+      }
     }
   }
 }
@@ -636,6 +666,8 @@ static int tc_prepare(KcDeviceScratch** out, size_t want_pairs) {
   }
   if (s->tc_count == nullptr) MVAL_CUDA(cudaMalloc(&s->tc_count, sizeof(unsigned int)));
   MVAL_CUDA(cudaFuncSetAttribute(kc_screen_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  MVAL_CUDA(cudaFuncSetAttribute(kc_recheck_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRcSmemBytes));
+  MVAL_CUDA(cudaFuncSetAttribute(kc_recheck_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRcSmemBytes));
   *out = s;
   return MVAL_OK;
 }
@@ -713,7 +745,7 @@ int kc_pairwise_tc(const float* X, const float* xx, const float* val, int n, int
   for (int t0 = 0; t0 < n; t0 += kTcBlockN) {
     const int tn = (n - t0) < kTcBlockN ? (n - t0) : kTcBlockN;
     if (int rc = tc_screen(s, X, xx, n, d, X + (int64_t)t0 * d, xx + t0, tn, val, 0, stream)) return rc;
-    kc_recheck_kernel<true><<<num_sms() * 4, kRcWarps * 32, 0, stream>>>(X, xx, d, X + (int64_t)t0 * d, xx + t0,
+    kc_recheck_kernel<true><<<num_sms() * 3, kRcWarps * 32, kRcSmemBytes, stream>>>(X, xx, d, X + (int64_t)t0 * d, xx + t0,
                                                                      static_cast<const TcPair*>(s->tc_pairs), s->tc_count,
                                                                      (unsigned int)s->tc_pairs_capacity, out_t, t0, n);
     MVAL_LAUNCH_CHECK("kc_recheck_store");
@@ -727,7 +759,7 @@ int kc_update_batch_tc(const float* X, const float* xx, int64_t n, int d, const 
   if (int rc = tc_prepare(&s, (size_t)n * 4)) return rc;
   if (int rc = tc_screen(s, X, xx, n, d, C, cc, T, min_dist, 1, stream)) return rc;
   const unsigned int cap = (unsigned int)s->tc_pairs_capacity;
-  kc_recheck_kernel<false><<<num_sms() * 4, kRcWarps * 32, 0, stream>>>(X, xx, d, C, cc, static_cast<const TcPair*>(s->tc_pairs),
+  kc_recheck_kernel<false><<<num_sms() * 3, kRcWarps * 32, kRcSmemBytes, stream>>>(X, xx, d, C, cc, static_cast<const TcPair*>(s->tc_pairs),
                                                                         s->tc_count, cap, min_dist, 0, 0);
   MVAL_LAUNCH_CHECK("kc_recheck");
   return kc_update_batch_exact_if(X, xx, n, d, C, cc, T, min_dist, s->tc_count, cap, stream);
