@@ -576,7 +576,7 @@ kc_unpack_kernel(const char* __restrict__ recs, int n_blocks, int K, int d, size
 // bookkeeping, 3 300 warp instructions per pick; 512 x 2: 0.72 us; 128 x 8: 1.1 us (one warp per scheduler AND a block
 // barrier).  Now:
 //   * the whole block computes the ranks / the staging order once (O(Kc^2) compares), then ONE warp runs the loop with 32
-//     candidates per lane in registers (candidate j = k * 32 + lane): no block barrier, no shared partials -- a pick is
+//     candidates per lane in registers (candidates 32 L .. 32 L + 31): no block barrier, no shared partials -- a pick is
 //     ~100 FMNMX / compare-selects, two REDUX pairs, 32 shared loads and 32 FMNMX per lane;
 //   * rows are staged ahead of time in shared memory: the kReplayStage rows of the candidates with the highest initial
 //     values are resident (running minima only decrease, so candidates are picked roughly in that order) and every lane
@@ -586,9 +586,14 @@ constexpr int kReplayPer = kKcMaxSlots / 32;  // 32 candidates per lane
 constexpr int kReplayInitThreads = 512;       // 512 threads: the loop warp may use 128 registers
 constexpr int kReplayStage = 40;   // staged rows (40 x 4 KiB at Kc = 1024)
 constexpr int kReplayDepth = 4;    // cp.async groups in flight: a staged row is usable kReplayDepth picks after its issue
+constexpr uint32_t kReplayLaneBytes = 144;                    // a lane's 128 bytes of a staged row + 16: conflict-free LDS.128
+constexpr uint32_t kReplayRowBytes = 32 * kReplayLaneBytes;   // 4 608 bytes per staged row
 
 __device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kN>
@@ -598,7 +603,7 @@ __global__ void __launch_bounds__(kReplayInitThreads)
 kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx, const float* __restrict__ dt, int Kc,
                  const float* __restrict__ tau_ptr, int max_picks, int64_t* __restrict__ selected_out,
                  int32_t* __restrict__ pick_slots, int32_t* __restrict__ n_picks_out) {
-  extern __shared__ float stage[];  // [kReplayStage][Kc]
+  extern __shared__ __align__(16) float stage[];  // [kReplayStage] rows of 32 lane segments (kReplayLaneBytes apart)
   __shared__ int64_t s_g[kKcMaxSlots];
   __shared__ float s_v0[kKcMaxSlots];
   __shared__ uint16_t s_rank[kKcMaxSlots];
@@ -636,25 +641,39 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
   __syncthreads();
   if (threadIdx.x >= 32) return;  // the loop belongs to warp 0 alone: only __syncwarp from here on
 
+  // Lane L owns the 32 CONSECUTIVE candidates 32 L .. 32 L + 31: its part of a row of dt is one 128-byte line, copied with
+  // eight 16-byte cp.async (element-wise 4-byte copies cost one LSU pass each: 1024 of them per pick made a one-warp loop
+  // 4x slower than the 16-warp one) into a staged row whose lane segments are 144 bytes apart (conflict-free LDS.128).
   const float tau = *tau_ptr;
+  const bool vec = (Kc % 32 == 0) && ((reinterpret_cast<uintptr_t>(dt) & 127) == 0);
   const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
+  const int jbase = lane * kReplayPer;
   float v[kReplayPer];
   uint32_t rank[kReplayPer];
 #pragma unroll
   for (int k = 0; k < kReplayPer; ++k) {
-    const int j = k * 32 + lane;
-    v[k] = s_v0[j];
-    rank[k] = s_rank[j];
+    v[k] = s_v0[jbase + k];
+    rank[k] = s_rank[jbase + k];
   }
+  const bool mine = jbase < Kc;  // with vec: all 32 of the lane's candidates exist or none does
+  auto issue_row = [&](int slot, int c) {  // stage row c of dt into `slot`: this lane's elements only
+    const float* grow = dt + (int64_t)c * Kc + jbase;
+    const uint32_t dst = stage_addr + (uint32_t)slot * kReplayRowBytes + (uint32_t)lane * kReplayLaneBytes;
+    if (vec) {
+      if (mine) {
+#pragma unroll
+        for (int q = 0; q < kReplayPer / 4; ++q) cp_async16(dst + 16u * q, grow + 4 * q);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kReplayPer; ++k)
+        if (jbase + k < Kc) cp_async4(dst + 4u * k, grow + k);
+    }
+  };
   const int n_stage = Kc < kReplayStage ? Kc : kReplayStage;
   for (int r = 0; r < n_stage; ++r) {
     const int c = s_order[r];
-    const float* grow = dt + (int64_t)c * Kc;
-#pragma unroll
-    for (int k = 0; k < kReplayPer; ++k) {
-      const int j = k * 32 + lane;
-      if (j < Kc) cp_async4(stage_addr + 4u * (uint32_t)(r * Kc + j), grow + j);
-    }
+    issue_row(r, c);
     if (lane == 0) {
       s_stage_slot[c] = (int16_t)r;
       s_stage_time[c] = -kReplayDepth;
@@ -693,18 +712,20 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
     const int slot = fetch ? (int)s_stage_slot[s] : -1;
     const bool ready = slot >= 0 && (t - s_stage_time[s]) >= kReplayDepth;
     if (ready) {
-      const float* row = stage + slot * Kc + lane;
+      const float4* row = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(stage) + (size_t)slot * kReplayRowBytes +
+                                                          (size_t)lane * kReplayLaneBytes);
 #pragma unroll
-      for (int k = 0; k < kReplayPer; ++k)
-        if (k * 32 + lane < Kc) v[k] = fminf(v[k], row[k * 32]);
+      for (int q = 0; q < kReplayPer / 4; ++q) {
+        const float4 x = row[q];
+        v[4 * q + 0] = fminf(v[4 * q + 0], x.x);
+        v[4 * q + 1] = fminf(v[4 * q + 1], x.y);
+        v[4 * q + 2] = fminf(v[4 * q + 2], x.z);
+        v[4 * q + 3] = fminf(v[4 * q + 3], x.w);
+      }
       // the winner's row is no longer needed: its slot takes the next row of the staging order
       if (next_stage < Kc) {
         const int c = s_order[next_stage];
-        const float* grow = dt + (int64_t)c * Kc + lane;
-        const uint32_t dst = stage_addr + 4u * (uint32_t)(slot * Kc + lane);
-#pragma unroll
-        for (int k = 0; k < kReplayPer; ++k)
-          if (k * 32 + lane < Kc) cp_async4(dst + 128u * k, grow + k * 32);
+        issue_row(slot, c);
         if (lane == 0) {
           s_stage_slot[c] = (int16_t)slot;
           s_stage_time[c] = t;
@@ -714,10 +735,10 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
     } else if (fetch) {
       // not staged (or its copy is still in flight -- such a slot is not reused, the new copy could be overtaken by the old
       // one; it simply stays unused): the dependent global read of round 1
-      const float* grow = dt + (int64_t)s * Kc + lane;
+      const float* grow = dt + (int64_t)s * Kc + jbase;
 #pragma unroll
       for (int k = 0; k < kReplayPer; ++k)
-        if (k * 32 + lane < Kc) v[k] = fminf(v[k], __ldg(grow + k * 32));
+        if (jbase + k < Kc) v[k] = fminf(v[k], __ldg(grow + k));
     }
     cp_async_commit();
     cp_async_wait<kReplayDepth - 1>();
@@ -771,8 +792,8 @@ int kc_resolve(const void* records, int n_blocks, int K, int d, int max_picks, v
     if (int rc = kc_pairwise_exact(rows, xx, Kc, d, dt, stream)) return rc;
   }
   const int threads = kReplayInitThreads;  // all of them rank the candidates once, warp 0 runs the loop
-  const size_t replay_smem = sizeof(float) * (size_t)(Kc < kReplayStage ? Kc : kReplayStage) * Kc;
-  MVAL_CUDA(cudaFuncSetAttribute(kc_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kReplayStage * kKcMaxSlots)));
+  const size_t replay_smem = (size_t)kReplayStage * kReplayRowBytes;
+  MVAL_CUDA(cudaFuncSetAttribute(kc_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)replay_smem));
   kc_replay_kernel<<<1, threads, replay_smem, stream>>>(val, gidx, dt, Kc, tau, max_picks, selected_out, pick_slots, n_picks);
   MVAL_LAUNCH_CHECK("kc_replay");
   kc_gather_centres_kernel<<<max_picks, 128, 0, stream>>>(rows, xx, pick_slots, n_picks, d, centres, centre_norms);
