@@ -316,7 +316,9 @@ int mval_pose_features(const void* xyz, int xyz_is_double, int64_t n_frames, int
  *                               device [n_centres][d], centre_norms their canonical squared norms.  flags: 0 = choose
  *                               (tcgen05 TF32 screening GEMM + exact recheck when d is large and 16-byte aligned,
  *                               register-tiled FFMA pass otherwise), 1 = force the FFMA pass, 2 = force the tensor-core
- *                               path whenever it is applicable.  The result does not depend on the path. */
+ *                               path whenever it is applicable; + 4 = the centres are the picks of one greedy round (all
+ *                               256-centre chunks are screened first and share one exact recheck).  The result does not
+ *                               depend on the path. */
 int mval_kcenter_norms(const float* features, int64_t n, int d, float* row_norms, void* stream);
 int mval_kcenter_update(const float* features, const float* row_norms, int64_t n, int d, const float* centre,
                         float* min_dist, int64_t index_offset, float* out_best_val, int64_t* out_best_idx,

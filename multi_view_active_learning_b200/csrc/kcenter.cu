@@ -570,123 +570,105 @@ kc_unpack_kernel(const char* __restrict__ recs, int n_blocks, int K, int d, size
 
 // One CTA replays the greedy loop on the Kc <= 1024 candidates.  dt[s * Kc + j] = dist(candidate j, centre = candidate s).
 //
-// A pick is an arg-max over the candidates followed, for every candidate, by ONE element of the winner's row of dt.  What
-// it costs is instruction latency on one SM, so the loop is organised to issue as little as possible (measured per pick on
-// a 125k x 2048 shard, ~1000 picks per launch): 1024 threads x 1 candidate (round 1) 0.82 us -- all 32 warps repeat the
-// bookkeeping, 3 300 warp instructions per pick; 512 x 2: 0.72 us; 128 x 8: 1.1 us (one warp per scheduler AND a block
-// barrier).  Now:
-//   * the whole block computes the ranks / the staging order once (O(Kc^2) compares), then ONE warp runs the loop with 32
-//     candidates per lane in registers (candidates 32 L .. 32 L + 31): no block barrier, no shared partials -- a pick is
-//     ~100 FMNMX / compare-selects, two REDUX pairs, 32 shared loads and 32 FMNMX per lane;
+// A pick is a block arg-max followed, for every candidate, by ONE element of the winner's row of dt.  Two things made the
+// round-1 kernel (1024 threads, one candidate each) cost 0.65-0.8 us per pick: every one of its 32 warps issued the whole
+// bookkeeping (~3 000 warp instructions per pick on one SM), and the row element is a dependent L2 access.  Here
+//   * 16 warps own 2 candidates per thread (candidate j = k * 512 + thread, coalesced rows), one barrier per pick (the
+//     per-warp partials are double-buffered).  Measured per pick on one 125k x 2048 shard (~1000 picks per launch,
+//     profiles/r2_summary.md): 1024 threads x 1 candidate (round 1) 0.82 us -- all 32 warps repeat the bookkeeping, 3 300
+//     warp instructions per pick; 512 x 2 (this kernel) 0.72 us; 128 x 8: 1.1 us -- one warp per scheduler, every latency
+//     exposed; ONE warp with 32 candidates per lane in registers and no barrier at all: 2.9 us with 4-byte cp.async staging
+//     (1024 LSU passes per pick), 1.95 us with 16-byte staging -- a single warp's dependent chain (32 compare-selects, two
+//     REDUX pairs, three dependent shared loads) is slower than 16 warps sharing the work across a barrier;
 //   * rows are staged ahead of time in shared memory: the kReplayStage rows of the candidates with the highest initial
-//     values are resident (running minima only decrease, so candidates are picked roughly in that order) and every lane
-//     copies exactly the elements it will read itself (cp.async, 4 B each), so staged data needs no synchronisation at
-//     all.  A winner whose row is not (yet) there is read from global memory: the result never depends on the staging.
-constexpr int kReplayPer = kKcMaxSlots / 32;  // 32 candidates per lane
-constexpr int kReplayInitThreads = 512;       // 512 threads: the loop warp may use 128 registers
+//     values are resident (running minima only decrease, so candidates are picked roughly in that order) and every
+//     thread copies exactly the elements it will read itself (cp.async, 4 B each), so staged data needs no block-level
+//     synchronisation.  A winner whose row is not (yet) there is read from global memory: the result never depends on
+//     the staging.
+constexpr int kReplayThreads = 512;
+constexpr int kReplayPer = kKcMaxSlots / kReplayThreads;  // 2 candidates per thread
 constexpr int kReplayStage = 40;   // staged rows (40 x 4 KiB at Kc = 1024)
-constexpr int kReplayDepth = 4;    // cp.async groups in flight: a staged row is usable kReplayDepth picks after its issue
-constexpr uint32_t kReplayLaneBytes = 144;                    // a lane's 128 bytes of a staged row + 16: conflict-free LDS.128
-constexpr uint32_t kReplayRowBytes = 32 * kReplayLaneBytes;   // 4 608 bytes per staged row
+constexpr int kReplayDepth = 8;    // cp.async groups in flight: a staged row is usable kReplayDepth picks after its issue
 
-__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kN>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory"); }
 
-__global__ void __launch_bounds__(kReplayInitThreads)
+__global__ void __launch_bounds__(kReplayThreads)
 kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx, const float* __restrict__ dt, int Kc,
                  const float* __restrict__ tau_ptr, int max_picks, int64_t* __restrict__ selected_out,
                  int32_t* __restrict__ pick_slots, int32_t* __restrict__ n_picks_out) {
-  extern __shared__ __align__(16) float stage[];  // [kReplayStage] rows of 32 lane segments (kReplayLaneBytes apart)
+  extern __shared__ float stage[];  // [kReplayStage][Kc]
+  __shared__ uint32_t w_val[2][kReplayThreads / 32];
+  __shared__ uint32_t w_rank[2][kReplayThreads / 32];
   __shared__ int64_t s_g[kKcMaxSlots];
   __shared__ float s_v0[kKcMaxSlots];
-  __shared__ uint16_t s_rank[kKcMaxSlots];
   __shared__ int16_t s_slot_of_rank[kKcMaxSlots];
   __shared__ int16_t s_order[kKcMaxSlots];       // candidates by (initial value desc, rank asc): the staging order
   __shared__ int16_t s_stage_slot[kKcMaxSlots];  // candidate -> stage slot holding its row, -1 = none
   __shared__ int32_t s_stage_time[kKcMaxSlots];  // pick counter at which that row was issued
-  const int lane = threadIdx.x & 31;
-  for (int j0 = threadIdx.x; j0 < kKcMaxSlots; j0 += kReplayInitThreads) {
-    s_g[j0] = (j0 < Kc) ? gidx[j0] : INT64_MAX;
-    s_v0[j0] = (j0 < Kc) ? val[j0] : -1.0f;
-    s_stage_slot[j0] = -1;
-    s_stage_time[j0] = 0;
-    s_rank[j0] = 0xffffu;
-  }
-  __syncthreads();
-  // rank of a slot among all slots by (global index, slot): lower global index = lower rank; and its place in the staging
-  // order by (initial value desc, rank asc) -- the whole block, once
-  for (int j0 = threadIdx.x; j0 < Kc; j0 += kReplayInitThreads) {
-    const int64_t g = s_g[j0];
-    const float v = s_v0[j0];
-    uint32_t r = 0;
-    int ord = 0;
-    for (int i = 0; i < Kc; ++i) {
-      const int64_t gi = s_g[i];
-      const bool before = gi < g || (gi == g && i < j0);
-      r += before ? 1u : 0u;
-      const float vi = s_v0[i];
-      ord += (vi > v || (vi == v && before)) ? 1 : 0;
-    }
-    s_rank[j0] = (uint16_t)r;
-    s_slot_of_rank[r] = (int16_t)j0;
-    s_order[ord] = (int16_t)j0;
-  }
-  __syncthreads();
-  if (threadIdx.x >= 32) return;  // the loop belongs to warp 0 alone: only __syncwarp from here on
-
-  // Lane L owns the 32 CONSECUTIVE candidates 32 L .. 32 L + 31: its part of a row of dt is one 128-byte line, copied with
-  // eight 16-byte cp.async (element-wise 4-byte copies cost one LSU pass each: 1024 of them per pick made a one-warp loop
-  // 4x slower than the 16-warp one) into a staged row whose lane segments are 144 bytes apart (conflict-free LDS.128).
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float tau = *tau_ptr;
-  const bool vec = (Kc % 32 == 0) && ((reinterpret_cast<uintptr_t>(dt) & 127) == 0);
-  const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(stage);
-  const int jbase = lane * kReplayPer;
   float v[kReplayPer];
   uint32_t rank[kReplayPer];
 #pragma unroll
   for (int k = 0; k < kReplayPer; ++k) {
-    v[k] = s_v0[jbase + k];
-    rank[k] = s_rank[jbase + k];
+    const int j = k * kReplayThreads + tid;
+    v[k] = (j < Kc) ? val[j] : -1.0f;
+    s_g[j] = (j < Kc) ? gidx[j] : INT64_MAX;
+    s_v0[j] = v[k];
+    s_stage_slot[j] = -1;
+    s_stage_time[j] = 0;
+    rank[k] = 0xffffffffu;
   }
-  const bool mine = jbase < Kc;  // with vec: all 32 of the lane's candidates exist or none does
-  auto issue_row = [&](int slot, int c) {  // stage row c of dt into `slot`: this lane's elements only
-    const float* grow = dt + (int64_t)c * Kc + jbase;
-    const uint32_t dst = stage_addr + (uint32_t)slot * kReplayRowBytes + (uint32_t)lane * kReplayLaneBytes;
-    if (vec) {
-      if (mine) {
+  __syncthreads();
+  // rank of a slot among all slots by (global index, slot): lower global index = lower rank; and its place in the staging
+  // order by (initial value desc, rank asc)
 #pragma unroll
-        for (int q = 0; q < kReplayPer / 4; ++q) cp_async16(dst + 16u * q, grow + 4 * q);
+  for (int k = 0; k < kReplayPer; ++k) {  // unrolled: rank[] must stay in registers
+    const int j = k * kReplayThreads + tid;
+    if (j < Kc) {
+      const int64_t g = s_g[j];
+      const float vj = s_v0[j];
+      uint32_t r = 0;
+      int ord = 0;
+      for (int i = 0; i < Kc; ++i) {
+        const int64_t gi = s_g[i];
+        const bool before = gi < g || (gi == g && i < j);
+        r += before ? 1u : 0u;
+        const float vi = s_v0[i];
+        ord += (vi > vj || (vi == vj && before)) ? 1 : 0;
       }
-    } else {
-#pragma unroll
-      for (int k = 0; k < kReplayPer; ++k)
-        if (jbase + k < Kc) cp_async4(dst + 4u * k, grow + k);
+      rank[k] = r;
+      s_slot_of_rank[r] = (int16_t)j;
+      s_order[ord] = (int16_t)j;
     }
-  };
+  }
+  __syncthreads();
   const int n_stage = Kc < kReplayStage ? Kc : kReplayStage;
   for (int r = 0; r < n_stage; ++r) {
     const int c = s_order[r];
-    issue_row(r, c);
-    if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kReplayPer; ++k) {
+      const int j = k * kReplayThreads + tid;
+      if (j < Kc) cp_async4(&stage[r * Kc + j], dt + (int64_t)c * Kc + j);
+    }
+    if (tid == 0) {
       s_stage_slot[c] = (int16_t)r;
       s_stage_time[c] = -kReplayDepth;
     }
   }
   cp_async_commit();
   cp_async_wait<0>();
-  __syncwarp();
+  __syncthreads();
   int next_stage = n_stage;
   int t = 0;
   for (; t < max_picks; ++t) {
-    // arg-max of (value desc, rank asc): the lane's 32 candidates, then the warp.  Invalid slots (v < 0) carry key 0 and
-    // never beat a valid one.  Values are >= 0, so the float bits order like the floats.
+    // arg-max of (value desc, rank asc): own candidates, warp, block.  Invalid slots (v < 0) carry key 0 and never beat a
+    // valid one.
     uint32_t bk = 0u, br = 0xffffffffu;
 #pragma unroll
     for (int k = 0; k < kReplayPer; ++k) {
@@ -695,13 +677,20 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
       bk = better ? key : bk;
       br = better ? rank[k] : br;
     }
-    const uint32_t bmax = __reduce_max_sync(kFull, bk);
-    const uint32_t brank = __reduce_min_sync(kFull, bk == bmax ? br : 0xffffffffu);
+    const uint32_t wmax = __reduce_max_sync(kFull, bk);
+    const uint32_t wrank = __reduce_min_sync(kFull, bk == wmax ? br : 0xffffffffu);
+    const int buf = t & 1;
+    if (lane == 0) { w_val[buf][warp] = wmax; w_rank[buf][warp] = wrank; }
+    __syncthreads();
+    const uint32_t k2 = (lane < kReplayThreads / 32) ? w_val[buf][lane] : 0u;
+    const uint32_t r2 = (lane < kReplayThreads / 32) ? w_rank[buf][lane] : 0xffffffffu;
+    const uint32_t bmax = __reduce_max_sync(kFull, k2);
+    const uint32_t brank = __reduce_min_sync(kFull, k2 == bmax ? r2 : 0xffffffffu);
     if (bmax == 0u) break;  // no valid candidate at all
     const float best_v = __uint_as_float(bmax - 1u);
     if (t > 0 && !(best_v > tau)) break;
     const int s = s_slot_of_rank[brank];
-    if (lane == 0) {
+    if (tid == 0) {
       selected_out[t] = s_g[s];
       pick_slots[t] = s;
     }
@@ -711,41 +700,35 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
     const bool fetch = best_v > 0.0f;
     const int slot = fetch ? (int)s_stage_slot[s] : -1;
     const bool ready = slot >= 0 && (t - s_stage_time[s]) >= kReplayDepth;
-    if (ready) {
-      const float4* row = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(stage) + (size_t)slot * kReplayRowBytes +
-                                                          (size_t)lane * kReplayLaneBytes);
+    if (fetch) {
+      const float* row = ready ? (stage + slot * Kc) : nullptr;
+      const float* grow = dt + (int64_t)s * Kc;
 #pragma unroll
-      for (int q = 0; q < kReplayPer / 4; ++q) {
-        const float4 x = row[q];
-        v[4 * q + 0] = fminf(v[4 * q + 0], x.x);
-        v[4 * q + 1] = fminf(v[4 * q + 1], x.y);
-        v[4 * q + 2] = fminf(v[4 * q + 2], x.z);
-        v[4 * q + 3] = fminf(v[4 * q + 3], x.w);
+      for (int k = 0; k < kReplayPer; ++k) {
+        const int j = k * kReplayThreads + tid;
+        if (j < Kc) v[k] = fminf(v[k], ready ? row[j] : __ldg(grow + j));
       }
-      // the winner's row is no longer needed: its slot takes the next row of the staging order
-      if (next_stage < Kc) {
-        const int c = s_order[next_stage];
-        issue_row(slot, c);
-        if (lane == 0) {
-          s_stage_slot[c] = (int16_t)slot;
-          s_stage_time[c] = t;
-        }
-      }
-      ++next_stage;
-    } else if (fetch) {
-      // not staged (or its copy is still in flight -- such a slot is not reused, the new copy could be overtaken by the old
-      // one; it simply stays unused): the dependent global read of round 1
-      const float* grow = dt + (int64_t)s * Kc + jbase;
-#pragma unroll
-      for (int k = 0; k < kReplayPer; ++k)
-        if (jbase + k < Kc) v[k] = fminf(v[k], __ldg(grow + k));
     }
+    // the winner's row is no longer needed: its slot takes the next row of the staging order.  (A slot whose copy is
+    // still in flight is not reused -- the new copy could be overtaken by the old one -- it simply stays unused.)
+    if (ready && next_stage < Kc) {
+      const int c = s_order[next_stage];
+#pragma unroll
+      for (int k = 0; k < kReplayPer; ++k) {
+        const int j = k * kReplayThreads + tid;
+        if (j < Kc) cp_async4(&stage[slot * Kc + j], dt + (int64_t)c * Kc + j);
+      }
+      if (tid == 0) {
+        s_stage_slot[c] = (int16_t)slot;
+        s_stage_time[c] = t;
+      }
+    }
+    if (ready) ++next_stage;
     cp_async_commit();
     cp_async_wait<kReplayDepth - 1>();
-    __syncwarp();  // lane 0's staging bookkeeping is read by every lane in later picks
   }
   cp_async_wait<0>();
-  if (lane == 0) *n_picks_out = t;
+  if (tid == 0) *n_picks_out = t;
 }
 
 __global__ void __launch_bounds__(128)
@@ -791,9 +774,9 @@ int kc_resolve(const void* records, int n_blocks, int K, int d, int max_picks, v
   } else {
     if (int rc = kc_pairwise_exact(rows, xx, Kc, d, dt, stream)) return rc;
   }
-  const int threads = kReplayInitThreads;  // all of them rank the candidates once, warp 0 runs the loop
-  const size_t replay_smem = (size_t)kReplayStage * kReplayRowBytes;
-  MVAL_CUDA(cudaFuncSetAttribute(kc_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)replay_smem));
+  const int threads = kReplayThreads;
+  const size_t replay_smem = sizeof(float) * (size_t)(Kc < kReplayStage ? Kc : kReplayStage) * Kc;
+  MVAL_CUDA(cudaFuncSetAttribute(kc_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kReplayStage * kKcMaxSlots)));
   kc_replay_kernel<<<1, threads, replay_smem, stream>>>(val, gidx, dt, Kc, tau, max_picks, selected_out, pick_slots, n_picks);
   MVAL_LAUNCH_CHECK("kc_replay");
   kc_gather_centres_kernel<<<max_picks, 128, 0, stream>>>(rows, xx, pick_slots, n_picks, d, centres, centre_norms);
@@ -1000,7 +983,7 @@ extern "C" int mval_kcenter_greedy(const float* features, int64_t n, int64_t n_u
         set_error("mval_kcenter_greedy: internal error, a round produced no pick");
         return MVAL_ERR_CUDA;
       }
-      if (int rc = kc_update_batch(features, norms, n, d, centres, cnorms, got, min_dist, 0, stream)) return rc;
+      if (int rc = kc_update_batch(features, norms, n, d, centres, cnorms, got, min_dist, kKcFlagGroupChunks, stream)) return rc;
       done += got;
     }
     return MVAL_OK;

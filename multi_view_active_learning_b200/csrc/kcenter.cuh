@@ -89,6 +89,7 @@ int kc_resolve(const void* records, int n_blocks, int K, int d, int max_picks, v
 // flags bit 0: force the exact FFMA pass; bit 1: force the tensor-core path when it is applicable at all.
 constexpr int kKcFlagForceExact = 1;
 constexpr int kKcFlagForceTc = 2;
+constexpr int kKcFlagGroupChunks = 4;  // the centres are the picks of one greedy round: screen all chunks, recheck once
 int kc_update_batch(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T, float* min_dist,
                     int flags, cudaStream_t stream);
 

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 kc_screen_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
                     const float* __restrict__ xx, const float* __restrict__ cc, const float* __restrict__ min_dist, int64_t n,
                     int d, int T, float alpha, int batch_min, TcPair* __restrict__ pairs, unsigned int* __restrict__ pair_count,
-                    unsigned int pair_capacity) {
+                    unsigned int pair_capacity, uint32_t t_base) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* hcc = reinterpret_cast<float*>(smem + kTcStages * kTcStageBytes);  // |c_t|^2 / 2, +inf for t >= T
@@ -276,7 +276,7 @@ kc_screen_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const float thr = fmaxf(0.5f * ((xr - s_i) - m2), vmax - s_i);
       for (int c = 0; c < n_chunks; ++c) {
         tmem_ld32(taddr + c * 32, v);
-        append_survivors(v, hcc + c * 32, thr, rok, (uint32_t)row, (uint32_t)(c * 32), lane, pairs, pair_count, pair_capacity);
+        append_survivors(v, hcc + c * 32, thr, rok, (uint32_t)row, (uint32_t)(c * 32) + t_base, lane, pairs, pair_count, pair_capacity);
       }
       tc_fence_before();
       __syncwarp();
@@ -379,7 +379,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 kc_screen_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c_half,
                      const float* __restrict__ xx, const float* __restrict__ cc, const float* __restrict__ min_dist, int64_t n,
                      int d, int T, float alpha, int batch_min, TcPair* __restrict__ pairs, unsigned int* __restrict__ pair_count,
-                     unsigned int pair_capacity) {
+                     unsigned int pair_capacity, uint32_t t_base) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* hcc = reinterpret_cast<float*>(smem + kTc2Stages * kTc2StageBytes);  // |c_t|^2 / 2, +inf for t >= T
@@ -501,7 +501,7 @@ kc_screen_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       const float thr = fmaxf(0.5f * ((xr - s_i) - m2), vmax - s_i);  // see kc_screen_tc_kernel
       for (int c = 0; c < n_chunks; ++c) {
         tmem_ld32(taddr + c * 32, v);
-        append_survivors(v, hcc + c * 32, thr, rok, (uint32_t)row, (uint32_t)(c * 32), lane, pairs, pair_count, pair_capacity);
+        append_survivors(v, hcc + c * 32, thr, rok, (uint32_t)row, (uint32_t)(c * 32) + t_base, lane, pairs, pair_count, pair_capacity);
       }
       tc_fence_before();
       __syncwarp();
@@ -678,12 +678,16 @@ static bool tc_use_pairs(int64_t n) {
   return !(e != nullptr && e[0] == '0') && n >= 4 * kTcBlockM;
 }
 
+// t_base is added to the centre index of every appended pair; reset = false appends to the list of the previous screen (several
+// 256-centre chunks then share ONE recheck launch, whose duration is a latency, not a throughput)
 static int tc_screen(KcDeviceScratch* s, const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T,
-                     const float* min_dist, int batch_min, cudaStream_t stream) {
+                     const float* min_dist, int batch_min, cudaStream_t stream, uint32_t t_base = 0, bool reset = true) {
   CUtensorMap map_x, map_c;
   if (int rc = make_map(&map_x, X, n, d, kTcBlockM)) return rc;
-  kc_tc_reset_kernel<<<1, 1, 0, stream>>>(s->tc_count);
-  MVAL_LAUNCH_CHECK("kc_tc_reset");
+  if (reset) {
+    kc_tc_reset_kernel<<<1, 1, 0, stream>>>(s->tc_count);
+    MVAL_LAUNCH_CHECK("kc_tc_reset");
+  }
   const float alpha2 = ldexpf(1.0f, -8) + (float)d * ldexpf(1.0f, -20);
   if (tc_use_pairs(n)) {
     if (int rc = make_map(&map_c, C, T, d, (int)kTc2HalfN)) return rc;
@@ -714,7 +718,7 @@ static int tc_screen(KcDeviceScratch* s, const float* X, const float* xx, int64_
     const int grid = 2 * (int)(n_pairs < max_clusters ? n_pairs : max_clusters);
     kc_screen_tc2_kernel<<<grid, kTcThreads, kTc2SmemBytes, stream>>>(map_x, map_c, xx, cc, min_dist, n, d, T, alpha2, batch_min,
                                                                      static_cast<TcPair*>(s->tc_pairs), s->tc_count,
-                                                                     (unsigned int)s->tc_pairs_capacity);
+                                                                     (unsigned int)s->tc_pairs_capacity, t_base);
     MVAL_LAUNCH_CHECK("kc_screen_tc2");
     return MVAL_OK;
   }
@@ -724,7 +728,7 @@ static int tc_screen(KcDeviceScratch* s, const float* X, const float* xx, int64_
   const float alpha = ldexpf(1.0f, -8) + (float)d * ldexpf(1.0f, -20);
   kc_screen_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(map_x, map_c, xx, cc, min_dist, n, d, T, alpha, batch_min,
                                                                   static_cast<TcPair*>(s->tc_pairs), s->tc_count,
-                                                                  (unsigned int)s->tc_pairs_capacity);
+                                                                  (unsigned int)s->tc_pairs_capacity, t_base);
   MVAL_LAUNCH_CHECK("kc_screen_tc");
   return MVAL_OK;
 }
@@ -744,25 +748,36 @@ int kc_pairwise_tc(const float* X, const float* xx, const float* val, int n, int
   MVAL_LAUNCH_CHECK("kc_fill_inf");
   for (int t0 = 0; t0 < n; t0 += kTcBlockN) {
     const int tn = (n - t0) < kTcBlockN ? (n - t0) : kTcBlockN;
-    if (int rc = tc_screen(s, X, xx, n, d, X + (int64_t)t0 * d, xx + t0, tn, val, 0, stream)) return rc;
-    kc_recheck_kernel<true><<<num_sms() * 3, kRcWarps * 32, kRcSmemBytes, stream>>>(X, xx, d, X + (int64_t)t0 * d, xx + t0,
-                                                                     static_cast<const TcPair*>(s->tc_pairs), s->tc_count,
-                                                                     (unsigned int)s->tc_pairs_capacity, out_t, t0, n);
-    MVAL_LAUNCH_CHECK("kc_recheck_store");
+    if (int rc = tc_screen(s, X, xx, n, d, X + (int64_t)t0 * d, xx + t0, tn, val, 0, stream, (uint32_t)t0, t0 == 0)) return rc;
   }
+  // every chunk's survivors in one list (centre index absolute), one exact pass
+  kc_recheck_kernel<true><<<num_sms() * 3, kRcWarps * 32, kRcSmemBytes, stream>>>(X, xx, d, X, xx, static_cast<const TcPair*>(s->tc_pairs),
+                                                                                   s->tc_count, (unsigned int)s->tc_pairs_capacity,
+                                                                                   out_t, 0, n);
+  MVAL_LAUNCH_CHECK("kc_recheck_store");
   return MVAL_OK;
 }
 
+// T centres (any number) through the tensor-core screen in chunks of 256: every chunk appends its survivors (absolute centre
+// index) to one list, then ONE recheck launch and one gated FFMA fallback per chunk (it only runs if the list overflowed).
 int kc_update_batch_tc(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T, float* min_dist,
                        cudaStream_t stream) {
   KcDeviceScratch* s = nullptr;
-  if (int rc = tc_prepare(&s, (size_t)n * 4)) return rc;
-  if (int rc = tc_screen(s, X, xx, n, d, C, cc, T, min_dist, 1, stream)) return rc;
+  const int n_chunks = (T + kTcBlockN - 1) / kTcBlockN;
+  if (int rc = tc_prepare(&s, (size_t)n * 4 * (size_t)n_chunks)) return rc;
+  for (int t0 = 0; t0 < T; t0 += kTcBlockN) {
+    const int tn = (T - t0) < kTcBlockN ? (T - t0) : kTcBlockN;
+    if (int rc = tc_screen(s, X, xx, n, d, C + (int64_t)t0 * d, cc + t0, tn, min_dist, 1, stream, (uint32_t)t0, t0 == 0)) return rc;
+  }
   const unsigned int cap = (unsigned int)s->tc_pairs_capacity;
   kc_recheck_kernel<false><<<num_sms() * 3, kRcWarps * 32, kRcSmemBytes, stream>>>(X, xx, d, C, cc, static_cast<const TcPair*>(s->tc_pairs),
                                                                         s->tc_count, cap, min_dist, 0, 0);
   MVAL_LAUNCH_CHECK("kc_recheck");
-  return kc_update_batch_exact_if(X, xx, n, d, C, cc, T, min_dist, s->tc_count, cap, stream);
+  for (int t0 = 0; t0 < T; t0 += kTcBlockN) {
+    const int tn = (T - t0) < kTcBlockN ? (T - t0) : kTcBlockN;
+    if (int rc = kc_update_batch_exact_if(X, xx, n, d, C + (int64_t)t0 * d, cc + t0, tn, min_dist, s->tc_count, cap, stream)) return rc;
+  }
+  return MVAL_OK;
 }
 
 int kc_tc_last_stats(uint64_t* survivors, uint64_t* capacity, cudaStream_t stream) {
@@ -783,14 +798,24 @@ int kc_update_batch(const float* X, const float* xx, int64_t n, int d, const flo
   if (n == 0 || T == 0) return MVAL_OK;
   const bool force_exact = (flags & kKcFlagForceExact) != 0;
   const bool force_tc = (flags & kKcFlagForceTc) != 0;
-  for (int t0 = 0; t0 < T; t0 += kTcBlockN) {
+  // full 256-centre chunks share one tensor-core call (one recheck launch for all of them); a short tail chunk is judged on
+  // its own: the tensor-core pass costs one sweep of the features whatever tn is, the FFMA pass ~ tn / 256 of 16 sweeps
+  auto eligible = [&](const float* Cb, int tn) {
+    return !force_exact && kc_tc_applicable(X, n, d, Cb, tn) && (force_tc || ((int64_t)tn * d >= 16 * 1024 && n >= 16384));
+  };
+  // (only for the picks of a greedy round, kKcFlagGroupChunks: there the running minima are settled and few pairs survive;
+  // while minima are still falling -- the labeled fold -- a chunk's screen profits from the previous chunk's update)
+  int t0 = 0;
+  const int full = (flags & kKcFlagGroupChunks) ? (T / kTcBlockN) * kTcBlockN : 0;
+  if (full > 0 && eligible(C, kTcBlockN)) {
+    if (int rc = kc_update_batch_tc(X, xx, n, d, C, cc, full, min_dist, stream)) return rc;
+    t0 = full;
+  }
+  for (; t0 < T; t0 += kTcBlockN) {
     const int tn = (T - t0) < kTcBlockN ? (T - t0) : kTcBlockN;
     const float* Cb = C + (int64_t)t0 * d;
-    const bool can = kc_tc_applicable(X, n, d, Cb, tn);
-    // the tensor-core pass costs one sweep of the features whatever tn is; the FFMA pass costs ~ tn / 256 of 16 sweeps
-    const bool use_tc = !force_exact && can && (force_tc || ((int64_t)tn * d >= 16 * 1024 && n >= 16384));
     int rc;
-    if (use_tc) rc = kc_update_batch_tc(X, xx, n, d, Cb, cc + t0, tn, min_dist, stream);
+    if (eligible(Cb, tn)) rc = kc_update_batch_tc(X, xx, n, d, Cb, cc + t0, tn, min_dist, stream);
     else rc = kc_update_batch_exact(X, xx, n, d, Cb, cc + t0, tn, min_dist, stream);
     if (rc) return rc;
   }

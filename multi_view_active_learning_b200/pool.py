@@ -135,7 +135,7 @@ def kcenter_rounds(state, budget, group=None, k_slots=None, flags=0, stats=None)
         t, centres, cnorms = resolver.resolve(gathered, budget - done, selected[done:])
         assert t >= 1
         for s in state:
-            ops.kcenter_update_batch(s["feat"], s["norms"], centres, cnorms, s["min"], flags)
+            ops.kcenter_update_batch(s["feat"], s["norms"], centres, cnorms, s["min"], flags | 4)  # 4: one recheck per round
         done += t
         if stats is not None:
             stats.append(t)
