@@ -597,60 +597,117 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kN>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory"); }
 
+// Ranks and the sorted order of the Kc candidates, computed by a small grid instead of inside the replay CTA:
+//   rank[j]          position of slot j among all slots by (global index, slot): the tie-break of the arg-max
+//   order[p]         the slot at position p by (value desc, rank asc): the order in which candidates are picked as long as
+//                    picks do not lower other candidates; also the staging order of the replay
+//   slot_of_rank[r]  inverse of rank
+constexpr int kOrderThreads = 128;
+__global__ void __launch_bounds__(kOrderThreads)
+kc_order_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx, int Kc, int32_t* __restrict__ rank,
+                int32_t* __restrict__ order, int32_t* __restrict__ slot_of_rank, int32_t* __restrict__ prefix_m) {
+  __shared__ int64_t s_g[kKcMaxSlots];
+  __shared__ float s_v[kKcMaxSlots];
+  for (int i = threadIdx.x; i < Kc; i += kOrderThreads) {
+    s_g[i] = gidx[i];
+    s_v[i] = val[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *prefix_m = Kc;
+  __syncthreads();
+  const int j = blockIdx.x * kOrderThreads + threadIdx.x;
+  if (j >= Kc) return;
+  const int64_t g = s_g[j];
+  const float v = s_v[j];
+  int r = 0, ord = 0;
+  for (int i = 0; i < Kc; ++i) {
+    const int64_t gi = s_g[i];
+    const bool before = gi < g || (gi == g && i < j);
+    r += before ? 1 : 0;
+    const float vi = s_v[i];
+    ord += (vi > v || (vi == v && before)) ? 1 : 0;
+  }
+  rank[j] = r;
+  slot_of_rank[r] = j;
+  order[ord] = j;
+}
+
+// Speculative look-ahead over a whole round.  As long as no pick lowers a later candidate, the greedy loop simply walks the
+// sorted order: the first m picks are order[0..m) with m the first position p such that
+//   some earlier candidate is closer to candidate p than p's own running minimum (dt[order[i]][order[p]] < val[order[p]], i < p),
+//   or p may not be picked at all (value not above tau, or not positive: a zero value means "picked before", see the replay).
+// That is Kc^2 / 2 independent comparisons -- one warp per position, a few microseconds on the whole GPU -- instead of m
+// dependent trips through the replay CTA (0.7 us each).  On near-orthogonal high-dimensional features (C4) m is the whole
+// round; on clustered pools it is short and the replay CTA takes over from pick m with the exact state.
+__global__ void __launch_bounds__(256)
+kc_prefix_kernel(const float* __restrict__ val, const float* __restrict__ dt, const int32_t* __restrict__ order, int Kc,
+                 const float* __restrict__ tau_ptr, int32_t* __restrict__ prefix_m) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (p < 1 || p >= Kc) return;
+  const int sp = order[p];
+  const float vp = val[sp];
+  bool stop = !(vp > 0.0f) || !(vp > *tau_ptr);
+  if (!stop) {
+    bool lowered = false;
+    for (int i = lane; i < p; i += 32) lowered |= dt[(int64_t)order[i] * Kc + sp] < vp;
+    stop = __any_sync(kFull, lowered);
+  }
+  if (stop && lane == 0) atomicMin(prefix_m, p);
+}
+
 __global__ void __launch_bounds__(kReplayThreads)
 kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx, const float* __restrict__ dt, int Kc,
-                 const float* __restrict__ tau_ptr, int max_picks, int64_t* __restrict__ selected_out,
-                 int32_t* __restrict__ pick_slots, int32_t* __restrict__ n_picks_out) {
+                 const float* __restrict__ tau_ptr, int max_picks, const int32_t* __restrict__ g_rank,
+                 const int32_t* __restrict__ g_order, const int32_t* __restrict__ g_slot_of_rank,
+                 const int32_t* __restrict__ prefix_m, int64_t* __restrict__ selected_out, int32_t* __restrict__ pick_slots,
+                 int32_t* __restrict__ n_picks_out) {
   extern __shared__ float stage[];  // [kReplayStage][Kc]
   __shared__ uint32_t w_val[2][kReplayThreads / 32];
   __shared__ uint32_t w_rank[2][kReplayThreads / 32];
   __shared__ int64_t s_g[kKcMaxSlots];
-  __shared__ float s_v0[kKcMaxSlots];
   __shared__ int16_t s_slot_of_rank[kKcMaxSlots];
   __shared__ int16_t s_order[kKcMaxSlots];       // candidates by (initial value desc, rank asc): the staging order
   __shared__ int16_t s_stage_slot[kKcMaxSlots];  // candidate -> stage slot holding its row, -1 = none
   __shared__ int32_t s_stage_time[kKcMaxSlots];  // pick counter at which that row was issued
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float tau = *tau_ptr;
+  // the look-ahead's picks: order[0 .. m)
+  int m = *prefix_m;
+  m = m < max_picks ? m : max_picks;
+  m = m < 1 ? 1 : m;  // the first pick of a round is always valid (the set holds the global arg-max)
   float v[kReplayPer];
   uint32_t rank[kReplayPer];
 #pragma unroll
   for (int k = 0; k < kReplayPer; ++k) {
     const int j = k * kReplayThreads + tid;
     v[k] = (j < Kc) ? val[j] : -1.0f;
+    rank[k] = (j < Kc) ? (uint32_t)g_rank[j] : 0xffffffffu;
     s_g[j] = (j < Kc) ? gidx[j] : INT64_MAX;
-    s_v0[j] = v[k];
+    s_slot_of_rank[j] = (j < Kc) ? (int16_t)g_slot_of_rank[j] : (int16_t)0;
+    s_order[j] = (j < Kc) ? (int16_t)g_order[j] : (int16_t)0;
     s_stage_slot[j] = -1;
     s_stage_time[j] = 0;
-    rank[k] = 0xffffffffu;
   }
   __syncthreads();
-  // rank of a slot among all slots by (global index, slot): lower global index = lower rank; and its place in the staging
-  // order by (initial value desc, rank asc)
+  if (!(val[s_order[0]] >= 0.0f)) m = 0;  // no valid candidate at all (uniform: every thread reads the same element)
+  for (int t = tid; t < m; t += kReplayThreads) {
+    const int sl = s_order[t];
+    selected_out[t] = s_g[sl];
+    pick_slots[t] = sl;
+  }
+  // the state after those m picks: every candidate folded against the m winners' rows (coalesced, independent loads)
+  for (int i = 0; i < m; ++i) {
+    const float* grow = dt + (int64_t)s_order[i] * Kc;
 #pragma unroll
-  for (int k = 0; k < kReplayPer; ++k) {  // unrolled: rank[] must stay in registers
-    const int j = k * kReplayThreads + tid;
-    if (j < Kc) {
-      const int64_t g = s_g[j];
-      const float vj = s_v0[j];
-      uint32_t r = 0;
-      int ord = 0;
-      for (int i = 0; i < Kc; ++i) {
-        const int64_t gi = s_g[i];
-        const bool before = gi < g || (gi == g && i < j);
-        r += before ? 1u : 0u;
-        const float vi = s_v0[i];
-        ord += (vi > vj || (vi == vj && before)) ? 1 : 0;
-      }
-      rank[k] = r;
-      s_slot_of_rank[r] = (int16_t)j;
-      s_order[ord] = (int16_t)j;
+    for (int k = 0; k < kReplayPer; ++k) {
+      const int j = k * kReplayThreads + tid;
+      if (j < Kc) v[k] = fminf(v[k], __ldg(grow + j));
     }
   }
-  __syncthreads();
-  const int n_stage = Kc < kReplayStage ? Kc : kReplayStage;
+  // stage the rows of the next candidates in the sorted order
+  const int n_stage = (Kc - m) < kReplayStage ? (Kc - m) : kReplayStage;
   for (int r = 0; r < n_stage; ++r) {
-    const int c = s_order[r];
+    const int c = s_order[m + r];
 #pragma unroll
     for (int k = 0; k < kReplayPer; ++k) {
       const int j = k * kReplayThreads + tid;
@@ -658,14 +715,14 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
     }
     if (tid == 0) {
       s_stage_slot[c] = (int16_t)r;
-      s_stage_time[c] = -kReplayDepth;
+      s_stage_time[c] = m - kReplayDepth;
     }
   }
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
-  int next_stage = n_stage;
-  int t = 0;
+  int next_stage = m + n_stage;
+  int t = m;
   for (; t < max_picks; ++t) {
     // arg-max of (value desc, rank asc): own candidates, warp, block.  Invalid slots (v < 0) carry key 0 and never beat a
     // valid one.
@@ -746,7 +803,7 @@ kc_gather_centres_kernel(const float* __restrict__ rows, const float* __restrict
 size_t kc_resolve_workspace_bytes(int n_blocks, int K, int d) {
   const size_t Kc = (size_t)n_blocks * K;
   return kc_align256(Kc * d * 4) + kc_align256(Kc * 4) * 2 + kc_align256(Kc * 8) + kc_align256(Kc * Kc * 4) +
-         kc_align256(Kc * 4) + 512;
+         kc_align256(Kc * 4) * 4 + 768;
 }
 
 int kc_resolve(const void* records, int n_blocks, int K, int d, int max_picks, void* workspace, float* centres,
@@ -764,8 +821,12 @@ int kc_resolve(const void* records, int n_blocks, int K, int d, int max_picks, v
   int64_t* gidx = reinterpret_cast<int64_t*>(w);        w += kc_align256((size_t)Kc * 8);
   float* dt = reinterpret_cast<float*>(w);              w += kc_align256((size_t)Kc * Kc * 4);
   int32_t* pick_slots = reinterpret_cast<int32_t*>(w);  w += kc_align256((size_t)Kc * 4);
+  int32_t* rank = reinterpret_cast<int32_t*>(w);        w += kc_align256((size_t)Kc * 4);
+  int32_t* order = reinterpret_cast<int32_t*>(w);       w += kc_align256((size_t)Kc * 4);
+  int32_t* slot_of_rank = reinterpret_cast<int32_t*>(w); w += kc_align256((size_t)Kc * 4);
   float* tau = reinterpret_cast<float*>(w);
   int32_t* n_picks = reinterpret_cast<int32_t*>(w + 256);
+  int32_t* prefix_m = reinterpret_cast<int32_t*>(w + 512);
   kc_unpack_kernel<<<Kc, 128, 0, stream>>>(static_cast<const char*>(records), n_blocks, K, d, kc_records_bytes(K, d), rows, val,
                                            xx, gidx, tau);
   MVAL_LAUNCH_CHECK("kc_unpack");
@@ -777,7 +838,13 @@ int kc_resolve(const void* records, int n_blocks, int K, int d, int max_picks, v
   const int threads = kReplayThreads;
   const size_t replay_smem = sizeof(float) * (size_t)(Kc < kReplayStage ? Kc : kReplayStage) * Kc;
   MVAL_CUDA(cudaFuncSetAttribute(kc_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * kReplayStage * kKcMaxSlots)));
-  kc_replay_kernel<<<1, threads, replay_smem, stream>>>(val, gidx, dt, Kc, tau, max_picks, selected_out, pick_slots, n_picks);
+  kc_order_kernel<<<(Kc + kOrderThreads - 1) / kOrderThreads, kOrderThreads, 0, stream>>>(val, gidx, Kc, rank, order, slot_of_rank,
+                                                                                         prefix_m);
+  MVAL_LAUNCH_CHECK("kc_order");
+  kc_prefix_kernel<<<(Kc + 7) / 8, 256, 0, stream>>>(val, dt, order, Kc, tau, prefix_m);
+  MVAL_LAUNCH_CHECK("kc_prefix");
+  kc_replay_kernel<<<1, threads, replay_smem, stream>>>(val, gidx, dt, Kc, tau, max_picks, rank, order, slot_of_rank, prefix_m,
+                                                        selected_out, pick_slots, n_picks);
   MVAL_LAUNCH_CHECK("kc_replay");
   kc_gather_centres_kernel<<<max_picks, 128, 0, stream>>>(rows, xx, pick_slots, n_picks, d, centres, centre_norms);
   MVAL_LAUNCH_CHECK("kc_gather_centres");
