@@ -356,9 +356,21 @@ int mval_kcenter_resolve(const void* records, int n_blocks, int k_slots, int d, 
                          float* centres_out, float* centre_norms_out, int64_t* selected_out, int32_t* n_picks_host,
                          void* stream);
 
+/* The same round WITHOUT the host in the loop: `state` is device int32 [4] = {picks made so far, picks of this round (out),
+ * budget, reserved}, initialised by the caller to {0, 0, budget, 0}.  resolve_async limits the round to budget - done picks,
+ * writes them to selected_out[done ..] (int64 device [budget]), advances state[0] / sets state[1] and does not synchronise;
+ * update_batch_dev folds the first *n_centres (device int32, e.g. state + 1) of `max_centres` centre rows into min_dist.  A
+ * round launched after the budget is reached does nothing, so the host may read state[0] late (e.g. one round behind).
+ * The result is identical to the synchronous calls. */
+int mval_kcenter_resolve_async(const void* records, int n_blocks, int k_slots, int d, void* workspace, float* centres_out,
+                               float* centre_norms_out, int64_t* selected_out, int32_t* state, void* stream);
+int mval_kcenter_update_batch_dev(const float* features, const float* row_norms, int64_t n, int d, const float* centres,
+                                  const float* centre_norms, int max_centres, const int32_t* n_centres, float* min_dist,
+                                  int flags, void* stream);
+
 /* Single-device selection (coreset.py:71-95): norms, the labeled rows [n_unlabeled, n) folded in, then `budget`
- * picks in rounds.  min_dist float32 device [n] (out), out_selected int64 device [budget].  Synchronises `stream`
- * once per round. */
+ * picks in rounds driven by device-side counters (the host reads the running total one round late).  min_dist float32
+ * device [n] (out), out_selected int64 device [budget].  Synchronises `stream` before returning. */
 int mval_kcenter_greedy(const float* features, int64_t n, int64_t n_unlabeled, int d, int32_t budget,
                         float* min_dist, int64_t* out_selected, void* stream);
 

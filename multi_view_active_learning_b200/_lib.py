@@ -72,6 +72,8 @@ PROTOTYPES = {
     "mval_kcenter_select": (C.c_int, [_p, _p, _p, _i64, _i, _i64, _i, _p, _p]),
     "mval_kcenter_resolve_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "mval_kcenter_resolve": (C.c_int, [_p, _i, _i, _i, _i, _p, _p, _p, _p, C.POINTER(C.c_int32), _p]),
+    "mval_kcenter_resolve_async": (C.c_int, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "mval_kcenter_update_batch_dev": (C.c_int, [_p, _p, _i64, _i, _p, _p, _i, _p, _p, _i, _p]),
     "mval_kcenter_greedy": (C.c_int, [_p, _i64, _i64, _i, C.c_int32, _p, _p, _p]),
     "mval_render_gt_heatmaps": (C.c_int, [_p, _i64, _i, _i, _d, _p, _p, _p]),
     "mval_synth_heatmaps": (C.c_int, [_p, _i64, _i, _i, _f, _f, _u64, _p, _p]),

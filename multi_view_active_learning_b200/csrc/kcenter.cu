@@ -145,9 +145,11 @@ template <int TN, bool kStore, bool kVec>
 __global__ void __launch_bounds__(kBatchThreads, 2)
 kc_batch_kernel(const float* __restrict__ X, const float* __restrict__ xx, int64_t n, int d, const float* __restrict__ C,
                 const float* __restrict__ cc, int T, int n_col_tiles, float* __restrict__ min_dist, float* __restrict__ out,
-                int64_t ld_out, const unsigned int* __restrict__ gate, unsigned int gate_capacity) {
+                int64_t ld_out, const unsigned int* __restrict__ gate, unsigned int gate_capacity, KcCount cnt) {
   constexpr int BN = 16 * TN;
   if (gate != nullptr && *gate <= gate_capacity) return;  // fallback pass of the tensor-core path: nothing overflowed
+  T = kc_effective_T(T, cnt);
+  if ((int)(blockIdx.x % n_col_tiles) * BN >= T) return;  // (device-side batch size: nothing to do for this column tile)
   constexpr int XS = kBM + 4, CS = BN + 4;
   __shared__ __align__(16) float xs[2][kBK][XS];
   __shared__ __align__(16) float cs[2][kBK][CS];
@@ -307,7 +309,7 @@ kc_batch_kernel(const float* __restrict__ X, const float* __restrict__ xx, int64
 template <int TN, bool kStore>
 static int launch_batch_tn(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T,
                            float* min_dist, float* out, int64_t ld_out, cudaStream_t stream,
-                           const unsigned int* gate = nullptr, unsigned int gate_capacity = 0) {
+                           const unsigned int* gate = nullptr, unsigned int gate_capacity = 0, KcCount cnt = KcCount{nullptr, 0}) {
   constexpr int BN = 16 * TN;
   const int n_col_tiles = (T + BN - 1) / BN;
   const int64_t n_row_tiles = (n + kBM - 1) / kBM;
@@ -316,17 +318,21 @@ static int launch_batch_tn(const float* X, const float* xx, int64_t n, int d, co
   const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
   if (vec)
     kc_batch_kernel<TN, kStore, true><<<(unsigned)blocks, kBatchThreads, 0, stream>>>(X, xx, n, d, C, cc, T, n_col_tiles,
-                                                                                        min_dist, out, ld_out, gate, gate_capacity);
+                                                                                        min_dist, out, ld_out, gate, gate_capacity, cnt);
   else
     kc_batch_kernel<TN, kStore, false><<<(unsigned)blocks, kBatchThreads, 0, stream>>>(X, xx, n, d, C, cc, T, n_col_tiles,
-                                                                                         min_dist, out, ld_out, gate, gate_capacity);
+                                                                                         min_dist, out, ld_out, gate, gate_capacity, cnt);
   MVAL_LAUNCH_CHECK("kc_batch");
   return MVAL_OK;
 }
 
 int kc_update_batch_exact(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T,
-                          float* min_dist, cudaStream_t stream) {
+                          float* min_dist, cudaStream_t stream, KcCount cnt) {
   if (n == 0 || T == 0) return MVAL_OK;
+  if (cnt.ptr != nullptr) {  // batch size known to the device only: the tiled kernel clamps it
+    if (T <= 64) return launch_batch_tn<4, false>(X, xx, n, d, C, cc, T, min_dist, nullptr, 0, stream, nullptr, 0, cnt);
+    return launch_batch_tn<8, false>(X, xx, n, d, C, cc, T, min_dist, nullptr, 0, stream, nullptr, 0, cnt);
+  }
   if (T == 1) {  // one centre: HBM-bound row-dot kernel
     kc_rowdot_kernel<1><<<rowdot_grid(n), kRdWarps * 32, 0, stream>>>(X, n, d, C, cc, xx, min_dist);
     MVAL_LAUNCH_CHECK("kc_rowdot_update");
@@ -339,9 +345,9 @@ int kc_update_batch_exact(const float* X, const float* xx, int64_t n, int d, con
 
 // The same pass, executed only if *count > capacity on the device (overflow of the tensor-core path's pair list).
 int kc_update_batch_exact_if(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T,
-                             float* min_dist, const unsigned int* count, unsigned int capacity, cudaStream_t stream) {
-  if (T <= 64) return launch_batch_tn<4, false>(X, xx, n, d, C, cc, T, min_dist, nullptr, 0, stream, count, capacity);
-  return launch_batch_tn<8, false>(X, xx, n, d, C, cc, T, min_dist, nullptr, 0, stream, count, capacity);
+                             float* min_dist, const unsigned int* count, unsigned int capacity, cudaStream_t stream, KcCount cnt) {
+  if (T <= 64) return launch_batch_tn<4, false>(X, xx, n, d, C, cc, T, min_dist, nullptr, 0, stream, count, capacity, cnt);
+  return launch_batch_tn<8, false>(X, xx, n, d, C, cc, T, min_dist, nullptr, 0, stream, count, capacity, cnt);
 }
 
 int kc_pairwise_exact(const float* X, const float* xx, int n, int d, float* out_t, cudaStream_t stream) {
@@ -660,7 +666,7 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
                  const float* __restrict__ tau_ptr, int max_picks, const int32_t* __restrict__ g_rank,
                  const int32_t* __restrict__ g_order, const int32_t* __restrict__ g_slot_of_rank,
                  const int32_t* __restrict__ prefix_m, int64_t* __restrict__ selected_out, int32_t* __restrict__ pick_slots,
-                 int32_t* __restrict__ n_picks_out) {
+                 int32_t* __restrict__ n_picks_out, int32_t* __restrict__ state) {
   extern __shared__ float stage[];  // [kReplayStage][Kc]
   __shared__ uint32_t w_val[2][kReplayThreads / 32];
   __shared__ uint32_t w_rank[2][kReplayThreads / 32];
@@ -671,10 +677,15 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
   __shared__ int32_t s_stage_time[kKcMaxSlots];  // pick counter at which that row was issued
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float tau = *tau_ptr;
+  if (state != nullptr) {  // device-side bookkeeping of the rounds: [0] picks so far, [2] budget
+    const int done = state[0], left = state[2] - done;
+    max_picks = left < max_picks ? (left < 0 ? 0 : left) : max_picks;
+    selected_out += done;
+  }
   // the look-ahead's picks: order[0 .. m)
   int m = *prefix_m;
-  m = m < max_picks ? m : max_picks;
   m = m < 1 ? 1 : m;  // the first pick of a round is always valid (the set holds the global arg-max)
+  m = m < max_picks ? m : max_picks;
   float v[kReplayPer];
   uint32_t rank[kReplayPer];
 #pragma unroll
@@ -785,7 +796,13 @@ kc_replay_kernel(const float* __restrict__ val, const int64_t* __restrict__ gidx
     cp_async_wait<kReplayDepth - 1>();
   }
   cp_async_wait<0>();
-  if (tid == 0) *n_picks_out = t;
+  if (tid == 0) {
+    *n_picks_out = t;
+    if (state != nullptr) {
+      state[1] = t;
+      state[0] += t;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(128)
@@ -807,7 +824,7 @@ size_t kc_resolve_workspace_bytes(int n_blocks, int K, int d) {
 }
 
 int kc_resolve(const void* records, int n_blocks, int K, int d, int max_picks, void* workspace, float* centres,
-               float* centre_norms, int64_t* selected_out, int32_t* n_picks_host, cudaStream_t stream) {
+               float* centre_norms, int64_t* selected_out, int32_t* n_picks_host, cudaStream_t stream, int32_t* state) {
   const int Kc = n_blocks * K;
   MVAL_REQUIRE(K % 4 == 0 && Kc >= 4 && Kc <= kKcMaxSlots, "kcenter resolve: k_slots %% 4 == 0 and n_blocks * k_slots <= %d required", kKcMaxSlots);
   MVAL_REQUIRE(max_picks >= 1, "kcenter resolve: max_picks must be >= 1");
@@ -844,10 +861,11 @@ int kc_resolve(const void* records, int n_blocks, int K, int d, int max_picks, v
   kc_prefix_kernel<<<(Kc + 7) / 8, 256, 0, stream>>>(val, dt, order, Kc, tau, prefix_m);
   MVAL_LAUNCH_CHECK("kc_prefix");
   kc_replay_kernel<<<1, threads, replay_smem, stream>>>(val, gidx, dt, Kc, tau, max_picks, rank, order, slot_of_rank, prefix_m,
-                                                        selected_out, pick_slots, n_picks);
+                                                        selected_out, pick_slots, n_picks, state);
   MVAL_LAUNCH_CHECK("kc_replay");
   kc_gather_centres_kernel<<<max_picks, 128, 0, stream>>>(rows, xx, pick_slots, n_picks, d, centres, centre_norms);
   MVAL_LAUNCH_CHECK("kc_gather_centres");
+  if (state != nullptr) return MVAL_OK;  // the caller reads the counters when it needs them; nothing waits here
   MVAL_CUDA(cudaMemcpyAsync(s->host_i32, n_picks, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   MVAL_CUDA(cudaStreamSynchronize(stream));
   *n_picks_host = s->host_i32[0];
@@ -1007,6 +1025,27 @@ extern "C" int mval_kcenter_resolve(const void* records, int n_blocks, int k_slo
                     n_picks_host, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int mval_kcenter_resolve_async(const void* records, int n_blocks, int k_slots, int d, void* workspace, float* centres_out,
+                                          float* centre_norms_out, int64_t* selected_out, int32_t* state, void* stream) {
+  if (int rc = require_device()) return rc;
+  MVAL_REQUIRE(n_blocks >= 1 && k_slots >= 2 && d > 0, "mval_kcenter_resolve_async: bad shape");
+  MVAL_REQUIRE(records && workspace && centres_out && centre_norms_out && selected_out && state,
+               "mval_kcenter_resolve_async: null pointer");
+  return kc_resolve(records, n_blocks, k_slots, d, n_blocks * k_slots, workspace, centres_out, centre_norms_out, selected_out,
+                    nullptr, static_cast<cudaStream_t>(stream), state);
+}
+
+extern "C" int mval_kcenter_update_batch_dev(const float* features, const float* row_norms, int64_t n, int d, const float* centres,
+                                             const float* centre_norms, int max_centres, const int32_t* n_centres, float* min_dist,
+                                             int flags, void* stream) {
+  if (int rc = require_device()) return rc;
+  MVAL_REQUIRE(n >= 0 && d > 0 && max_centres >= 0, "mval_kcenter_update_batch_dev: bad shape");
+  if (n == 0 || max_centres == 0) return MVAL_OK;
+  MVAL_REQUIRE(features && row_norms && centres && centre_norms && min_dist && n_centres, "mval_kcenter_update_batch_dev: null pointer");
+  return kc_update_batch(features, row_norms, n, d, centres, centre_norms, max_centres, min_dist, flags,
+                         static_cast<cudaStream_t>(stream), n_centres);
+}
+
 extern "C" int mval_kcenter_greedy(const float* features, int64_t n, int64_t n_unlabeled, int d, int32_t budget,
                                    float* min_dist, int64_t* out_selected, void* stream_) {
   if (int rc = require_device()) return rc;
@@ -1019,7 +1058,7 @@ extern "C" int mval_kcenter_greedy(const float* features, int64_t n, int64_t n_u
   const size_t sz_norms = kc_align256(sizeof(float) * (size_t)n);
   const size_t sz_rec = kc_align256(kc_records_bytes(K, d));
   const size_t sz_ws = kc_align256(kc_resolve_workspace_bytes(1, K, d));
-  const size_t sz_centres = kc_align256((size_t)K * d * 4);
+  const size_t sz_centres = kc_align256((size_t)K * d * 4 + 64);  // + the rounds' device counters
   const size_t sz_cn = kc_align256((size_t)K * 4);
   char* ws = nullptr;
   MVAL_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), sz_norms + sz_rec + sz_ws + sz_centres + sz_cn, stream));
@@ -1040,19 +1079,40 @@ extern "C" int mval_kcenter_greedy(const float* features, int64_t n, int64_t n_u
                                    min_dist, 0, stream))
         return rc;
     }
-    // coreset.py:86-93 in rounds
-    int32_t done = 0;
-    while (done < budget) {
-      if (int rc = kc_select(features, norms, min_dist, n, d, 0, K, rec, stream)) return rc;
-      int32_t got = 0;
-      if (int rc = kc_resolve(rec, 1, K, d, budget - done, rws, centres, cnorms, out_selected + done, &got, stream)) return rc;
-      if (got <= 0) {
-        set_error("mval_kcenter_greedy: internal error, a round produced no pick");
-        return MVAL_ERR_CUDA;
+    // coreset.py:86-93 in rounds.  The number of picks of a round is only known on the device: resolve advances the
+    // counters there and the update reads the round's count there, so no round waits for the host.  The host learns the
+    // total one round late (pinned copy + event) and stops launching when it sees the budget reached; the one round that
+    // was launched in the meantime finds budget - done = 0 and does nothing.
+    KcDeviceScratch* sc = nullptr;
+    if (int rc = kc_scratch(&sc)) return rc;
+    int32_t* state = reinterpret_cast<int32_t*>(centres + (size_t)K * d);  // behind the centre rows: 4 x int32
+    const int32_t init[4] = {0, 0, budget, 0};
+    MVAL_CUDA(cudaMemcpyAsync(state, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+    cudaEvent_t ev[2];
+    MVAL_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    MVAL_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    int rc = MVAL_OK;
+    for (int r = 0; rc == MVAL_OK && budget > 0; ++r) {
+      rc = kc_select(features, norms, min_dist, n, d, 0, K, rec, stream);
+      if (rc == MVAL_OK) rc = kc_resolve(rec, 1, K, d, K, rws, centres, cnorms, out_selected, nullptr, stream, state);
+      if (rc == MVAL_OK) rc = kc_update_batch(features, norms, n, d, centres, cnorms, K, min_dist, kKcFlagGroupChunks, stream, state + 1);
+      if (rc != MVAL_OK) break;
+      cudaError_t e = cudaMemcpyAsync(sc->host_i32 + (r & 1), state, sizeof(int32_t), cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess) e = cudaEventRecord(ev[r & 1], stream);
+      if (e == cudaSuccess && r >= 1) {
+        e = cudaEventSynchronize(ev[(r - 1) & 1]);
+        if (e == cudaSuccess && sc->host_i32[(r - 1) & 1] >= budget) break;
       }
-      if (int rc = kc_update_batch(features, norms, n, d, centres, cnorms, got, min_dist, kKcFlagGroupChunks, stream)) return rc;
-      done += got;
+      if (e != cudaSuccess) rc = cuda_fail(e, "mval_kcenter_greedy round bookkeeping");
+      if (r > 4 * (budget + 8)) {
+        set_error("mval_kcenter_greedy: internal error, the rounds make no progress");
+        rc = MVAL_ERR_CUDA;
+      }
     }
+    cudaStreamSynchronize(stream);
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (rc != MVAL_OK) return rc;
     return MVAL_OK;
   };
   const int rc = run();

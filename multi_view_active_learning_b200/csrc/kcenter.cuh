@@ -15,6 +15,18 @@ __device__ __forceinline__ float kc_dist(float dot, float xx, float cc) {
   return __fadd_rn(__fsqrt_rn(fmaxf(d2, 0.0f)), 0.0f);
 }
 
+// Number of centres of a batched update when only the DEVICE knows it (the picks of a greedy round): the kernels are launched
+// for the largest possible batch and clamp it themselves, T_effective = clamp(*ptr - off, 0, T).  ptr == nullptr: T as given.
+struct KcCount {
+  const int32_t* ptr;
+  int off;
+};
+__device__ __forceinline__ int kc_effective_T(int T, KcCount c) {
+  if (c.ptr == nullptr) return T;
+  const int r = *c.ptr - c.off;
+  return r < T ? (r < 0 ? 0 : r) : T;
+}
+
 struct KcPartial {
   float val;
   int64_t idx;
@@ -78,12 +90,15 @@ __host__ __device__ inline KcRecordView kc_record_view(char* base, int K, int d)
 // kcenter.cu
 int kc_norms(const float* X, int64_t n, int d, float* out, cudaStream_t stream);
 int kc_update_batch_exact(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T,
-                          float* min_dist, cudaStream_t stream);
+                          float* min_dist, cudaStream_t stream, KcCount cnt = KcCount{nullptr, 0});
 int kc_select(const float* X, const float* xx, const float* m, int64_t n, int d, int64_t index_offset, int K, void* records,
               cudaStream_t stream);
 size_t kc_resolve_workspace_bytes(int n_blocks, int K, int d);
+// state (device int32 [4], optional): [0] picks made so far, [1] picks of this round (out), [2] budget.  With a state the
+// round's limit is budget - done, the picks go to selected_out[done ..], the counters are advanced on the device and the
+// call does NOT synchronise (n_picks_host is not written).
 int kc_resolve(const void* records, int n_blocks, int K, int d, int max_picks, void* workspace, float* centres,
-               float* centre_norms, int64_t* selected_out, int32_t* n_picks_host, cudaStream_t stream);
+               float* centre_norms, int64_t* selected_out, int32_t* n_picks_host, cudaStream_t stream, int32_t* state = nullptr);
 
 // Dispatcher: exact FFMA pass, or (large aligned d, enough rows and centres) tensor-core screening + exact recheck.
 // flags bit 0: force the exact FFMA pass; bit 1: force the tensor-core path when it is applicable at all.
@@ -91,7 +106,7 @@ constexpr int kKcFlagForceExact = 1;
 constexpr int kKcFlagForceTc = 2;
 constexpr int kKcFlagGroupChunks = 4;  // the centres are the picks of one greedy round: screen all chunks, recheck once
 int kc_update_batch(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T, float* min_dist,
-                    int flags, cudaStream_t stream);
+                    int flags, cudaStream_t stream, const int32_t* t_dev = nullptr);
 
 // candidate pairwise matrix through the tensor-core screen (kcenter_tc.cu)
 bool kc_pairwise_tc_applicable(const float* X, int n, int d);

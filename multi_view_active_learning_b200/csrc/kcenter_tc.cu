@@ -157,7 +157,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 kc_screen_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c,
                     const float* __restrict__ xx, const float* __restrict__ cc, const float* __restrict__ min_dist, int64_t n,
                     int d, int T, float alpha, int batch_min, TcPair* __restrict__ pairs, unsigned int* __restrict__ pair_count,
-                    unsigned int pair_capacity, uint32_t t_base) {
+                    unsigned int pair_capacity, uint32_t t_base, KcCount cnt) {
+  T = kc_effective_T(T, cnt);
+  if (T <= 0) return;  // (device-side batch size: this chunk holds no centre; every thread of every CTA leaves)
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* hcc = reinterpret_cast<float*>(smem + kTcStages * kTcStageBytes);  // |c_t|^2 / 2, +inf for t >= T
@@ -379,7 +381,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 kc_screen_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_c_half,
                      const float* __restrict__ xx, const float* __restrict__ cc, const float* __restrict__ min_dist, int64_t n,
                      int d, int T, float alpha, int batch_min, TcPair* __restrict__ pairs, unsigned int* __restrict__ pair_count,
-                     unsigned int pair_capacity, uint32_t t_base) {
+                     unsigned int pair_capacity, uint32_t t_base, KcCount cnt) {
+  T = kc_effective_T(T, cnt);
+  if (T <= 0) return;  // (device-side batch size: this chunk holds no centre; every thread of every CTA leaves)
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* hcc = reinterpret_cast<float*>(smem + kTc2Stages * kTc2StageBytes);  // |c_t|^2 / 2, +inf for t >= T
@@ -645,7 +649,8 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int d, int box_r
 
 // ffma fallback that only runs when the pair list overflowed (kcenter.cu)
 int kc_update_batch_exact_if(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T,
-                             float* min_dist, const unsigned int* count, unsigned int capacity, cudaStream_t stream);
+                             float* min_dist, const unsigned int* count, unsigned int capacity, cudaStream_t stream,
+                             KcCount cnt = KcCount{nullptr, 0});
 
 bool kc_tc_applicable(const float* X, int64_t n, int d, const float* C, int T) {
   return d % 4 == 0 && d >= 64 && n >= 128 && T >= 2 && T <= kTcBlockN && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
@@ -681,7 +686,8 @@ static bool tc_use_pairs(int64_t n) {
 // t_base is added to the centre index of every appended pair; reset = false appends to the list of the previous screen (several
 // 256-centre chunks then share ONE recheck launch, whose duration is a latency, not a throughput)
 static int tc_screen(KcDeviceScratch* s, const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T,
-                     const float* min_dist, int batch_min, cudaStream_t stream, uint32_t t_base = 0, bool reset = true) {
+                     const float* min_dist, int batch_min, cudaStream_t stream, uint32_t t_base = 0, bool reset = true,
+                     KcCount cnt = KcCount{nullptr, 0}) {
   CUtensorMap map_x, map_c;
   if (int rc = make_map(&map_x, X, n, d, kTcBlockM)) return rc;
   if (reset) {
@@ -718,7 +724,7 @@ static int tc_screen(KcDeviceScratch* s, const float* X, const float* xx, int64_
     const int grid = 2 * (int)(n_pairs < max_clusters ? n_pairs : max_clusters);
     kc_screen_tc2_kernel<<<grid, kTcThreads, kTc2SmemBytes, stream>>>(map_x, map_c, xx, cc, min_dist, n, d, T, alpha2, batch_min,
                                                                      static_cast<TcPair*>(s->tc_pairs), s->tc_count,
-                                                                     (unsigned int)s->tc_pairs_capacity, t_base);
+                                                                     (unsigned int)s->tc_pairs_capacity, t_base, cnt);
     MVAL_LAUNCH_CHECK("kc_screen_tc2");
     return MVAL_OK;
   }
@@ -728,7 +734,7 @@ static int tc_screen(KcDeviceScratch* s, const float* X, const float* xx, int64_
   const float alpha = ldexpf(1.0f, -8) + (float)d * ldexpf(1.0f, -20);
   kc_screen_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(map_x, map_c, xx, cc, min_dist, n, d, T, alpha, batch_min,
                                                                   static_cast<TcPair*>(s->tc_pairs), s->tc_count,
-                                                                  (unsigned int)s->tc_pairs_capacity, t_base);
+                                                                  (unsigned int)s->tc_pairs_capacity, t_base, cnt);
   MVAL_LAUNCH_CHECK("kc_screen_tc");
   return MVAL_OK;
 }
@@ -761,13 +767,15 @@ int kc_pairwise_tc(const float* X, const float* xx, const float* val, int n, int
 // T centres (any number) through the tensor-core screen in chunks of 256: every chunk appends its survivors (absolute centre
 // index) to one list, then ONE recheck launch and one gated FFMA fallback per chunk (it only runs if the list overflowed).
 int kc_update_batch_tc(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T, float* min_dist,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const int32_t* t_dev = nullptr, int t_dev_off = 0) {
   KcDeviceScratch* s = nullptr;
   const int n_chunks = (T + kTcBlockN - 1) / kTcBlockN;
   if (int rc = tc_prepare(&s, (size_t)n * 4 * (size_t)n_chunks)) return rc;
   for (int t0 = 0; t0 < T; t0 += kTcBlockN) {
     const int tn = (T - t0) < kTcBlockN ? (T - t0) : kTcBlockN;
-    if (int rc = tc_screen(s, X, xx, n, d, C + (int64_t)t0 * d, cc + t0, tn, min_dist, 1, stream, (uint32_t)t0, t0 == 0)) return rc;
+    if (int rc = tc_screen(s, X, xx, n, d, C + (int64_t)t0 * d, cc + t0, tn, min_dist, 1, stream, (uint32_t)t0, t0 == 0,
+                           KcCount{t_dev, t_dev_off + t0}))
+      return rc;
   }
   const unsigned int cap = (unsigned int)s->tc_pairs_capacity;
   kc_recheck_kernel<false><<<num_sms() * 3, kRcWarps * 32, kRcSmemBytes, stream>>>(X, xx, d, C, cc, static_cast<const TcPair*>(s->tc_pairs),
@@ -775,7 +783,9 @@ int kc_update_batch_tc(const float* X, const float* xx, int64_t n, int d, const 
   MVAL_LAUNCH_CHECK("kc_recheck");
   for (int t0 = 0; t0 < T; t0 += kTcBlockN) {
     const int tn = (T - t0) < kTcBlockN ? (T - t0) : kTcBlockN;
-    if (int rc = kc_update_batch_exact_if(X, xx, n, d, C + (int64_t)t0 * d, cc + t0, tn, min_dist, s->tc_count, cap, stream)) return rc;
+    if (int rc = kc_update_batch_exact_if(X, xx, n, d, C + (int64_t)t0 * d, cc + t0, tn, min_dist, s->tc_count, cap, stream,
+                                          KcCount{t_dev, t_dev_off + t0}))
+      return rc;
   }
   return MVAL_OK;
 }
@@ -794,7 +804,7 @@ int kc_tc_last_stats(uint64_t* survivors, uint64_t* capacity, cudaStream_t strea
 }
 
 int kc_update_batch(const float* X, const float* xx, int64_t n, int d, const float* C, const float* cc, int T, float* min_dist,
-                    int flags, cudaStream_t stream) {
+                    int flags, cudaStream_t stream, const int32_t* t_dev) {
   if (n == 0 || T == 0) return MVAL_OK;
   const bool force_exact = (flags & kKcFlagForceExact) != 0;
   const bool force_tc = (flags & kKcFlagForceTc) != 0;
@@ -808,15 +818,15 @@ int kc_update_batch(const float* X, const float* xx, int64_t n, int d, const flo
   int t0 = 0;
   const int full = (flags & kKcFlagGroupChunks) ? (T / kTcBlockN) * kTcBlockN : 0;
   if (full > 0 && eligible(C, kTcBlockN)) {
-    if (int rc = kc_update_batch_tc(X, xx, n, d, C, cc, full, min_dist, stream)) return rc;
+    if (int rc = kc_update_batch_tc(X, xx, n, d, C, cc, full, min_dist, stream, t_dev, 0)) return rc;
     t0 = full;
   }
   for (; t0 < T; t0 += kTcBlockN) {
     const int tn = (T - t0) < kTcBlockN ? (T - t0) : kTcBlockN;
     const float* Cb = C + (int64_t)t0 * d;
     int rc;
-    if (eligible(Cb, tn)) rc = kc_update_batch_tc(X, xx, n, d, Cb, cc + t0, tn, min_dist, stream);
-    else rc = kc_update_batch_exact(X, xx, n, d, Cb, cc + t0, tn, min_dist, stream);
+    if (eligible(Cb, tn)) rc = kc_update_batch_tc(X, xx, n, d, Cb, cc + t0, tn, min_dist, stream, t_dev, t0);
+    else rc = kc_update_batch_exact(X, xx, n, d, Cb, cc + t0, tn, min_dist, stream, KcCount{t_dev, t0});
     if (rc) return rc;
   }
   return MVAL_OK;

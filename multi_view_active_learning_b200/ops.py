@@ -577,3 +577,26 @@ class KcenterResolver:
                                                    _ptr(selected_out), C.byref(self._n), _stream()))
         t = int(self._n.value)
         return t, self.centres[:t], self.centre_norms[:t]
+
+    def resolve_async(self, records, selected_out, state):
+        """The same round without the host in the loop (mval_kcenter_resolve_async): ``state`` int32 CUDA [4] = {picks so
+        far, picks of this round, budget, -}; the picks go to selected_out[state[0] ..], nothing is synchronised.  Fold them
+        in with kcenter_update_batch_dev(..., self.centres, self.centre_norms, state[1:2], ...)."""
+        with torch.cuda.device(records.device):
+            check(_lib.load().mval_kcenter_resolve_async(_ptr(records), self.n_blocks, self.k_slots, self.d, _ptr(self.workspace),
+                                                         _ptr(self.centres), _ptr(self.centre_norms), _ptr(selected_out),
+                                                         _ptr(state), _stream()))
+
+
+def kcenter_update_batch_dev(features, norms, centres, centre_norms, n_centres, min_dist, flags=0):
+    """kcenter_update_batch for a batch whose size only the device knows: the first ``n_centres[0]`` (int32 CUDA [1]) of the
+    rows of ``centres`` are folded into min_dist (include/mval_b200.h: mval_kcenter_update_batch_dev)."""
+    f = _cuda(features, torch.float32, "features")
+    n, d = f.shape
+    c = _cuda(centres, torch.float32, "centres").reshape(-1, d)
+    cn = _cuda(centre_norms, torch.float32, "centre_norms").reshape(-1)
+    assert cn.numel() == c.shape[0] and min_dist.dtype == torch.float32 and min_dist.is_contiguous() and min_dist.numel() == n
+    assert n_centres.dtype == torch.int32 and n_centres.is_cuda
+    with torch.cuda.device(f.device):
+        check(_lib.load().mval_kcenter_update_batch_dev(_ptr(f), _ptr(norms), n, d, _ptr(c), _ptr(cn), c.shape[0], _ptr(n_centres),
+                                                        _ptr(min_dist), int(flags), _stream()))

@@ -111,8 +111,9 @@ def kcenter_rounds(state, budget, group=None, k_slots=None, flags=0, stats=None)
     into its own shards.  Returns the selected global indices (int64 CUDA [budget])."""
     from . import ops
 
-    dev = state[0]["feat"].device
-    d = state[0]["feat"].shape[1]
+    state_list = state
+    dev = state_list[0]["feat"].device
+    d = state_list[0]["feat"].shape[1]
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     world = dist.get_world_size(group) if multi else 1
     n_local = len(state)
@@ -126,19 +127,39 @@ def kcenter_rounds(state, budget, group=None, k_slots=None, flags=0, stats=None)
     gathered = torch.empty(world * n_local * rb, dtype=torch.uint8, device=dev) if multi else local
     resolver = ops.KcenterResolver(n_blocks, k_slots, d, dev)
     selected = torch.empty(max(int(budget), 1), dtype=torch.int64, device=dev)
-    done = 0
-    while done < budget:
-        for i, s in enumerate(state):
+    if int(budget) <= 0:
+        return selected[:0]
+    # The number of picks of a round is only known on the device (the replay decides it): resolve_async advances the
+    # counters there and update_batch_dev reads the round's count there, so no round waits for the host.  The host learns
+    # the running total one round late (pinned copy + event) and stops launching when it sees the budget reached; the round
+    # launched in the meantime finds budget - done = 0 and does nothing.  Every rank sees the same totals (the replay is
+    # replicated), so all ranks launch the same number of rounds -- and of all_gathers.
+    state = torch.tensor([0, 0, int(budget), 0], dtype=torch.int32, device=dev)
+    done_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+    events = [torch.cuda.Event(), torch.cuda.Event()]
+    picks_log = []
+    r = 0
+    while True:
+        for i, s in enumerate(state_list):
             ops.kcenter_select(s["feat"], s["norms"], s["min"], s["off"], k_slots, out=local[i * rb:(i + 1) * rb])
         if multi:
             dist.all_gather_into_tensor(gathered, local, group=group)
-        t, centres, cnorms = resolver.resolve(gathered, budget - done, selected[done:])
-        assert t >= 1
-        for s in state:
-            ops.kcenter_update_batch(s["feat"], s["norms"], centres, cnorms, s["min"], flags | 4)  # 4: one recheck per round
-        done += t
+        resolver.resolve_async(gathered, selected, state)
+        for s in state_list:
+            ops.kcenter_update_batch_dev(s["feat"], s["norms"], resolver.centres, resolver.centre_norms, state[1:2], s["min"],
+                                         flags | 4)  # 4: the picks of a round share one recheck
         if stats is not None:
-            stats.append(t)
+            picks_log.append(state[1:2].clone())
+        done_host[r & 1:(r & 1) + 1].copy_(state[0:1], non_blocking=True)
+        events[r & 1].record()
+        if r >= 1:
+            events[(r - 1) & 1].synchronize()
+            if int(done_host[(r - 1) & 1]) >= int(budget):
+                break
+        r += 1
+        assert r <= 4 * (int(budget) + 8), "kcenter rounds make no progress"
+    if stats is not None:
+        stats.extend(t for t in torch.cat(picks_log).cpu().tolist() if t > 0)
     return selected[: int(budget)]
 
 
