@@ -99,13 +99,18 @@ class PoolTable:
         return r
 
     def rows_of(self, guids, missing_ok=False):
+        """Rows of the given guids, in their order.  Guids this table formatted itself (guid_at: the selections) come out of
+        a dict; only foreign ones (e.g. pseudo labels of earlier iterations) need the sorted index -- one vectorised search
+        for all of them."""
         guids = list(guids)
-        if len(guids) > 256:  # e.g. the accumulated pseudo_label_guids: one vectorised search instead of one per guid
-            if self._index is None:
+        rows = [self._known.get(g) for g in guids]
+        unknown = [i for i, r in enumerate(rows) if r is None]
+        if unknown:
+            if len(unknown) > 64 and self._index is None:
                 self._build_index()
-            if not isinstance(self._index, dict):
+            if len(unknown) > 64 and not isinstance(self._index, dict):
                 try:
-                    parsed = np.array([self._parse(g) for g in guids], dtype=np.int64).reshape(-1, 2)
+                    parsed = np.array([self._parse(guids[i]) for i in unknown], dtype=np.int64).reshape(-1, 2)
                 except (ValueError, AttributeError):
                     parsed = None
                 if parsed is not None and (parsed >= 0).all() and (parsed[:, 0] < 1 << 31).all() and (parsed[:, 1] < 1 << 32).all():
@@ -113,17 +118,21 @@ class PoolTable:
                     k = (parsed[:, 0] << 32) | parsed[:, 1]
                     pos = np.minimum(np.searchsorted(keys, k), max(len(keys) - 1, 0))
                     hit = (keys[pos] == k) if len(keys) else np.zeros(len(k), dtype=bool)
-                    if not hit.all() and not missing_ok:
-                        raise KeyError(guids[int(np.nonzero(~hit)[0][0])])
-                    return order[pos[hit]].tolist()
-        rows = []
-        for g in guids:
-            try:
-                rows.append(self.row_of(g))
-            except KeyError:
-                if not missing_ok:
-                    raise
-        return rows
+                    found = order[pos]
+                    for n_, i in enumerate(unknown):
+                        if hit[n_]:
+                            rows[i] = int(found[n_])
+                    unknown = [i for n_, i in enumerate(unknown) if not hit[n_]]
+                    if unknown and not missing_ok:
+                        raise KeyError(guids[unknown[0]])
+                    unknown = []
+            for i in unknown:
+                try:
+                    rows[i] = self.row_of(guids[i])
+                except KeyError:
+                    if not missing_ok:
+                        raise
+        return [r for r in rows if r is not None]
 
     # ---- values ----------------------------------------------------------------------------------------------------
     def host(self, name):
