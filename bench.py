@@ -318,10 +318,14 @@ def run_ours(args):
     fused_ms = float(np.mean([a.elapsed_time(b) for a, b in k_events]))  # the dominant kernel, live, inside the timed region
     sel = [sel_host.tolist()]
     clocks = sampler.stop() if rank == 0 else None
+    per_rank_fused_ms = [fused_ms]
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
+        g = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(g, torch.tensor([fused_ms], dtype=torch.float64, device=dev))
+        per_rank_fused_ms = g.cpu().tolist()
     ms_per_step = elapsed_ms / args.steps
     value = pool_frames * n_gpus / (ms_per_step * 1e-3)
 
@@ -371,6 +375,10 @@ def run_ours(args):
         "algorithmic_bytes_per_frame": FRAME_ALGO_BYTES, "frames_per_launch": pool_frames, "avg_launch_ms": fused_ms,
         "launch_timing": "CUDA events around the launch in every timed step (mean of %d)" % args.steps,
         "share_of_step": fused_ms / ms_per_step,
+        # every rank scores the same number of frames; under the power cap the GPUs of a box settle at different clocks and
+        # the step (max over ranks, coupled by the ranking exchange) follows the slowest one
+        "per_rank_avg_launch_ms": [round(x, 3) for x in per_rank_fused_ms],
+        "share_of_step_slowest_rank": max(per_rank_fused_ms) / ms_per_step,
         "other_kernels": {
             "decode_argmax_kernel": {"achieved": dec_gbs, "frac": dec_gbs / hbm_peak, "avg_launch_ms": dec_ms,
                                      "algorithmic_bytes_per_launch": R * FRAME_HEATMAP_BYTES},
@@ -1062,10 +1070,11 @@ def run_api(args):
     P_res = torch.from_numpy(host_pool["P"]).to(dev)
     ctx = {"world": world, "rank": rank, "dev": dev}
     n_local = args.pool_frames
+    variants = [tuple(v.split("/")) for v in args.api_variants.split(",")] if args.api_variants else None
     rec = api_selection(ctx, hm, P_res, n_local, args.api_batch, args.coreset_budget, args.coreset_labeled, args.api_pseudo,
-                        args.steps)
+                        args.steps, variants)
     if rank == 0:
-        head = rec["CORESET/AL"]
+        head = rec.get("CORESET/AL") or next(iter(rec.values()))
         print(json.dumps({
             "metric": "selection through sample_next_batch: pool frames scored + selected / sec", "value": head["value"],
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "ms_per_step": head["ms_per_call"], "higher_is_better": True,
@@ -1220,6 +1229,8 @@ def main():
     ap.add_argument("--workload", default="scoring", choices=["scoring", "coreset", "scores", "hybrid", "backbone", "api"])
     ap.add_argument("--api-batch", type=int, default=8192, help="api workload: frames per loader batch")
     ap.add_argument("--api-pseudo", type=int, default=1000, help="api workload: sal_num_frames of the SAL variant")
+    ap.add_argument("--api-variants", default="", help="api workload: comma list of STRATEGY/EXPR_TYPE (default: TRIANGULATION/AL,"
+                    "CORESET/AL,TRIANGULATION/SAL), e.g. HP/AL,MPE/AL,BSB/AL")
     ap.add_argument("--coreset-rows", type=int, default=1_000_000)
     ap.add_argument("--coreset-dim", type=int, default=2048)
     ap.add_argument("--coreset-labeled", type=int, default=None, help="labeled centres (coreset: 64; api / hybrid: 1000)")
