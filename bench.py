@@ -297,11 +297,13 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step()
-    barrier()
     ops.check_async()
+    # the clock sampler (NVML initialisation, tens of ms) starts BEFORE the barrier: started after it, on rank 0 only, it
+    # delayed rank 0's first step and every other rank waited for it in the ranking exchange inside its own timed region
     sampler = ClockSampler(local_rank)
     if rank == 0 and not args.no_clocks:
         sampler.start()
+    barrier()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -1128,7 +1130,7 @@ def run_scores(args):
     # the fused pass with the AL score of the same maps evaluated by its decode warps (one read of the pool instead of
     # two: compare with the sum of the fused line and the map_stream line of that score)
     for kind in ("HP", "MPE", "BSB"):
-        kernels["score_pool_fused_kernel<%s> (a1+a4..a8)" % kind] = (
+        kernels["mval_score_pool_scored<%s> (a1+a4..a8: fused launch for HP; stream kernel + RANSAC launches for MPE / BSB)" % kind] = (
             lambda kind=kind: ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False, map_score=kind))
     # arg-max flavour A/B (csrc/fused.cu: launch_score_pool_fused): the non-default flavour of each variant
     def flavoured(value, kind):
@@ -1140,6 +1142,19 @@ def run_scores(args):
                 del os.environ["MVAL_ROW_ARGMAX"]
         return run
 
+    def unsplit(kind):
+        def run():
+            os.environ["MVAL_SCORED_SPLIT"] = "0"
+            try:
+                return ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False, map_score=kind)
+            finally:
+                del os.environ["MVAL_SCORED_SPLIT"]
+        return run
+
+    # MPE / BSB take the split path by default (stream kernel: score + arg-max key-point; then RANSAC from the key-points);
+    # the lines above are that path, these two are the single fused launch of round 1f
+    kernels["score_pool_fused_kernel<MPE> in ONE launch (MVAL_SCORED_SPLIT=0)"] = unsplit("MPE")
+    kernels["score_pool_fused_kernel<BSB> in ONE launch (MVAL_SCORED_SPLIT=0)"] = unsplit("BSB")
     kernels["score_pool_fused_kernel, lane=row arg-max (MVAL_ROW_ARGMAX=1)"] = flavoured("1", None)
     kernels["score_pool_fused_kernel<MPE>, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = flavoured("0", "MPE")
     kernels["score_pool_fused_kernel<BSB>, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = flavoured("0", "BSB")

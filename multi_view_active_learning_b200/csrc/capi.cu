@@ -87,6 +87,18 @@ int launch_score_pool_fused_segments(const float* const* seg_ptr, const int64_t*
                                      double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
                                      float* out_map_score, cudaStream_t stream);
 
+bool map_stream_applicable(const float* hm, int H, int W);
+int stream_peaks_argmax(const float* hm, int64_t n_maps, int V, int J, int mode, const uint8_t* valid, int stride, float* out,
+                        int32_t* out_xy, cudaStream_t stream);
+
+// MPE / BSB with the triangulation: one fused launch (MVAL_SCORED_SPLIT=0) or the stream kernel (score + arg-max key-point,
+// one read of the heat maps) followed by the RANSAC launches from the key-points (default since round 2, see score_pool).
+// Read on every call (A/B measurements and tests).
+static bool scored_split_enabled() {
+  const char* e = getenv("MVAL_SCORED_SPLIT");
+  return !(e != nullptr && e[0] == '0');
+}
+
 // MVAL_FUSED=0 in the environment forces the three-launch path (A/B measurements only).
 static bool fused_enabled() {
   static int cached = -1;
@@ -115,6 +127,30 @@ int score_pool(const float* heatmaps, const double* proj, const uint8_t* valid, 
                double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
                float* out_map_score, cudaStream_t stream) {
   if (n_frames == 0) return MVAL_OK;
+  if ((map_score == MVAL_MAP_SCORE_MPE || map_score == MVAL_MAP_SCORE_BSB) && scored_split_enabled() && fused_enabled() &&
+      params->pairs == nullptr && map_stream_applicable(heatmaps, H, W)) {
+    // The peak scores cost ~2 300-3 000 warp instructions per map: inside the fused kernel they share the SM with the
+    // float64 RANSAC warps and the pass is issue-bound at 0.58 / 0.48 of the copy bandwidth, while the same Op in the
+    // stream kernel alone runs at 0.95 / 0.73.  Here the heat maps are still read ONCE (score and arg-max key-point of a
+    // map come from the same staged copy); the triangulation follows from the 8-byte key-points.  Same device functions
+    // as the fused kernel, hence bit-identical results.
+    int32_t* xy = out_xy;
+    void* scratch = nullptr;
+    if (xy == nullptr) {
+      MVAL_CUDA(cudaMallocAsync(&scratch, sizeof(int32_t) * 2 * n_frames * V * J, stream));
+      xy = static_cast<int32_t*>(scratch);
+    }
+    int rc = stream_peaks_argmax(heatmaps, n_frames * V * J, V, J, map_score == MVAL_MAP_SCORE_MPE ? 0 : 1, valid, stride,
+                                 out_map_score, xy, stream);
+    if (rc == MVAL_OK)
+      rc = triangulate_ransac(xy, 0, proj, valid, n_frames, V, J, params, out_xyz, out_reproj, out_inliers, nullptr, out_metric,
+                              out_inlier_count, stream);
+    if (scratch) {
+      cudaError_t e = cudaFreeAsync(scratch, stream);
+      if (rc == MVAL_OK && e != cudaSuccess) return cuda_fail(e, "cudaFreeAsync");
+    }
+    return rc;
+  }
   if (fused_enabled()) {
     const int rc = launch_score_pool_fused(heatmaps, proj, valid, n_frames, V, J, H, W, stride, *params, map_score, out_xy,
                                            out_xyz, out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score, stream);

@@ -93,6 +93,31 @@ map_stream_kernel(const float* __restrict__ hm, int64_t n_maps, const uint8_t* _
   }
 }
 
+// The per-map Op preceded by the arg-max key-point of the same staged map (the lane = row sweep of mapops.cuh, the very
+// function the fused kernel's decode warps run): what a scoring pass needs from the heat maps WITHOUT the triangulation.
+// mval_score_pool_scored uses it for MPE / BSB when the split path is selected (capi.cu): the float64 RANSAC then runs as
+// its own launch from the key-points instead of sharing the SM with an issue-bound score.
+template <class Inner>
+struct ArgmaxPlusOp {
+  struct Args {
+    typename Inner::Args inner;
+    int2* out_xy;
+    int stride;
+  };
+  using Pre = typename Inner::Pre;
+  static constexpr bool kWritesSmem = Inner::kWritesSmem;
+  __device__ static __forceinline__ Pre prefetch(int64_t m, const Args& a) { return Inner::prefetch(m, a.inner); }
+  __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char* scratch,
+                                             const Pre& pre) {
+    uint32_t idx = 0u;
+    if (ok) idx = warp_argmax_map64(map, lane);
+    if (lane == 0)  // evaluation.py:21-26: (c % H, c / H) * stride, (0, 0) for an invalid joint
+      a.out_xy[m] = ok ? make_int2((int)(idx % (uint32_t)kMapDim) * a.stride, (int)(idx / (uint32_t)kMapDim) * a.stride) : make_int2(0, 0);
+    __syncwarp();
+    Inner::run(map, m, ok, lane, a.inner, scratch, pre);
+  }
+};
+
 bool map_stream_applicable(const float* hm, int H, int W) {
   const char* off = getenv("MVAL_NO_STREAM");  // A/B measurements and tests only; read on every call
   return !(off != nullptr && off[0] == '1') && H == kMapDim && W == kMapDim && (reinterpret_cast<uintptr_t>(hm) & 15) == 0;
@@ -123,6 +148,13 @@ int stream_peaks(const float* hm, int64_t n_maps, int V, int J, int mode, const 
                  cudaStream_t stream) {
   if (mode == 0) return launch_map_stream<PeaksOp<0>>("map_stream<MPE>", hm, n_maps, valid, V, J, {out}, stream);
   return launch_map_stream<PeaksOp<1>>("map_stream<BSB>", hm, n_maps, valid, V, J, {out}, stream);
+}
+int stream_peaks_argmax(const float* hm, int64_t n_maps, int V, int J, int mode, const uint8_t* valid, int stride, float* out,
+                        int32_t* out_xy, cudaStream_t stream) {
+  int2* xy = reinterpret_cast<int2*>(out_xy);
+  if (mode == 0)
+    return launch_map_stream<ArgmaxPlusOp<PeaksOp<0>>>("map_stream<argmax+MPE>", hm, n_maps, valid, V, J, {{out}, xy, stride}, stream);
+  return launch_map_stream<ArgmaxPlusOp<PeaksOp<1>>>("map_stream<argmax+BSB>", hm, n_maps, valid, V, J, {{out}, xy, stride}, stream);
 }
 int stream_xe(const float* hm, const double* proj, const double* xyz, int64_t n_maps, int V, int J, double inv_two_sigma2,
               double* out_map, cudaStream_t stream) {

@@ -653,9 +653,12 @@ def test_fused_scored_pass_equals_separate_passes(ops, N, V, J, vp):
     rows = _with_env("MVAL_ROW_ARGMAX", "1", lambda: ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345))
     assert torch.equal(plain["keypoints_2d"], rows["keypoints_2d"]) and torch.equal(plain["keypoints_3d"], rows["keypoints_3d"])
     assert torch.equal(plain["keypoints_2d"], ops.decode_argmax(hm, 4, valid))
-    for kind, flavour in (("HP", "1"), ("MPE", "0"), ("MPE", "1"), ("BSB", "0"), ("BSB", "1")):
-        both = _with_env("MVAL_ROW_ARGMAX", flavour, lambda: ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345,
-                                                                            map_score=kind))
+    # MPE / BSB: the fused kernel with either arg-max flavour (MVAL_SCORED_SPLIT=0) and the default split path (stream kernel
+    # with score + arg-max key-point, then RANSAC from the key-points) must all give the same bits
+    for kind, flavour, split in (("HP", "1", "1"), ("MPE", "0", "0"), ("MPE", "1", "0"), ("BSB", "0", "0"), ("BSB", "1", "0"),
+                                 ("MPE", "1", "1"), ("BSB", "1", "1")):
+        both = _with_env("MVAL_SCORED_SPLIT", split, lambda: _with_env(
+            "MVAL_ROW_ARGMAX", flavour, lambda: ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345, map_score=kind)))
         for k in ("keypoints_2d", "keypoints_3d", "inliers", "inlier_count"):
             assert torch.equal(both[k], plain[k]), (kind, k)
         for k in ("metric", "reproj_mean"):
