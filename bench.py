@@ -1130,7 +1130,7 @@ def run_scores(args):
     # the fused pass with the AL score of the same maps evaluated by its decode warps (one read of the pool instead of
     # two: compare with the sum of the fused line and the map_stream line of that score)
     for kind in ("HP", "MPE", "BSB"):
-        kernels["mval_score_pool_scored<%s> (a1+a4..a8: fused launch for HP; stream kernel + RANSAC launches for MPE / BSB)" % kind] = (
+        kernels["mval_score_pool_scored<%s> (a1+a4..a8; default path)" % kind] = (
             lambda kind=kind: ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False, map_score=kind))
     # arg-max flavour A/B (csrc/fused.cu: launch_score_pool_fused): the non-default flavour of each variant
     def flavoured(value, kind):
@@ -1142,19 +1142,20 @@ def run_scores(args):
                 del os.environ["MVAL_ROW_ARGMAX"]
         return run
 
-    def unsplit(kind):
+    def unsplit(kind, value):
         def run():
-            os.environ["MVAL_SCORED_SPLIT"] = "0"
+            os.environ["MVAL_SCORED_SPLIT"] = value
             try:
                 return ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False, map_score=kind)
             finally:
                 del os.environ["MVAL_SCORED_SPLIT"]
         return run
 
-    # MPE / BSB take the split path by default (stream kernel: score + arg-max key-point; then RANSAC from the key-points);
-    # the lines above are that path, these two are the single fused launch of round 1f
-    kernels["score_pool_fused_kernel<MPE> in ONE launch (MVAL_SCORED_SPLIT=0)"] = unsplit("MPE")
-    kernels["score_pool_fused_kernel<BSB> in ONE launch (MVAL_SCORED_SPLIT=0)"] = unsplit("BSB")
+    # the default is the faster of the two per score (MPE: fused launch, BSB: stream kernel + RANSAC launches); both forced:
+    kernels["score_pool_fused_kernel<MPE> in ONE launch (MVAL_SCORED_SPLIT=0)"] = unsplit("MPE", "0")
+    kernels["score_pool_fused_kernel<BSB> in ONE launch (MVAL_SCORED_SPLIT=0)"] = unsplit("BSB", "0")
+    kernels["map_stream<argmax+MPE> + RANSAC launches (MVAL_SCORED_SPLIT=1)"] = unsplit("MPE", "1")
+    kernels["map_stream<argmax+BSB> + RANSAC launches (MVAL_SCORED_SPLIT=1)"] = unsplit("BSB", "1")
     kernels["score_pool_fused_kernel, lane=row arg-max (MVAL_ROW_ARGMAX=1)"] = flavoured("1", None)
     kernels["score_pool_fused_kernel<MPE>, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = flavoured("0", "MPE")
     kernels["score_pool_fused_kernel<BSB>, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = flavoured("0", "BSB")

@@ -268,6 +268,18 @@ int mval_topk_merge(const double* scores, const int64_t* indices, int64_t n, int
 int mval_first_occurrence(const int64_t* pose, const int64_t* frame, int64_t n, uint8_t* out_keep, int32_t* out_src,
                           int32_t* out_unique, void* stream);
 
+/* Replaces the frame aggregation of strategy.py:1151-1158 (_compute_mpe), :1188-1193 (_compute_hp) and :1210-1215
+ * (_compute_bsb) for a whole pool: the frame score from the per-map scores over (view, valid joint), view-major, with the
+ * reference's own arithmetic -- HP: Python floats (AVG = builtin sum() / len in double, Neumaier-compensated iff
+ * compensated_sum != 0, i.e. iff the interpreter is Python >= 3.12; STD = np.std in float64); MPE / BSB: np.float32 scalars
+ * (AVG = sequential float32 adds / len; STD = np.std in float32); np.std with NumPy's pairwise summation.  Bit-identical to
+ * the reference's expressions (the host restatement strategy._aggregate_map_scores is pinned to its golden values).
+ * per_map float32 device [n_frames][V][J] (mval_score_hp / mval_score_peaks / mval_score_pool_scored); valid uint8 device
+ * [n_frames][J] or NULL; kind MVAL_MAP_SCORE_HP / MPE / BSB; config_std 0 = AVG, 1 = STD.
+ * out float64 device [n_frames] (float32-typed results widened; NaN for a frame without a valid joint).  J <= 128. */
+int mval_aggregate_map_scores(const float* per_map, const uint8_t* valid, int64_t n_frames, int V, int J, int kind,
+                              int config_std, int compensated_sum, double* out, void* stream);
+
 /* Replaces strategy.py:957-975 (the pseudo-label candidate filter and its sort): frames with a non-NaN sal_metric,
  * inlier_count > inlier_threshold (SAL.INLIER_THRESHOLD) and excluded[i] == 0 (the caller marks frames already picked by
  * the AL step or already pseudo-labelled), in ascending sal_metric order, ties in pool order (sorted() is stable).

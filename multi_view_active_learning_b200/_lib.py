@@ -60,6 +60,7 @@ PROTOTYPES = {
     "mval_topk_desc": (C.c_int, [_p, _i64, _i64, C.c_int32, _p, _p, _p, _p]),
     "mval_topk_merge": (C.c_int, [_p, _p, _i64, C.c_int32, _p, _p, _p, _p]),
     "mval_first_occurrence": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p]),
+    "mval_aggregate_map_scores": (C.c_int, [_p, _p, _i64, _i, _i, _i, _i, _i, _p, _p]),
     "mval_sal_rank": (C.c_int, [_p, _p, _p, _i64, _f, C.c_int32, _p, _p, _p]),
     "mval_mkpe": (C.c_int, [_p, _p, _p, _i64, _i, _i, _p, _p]),
     "mval_kmeans_assign": (C.c_int, [_p, _i64, _i, _i, _p, _i, _p, _p, _p]),

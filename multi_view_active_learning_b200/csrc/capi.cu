@@ -91,12 +91,14 @@ bool map_stream_applicable(const float* hm, int H, int W);
 int stream_peaks_argmax(const float* hm, int64_t n_maps, int V, int J, int mode, const uint8_t* valid, int stride, float* out,
                         int32_t* out_xy, cudaStream_t stream);
 
-// MPE / BSB with the triangulation: one fused launch (MVAL_SCORED_SPLIT=0) or the stream kernel (score + arg-max key-point,
-// one read of the heat maps) followed by the RANSAC launches from the key-points (default since round 2, see score_pool).
-// Read on every call (A/B measurements and tests).
-static bool scored_split_enabled() {
+// MPE / BSB with the triangulation: one fused launch, or the stream kernel (score + arg-max key-point, one read of the heat
+// maps) followed by the RANSAC launches from the key-points.  Measured per 16 384 frames (profiles/r2_summary.md): MPE 9.84 ms
+// fused / 9.99 ms split, BSB 12.92 ms fused / 12.00 ms split -- so BSB takes the split path by default and MPE the fused one.
+// MVAL_SCORED_SPLIT=0 / 1 forces one of them for both (A/B measurements and tests; read on every call).
+static bool scored_split_enabled(int map_score) {
   const char* e = getenv("MVAL_SCORED_SPLIT");
-  return !(e != nullptr && e[0] == '0');
+  if (e != nullptr && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+  return map_score == MVAL_MAP_SCORE_BSB;
 }
 
 // MVAL_FUSED=0 in the environment forces the three-launch path (A/B measurements only).
@@ -127,13 +129,11 @@ int score_pool(const float* heatmaps, const double* proj, const uint8_t* valid, 
                double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
                float* out_map_score, cudaStream_t stream) {
   if (n_frames == 0) return MVAL_OK;
-  if ((map_score == MVAL_MAP_SCORE_MPE || map_score == MVAL_MAP_SCORE_BSB) && scored_split_enabled() && fused_enabled() &&
+  if ((map_score == MVAL_MAP_SCORE_MPE || map_score == MVAL_MAP_SCORE_BSB) && scored_split_enabled(map_score) && fused_enabled() &&
       params->pairs == nullptr && map_stream_applicable(heatmaps, H, W)) {
-    // The peak scores cost ~2 300-3 000 warp instructions per map: inside the fused kernel they share the SM with the
-    // float64 RANSAC warps and the pass is issue-bound at 0.58 / 0.48 of the copy bandwidth, while the same Op in the
-    // stream kernel alone runs at 0.95 / 0.73.  Here the heat maps are still read ONCE (score and arg-max key-point of a
-    // map come from the same staged copy); the triangulation follows from the 8-byte key-points.  Same device functions
-    // as the fused kernel, hence bit-identical results.
+    // The heat maps are still read ONCE (score and arg-max key-point of a map come from the same staged copy); the
+    // triangulation follows from the 8-byte key-points as its own launches instead of sharing the SM with an issue-bound
+    // score.  Same device functions as the fused kernel, hence bit-identical results.
     int32_t* xy = out_xy;
     void* scratch = nullptr;
     if (xy == nullptr) {

@@ -104,7 +104,155 @@ __global__ void __launch_bounds__(128) centre_sq_kernel(const double* __restrict
   out[c] = s;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Frame aggregation of the per-map scores with the REFERENCE'S OWN arithmetic (strategy.py:1151-1158, 1188-1193, 1210-1215),
+// one thread per frame, so that the HP / MPE / BSB frame scores -- and with them the ranking -- never visit the host:
+//   values of a frame = its per-map scores in view-major order over the VALID joints (m = V * #valid);
+//   HP   (Python floats, .item()):  AVG = builtin sum() / len in double -- since Python 3.12 sum() is Neumaier-compensated
+//        (Python/bltinmodule.c), before that a plain left-to-right sum: `compensated` says which;  STD = np.std of a float64
+//        array;
+//   MPE / BSB (np.float32 scalars): AVG = builtin sum() = one float32 add after the other, / len in float32;  STD = np.std of
+//        a float32 array (NumPy >= 2 promotion).
+// np.std = sqrt(pairwise_sum((x - pairwise_sum(x) / m)^2) / m) in the array's precision, with NumPy's pairwise summation:
+// fewer than 8 values: left to right from 0; up to 128: eight interleaved accumulators r[k] += a[i + k], combined as
+// ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7)), the tail added left to right; above 128: split at n / 2 rounded down to
+// a multiple of 8 (numpy/core/src/umath/loops_utils.h).  Every operation is an explicitly rounded add / mul / div / sqrt:
+// no fused multiply-add may sneak into (x - mean)^2 + acc.  Checked bit for bit against the host restatement
+// (strategy._aggregate_map_scores), which is itself pinned to the reference's golden values.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kAggMaxJoints = 128;
+
+template <typename T> struct Rn;
+template <> struct Rn<double> {
+  __device__ static __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  __device__ static __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  __device__ static __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  __device__ static __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  __device__ static __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+};
+template <> struct Rn<float> {
+  __device__ static __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  __device__ static __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  __device__ static __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  __device__ static __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  __device__ static __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+};
+
+// the i-th value of a frame (view-major over the valid joints), optionally as its squared deviation from `mean`
+template <typename T>
+struct FrameValues {
+  const float* maps;        // the frame's [V][J] scores
+  const int16_t* jidx;      // indices of its valid joints
+  int J, c;                 // joints per view, valid joints
+  bool squared;
+  T mean;
+  __device__ __forceinline__ T at(int i) const {
+    const int v = i / c;
+    const T x = (T)maps[v * J + jidx[i - v * c]];
+    if (!squared) return x;
+    const T d = Rn<T>::sub(x, mean);
+    return Rn<T>::mul(d, d);
+  }
+};
+
+template <typename T>
+__device__ T np_pairwise_sum(const FrameValues<T>& a, int lo, int n) {
+  if (n < 8) {
+    T res = (T)0;
+    for (int i = 0; i < n; ++i) res = Rn<T>::add(res, a.at(lo + i));
+    return res;
+  }
+  if (n <= 128) {
+    T r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = a.at(lo + k);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] = Rn<T>::add(r[k], a.at(lo + i + k));
+    }
+    T res = Rn<T>::add(Rn<T>::add(Rn<T>::add(r[0], r[1]), Rn<T>::add(r[2], r[3])),
+                       Rn<T>::add(Rn<T>::add(r[4], r[5]), Rn<T>::add(r[6], r[7])));
+    for (; i < n; ++i) res = Rn<T>::add(res, a.at(lo + i));
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return Rn<T>::add(np_pairwise_sum(a, lo, n2), np_pairwise_sum(a, lo + n2, n - n2));
+}
+
+template <typename T>
+__device__ T np_std(FrameValues<T> a, int m) {
+  a.squared = false;
+  const T mean = Rn<T>::div(np_pairwise_sum(a, 0, m), (T)m);
+  a.squared = true;
+  a.mean = mean;
+  return Rn<T>::sqrt(Rn<T>::div(np_pairwise_sum(a, 0, m), (T)m));
+}
+
+__global__ void __launch_bounds__(128)
+frame_aggregate_kernel(const float* __restrict__ per_map, const uint8_t* __restrict__ valid, int64_t n_frames, int V, int J,
+                       int kind_hp, int config_std, int compensated, double* __restrict__ out) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  int16_t jidx[kAggMaxJoints];
+  int c = 0;
+  for (int j = 0; j < J; ++j)
+    if (valid == nullptr || valid[f * J + j] != 0) jidx[c++] = (int16_t)j;
+  const int m = V * c;
+  const float* maps = per_map + f * (int64_t)V * J;
+  double res;
+  if (m == 0) {
+    res = __longlong_as_double(0x7ff8000000000000ll);  // the reference divides by len([]) / takes np.std([]) here
+  } else if (config_std) {
+    if (kind_hp) {
+      FrameValues<double> a{maps, jidx, J, c, false, 0.0};
+      res = np_std<double>(a, m);
+    } else {
+      FrameValues<float> a{maps, jidx, J, c, false, 0.0f};
+      res = (double)np_std<float>(a, m);
+    }
+  } else if (kind_hp) {
+    // builtin sum() over Python floats, then / len
+    FrameValues<double> a{maps, jidx, J, c, false, 0.0};
+    double s = 0.0, comp = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const double x = a.at(i);
+      const double nxt = __dadd_rn(s, x);
+      if (compensated) comp = __dadd_rn(comp, fabs(s) >= fabs(x) ? __dadd_rn(__dsub_rn(s, nxt), x) : __dadd_rn(__dsub_rn(x, nxt), s));
+      s = nxt;
+    }
+    if (compensated && comp != 0.0 && isfinite(comp)) s = __dadd_rn(s, comp);
+    res = __ddiv_rn(s, (double)m);
+  } else {
+    // builtin sum() over np.float32 scalars: one float32 add after the other (0 + x0 first), then / len in float32
+    FrameValues<float> a{maps, jidx, J, c, false, 0.0f};
+    float s = 0.0f;
+    for (int i = 0; i < m; ++i) s = __fadd_rn(s, a.at(i));
+    res = (double)__fdiv_rn(s, (float)m);
+  }
+  out[f] = res;
+}
+
 }  // namespace mval
+
+extern "C" int mval_aggregate_map_scores(const float* per_map, const uint8_t* valid, int64_t n_frames, int V, int J, int kind,
+                                         int config_std, int compensated_sum, double* out, void* stream) {
+  using namespace mval;
+  if (int rc = require_device()) return rc;
+  MVAL_REQUIRE(n_frames >= 0 && V > 0 && J > 0, "mval_aggregate_map_scores: bad shape");
+  MVAL_REQUIRE(kind >= MVAL_MAP_SCORE_HP && kind <= MVAL_MAP_SCORE_BSB, "mval_aggregate_map_scores: kind must be MVAL_MAP_SCORE_HP / MPE / BSB");
+  if (J > kAggMaxJoints) {
+    set_error("mval_aggregate_map_scores: J=%d exceeds %d", J, kAggMaxJoints);
+    return MVAL_ERR_UNSUPPORTED;
+  }
+  if (n_frames == 0) return MVAL_OK;
+  MVAL_REQUIRE(per_map && out, "mval_aggregate_map_scores: null pointer");
+  frame_aggregate_kernel<<<(unsigned)((n_frames + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      per_map, valid, n_frames, V, J, kind == MVAL_MAP_SCORE_HP ? 1 : 0, config_std ? 1 : 0, compensated_sum ? 1 : 0, out);
+  MVAL_LAUNCH_CHECK("frame_aggregate");
+  return MVAL_OK;
+}
 
 extern "C" int mval_kmeans_assign(const float* pred, int64_t n_frames, int J, int root, const double* centres, int k,
                                   int32_t* out_label, double* out_margin, void* stream_) {

@@ -398,6 +398,20 @@ def first_occurrence(pose, frame):
     return keep, src, unique
 
 
+def aggregate_map_scores(per_map, valid, kind, config, compensated_sum):
+    """strategy.py:1151-1158 / 1188-1193 / 1210-1215 for a pool: per_map float32 CUDA [N, V, J], valid [N, J] (anything truthy)
+    or None -> float64 CUDA [N] frame scores with the reference's arithmetic (include/mval_b200.h:
+    mval_aggregate_map_scores).  kind "HP" / "MPE" / "BSB", config "AVG" / "STD"."""
+    pm = _cuda(per_map, torch.float32, "per_map")
+    N, V, J = pm.shape
+    v = _valid_u8(valid, N, J, pm.device)
+    out = torch.empty((N,), dtype=torch.float64, device=pm.device)
+    with torch.cuda.device(pm.device):
+        check(_lib.load().mval_aggregate_map_scores(_ptr(pm), _ptr(v), N, V, J, _lib.MAP_SCORE[kind], int(config == "STD"),
+                                                    int(bool(compensated_sum)), _ptr(out), _stream()))
+    return out
+
+
 def sal_rank(sal_metric, inlier_count, excluded, inlier_threshold, k):
     """strategy.py:957-975 on the device: pool indices (int64 CUDA [m]) of the pseudo-label candidates -- non-NaN
     sal_metric, inlier_count > threshold, not excluded -- in ascending sal_metric order (ties in pool order), first k."""

@@ -311,9 +311,14 @@ class ScoringSelectionMixin:
         scores float64 CUDA [N], whether the reference's tensor is float64) -- strategy.py:1076-1090 for the whole pool."""
         cfg = self.al_cfg.AL
         config = {"HP": cfg.HP_CONFIG, "MPE": cfg.MPE_CONFIG, "BSB": cfg.BSB_CONFIG}[cfg.STRATEGY]
-        vals = self._compute_map_score_batch(cfg.STRATEGY, config, per_map, valid, per_map)
         # torch.tensor(...) of the reference: float64 only for HP's np.std of Python floats (:1081-1085)
-        return torch.from_numpy(np.asarray(vals, dtype=np.float64)).to(per_map.device), config == "STD" and cfg.STRATEGY == "HP"
+        al_is_f64 = config == "STD" and cfg.STRATEGY == "HP"
+        if per_map.is_cuda and config in ("AVG", "STD") and per_map.shape[2] <= 128:
+            # the reference's summation rules evaluated per frame on the device (mval_aggregate_map_scores): the per-map
+            # scores of a 125 k-frame shard are 76 MB that used to travel to the host for ~0.2 s of numpy
+            return ops.aggregate_map_scores(per_map, valid, cfg.STRATEGY, config, _SUM_IS_COMPENSATED), al_is_f64
+        vals = self._compute_map_score_batch(cfg.STRATEGY, config, per_map, valid, per_map)
+        return torch.from_numpy(np.asarray(vals, dtype=np.float64)).to(per_map.device), al_is_f64
 
     @staticmethod
     def _compute_map_score_batch(kind, config, heatmaps, joint_valid, per_map=None):

@@ -426,3 +426,40 @@ def test_watchdog_is_reported_and_recovers():
     again = ops.score_pool(hm, P, 4)
     ops.check_async()
     assert torch.equal(again["metric"], good["metric"]) and torch.equal(again["inlier_count"], good["inlier_count"])
+
+
+@pytest.mark.parametrize("V,J", [(8, 19), (5, 19), (20, 42), (2, 3), (31, 19)])
+def test_frame_aggregation_kernel_equals_the_reference_arithmetic(V, J):
+    """mval_aggregate_map_scores against strategy._aggregate_map_scores (the host restatement of strategy.py:1151-1158 /
+    1188-1193 / 1210-1215 that is pinned to the reference's golden values): AVG and STD of HP / MPE / BSB, bit for bit, with
+    ragged validity masks (1 .. J valid joints: fewer than 8, up to 128 and more than 128 values per frame), NaN scores and both
+    flavours of builtin sum()."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from multi_view_active_learning_b200 import ops, strategy as ST
+
+    rng = np.random.default_rng(V * 100 + J)
+    N = 700
+    per_map = (rng.random((N, V, J)) * 0.3 + 0.5).astype(np.float32)
+    per_map[rng.integers(0, N, 5), rng.integers(0, V, 5), rng.integers(0, J, 5)] = np.nan
+    valid = rng.random((N, J)) < 0.8
+    valid[:, 0] = True
+    valid[:50] = True
+    valid[50:60, 1:] = False  # a single valid joint: V values
+    dev_map, dev_valid = torch.from_numpy(per_map).cuda(), torch.from_numpy(valid.astype(np.float32)).cuda()
+    for kind in ("HP", "MPE", "BSB"):
+        for config in ("AVG", "STD"):
+            exp = np.asarray(ST._aggregate_map_scores(kind, config, per_map, valid), dtype=np.float64)
+            got = ops.aggregate_map_scores(dev_map, dev_valid, kind, config, ST._SUM_IS_COMPENSATED).cpu().numpy()
+            assert np.array_equal(np.isnan(exp), np.isnan(got)), (kind, config)
+            ok = ~np.isnan(exp)
+            assert np.array_equal(exp[ok], got[ok]), (kind, config, np.abs(exp[ok] - got[ok]).max())
+    # the plain left-to-right sum of Python < 3.12
+    plain = ops.aggregate_map_scores(dev_map, dev_valid, "HP", "AVG", False).cpu().numpy()
+    x = np.where(valid[:, None, :], per_map, 0.0).astype(np.float64)
+    for f in (0, 55, 300):
+        s = 0.0
+        for v in x[f][np.broadcast_to(valid[f][None, :], (V, J))].tolist():
+            s += v
+        m = V * int(valid[f].sum())
+        assert plain[f] == s / m or (np.isnan(plain[f]) and np.isnan(s))
