@@ -220,3 +220,32 @@ def test_zero_padding_leaves_the_canonical_coreset_arithmetic_unchanged():
     sel_p, mins_p = C.kcenter_greedy_f32(Fp, 560, 30)
     assert sel == sel_p and np.array_equal(mins, mins_p)
     assert np.array_equal(C.canonical_dot_f32(F), C.canonical_dot_f32(Fp))
+
+
+def test_coreset_float32_contract_against_float64_on_near_ties():
+    """The contract of the coreset arithmetic (north star: "bit-exact when distances are computed in fp32 with the reference's
+    tie-break order"): on pools without near-ties the float32 canonical selection equals the
+    reference's float64 selection; when two candidates' distances differ by less than float32 can resolve, float32 sees a
+    tie and takes the LOWER index (np.argmax's rule on equal values), float64 the farther one."""
+    from oracle import coreset_oracle as CO
+
+    rng = np.random.default_rng(23)
+    # (1) generic pools: identical selections
+    for n, L, d in ((300, 10, 57), (200, 5, 126)):
+        F = rng.normal(size=(n + L, d)) * 300
+        a, _ = CO.kcenter_greedy_f32(F, n, 25)
+        b, _ = CO.kcenter_greedy_f64(F, n, 25)
+        assert a == b
+    # (2) an adversarial near-tie: rows 0 and 1 at distances r and r * (1 + 1e-9) from the single labeled centre
+    d = 57
+    u = rng.normal(size=d)
+    u /= np.linalg.norm(u)
+    w = rng.normal(size=d)
+    w -= w.dot(u) * u
+    w /= np.linalg.norm(w)
+    centre = np.zeros(d)
+    F = np.stack([1000.0 * u, 1000.0 * (1 + 1e-9) * w, 10.0 * u, centre])
+    pick64, _ = CO.kcenter_greedy_f64(F, 3, 1)
+    pick32, _ = CO.kcenter_greedy_f32(F, 3, 1)
+    assert pick64 == [1]  # the farther row, by 1e-6 units
+    assert pick32 == [0]  # float32 cannot tell them apart: first index wins
