@@ -370,14 +370,13 @@ struct PeaksOp {
       __syncwarp();
     }
     const int rbase = half * 30;
-    float h[4][5], xs[4][5];
+    float h[4][5], xs[4][3];
     uint32_t bits[4] = {0u, 0u, 0u, 0u};
-    // One step of the scan: row rbase + t enters the rings (slot t % 5 of the horizontal 5-maxima and of the raw values); from
-    // t = 4 on, row rbase + t - 2 has its five window rows in the ring and its four columns are tested.  The ring slots must
-    // be compile-time (registers), so the 34 steps run as 6 x 5 rolled + 4: the body exists 9 times instead of 34 (round 2:
-    // the scored kernels' hot code exceeded the 32 KB L1.5 instruction cache; the raw-value ring has 5 slots instead of the
-    // 3 it needs so that 5 divides the unrolled period).
-    auto scan_step = [&](const int t, const int s5, const int c5) {
+    // One step of the scan: row rbase + t enters the rings (slot t % 5 of the horizontal 5-maxima, slot t % 3 of the raw
+    // values); from t = 4 on, row rbase + t - 2 has its five window rows in the ring and its four columns are tested.
+    // The ring slots must be compile-time (registers), so the 34 steps run as 2 x 15 rolled + 4: the body exists 19 times
+    // instead of 34 (round 2: the scored fused kernels were 142 KB of SASS and stalled on instruction fetch).
+    auto scan_step = [&](const int t, const int s5, const int s3, const int c3) {
       const float4 x = p4[(rbase + t) * 16 + l16];
       const float m01 = fmaxf(x.x, x.y), m23 = fmaxf(x.z, x.w);
       if (kMode == 0) {
@@ -392,23 +391,23 @@ struct PeaksOp {
       h[1][s5] = max3(Lc3, m01, m23);
       h[2][s5] = max3(m01, m23, Rc0);
       h[3][s5] = max3(x.y, m23, Rm);
-      xs[0][s5] = x.x; xs[1][s5] = x.y; xs[2][s5] = x.z; xs[3][s5] = x.w;
+      xs[0][s3] = x.x; xs[1][s3] = x.y; xs[2][s3] = x.z; xs[3][s3] = x.w;
       if (t >= 4) {
         const uint32_t bit = 1u << (t - 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float w = max3(max3(h[k][0], h[k][1], h[k][2]), h[k][3], h[k][4]);
-          if (xs[k][c5] == w) bits[k] |= bit;
+          if (xs[k][c3] == w) bits[k] |= bit;
         }
       }
     };
 #pragma unroll 1
-    for (int tb = 0; tb < 30; tb += 5) {
+    for (int tb = 0; tb < 30; tb += 15) {
 #pragma unroll
-      for (int u = 0; u < 5; ++u) scan_step(tb + u, u, (u + 3) % 5);  // (t - 2) % 5 with t = tb + u, 5 | tb
+      for (int u = 0; u < 15; ++u) scan_step(tb + u, u % 5, u % 3, (u + 13) % 3);  // (t - 2) % 3 with t = tb + u, 15 | tb
     }
 #pragma unroll
-    for (int t = 30; t < 34; ++t) scan_step(t, t % 5, (t - 2) % 5);
+    for (int t = 30; t < 34; ++t) scan_step(t, t % 5, t % 3, (t - 2) % 3);
     if (l16 == 0) bits[0] = bits[1] = 0u;   // columns 0, 1
     if (l16 == 15) bits[2] = bits[3] = 0u;  // columns 62, 63
     gmin = warp_min_f(gmin);

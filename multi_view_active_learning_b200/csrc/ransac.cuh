@@ -65,28 +65,22 @@ __device__ __forceinline__ void jacobi_rotate(double (&m)[4][4], double (&v)[4][
   }
 }
 
-// The cyclic Jacobi sweeps on a symmetric 4 x 4 matrix (upper triangle in ms[10], row-major: 00 01 02 03 11 12 13 22 23 33)
-// with the accumulated rotations in vs[16] (row-major), as ONE out-of-line function: inlined into the vote loop and into the
-// final solve it was ~10 KB of SASS twice, and the fused kernels stall on instruction fetch (their hot code exceeded the
-// 32 KB L1.5 instruction cache; round 2).  The arrays travel through local memory once per call (~100 loads / stores against
-// ~2 500 instructions of sweeps).  warp_uniform: all 32 lanes call this together and leave the sweep loop together.
-static __device__ __noinline__ void jacobi_sweeps(double* __restrict__ ms, double* __restrict__ vs, int warp_uniform) {
-  double m[4][4], v[4][4];
-  m[0][0] = ms[0]; m[0][1] = ms[1]; m[0][2] = ms[2]; m[0][3] = ms[3];
-  m[1][1] = ms[4]; m[1][2] = ms[5]; m[1][3] = ms[6];
-  m[2][2] = ms[7]; m[2][3] = ms[8];
-  m[3][3] = ms[9];
+// Eigenvector of the smallest eigenvalue of the symmetric PSD matrix m (upper triangle), de-homogenised like
+// utils/triangulation.py:387-399 (a 4th component of exactly 0 is replaced by 1).  kWarpUniform: all 32 lanes
+// call this together and leave the sweep loop together.
+template <bool kWarpUniform>
+__device__ __forceinline__ void smallest_eigvec_dehom(double (&m)[4][4], double& X, double& Y, double& Z) {
+  double v[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
-#pragma unroll 1
   for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
     const double off = m[0][1] * m[0][1] + m[0][2] * m[0][2] + m[0][3] * m[0][3] + m[1][2] * m[1][2] +
                        m[1][3] * m[1][3] + m[2][3] * m[2][3];
     const double dg = m[0][0] * m[0][0] + m[1][1] * m[1][1] + m[2][2] * m[2][2] + m[3][3] * m[3][3];
     const bool done = !(off > 1e-34 * dg);
-    if (warp_uniform ? __all_sync(kFull, done) : done) break;
+    if (kWarpUniform ? __all_sync(kFull, done) : done) break;
     jacobi_rotate<0, 1>(m, v);
     jacobi_rotate<0, 2>(m, v);
     jacobi_rotate<0, 3>(m, v);
@@ -94,32 +88,13 @@ static __device__ __noinline__ void jacobi_sweeps(double* __restrict__ ms, doubl
     jacobi_rotate<1, 3>(m, v);
     jacobi_rotate<2, 3>(m, v);
   }
-  ms[0] = m[0][0]; ms[4] = m[1][1]; ms[7] = m[2][2]; ms[9] = m[3][3];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) vs[i * 4 + j] = v[i][j];
-}
-
-// Eigenvector of the smallest eigenvalue of the symmetric PSD matrix m (upper triangle), de-homogenised like
-// utils/triangulation.py:387-399 (a 4th component of exactly 0 is replaced by 1).  kWarpUniform: all 32 lanes
-// call this together and leave the sweep loop together.
-template <bool kWarpUniform>
-__device__ __forceinline__ void smallest_eigvec_dehom(double (&m)[4][4], double& X, double& Y, double& Z) {
-  double ms[10], vs[16];
-  ms[0] = m[0][0]; ms[1] = m[0][1]; ms[2] = m[0][2]; ms[3] = m[0][3];
-  ms[4] = m[1][1]; ms[5] = m[1][2]; ms[6] = m[1][3];
-  ms[7] = m[2][2]; ms[8] = m[2][3];
-  ms[9] = m[3][3];
-  jacobi_sweeps(ms, vs, kWarpUniform ? 1 : 0);
-  const double dgl[4] = {ms[0], ms[4], ms[7], ms[9]};
-  double best = dgl[0];
-  double e0 = vs[0], e1 = vs[4], e2 = vs[8], e3 = vs[12];
+  double best = m[0][0];
+  double e0 = v[0][0], e1 = v[1][0], e2 = v[2][0], e3 = v[3][0];
 #pragma unroll
   for (int k = 1; k < 4; ++k) {
-    if (dgl[k] < best) {
-      best = dgl[k];
-      e0 = vs[k]; e1 = vs[4 + k]; e2 = vs[8 + k]; e3 = vs[12 + k];
+    if (m[k][k] < best) {
+      best = m[k][k];
+      e0 = v[0][k]; e1 = v[1][k]; e2 = v[2][k]; e3 = v[3][k];
     }
   }
   const double w = (e3 == 0.0) ? 1.0 : e3;
@@ -223,7 +198,6 @@ __device__ __forceinline__ void ransac_final_thread(const double* __restrict__ P
   }
   smallest_eigvec_dehom<false>(m, X, Y, Z);
   double sum = 0.0;
-#pragma unroll 1
   for (int v = 0; v < V; ++v) {
     if (mask >> v & 1u) {
       const double* Pv = P + v * 12;
