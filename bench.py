@@ -576,7 +576,7 @@ def extra_records(ctx, args, hm, P_res, hbm_peak, peak_src, time_ms):
 
     world, rank = ctx["world"], ctx["rank"]
     extra = {}
-    api = api_selection(ctx, hm, P_res, args.extra_api_frames, 8192, 10_000, 1000, 1000, 2)
+    api = api_selection(ctx, hm, P_res, args.extra_api_frames, 8192, 10_000, 1000, 1000, 5)
     if rank == 0:
         extra["T_api_sample_next_batch"] = {
             "workload": "north-star target through the API: %d frames per GPU x %d GPU(s) = %d frames, 8 views, 19 joints; "
@@ -646,6 +646,7 @@ def coreset_record(ctx, n_total, d, L, budget, path="auto", data="gaussian", ksl
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     # tcgen05 kind::tf32 runs at half the dense bf16 rate; the measured bf16 figure (a cuBLAS GEMM) halved is the peak
     tf32_peak = float(peaks.get("bf16_tflops", 2250.0)) / 2.0
+    tf32_sustained = float(peaks["bf16_tflops_sustained"]) / 2.0 if "bf16_tflops_sustained" in peaks else None
     tf32_src = ("MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 issues at half the bf16 rate)" if "bf16_tflops" in peaks
                 else "fallback: nominal 2250 dense bf16 TFLOP/s / 2")
 
@@ -686,9 +687,25 @@ def coreset_record(ctx, n_total, d, L, budget, path="auto", data="gaussian", ksl
         torch.cuda.synchronize()
         l0 = _lib.launch_count()
         stats = []
-        total_ms, (sel, _) = _timed(lambda: poolmod.kcenter_greedy_sharded([(feat, lo)], labeled, budget, flags=flags, stats=stats,
-                                                                               k_slots=kslots or None))
+        total_ms, (sel, fin) = _timed(lambda: poolmod.kcenter_greedy_sharded([(feat, lo)], labeled, budget, flags=flags, stats=stats,
+                                                                                 k_slots=kslots or None))
         launches = _lib.launch_count() - l0
+    # the same 256-centre update against the SETTLED minima the rounds work on (after the labeled fold alone the running
+    # minima are still high and the exact recheck of the screen's survivors is several times longer than in any round)
+    steady_ms, steady_survivors = None, None
+    if flags != 1 and auto_ms is not None:
+        min_fin = fin[0]
+        scratch = min_fin.clone()
+
+        def update_steady():
+            scratch.copy_(min_fin)
+            ops.kcenter_update_batch(feat, norms, cent_rows, cent_norms, scratch, flags)
+
+        update_steady()
+        steady_ms, _ = _timed(update_steady, 3)
+        steady_survivors, _ = ops.kcenter_tc_stats()
+        del scratch, min_fin
+    del fin
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -717,7 +734,10 @@ def coreset_record(ctx, n_total, d, L, budget, path="auto", data="gaussian", ksl
         cpu["gpu_matches_oracle_on_sample"] = bool(gsel.cpu().tolist() == cpu_sel)
     out = None
     if rank == 0:
-        upd_ms = (auto_ms if auto_ms is not None else ffma_ms) - clone_ms
+        fold_ms = (auto_ms if auto_ms is not None else ffma_ms) - clone_ms
+        upd_ms = (steady_ms - clone_ms) if steady_ms is not None else fold_ms
+        if steady_survivors is not None:
+            tc_survivors = steady_survivors
         ffma_only = ffma_ms - clone_ms
         flops = 2.0 * n * T * d
         step_bytes = n * (d * 4 + 12)
@@ -734,14 +754,21 @@ def coreset_record(ctx, n_total, d, L, budget, path="auto", data="gaussian", ksl
             "ms_per_pick": total_ms / budget,
             "equivalent_sequential_ms": (L + budget) * single_ms,
             "kernels_ms": {"norms": norms_ms, "single_centre_update": single_ms, "update_256_centres_ffma": ffma_only,
-                           "update_256_centres_selected_path": upd_ms, "select_256": select_ms},
+                           "update_256_centres_selected_path": upd_ms, "update_256_centres_selected_path_minima_after_labeled_fold_only": fold_ms,
+                           "select_256": select_ms},
             "roofline": {"bound": "tensor", "kernel": "kc_screen_tc2_kernel (+ kc_recheck_kernel + the no-op FFMA guard): one "
-                         "batched update of %d centres over this rank's %d rows" % (T, n) if tc_ran else
+                         "batched update of %d centres over this rank's %d rows, running minima as the greedy rounds see them "
+                         "(the selection's final state)" % (T, n) if tc_ran else
                          "kc_batch_kernel (FFMA; the tensor-core screen does not apply to this shape)",
                          "achieved": flops / (upd_ms * 1e-3) / 1e12, "peak": tf32_peak if tc_ran else 72.0, "unit": "TFLOP/s",
                          "frac": flops / (upd_ms * 1e-3) / 1e12 / (tf32_peak if tc_ran else 72.0), "traffic": None,
                          "peak_source": tf32_src if tc_ran else "fp32 FFMA pipe: 148 SMs x 128 lanes x 2 x 1.9 GHz",
                          "algorithmic_flops_per_launch": flops, "avg_launch_ms": upd_ms,
+                         "frac_of_sustained_peak": (flops / (upd_ms * 1e-3) / 1e12 / tf32_sustained) if tc_ran and tf32_sustained else None,
+                         "sustained_peak": tf32_sustained if tc_ran else None,
+                         "sustained_peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (under the power cap the SM clock "
+                                                  "settles near 1.1-1.3 GHz while the tensor pipe is busy; profiles/r2r_ncu_screen_c4_"
+                                                  "key_metrics.json: pipe active 91 % of the cycles at 1.13 GHz)" if tc_ran else None,
                          "tc_survivor_pairs": tc_survivors, "tc_pair_capacity": tc_capacity,
                          "ffma_tflops_same_update": flops / (ffma_only * 1e-3) / 1e12},
             "roofline_single_step": {"bound": "hbm", "kernel": "kc_rowdot_kernel<1> (single-centre update, one greedy step of the reference)",
@@ -994,6 +1021,7 @@ def api_selection(ctx, hm, P_res, n_local, batch, budget, n_labeled, pseudo, rep
     """Times ActiveLearningStrategy.sample_next_batch(iteration >= 1) end to end (wall clock between a barrier +
     synchronize on both sides, max over ranks, median over `reps` calls after one warm-up call) for the given
     (strategy, EXPR_TYPE) variants.  Returns {variant: record}."""
+    import gc
     import random
 
     import torch
@@ -1013,6 +1041,7 @@ def api_selection(ctx, hm, P_res, n_local, batch, budget, n_labeled, pseudo, rep
             ds = DevicePoolDataset(hm, P_pool, n_local, rank, world, batch, n_labeled, J, dev)
             st._get_dataloader = lambda d, bs, nw, ds=ds: ds.loader()
             random.seed(5)
+            gc.collect()  # the previous call's dataset / table: a generation-2 pass inside a 60 ms call was a 30 ms outlier
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
