@@ -696,6 +696,9 @@ def coreset_record(ctx, n_total, d, L, budget, path="auto", data="gaussian", ksl
     if flags != 1 and auto_ms is not None:
         min_fin = fin[0]
         scratch = min_fin.clone()
+        own = sel[(sel >= lo) & (sel < hi)] - lo  # centres = the last picks that live in this shard: far points, as in a round
+        if own.numel() >= T:
+            cent_rows, cent_norms = feat[own[-T:]].contiguous(), norms[own[-T:]].contiguous()
 
         def update_steady():
             scratch.copy_(min_fin)
@@ -757,8 +760,8 @@ def coreset_record(ctx, n_total, d, L, budget, path="auto", data="gaussian", ksl
                            "update_256_centres_selected_path": upd_ms, "update_256_centres_selected_path_minima_after_labeled_fold_only": fold_ms,
                            "select_256": select_ms},
             "roofline": {"bound": "tensor", "kernel": "kc_screen_tc2_kernel (+ kc_recheck_kernel + the no-op FFMA guard): one "
-                         "batched update of %d centres over this rank's %d rows, running minima as the greedy rounds see them "
-                         "(the selection's final state)" % (T, n) if tc_ran else
+                         "batched update of %d centres (the selection's last picks in this shard) over this rank's %d rows, running "
+                         "minima as the greedy rounds see them (the selection's final state)" % (T, n) if tc_ran else
                          "kc_batch_kernel (FFMA; the tensor-core screen does not apply to this shape)",
                          "achieved": flops / (upd_ms * 1e-3) / 1e12, "peak": tf32_peak if tc_ran else 72.0, "unit": "TFLOP/s",
                          "frac": flops / (upd_ms * 1e-3) / 1e12 / (tf32_peak if tc_ran else 72.0), "traffic": None,
