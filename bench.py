@@ -1183,7 +1183,7 @@ def run_scores(args):
                 del os.environ["MVAL_SCORED_SPLIT"]
         return run
 
-    # the default is the faster of the two per score (MPE: fused launch, BSB: stream kernel + RANSAC launches); both forced:
+    # the default is the faster of the two per score (MPE, BSB: stream kernel + RANSAC launches); both forced:
     kernels["score_pool_fused_kernel<MPE> in ONE launch (MVAL_SCORED_SPLIT=0)"] = unsplit("MPE", "0")
     kernels["score_pool_fused_kernel<BSB> in ONE launch (MVAL_SCORED_SPLIT=0)"] = unsplit("BSB", "0")
     kernels["map_stream<argmax+MPE> + RANSAC launches (MVAL_SCORED_SPLIT=1)"] = unsplit("MPE", "1")
@@ -1191,6 +1191,21 @@ def run_scores(args):
     kernels["score_pool_fused_kernel, lane=row arg-max (MVAL_ROW_ARGMAX=1)"] = flavoured("1", None)
     kernels["score_pool_fused_kernel<MPE>, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = flavoured("0", "MPE")
     kernels["score_pool_fused_kernel<BSB>, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = flavoured("0", "BSB")
+    def with_env(kind, env):
+        def run():
+            os.environ.update(env)
+            try:
+                return ops.score_pool(hm, P, STRIDE, return_keypoints_2d=False, map_score=kind)
+            finally:
+                for k in env:
+                    del os.environ[k]
+        return run
+
+    # warp split of the scored fused launch: (12 - s) decode + (3 + s) RANSAC warps
+    for kind in ("HP", "MPE", "BSB"):
+        for shape in ("0", "1"):
+            kernels["score_pool_fused_kernel<%s> in ONE launch, %d decode + %d RANSAC warps (MVAL_FUSED_SHAPE=%s)"
+                    % (kind, 12 - int(shape), 3 + int(shape), shape)] = with_env(kind, {"MVAL_SCORED_SPLIT": "0", "MVAL_FUSED_SHAPE": shape})
     if args.scores_only:
         kernels = {k: f for k, f in kernels.items() if args.scores_only in k}
     out = {}

@@ -92,13 +92,13 @@ int stream_peaks_argmax(const float* hm, int64_t n_maps, int V, int J, int mode,
                         int32_t* out_xy, cudaStream_t stream);
 
 // MPE / BSB with the triangulation: one fused launch, or the stream kernel (score + arg-max key-point, one read of the heat
-// maps) followed by the RANSAC launches from the key-points.  Measured per 16 384 frames (profiles/r2_summary.md): MPE 9.84 ms
-// fused / 9.99 ms split, BSB 12.92 ms fused / 12.00 ms split -- so BSB takes the split path by default and MPE the fused one.
+// maps) followed by the RANSAC launches from the key-points.  Measured per 16 384 frames (profiles/r2_summary.md section 5,
+// final state): MPE 9.8 ms fused / 8.4 ms split, BSB 11.5 ms fused / 10.9 ms split -- both take the split path by default.
 // MVAL_SCORED_SPLIT=0 / 1 forces one of them for both (A/B measurements and tests; read on every call).
 static bool scored_split_enabled(int map_score) {
   const char* e = getenv("MVAL_SCORED_SPLIT");
   if (e != nullptr && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
-  return map_score == MVAL_MAP_SCORE_BSB;
+  return map_score == MVAL_MAP_SCORE_MPE || map_score == MVAL_MAP_SCORE_BSB;
 }
 
 // MVAL_FUSED=0 in the environment forces the three-launch path (A/B measurements only).

@@ -38,16 +38,18 @@
 namespace mval {
 
 // Warp budget and per-map evaluator of each variant.  The register file is split per scheduler (16 384 registers
-// each), so 17-20 warps per CTA cap a thread at 96 registers and 13-16 warps at 128.  Measured on 16 384 frames
+// each), so 17-20 warps per CTA cap a thread at 96 registers and 13-16 warps at 128.  Round 1f, per 16 384 frames
 // (profiles/r1f_summary.md): 12 decode + 6 RANSAC warps at 96 registers (ptxas spills) 10.1 / 11.0 / 18.5 ms for HP /
-// MPE / BSB, 10 + 5 warps at 128 registers 9.4 / 10.6 / 13.9 ms, 12 + 3 warps at 128 registers 8.9 / 10.2 / 13.1 ms:
-// the scored variants are bound by the decode warps, and three RANSAC warps keep up with the float64 work of a pass
-// that takes 1.5-2x as long as the unscored one.
-template <int kScore> struct FusedCfg;
-template <> struct FusedCfg<MVAL_MAP_SCORE_NONE> { static constexpr int kD = 6, kR = 8; using Op = void; };       // 480 threads
-template <> struct FusedCfg<MVAL_MAP_SCORE_HP> { static constexpr int kD = 12, kR = 3; using Op = HpOp; };        // 512 threads
-template <> struct FusedCfg<MVAL_MAP_SCORE_MPE> { static constexpr int kD = 12, kR = 3; using Op = PeaksOp<0>; };
-template <> struct FusedCfg<MVAL_MAP_SCORE_BSB> { static constexpr int kD = 12, kR = 3; using Op = PeaksOp<1>; };
+// MPE / BSB, 10 + 5 warps at 128 registers 9.4 / 10.6 / 13.9 ms, 12 + 3 warps at 128 registers 8.9 / 10.2 / 13.1 ms.
+// Round 2, after the decode warps' instruction cuts (profiles/r2_summary.md section 5): HP 12 + 3: 7.23 ms, 11 + 4:
+// 5.76 ms, 10 + 5: 6.66 ms -- HP's row sweep is short enough now that three RANSAC warps no longer keep up, so HP runs
+// 11 + 4 (kShape 1); MPE / BSB show no such preference (9.3-10.1 ms for all three splits) and keep 12 + 3.
+// kShape s = (12 - s) decode + (3 + s) RANSAC warps; MVAL_FUSED_SHAPE = 0 / 1 forces one split (A/B measurements).
+template <int kScore, int kShape = 0> struct FusedCfg;
+template <> struct FusedCfg<MVAL_MAP_SCORE_NONE, 0> { static constexpr int kD = 6, kR = 8; using Op = void; };       // 480 threads
+template <int kShape> struct FusedCfg<MVAL_MAP_SCORE_HP, kShape> { static constexpr int kD = 12 - kShape, kR = 3 + kShape; using Op = HpOp; };  // 512 threads
+template <int kShape> struct FusedCfg<MVAL_MAP_SCORE_MPE, kShape> { static constexpr int kD = 12 - kShape, kR = 3 + kShape; using Op = PeaksOp<0>; };
+template <int kShape> struct FusedCfg<MVAL_MAP_SCORE_BSB, kShape> { static constexpr int kD = 12 - kShape, kR = 3 + kShape; using Op = PeaksOp<1>; };
 // Heat maps of one launch: up to MVAL_MAX_SEGMENTS device buffers of whole frames, frame f of the launch lives in segment
 // s with start[s] <= f < start[s + 1] at ptr[s] + (f - start[s]) * V * J * H * W (mval_score_pool_segments: a pool is
 // usually produced batch by batch by the pose estimator and need not be contiguous).  Passed by value as a
@@ -102,16 +104,16 @@ __host__ __device__ inline FusedSmem fused_layout(int V, int J, int HW, int stag
 
 // kRowArgmax: 64 x 64 maps are arg-maxed by the lane = row sweep of mapops.cuh (warp_argmax_map64) instead of the
 // generic per-vector scan; both are the same function of the map.
-template <int kScore, bool kRowArgmax>
-__global__ void __launch_bounds__(kWarp * (1 + FusedCfg<kScore>::kD + FusedCfg<kScore>::kR), 1)
+template <int kScore, bool kRowArgmax, int kShape = 0>
+__global__ void __launch_bounds__(kWarp * (1 + FusedCfg<kScore, kShape>::kD + FusedCfg<kScore, kShape>::kR), 1)
 score_pool_fused_kernel(const __grid_constant__ SegTable segs, const double* __restrict__ proj, const uint8_t* __restrict__ valid,
                         int64_t n_frames, int V, int J, int H, int HW, int stride, int stages, int slots, int n_iters, double eps,
                         uint64_t seed, int64_t frame_offset, const int64_t* __restrict__ frame_keys, int32_t* __restrict__ out_xy,
                         double* __restrict__ out_xyz,
                         double* __restrict__ out_reproj, int32_t* __restrict__ out_inliers, double* __restrict__ out_metric,
                         int32_t* __restrict__ out_inlier_count, float* __restrict__ out_map_score) {
-  constexpr int kFusedDecodeWarps = FusedCfg<kScore>::kD;
-  constexpr int kFusedRansacWarps = FusedCfg<kScore>::kR;
+  constexpr int kFusedDecodeWarps = FusedCfg<kScore, kShape>::kD;
+  constexpr int kFusedRansacWarps = FusedCfg<kScore, kShape>::kR;
   extern __shared__ __align__(128) unsigned char smem[];
   const FusedSmem L = fused_layout(V, J, HW, stages, slots, kFusedRansacWarps);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
@@ -158,7 +160,9 @@ score_pool_fused_kernel(const __grid_constant__ SegTable segs, const double* __r
         for (int m = 0; m < VJ; ++m, ++c) {
           const int st = (int)(c % stages);
           const uint32_t kf = (uint32_t)(c / stages);
-          if (!mbar_wait(&empty[st], (kf & 1u) ^ 1u, g_fused_abort, 2, i, st)) return;
+          // (the MPE / BSB variants are issue-bound: the producer waits here nearly always and must not spin)
+          constexpr int kProducerBackoff = (kScore == MVAL_MAP_SCORE_MPE || kScore == MVAL_MAP_SCORE_BSB) ? 2 : 0;
+          if (!mbar_wait<kProducerBackoff>(&empty[st], (kf & 1u) ^ 1u, g_fused_abort, 2, i, st)) return;
           mbar_arrive_expect_tx(&full[st], L.stage_bytes);
           bulk_g2s(smem + L.ring + (uint32_t)st * L.stage_bytes, src + (int64_t)m * HW, L.stage_bytes, &full[st]);
         }
@@ -210,7 +214,7 @@ score_pool_fused_kernel(const __grid_constant__ SegTable segs, const double* __r
           mbar_arrive(&kp_ready[sl]);  // the RANSAC warps may start on this key-point while the score is evaluated
         }
         if constexpr (kScoreAfter) {
-          using Op = typename FusedCfg<kScore>::Op;
+          using Op = typename FusedCfg<kScore, kShape>::Op;
           __syncwarp();
           Op::run(stage, frame * VJ + m, ok, lane, typename Op::Args{out_map_score}, nullptr, typename Op::Pre{});
           if (Op::kWritesSmem) fence_proxy_async_smem();  // BSB rewrote the stage; order that before the TMA refill
@@ -326,12 +330,12 @@ score_pool_fused_kernel(const __grid_constant__ SegTable segs, const double* __r
 
 // Returns MVAL_ERR_UNSUPPORTED (without setting an error) when the shape does not fit the fused kernel; the caller
 // then takes the multi-launch path.
-template <int kScore, bool kRowArgmax>
+template <int kScore, bool kRowArgmax, int kShape = 0>
 static int launch_fused_variant(const SegTable& segs, const double* proj, const uint8_t* valid, int64_t n_frames, int V, int J,
                                 int H, int W, int stride, const mval_ransac_params& prm, int32_t* out_xy, double* out_xyz,
                                 double* out_reproj, int32_t* out_inliers, double* out_metric, int32_t* out_inlier_count,
                                 float* out_map_score, cudaStream_t stream) {
-  constexpr int kD = FusedCfg<kScore>::kD, kR = FusedCfg<kScore>::kR;
+  constexpr int kD = FusedCfg<kScore, kShape>::kD, kR = FusedCfg<kScore, kShape>::kR;
   const int HW = H * W;
   if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(proj) & 15) != 0 || prm.pairs != nullptr) return MVAL_ERR_UNSUPPORTED;
   for (int s = 0; s < segs.n; ++s)
@@ -353,12 +357,12 @@ static int launch_fused_variant(const SegTable& segs, const double* proj, const 
   }
   if (stages < kD) return MVAL_ERR_UNSUPPORTED;
   const FusedSmem L = fused_layout(V, J, HW, stages, slots, kR);
-  MVAL_CUDA(cudaFuncSetAttribute(score_pool_fused_kernel<kScore, kRowArgmax>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  MVAL_CUDA(cudaFuncSetAttribute(score_pool_fused_kernel<kScore, kRowArgmax, kShape>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   const int64_t sms = num_sms();
   const int grid = (int)(n_frames < sms ? n_frames : sms);
   // a watchdog trip of an EARLIER launch surfaces here (or in mval_check_async), never silently
   if (int rc = g_fused_watchdog.prepare(g_fused_abort, "score_pool_fused")) return rc;
-  score_pool_fused_kernel<kScore, kRowArgmax><<<grid, kWarp * (1 + kD + kR), L.total, stream>>>(
+  score_pool_fused_kernel<kScore, kRowArgmax, kShape><<<grid, kWarp * (1 + kD + kR), L.total, stream>>>(
       segs, proj, valid, n_frames, V, J, H, HW, stride, stages, slots, prm.n_iters, prm.epsilon, prm.pair_seed, prm.frame_offset,
       prm.frame_keys, out_xy, out_xyz, out_reproj, out_inliers, out_metric, out_inlier_count, out_map_score);
   MVAL_LAUNCH_CHECK("score_pool_fused");
@@ -393,18 +397,25 @@ int launch_score_pool_fused_segments(const float* const* seg_ptr, const int64_t*
   const char* env = getenv("MVAL_ROW_ARGMAX");
   const int force = (env != nullptr && (env[0] == '0' || env[0] == '1')) ? env[0] - '0' : -1;
   const bool is64 = H == kMapDim && W == kMapDim;
+  // warp split of the scored variants (FusedCfg)
+  const char* shape_env = getenv("MVAL_FUSED_SHAPE");
+  const int shape = (shape_env != nullptr && (shape_env[0] == '0' || shape_env[0] == '1')) ? shape_env[0] - '0'
+                                                                                           : (map_score == MVAL_MAP_SCORE_HP ? 1 : 0);
   switch (map_score) {
     case MVAL_MAP_SCORE_NONE:
       out_map_score = nullptr;
       if (is64 && force == 1) return launch_fused_variant<MVAL_MAP_SCORE_NONE, true>(MVAL_FUSED_ARGS);
       return launch_fused_variant<MVAL_MAP_SCORE_NONE, false>(MVAL_FUSED_ARGS);
     case MVAL_MAP_SCORE_HP:  // the arg-max is a by-product of HP's own row sweep
-      return launch_fused_variant<MVAL_MAP_SCORE_HP, true>(MVAL_FUSED_ARGS);
+      if (shape == 0) return launch_fused_variant<MVAL_MAP_SCORE_HP, true, 0>(MVAL_FUSED_ARGS);
+      return launch_fused_variant<MVAL_MAP_SCORE_HP, true, 1>(MVAL_FUSED_ARGS);
     case MVAL_MAP_SCORE_MPE:
       if (force == 0) return launch_fused_variant<MVAL_MAP_SCORE_MPE, false>(MVAL_FUSED_ARGS);
+      if (shape == 1) return launch_fused_variant<MVAL_MAP_SCORE_MPE, true, 1>(MVAL_FUSED_ARGS);
       return launch_fused_variant<MVAL_MAP_SCORE_MPE, true>(MVAL_FUSED_ARGS);
     case MVAL_MAP_SCORE_BSB:
       if (force == 0) return launch_fused_variant<MVAL_MAP_SCORE_BSB, false>(MVAL_FUSED_ARGS);
+      if (shape == 1) return launch_fused_variant<MVAL_MAP_SCORE_BSB, true, 1>(MVAL_FUSED_ARGS);
       return launch_fused_variant<MVAL_MAP_SCORE_BSB, true>(MVAL_FUSED_ARGS);
     default:
       return MVAL_ERR_UNSUPPORTED;

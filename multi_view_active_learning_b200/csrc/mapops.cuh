@@ -5,6 +5,8 @@
 // An Op evaluates one 64 x 64 float32 map that already sits in shared memory, with one warp:
 //   Op::run(map, m, ok, lane, args, scratch, pre)   m = global map index of the output, ok = joint is valid
 //   Op::kWritesSmem                                 the Op rewrites the stage (the caller must fence before the refill)
+//   Op::kProducerBackoff                            0: the stream is HBM-bound; 2: the Op is issue-bound and the producer sleeps
+//                                                   between polls for a free stage (tma.cuh: mbar_wait)
 //   Op::prefetch(m, args)                           per-map inputs fetched one map ahead (XE only)
 #pragma once
 #include "tma.cuh"
@@ -29,6 +31,28 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
   float y;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
   return y;
+}
+// bits |= bit where x == w, as FSETP + a predicated IMAD (bits + bit * 1: the bit is not set yet).  The C form came out
+// as FSETP + SEL + LOP3 for three of the four columns of a scan step; and the scan is bound by the ALU pipe (FMNMX, LOP3,
+// IADD3 issue every second cycle per scheduler, B300_MICROARCH "pipe rates"), where 26 of its 31 instructions per step ran,
+// while the FMA pipe (FFMA, IMAD) idles -- so the OR is spelled as a multiply-add.
+__device__ __forceinline__ void or_if_equal(uint32_t& bits, float x, float w, uint32_t bit) {
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.f32 p, %1, %2;\n\t@p mad.lo.u32 %0, %3, 1, %0;\n\t}" : "+r"(bits) : "f"(x), "f"(w), "r"(bit));
+}
+// Highest set bit of a peak mask, branch-free: returns its index (-1 for an empty mask: bfind) and clears it (PTX shl clamps
+// a shift of 0xffffffff to 0, which C++ does not promise).
+__device__ __forceinline__ int pop_highest_bit(uint32_t& b) {
+  int i;
+  uint32_t t;
+  asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(b));
+  asm("shl.b32 %0, %1, %2;" : "=r"(t) : "r"(1u), "r"(i));
+  b ^= t;
+  return i;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -118,6 +142,7 @@ struct SoftArgmaxOp {
   };
   using Pre = NoPrefetch;
   static constexpr bool kWritesSmem = false;
+  static constexpr int kProducerBackoff = 0;
   __device__ static __forceinline__ Pre prefetch(int64_t, const Args&) { return {}; }
   __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*, const Pre&) {
     (void)ok;
@@ -176,6 +201,7 @@ struct HpOp {
   };
   using Pre = NoPrefetch;
   static constexpr bool kWritesSmem = false;
+  static constexpr int kProducerBackoff = 0;
   __device__ static __forceinline__ Pre prefetch(int64_t, const Args&) { return {}; }
   template <bool kArgmax>
   __device__ static __forceinline__ uint32_t eval(const float* map, int64_t m, int lane, const Args& a) {
@@ -319,6 +345,7 @@ struct PeaksOp {
   };
   using Pre = NoPrefetch;
   static constexpr bool kWritesSmem = (kMode == 1);
+  static constexpr int kProducerBackoff = 2;
   __device__ static __forceinline__ Pre prefetch(int64_t, const Args&) { return {}; }
   __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*, const Pre&) {
     if (!ok) {
@@ -372,11 +399,13 @@ struct PeaksOp {
     const int rbase = half * 30;
     float h[4][5], xs[4][3];
     uint32_t bits[4] = {0u, 0u, 0u, 0u};
-    // One step of the scan: row rbase + t enters the rings (slot t % 5 of the horizontal 5-maxima, slot t % 3 of the raw
-    // values); from t = 4 on, row rbase + t - 2 has its five window rows in the ring and its four columns are tested.
-    // The ring slots must be compile-time (registers), so the 34 steps run as 2 x 15 rolled + 4: the body exists 19 times
-    // instead of 34 (round 2: the scored fused kernels were 142 KB of SASS and stalled on instruction fetch).
-    auto scan_step = [&](const int t, const int s5, const int s3, const int c3) {
+    // The scan: row rbase + t enters the rings (slot t % 5 of the horizontal 5-maxima, slot t % 3 of the raw values); from
+    // t = 4 on, row rbase + t - 2 has its five window rows in the ring and its four columns are tested.  The ring slots
+    // must be compile-time (registers): steps 0..3 only fill, steps 4..33 run as 2 x 15 rolled.  The per-line instruction
+    // counts of round 2 (profiles/r2u_*) showed 42 instructions per step for 30 useful ones: a run-time "t >= 4" branch
+    // with its reconvergence pair, 1 << (t - 4) rebuilt every step, and SEL + LOP3 instead of a predicated LOP3 -- hence
+    // the peeled head, the carried `bit` and or_if_equal.
+    auto fill = [&](const int t, const int s5, const int s3) {
       const float4 x = p4[(rbase + t) * 16 + l16];
       const float m01 = fmaxf(x.x, x.y), m23 = fmaxf(x.z, x.w);
       if (kMode == 0) {
@@ -392,22 +421,28 @@ struct PeaksOp {
       h[2][s5] = max3(m01, m23, Rc0);
       h[3][s5] = max3(x.y, m23, Rm);
       xs[0][s3] = x.x; xs[1][s3] = x.y; xs[2][s3] = x.z; xs[3][s3] = x.w;
-      if (t >= 4) {
-        const uint32_t bit = 1u << (t - 4);
+    };
+    auto test = [&](const int c3, const uint32_t bit) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float w = max3(max3(h[k][0], h[k][1], h[k][2]), h[k][3], h[k][4]);
-          if (xs[k][c3] == w) bits[k] |= bit;
-        }
+      for (int k = 0; k < 4; ++k) {
+        const float w = max3(max3(h[k][0], h[k][1], h[k][2]), h[k][3], h[k][4]);
+        or_if_equal(bits[k], xs[k][c3], w, bit);
       }
     };
+#pragma unroll
+    for (int t = 0; t < 4; ++t) fill(t, t % 5, t % 3);
+    {
+      uint32_t bit = 1u;  // bit t - 4 <-> row rbase + t - 2
 #pragma unroll 1
-    for (int tb = 0; tb < 30; tb += 15) {
+      for (int tb = 4; tb < 34; tb += 15) {
 #pragma unroll
-      for (int u = 0; u < 15; ++u) scan_step(tb + u, u % 5, u % 3, (u + 13) % 3);  // (t - 2) % 3 with t = tb + u, 15 | tb
+        for (int u = 0; u < 15; ++u) {  // t = tb + u with 15 | tb - 4
+          fill(tb + u, (4 + u) % 5, (4 + u) % 3);
+          test((2 + u) % 3, bit);
+          bit += bit;
+        }
+      }
     }
-#pragma unroll
-    for (int t = 30; t < 34; ++t) scan_step(t, t % 5, t % 3, (t - 2) % 3);
     if (l16 == 0) bits[0] = bits[1] = 0u;   // columns 0, 1
     if (l16 == 15) bits[2] = bits[3] = 0u;  // columns 62, 63
     gmin = warp_min_f(gmin);
@@ -441,23 +476,25 @@ struct PeaksOp {
     if (kMode == 0) {
       constexpr float kLog2e = 1.4426950408889634f;
       gmax = warp_max_f(gmax);
-      float S = 0.f, T = 0.f, M = -INFINITY;
+      // Walk of the set bits, one bit of each of the four column masks per trip, branch-free inside the trip (round 2: the
+      // guarded form spent 25 of its ~90 instructions per trip on branch / reconvergence pairs and register moves): an
+      // exhausted mask yields row -1 of `col` (inside the map: rbase + 1 >= 1), which the predicate discards.
+      const uint32_t col_s = (uint32_t)__cvta_generic_to_shared(col);
+      float S = 0.f, T = 0.f;
       int n = 0;
-      uint32_t b0 = bits[0], b1 = bits[1], b2 = bits[2], b3 = bits[3];
-      while (b0 | b1 | b2 | b3) {
+      {
+        uint32_t b[4] = {bits[0], bits[1], bits[2], bits[3]};
+        while (b[0] | b[1] | b[2] | b[3]) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint32_t& b = (k == 0) ? b0 : (k == 1) ? b1 : (k == 2) ? b2 : b3;
-          if (b) {
-            const int i = __ffs(b) - 1;
-            b &= b - 1;
-            const float v = col[i * kMapDim + k];
-            if (v > gmin) {  // image > image.min(): peaks sitting at the map minimum are not peaks
+          for (int k = 0; k < 4; ++k) {
+            const bool any = b[k] != 0u;
+            const int i = pop_highest_bit(b[k]);
+            const float v = lds_f32(col_s + 4u * k + (uint32_t)(i * (kMapDim * 4)));
+            if (any && v > gmin) {  // image > image.min(): peaks sitting at the map minimum are not peaks
               const float d = v - gmax;
               const float w = ex2_approx(d * kLog2e);
               S += w;
               T = fmaf(d, w, T);
-              M = fmaxf(M, v);
               ++n;
             }
           }
@@ -470,6 +507,17 @@ struct PeaksOp {
         T += __shfl_xor_sync(kFull, T, o);
       }
       if (n > 0 && !(S >= 1e-30f)) {  // every term underflowed: shift by the largest peak instead (never on real maps)
+        float M = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t b = bits[k];
+          while (b) {
+            const int i = __ffs(b) - 1;
+            b &= b - 1;
+            const float v = col[i * kMapDim + k];
+            if (v > gmin) M = fmaxf(M, v);
+          }
+        }
         M = warp_max_f(M);
         S = 0.f;
         T = 0.f;
@@ -499,16 +547,16 @@ struct PeaksOp {
     } else {
       float t1 = -INFINITY, t2 = -INFINITY;
       int n = 0;
-      uint32_t b0 = bits[0], b1 = bits[1], b2 = bits[2], b3 = bits[3];
-      while (b0 | b1 | b2 | b3) {
+      {
+        const uint32_t col_s = (uint32_t)__cvta_generic_to_shared(col);  // as in the MPE walk above
+        uint32_t b[4] = {bits[0], bits[1], bits[2], bits[3]};
+        while (b[0] | b[1] | b[2] | b[3]) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint32_t& b = (k == 0) ? b0 : (k == 1) ? b1 : (k == 2) ? b2 : b3;
-          if (b) {
-            const int i = __ffs(b) - 1;
-            b &= b - 1;
-            const float v = col[i * kMapDim + k];
-            if (v > gmin) {
+          for (int k = 0; k < 4; ++k) {
+            const bool any = b[k] != 0u;
+            const int i = pop_highest_bit(b[k]);
+            const float v = lds_f32(col_s + 4u * k + (uint32_t)(i * (kMapDim * 4)));
+            if (any && v > gmin) {
               ++n;
               t2 = fmaxf(t2, fminf(t1, v));  // (t1, t2) = the two largest of {t1, t2, v}
               t1 = fmaxf(t1, v);
@@ -552,6 +600,7 @@ struct XeOp {
     double P[12], X[3];
   };
   static constexpr bool kWritesSmem = false;
+  static constexpr int kProducerBackoff = 0;
   __device__ static __forceinline__ Pre prefetch(int64_t m, const Args& a) {
     Pre q;
     const int j = (int)(m % a.J);

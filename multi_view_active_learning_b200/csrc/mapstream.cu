@@ -63,7 +63,7 @@ map_stream_kernel(const float* __restrict__ hm, int64_t n_maps, const uint8_t* _
         const int64_t m = blockIdx.x + c * (int64_t)gridDim.x;
         const int st = (int)(c % kStreamStages);
         const uint32_t kf = (uint32_t)(c / kStreamStages);
-        if (!mbar_wait(&empty[st], (kf & 1u) ^ 1u, g_stream_abort, 1, c, st)) return;
+        if (!mbar_wait<Op::kProducerBackoff>(&empty[st], (kf & 1u) ^ 1u, g_stream_abort, 1, c, st)) return;
         if (valid != nullptr && valid[(m / VJ) * J + m % J] == 0) {
           mbar_arrive(&full[st]);  // nothing to read for an invalid joint
         } else {
@@ -106,6 +106,7 @@ struct ArgmaxPlusOp {
   };
   using Pre = typename Inner::Pre;
   static constexpr bool kWritesSmem = Inner::kWritesSmem;
+  static constexpr int kProducerBackoff = Inner::kProducerBackoff;
   __device__ static __forceinline__ Pre prefetch(int64_t m, const Args& a) { return Inner::prefetch(m, a.inner); }
   __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char* scratch,
                                              const Pre& pre) {

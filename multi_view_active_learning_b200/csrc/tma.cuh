@@ -34,7 +34,7 @@ __device__ __forceinline__ bool watchdog_stalled(const unsigned long long* abort
   return *((const volatile unsigned long long*)&abort_rec[kWdStall]) != 0ull;
 }
 
-// kBackoff: the waiter expects to wait long; it sleeps between polls so that it does not take issue slots from the
+// kBackoff (1 long, 2 short): the waiter expects to wait; it sleeps between polls so that it does not take issue slots from the
 // other warps of its scheduler.
 // The poll loop with its watchdog is ONE out-of-line function per flavour: inlined at every wait site it was 9 KB of the
 // fused kernels' SASS (round 2), and those kernels stall on instruction fetch.
@@ -50,7 +50,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar_addr, uint32_t pa
   return ok;
 }
 
-template <bool kBackoff>
+template <int kBackoff>
 __device__ __noinline__ bool mbar_wait_slow(uint32_t bar_addr, uint32_t parity, unsigned long long* abort_rec, uint32_t code,
                                             long long iter, int index) {
   long long t0 = 0;
@@ -59,7 +59,11 @@ __device__ __noinline__ bool mbar_wait_slow(uint32_t bar_addr, uint32_t parity, 
     // A long waiter (the RANSAC warps wait ~50 us for the key-points of a frame, with up to three frames of slack) sleeps
     // between polls: try_wait alone comes back every ~0.1 us whatever its suspend-time hint says (measured, round 2: the poll
     // loop was 25 % of all executed warp instructions of the fused kernel), a 2-4 us sleep cuts that by ~20x.
-    if (kBackoff) __nanosleep(polls < 2u ? 500u : 3000u);
+    // kBackoff == 2: the producer of an issue-bound kernel (MPE / BSB scoring).  It waits for a free stage almost always,
+    // and its bare poll loop was 440 of the 2 970 warp instructions per map of the fused MPE pass (profiles/r2u_*); a stage
+    // frees every ~0.6 us, so a short sleep costs no bandwidth and gives the slots to the decode warps.
+    if (kBackoff == 1) __nanosleep(polls < 2u ? 500u : 3000u);
+    if (kBackoff == 2) __nanosleep(250u);
     if (mbar_try_wait(bar_addr, parity)) return true;
     if ((++polls & (kBackoff ? 15u : 255u)) == 0u) {
       if (*((volatile unsigned long long*)&abort_rec[0]) != 0ull) return false;
@@ -93,7 +97,7 @@ __device__ __noinline__ bool mbar_wait_slow(uint32_t bar_addr, uint32_t parity, 
   }
 }
 
-template <bool kBackoff = false>
+template <int kBackoff = 0>
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, unsigned long long* abort_rec, uint32_t code,
                                           long long iter, int index) {
   const uint32_t addr = smem_u32(bar);
