@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Executed warp instructions per source line: joins the SASS page of an ncu capture (ncu -i X.ncu-rep --page source --csv)
 with the line table of the same kernel (nvdisasm -g of the cubin, cuobjdump -xelf all <obj>), instruction by instruction.
-    python tools/ncu_lines.py sass_page.csv dis.txt <substring of the .text section name> [top]
+    python tools/ncu_lines.py sass_page.csv dis.txt <substring of the .text section name> [top] [units] [source dir]
+units: divide the counts by this number (e.g. maps per launch); source dir: print the text of each line from there.
 """
 import collections
 import csv
@@ -32,6 +33,20 @@ def line_table(path, needle):
 def main():
     page, dis, needle = sys.argv[1], sys.argv[2], sys.argv[3]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    units = float(sys.argv[5]) if len(sys.argv) > 5 else 0.0
+    srcdir = sys.argv[6] if len(sys.argv) > 6 else None
+    cache = {}
+
+    def source_text(line):
+        if not srcdir or not line:
+            return ""
+        if line[0] not in cache:
+            try:
+                cache[line[0]] = open(srcdir + "/" + line[0]).read().splitlines()
+            except OSError:
+                cache[line[0]] = []
+        src = cache[line[0]]
+        return "  | " + src[line[1] - 1].strip()[:110] if 0 < line[1] <= len(src) else ""
     rows = list(csv.reader(open(page)))
     hdr = rows[1]
     ia, isrc, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed")
@@ -48,10 +63,10 @@ def main():
         per_line[line] += ex
         per_file[line[0] if line else None] += ex
         total += ex
-    print("executed warp instructions:", total, " opcode mismatches:", mismatch)
-    print("per file:", [(k, v, round(v / total, 3)) for k, v in per_file.most_common()])
+    print("executed warp instructions:", total, " opcode mismatches:", mismatch, (" per unit: %.1f" % (total / units)) if units else "")
+    print("per file:", [(k, round(v / units, 1) if units else v, round(v / total, 3)) for k, v in per_file.most_common()])
     for k, v in per_line.most_common(top):
-        print("  ", k, v, round(v / total, 4))
+        print("  %-28s %12s  %.4f%s" % (k, ("%.1f" % (v / units)) if units else v, v / total, source_text(k)))
 
 
 if __name__ == "__main__":
