@@ -27,7 +27,7 @@ constexpr int kVoteThreads = 256;
 constexpr int kVoteWarps = kVoteThreads / kWarp;
 
 template <typename PT>
-__global__ void __launch_bounds__(kVoteThreads)
+__global__ void __launch_bounds__(kVoteThreads, 3)
 ransac_vote_kernel(const PT* __restrict__ xy, const double* __restrict__ proj, const uint8_t* __restrict__ valid,
                    int64_t n_tasks, int V, int J, int n_iters, double eps, uint64_t seed, int64_t frame_offset,
                    const int64_t* __restrict__ frame_keys, const uint8_t* __restrict__ pairs_explicit,
