@@ -98,7 +98,7 @@ __host__ __device__ inline FusedSmem fused_layout(int V, int J, int HW, int stag
   L.perm = o;        o = align_up(o + (uint32_t)ransac_warps * n_all * 2u, 16);
   L.pxy = o;         o = align_up(o + (uint32_t)ransac_warps * 2u * V * 8u, 16);
   L.bars = o;        o = o + (2u * stages + 3u * (uint32_t)slots) * 8u;
-  L.total = o;
+  L.total = o + kMapAlign;  // slack for aligning the ring (offset 0) to kMapAlign inside the kernel
   return L;
 }
 
@@ -114,7 +114,9 @@ score_pool_fused_kernel(const __grid_constant__ SegTable segs, const double* __r
                         int32_t* __restrict__ out_inlier_count, float* __restrict__ out_map_score) {
   constexpr int kFusedDecodeWarps = FusedCfg<kScore, kShape>::kD;
   constexpr int kFusedRansacWarps = FusedCfg<kScore, kShape>::kR;
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // the staged maps sit on kMapAlign boundaries (mapops.cuh: load_row_rotated); L.total holds the slack
+  unsigned char* smem = smem_raw + ((kMapAlign - (smem_u32(smem_raw) & (kMapAlign - 1u))) & (kMapAlign - 1u));
   const FusedSmem L = fused_layout(V, J, HW, stages, slots, kFusedRansacWarps);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* empty = full + stages;

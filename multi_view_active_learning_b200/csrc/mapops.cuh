@@ -81,10 +81,27 @@ __device__ __forceinline__ float warp_max_f(float v) { return order_key_inv(__re
 // warp_argmax_map; a map whose sentinel fires (NaN, +-inf, or a sum that overflows) is re-scanned by warp_argmax_map
 // with its exact monotone-key compare, so the result is the same function of the map in every case.
 // ---------------------------------------------------------------------------------------------------------------
+// Rows of a staged map are visited with lane = row; a lane takes the sixteen 16-byte blocks of its row in the order
+// k ^ (lane & 15), which keeps every quarter-warp on eight distinct bank groups (conflict-free LDS.128 / STS.128).  The staged
+// maps are 256-byte aligned (kMapAlign: both kernels align their ring), so block k sits at (row address ^ lane bits) ^ (k << 4):
+// ONE LOP3 per access.  (Round 2: the (k + lane) & 15 rotation kept sixteen index registers alive and cost two IMADs per
+// access, 96 instructions per map in the arg-max sweep and ~250 in BSB's softmax pass -- profiles/r2z_lines_*.)
+constexpr uint32_t kMapAlign = 256;
+__device__ __forceinline__ uint32_t row_block_base(const void* map, int row, int lane) {
+  return ((uint32_t)__cvta_generic_to_shared(map) + (uint32_t)row * (kMapDim * 4u)) ^ ((uint32_t)(lane & 15) << 4);
+}
+__device__ __forceinline__ float4 lds_block(uint32_t rx, int k) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rx ^ ((uint32_t)k << 4)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_block(uint32_t rx, int k, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rx ^ ((uint32_t)k << 4)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void load_row_rotated(const float4* p4, int row, int lane, float4 (&x)[16]) {
-  const float4* rp = p4 + row * 16;
+  const uint32_t rx = row_block_base(p4, row, lane);
 #pragma unroll
-  for (int k = 0; k < 16; ++k) x[k] = rp[(k + lane) & 15];
+  for (int k = 0; k < 16; ++k) x[k] = lds_block(rx, k);
 }
 __device__ __forceinline__ float row_max(const float4 (&x)[16]) {
   float rm = -INFINITY;
@@ -333,9 +350,8 @@ static __device__ __noinline__ uint4 prune_touching_peaks(uint32_t b0, uint32_t 
 // a subset of them that depends on an unstable argsort -- see DESIGN.md section 2.
 // BSB works on the ROW-softmaxed map (F.softmax without dim on a 2-D tensor), so a first pass rewrites the stage in
 // place, p = exp(x - rowmax) / rowsum.  That pass runs with lane = row (rows l and l + 32): a lane holds its whole row in
-// 64 registers, so the row statistics need no shuffles at all; the float4 column blocks are visited in the rotated
-// order (k + lane) % 16, which keeps every quarter-warp on eight distinct 16-byte bank groups (conflict-free LDS.128 /
-// STS.128).  exp = ex2.approx of the exactly formed difference times log2e (the row maximum contributes exactly 1), the
+// 64 registers, so the row statistics need no shuffles at all; the float4 column blocks are visited in the order
+// k ^ (lane & 15) (load_row_rotated above: conflict-free LDS.128 / STS.128).  exp = ex2.approx of the exactly formed difference times log2e (the row maximum contributes exactly 1), the
 // quotient is e * (1/s) corrected by one residual step.
 // ---------------------------------------------------------------------------------------------------------------
 template <int kMode>
@@ -359,10 +375,10 @@ struct PeaksOp {
       constexpr float kLog2e = 1.4426950408889634f;
 #pragma unroll 1
       for (int rr = 0; rr < 2; ++rr) {
-        float4* row = p4 + (lane + 32 * rr) * 16;
+        const uint32_t rx = row_block_base(p4, lane + 32 * rr, lane);
         float4 x[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = row[(k + lane) & 15];
+        for (int k = 0; k < 16; ++k) x[k] = lds_block(rx, k);
         float rm = -INFINITY;
 #pragma unroll
         for (int k = 0; k < 16; k += 2)
@@ -391,7 +407,7 @@ struct PeaksOp {
           // 22 packed instructions per float4 and changed nothing at the 2e-6 contract of this score)
           const float2 qa = __fmul2_rn(ea, r2), qb = __fmul2_rn(eb, r2);
           gmin = min3(min3(qa.x, qa.y, qb.x), qb.y, gmin);
-          row[(k + lane) & 15] = make_float4(qa.x, qa.y, qb.x, qb.y);
+          sts_block(rx, k, make_float4(qa.x, qa.y, qb.x, qb.y));
         }
       }
       __syncwarp();

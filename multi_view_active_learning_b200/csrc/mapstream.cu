@@ -26,7 +26,7 @@ constexpr int kStreamWarps = 12;
 constexpr int kStreamStages = 12;
 constexpr int kStreamThreads = kWarp * (1 + kStreamWarps);  // 416
 constexpr uint32_t kScratchPerWarp = 1024;  // XE: two tables of 64 doubles
-constexpr uint32_t kStreamSmem = kStreamStages * kMapBytes + 2u * kStreamStages * 8u + kStreamWarps * kScratchPerWarp;
+constexpr uint32_t kStreamSmem = kStreamStages * kMapBytes + 2u * kStreamStages * 8u + kStreamWarps * kScratchPerWarp + kMapAlign;
 
 __device__ unsigned long long g_stream_abort[kWdWords];
 static WatchdogHost g_stream_watchdog;
@@ -41,7 +41,9 @@ template <class Op>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 map_stream_kernel(const float* __restrict__ hm, int64_t n_maps, const uint8_t* __restrict__ valid, int V, int J,
                   typename Op::Args args) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // the staged maps sit on kMapAlign boundaries (mapops.cuh: load_row_rotated); the launch reserves the slack
+  unsigned char* smem = smem_raw + ((kMapAlign - (smem_u32(smem_raw) & (kMapAlign - 1u))) & (kMapAlign - 1u));
   float* ring = reinterpret_cast<float*>(smem);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStreamStages * kMapBytes);
   uint64_t* empty = full + kStreamStages;
