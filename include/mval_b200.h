@@ -171,9 +171,11 @@ int mval_score_pool(const float* heatmaps, const double* proj, const uint8_t* va
 
 /* mval_score_pool + one of mval_score_hp / mval_score_peaks over the SAME heat maps in a single pass: what
  * strategy.py:1036-1045 (triangulation of every frame) and :1072-1094 (the HP / MPE / BSB metric of the same frame) do
- * together inside _compute_sal_dict.  On 64 x 64 maps the decode warps of the fused kernel evaluate the score on the
- * staged map right after its arg-max, so every heat-map byte is read once instead of twice; other shapes run the two
- * calls back to back.  Results are bit-identical to the separate calls.
+ * together inside _compute_sal_dict.  On 64 x 64 maps every heat-map byte is read once instead of twice: for HP the
+ * decode warps of the fused kernel evaluate the score on the staged map together with its arg-max; for MPE / BSB one
+ * streaming kernel emits the score and the arg-max key-point of every staged map and the RANSAC kernels follow from the
+ * 8-byte key-points (their fused launch stays selectable, MVAL_SCORED_SPLIT=0).  Other shapes run the two calls back to
+ * back.  Results are bit-identical to the separate calls.
  * map_score      one of MVAL_MAP_SCORE_* (NONE: out_map_score is ignored, same as mval_score_pool)
  * out_map_score  float32 device [n_frames][V][J], NaN for invalid joints. */
 int mval_score_pool_scored(const float* heatmaps, const double* proj, const uint8_t* valid, int64_t n_frames, int V,
