@@ -43,6 +43,11 @@ def main():
         # batches already collated and on the device: what is left is the per-batch cost of the scoring pipeline itself
         batches = [{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.items()} for b in loader()]
         loader = lambda: batches  # noqa: E731
+    if len(sys.argv) > 4 and sys.argv[4] == "pinned":
+        # batches already collated in pinned host memory: what is left is the upload (copy stream, one batch ahead) under the
+        # scoring launches -- the host side of a loader with enough workers
+        batches = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()} for b in loader()]
+        loader = lambda: batches  # noqa: E731
     for it in range(3):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
