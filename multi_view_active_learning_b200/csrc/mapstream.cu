@@ -26,7 +26,19 @@ constexpr int kStreamWarps = 12;
 constexpr int kStreamStages = 12;
 constexpr int kStreamThreads = kWarp * (1 + kStreamWarps);  // 416
 constexpr uint32_t kScratchPerWarp = 1024;  // XE: two tables of 64 doubles
-constexpr uint32_t kStreamSmem = kStreamStages * kMapBytes + 2u * kStreamStages * 8u + kStreamWarps * kScratchPerWarp + kMapAlign;
+// Ops that are bound by the SM (issue slots / ALU pipe: MPE, BSB) run the ring in DYNAMIC mode: 14 stages for the 12 consumer
+// warps, and a warp takes the next map of the CTA (an atomic counter in shared memory) instead of owning a stage.  With one
+// stage per warp a consumer idles for the whole refill of its stage after every map (producer reaction + HBM latency + 16 KiB
+// at a 148th of the bandwidth, ~1.2 us of the ~6 us a BSB map takes); the two spare stages are always being refilled, so a
+// warp that finishes usually finds its next map waiting.  (No aliasing of barrier phases: a warp holds one map, the producer
+// fills in order and stalls at the first stage that is still held, so claims reach at most 11 + 13 < 2 x 14 maps ahead.)
+template <class Op>
+struct StreamCfg {
+  static constexpr bool kDynamic = Op::kProducerBackoff != 0;
+  static constexpr int kStages = kDynamic ? 14 : kStreamStages;
+  static constexpr uint32_t kScratch = kDynamic ? 0u : kStreamWarps * kScratchPerWarp;  // only XeOp uses scratch
+  static constexpr uint32_t kSmem = kStages * kMapBytes + 2u * kStages * 8u + 16u + kScratch + kMapAlign;
+};
 
 __device__ unsigned long long g_stream_abort[kWdWords];
 static WatchdogHost g_stream_watchdog;
@@ -44,16 +56,20 @@ map_stream_kernel(const float* __restrict__ hm, int64_t n_maps, const uint8_t* _
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // the staged maps sit on kMapAlign boundaries (mapops.cuh: load_row_rotated); the launch reserves the slack
   unsigned char* smem = smem_raw + ((kMapAlign - (smem_u32(smem_raw) & (kMapAlign - 1u))) & (kMapAlign - 1u));
+  using Cfg = StreamCfg<Op>;
+  constexpr int kStages = Cfg::kStages;
   float* ring = reinterpret_cast<float*>(smem);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStreamStages * kMapBytes);
-  uint64_t* empty = full + kStreamStages;
-  unsigned char* scratch = smem + kStreamStages * kMapBytes + 2u * kStreamStages * 8u;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kMapBytes);
+  uint64_t* empty = full + kStages;
+  int* next_map = reinterpret_cast<int*>(empty + kStages);  // dynamic mode: next unclaimed map of this CTA
+  unsigned char* scratch = smem + kStages * kMapBytes + 2u * kStages * 8u + 16u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStreamStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
+    *next_map = 0;
     mbar_fence_init();
   }
   __syncthreads();
@@ -63,8 +79,8 @@ map_stream_kernel(const float* __restrict__ hm, int64_t n_maps, const uint8_t* _
     if (lane == 0 && !watchdog_stalled(g_stream_abort)) {
       for (int64_t c = 0; c < nm; ++c) {
         const int64_t m = blockIdx.x + c * (int64_t)gridDim.x;
-        const int st = (int)(c % kStreamStages);
-        const uint32_t kf = (uint32_t)(c / kStreamStages);
+        const int st = (int)(c % kStages);
+        const uint32_t kf = (uint32_t)(c / kStages);
         if (!mbar_wait<Op::kProducerBackoff>(&empty[st], (kf & 1u) ^ 1u, g_stream_abort, 1, c, st)) return;
         if (valid != nullptr && valid[(m / VJ) * J + m % J] == 0) {
           mbar_arrive(&full[st]);  // nothing to read for an invalid joint
@@ -73,6 +89,23 @@ map_stream_kernel(const float* __restrict__ hm, int64_t n_maps, const uint8_t* _
           bulk_g2s(ring + (size_t)st * kMapFloats, hm + m * kMapFloats, kMapBytes, &full[st]);
         }
       }
+    }
+  } else if constexpr (Cfg::kDynamic) {
+    static_assert(kStreamWarps <= kStages + 1, "claims must stay less than two ring rounds ahead (barrier phase parity)");
+    for (;;) {
+      int claimed = 0;
+      if (lane == 0) claimed = atomicAdd(next_map, 1);
+      const int64_t c = __shfl_sync(kFull, claimed, 0);
+      if (c >= nm) break;
+      const int st = (int)(c % kStages);
+      const uint32_t kf = (uint32_t)(c / kStages);
+      const int64_t m = blockIdx.x + c * (int64_t)gridDim.x;
+      const bool ok = valid == nullptr || valid[(m / VJ) * J + m % J] != 0;
+      if (!mbar_wait(&full[st], kf & 1u, g_stream_abort, 2, c, st)) return;
+      Op::run(ring + (size_t)st * kMapFloats, m, ok, lane, args, nullptr, typename Op::Pre{});
+      if (Op::kWritesSmem) fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
     }
   } else {
     const int w = warp - 1;
@@ -130,6 +163,7 @@ template <class Op>
 static int launch_map_stream(const char* name, const float* hm, int64_t n_maps, const uint8_t* valid, int V, int J,
                              const typename Op::Args& args, cudaStream_t stream) {
   if (n_maps == 0) return MVAL_OK;
+  constexpr uint32_t kStreamSmem = StreamCfg<Op>::kSmem;
   MVAL_CUDA(cudaFuncSetAttribute(map_stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmem));
   const int64_t sms = num_sms();
   const int grid = (int)(n_maps < sms ? n_maps : sms);
