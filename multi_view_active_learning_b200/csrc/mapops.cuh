@@ -119,7 +119,9 @@ __device__ __forceinline__ uint32_t argmax_from_row_maxima(const float4* p4, int
   const uint32_t col = __reduce_min_sync(kFull, c == 0xffffu ? 0xffffffffu : (uint32_t)(lane & 15) * 4u + c);
   return row * (uint32_t)kMapDim + col;
 }
-__device__ __forceinline__ uint32_t warp_argmax_map64(const float* map, int lane) {
+// row_max_out (may be nullptr): the maxima of rows lane and lane + 32 as row_max() computes them -- BSB's softmax pass over
+// the same staged map starts from them instead of recomputing 32 FMNMX3 per row.
+__device__ __forceinline__ uint32_t warp_argmax_map64(const float* map, int lane, float2* row_max_out = nullptr) {
   const float4* p4 = reinterpret_cast<const float4*>(map);
   float best = -INFINITY;
   int best_row = lane;
@@ -130,6 +132,9 @@ __device__ __forceinline__ uint32_t warp_argmax_map64(const float* map, int lane
     float4 x[16];
     load_row_rotated(p4, row, lane, x);
     const float rm = row_max(x);
+    if (row_max_out != nullptr) {  // (a select, not an index: the pair stays in registers)
+      if (rr == 0) row_max_out->x = rm; else row_max_out->y = rm;
+    }
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc = __fadd2_rn(acc, __fadd2_rn(make_float2(x[k].x, x[k].y), make_float2(x[k].z, x[k].w)));
     const bool gt = rm > best;  // strict: the lower row is kept on ties
@@ -364,6 +369,10 @@ struct PeaksOp {
   static constexpr int kProducerBackoff = 2;
   __device__ static __forceinline__ Pre prefetch(int64_t, const Args&) { return {}; }
   __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char*, const Pre&) {
+    run_rows(map, m, ok, lane, a, nullptr);
+  }
+  // known_row_max (BSB only, may be nullptr): maxima of rows lane and lane + 32 from an arg-max sweep over the same map
+  __device__ static __forceinline__ void run_rows(float* map, int64_t m, bool ok, int lane, const Args& a, const float2* known_row_max) {
     if (!ok) {
       if (lane == 0) a.out[m] = __int_as_float(0x7fc00000);
       return;
@@ -379,10 +388,7 @@ struct PeaksOp {
         float4 x[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) x[k] = lds_block(rx, k);
-        float rm = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < 16; k += 2)
-          rm = max3(rm, max3(x[k].x, x[k].y, x[k].z), max3(x[k].w, x[k + 1].x, max3(x[k + 1].y, x[k + 1].z, x[k + 1].w)));
+        const float rm = known_row_max != nullptr ? (rr == 0 ? known_row_max->x : known_row_max->y) : row_max(x);
         // packed float32x2 arithmetic (FADD2 / FMUL2 / FFMA2, sm_100): half the issue slots of the scalar forms
         const float2 nrm = make_float2(-rm, -rm), l2e = make_float2(kLog2e, kLog2e);
         float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);

@@ -142,15 +142,20 @@ struct ArgmaxPlusOp {
   using Pre = typename Inner::Pre;
   static constexpr bool kWritesSmem = Inner::kWritesSmem;
   static constexpr int kProducerBackoff = Inner::kProducerBackoff;
+  static constexpr bool kShareRowMax = Inner::kWritesSmem;  // PeaksOp<1> (BSB): the only Op with a row-softmax pass
   __device__ static __forceinline__ Pre prefetch(int64_t m, const Args& a) { return Inner::prefetch(m, a.inner); }
   __device__ static __forceinline__ void run(float* map, int64_t m, bool ok, int lane, const Args& a, unsigned char* scratch,
                                              const Pre& pre) {
     uint32_t idx = 0u;
-    if (ok) idx = warp_argmax_map64(map, lane);
+    float2 rm = make_float2(0.f, 0.f);
+    if (ok) idx = warp_argmax_map64(map, lane, kShareRowMax ? &rm : nullptr);
     if (lane == 0)  // evaluation.py:21-26: (c % H, c / H) * stride, (0, 0) for an invalid joint
       a.out_xy[m] = ok ? make_int2((int)(idx % (uint32_t)kMapDim) * a.stride, (int)(idx / (uint32_t)kMapDim) * a.stride) : make_int2(0, 0);
     __syncwarp();
-    Inner::run(map, m, ok, lane, a.inner, scratch, pre);
+    if constexpr (kShareRowMax)
+      Inner::run_rows(map, m, ok, lane, a.inner, &rm);  // BSB's row softmax starts from the sweep's row maxima
+    else
+      Inner::run(map, m, ok, lane, a.inner, scratch, pre);
   }
 };
 
