@@ -392,9 +392,10 @@ int launch_score_pool_fused_segments(const float* const* seg_ptr, const int64_t*
 #define MVAL_FUSED_ARGS                                                                                               \
   segs, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz, out_reproj, out_inliers, out_metric,           \
       out_inlier_count, out_map_score, stream
-  // Arg-max flavour on 64 x 64 maps.  Measured (profiles/r1f_summary.md): the unscored pass is faster with the generic
-  // per-vector scan (5.78 against 6.06 ms per 16 384 frames: its six decode warps are latency-, not issue-bound), the
-  // MPE / BSB passes are issue-bound and take the lane = row sweep (170 instead of 400 instructions per map).
+  // Arg-max flavour on 64 x 64 maps: the lane = row sweep (170 instead of 400 instructions per map) everywhere.  Round 1f had
+  // measured the unscored pass faster with the generic per-vector scan on SHORT runs (5.78 against 6.06 ms per 16 384 frames);
+  // in the sustained 100 000-frame step, where the power cap sets the clocks, the sweep is 6 % faster (round 2, A/B/A/B on one
+  // box, profiles/r2p2_*: 36.2-36.5 ms against 34.0-34.2 ms per step) -- fewer instructions is less power is more clock.
   // MVAL_ROW_ARGMAX = 0 / 1 forces one flavour everywhere (A/B measurements and tests; read on every call).
   const char* env = getenv("MVAL_ROW_ARGMAX");
   const int force = (env != nullptr && (env[0] == '0' || env[0] == '1')) ? env[0] - '0' : -1;
@@ -406,7 +407,7 @@ int launch_score_pool_fused_segments(const float* const* seg_ptr, const int64_t*
   switch (map_score) {
     case MVAL_MAP_SCORE_NONE:
       out_map_score = nullptr;
-      if (is64 && force == 1) return launch_fused_variant<MVAL_MAP_SCORE_NONE, true>(MVAL_FUSED_ARGS);
+      if (is64 && force != 0) return launch_fused_variant<MVAL_MAP_SCORE_NONE, true>(MVAL_FUSED_ARGS);
       return launch_fused_variant<MVAL_MAP_SCORE_NONE, false>(MVAL_FUSED_ARGS);
     case MVAL_MAP_SCORE_HP:  // the arg-max is a by-product of HP's own row sweep
       if (shape == 0) return launch_fused_variant<MVAL_MAP_SCORE_HP, true, 0>(MVAL_FUSED_ARGS);

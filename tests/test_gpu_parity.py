@@ -650,8 +650,9 @@ def test_fused_scored_pass_equals_separate_passes(ops, N, V, J, vp):
     P, valid = _cuda(pool["P"]), torch.from_numpy(pool["valid"])
     v = np.broadcast_to(pool["valid"][:, None, :], (N, V, J))
     plain = ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345)
-    rows = _with_env("MVAL_ROW_ARGMAX", "1", lambda: ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345))
-    assert torch.equal(plain["keypoints_2d"], rows["keypoints_2d"]) and torch.equal(plain["keypoints_3d"], rows["keypoints_3d"])
+    for flavour in ("0", "1"):  # generic per-vector scan / lane = row sweep (the default on 64 x 64 maps)
+        rows = _with_env("MVAL_ROW_ARGMAX", flavour, lambda: ops.score_pool(hm, P, 4, valid, pair_seed=3, frame_offset=12345))
+        assert torch.equal(plain["keypoints_2d"], rows["keypoints_2d"]) and torch.equal(plain["keypoints_3d"], rows["keypoints_3d"])
     assert torch.equal(plain["keypoints_2d"], ops.decode_argmax(hm, 4, valid))
     # MPE / BSB: the fused kernel with either arg-max flavour (MVAL_SCORED_SPLIT=0) and the default split path (stream kernel
     # with score + arg-max key-point, then RANSAC from the key-points) must all give the same bits
