@@ -1193,7 +1193,7 @@ def run_scores(args):
     kernels["score_pool_fused_kernel<BSB> in ONE launch (MVAL_SCORED_SPLIT=0)"] = unsplit("BSB", "0")
     kernels["map_stream<argmax+MPE> + RANSAC launches (MVAL_SCORED_SPLIT=1)"] = unsplit("MPE", "1")
     kernels["map_stream<argmax+BSB> + RANSAC launches (MVAL_SCORED_SPLIT=1)"] = unsplit("BSB", "1")
-    kernels["score_pool_fused_kernel, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = flavoured("0", None)
+    kernels["score_pool_fused_kernel, lane=row arg-max (MVAL_ROW_ARGMAX=1)"] = flavoured("1", None)
     kernels["score_pool_fused_kernel<MPE>, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = flavoured("0", "MPE")
     kernels["score_pool_fused_kernel<BSB>, generic arg-max scan (MVAL_ROW_ARGMAX=0)"] = flavoured("0", "BSB")
     def with_env(kind, env):

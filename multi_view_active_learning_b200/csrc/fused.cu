@@ -392,11 +392,15 @@ int launch_score_pool_fused_segments(const float* const* seg_ptr, const int64_t*
 #define MVAL_FUSED_ARGS                                                                                               \
   segs, proj, valid, n_frames, V, J, H, W, stride, prm, out_xy, out_xyz, out_reproj, out_inliers, out_metric,           \
       out_inlier_count, out_map_score, stream
-  // Arg-max flavour on 64 x 64 maps: the lane = row sweep (170 instead of 400 instructions per map) everywhere.  Round 1f had
-  // measured the unscored pass faster with the generic per-vector scan on SHORT runs (5.78 against 6.06 ms per 16 384 frames);
-  // in the sustained 100 000-frame step, where the power cap sets the clocks, the sweep is 6 % faster (round 2, A/B/A/B on one
-  // box, profiles/r2p2_*: 36.2-36.5 ms against 34.0-34.2 ms per step) -- fewer instructions is less power is more clock.
-  // MVAL_ROW_ARGMAX = 0 / 1 forces one flavour everywhere (A/B measurements and tests; read on every call).
+  // Arg-max flavour on 64 x 64 maps.  The scored variants take the lane = row sweep (170 instead of 400 instructions per map:
+  // they are bound by the SM).  The unscored pass is HBM-bound either way and the choice is about POWER: on short launches the
+  // generic per-vector scan is faster (API batches of 8 192 frames, A/B/A/B on one box, profiles/r2q2_*: 52.3 / 52.9 ms per
+  // 125 000-frame call against 54.8 / 54.7 ms; the 20- and 31-view rigs 1.04 / 1.08 against 0.98 / 1.00 of the copy peak), but
+  // in a long launch the power cap sets the clocks and the sweep's smaller instruction count buys 6 % (100 000-frame step,
+  // A/B/A/B, profiles/r2p2_*: 36.2-36.5 ms against 34.0-34.2 ms).  So: the sweep from kRowArgmaxMinMaps maps per launch on
+  // (~12 ms at 8 x 19 maps per frame), the scan below.  MVAL_ROW_ARGMAX = 0 / 1 forces one flavour everywhere (A/B
+  // measurements and tests; read on every call).
+  constexpr int64_t kRowArgmaxMinMaps = 32768ll * 152ll;
   const char* env = getenv("MVAL_ROW_ARGMAX");
   const int force = (env != nullptr && (env[0] == '0' || env[0] == '1')) ? env[0] - '0' : -1;
   const bool is64 = H == kMapDim && W == kMapDim;
@@ -407,7 +411,8 @@ int launch_score_pool_fused_segments(const float* const* seg_ptr, const int64_t*
   switch (map_score) {
     case MVAL_MAP_SCORE_NONE:
       out_map_score = nullptr;
-      if (is64 && force != 0) return launch_fused_variant<MVAL_MAP_SCORE_NONE, true>(MVAL_FUSED_ARGS);
+      if (is64 && (force == 1 || (force < 0 && n_frames * (int64_t)V * J >= kRowArgmaxMinMaps)))
+        return launch_fused_variant<MVAL_MAP_SCORE_NONE, true>(MVAL_FUSED_ARGS);
       return launch_fused_variant<MVAL_MAP_SCORE_NONE, false>(MVAL_FUSED_ARGS);
     case MVAL_MAP_SCORE_HP:  // the arg-max is a by-product of HP's own row sweep
       if (shape == 0) return launch_fused_variant<MVAL_MAP_SCORE_HP, true, 0>(MVAL_FUSED_ARGS);
