@@ -48,6 +48,8 @@ def main():
         src = cache[line[0]]
         return "  | " + src[line[1] - 1].strip()[:110] if 0 < line[1] <= len(src) else ""
     rows = list(csv.reader(open(page)))
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]  # one table per captured launch: take the last
+    rows = rows[starts[-1]:]
     hdr = rows[1]
     ia, isrc, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("Instructions Executed")
     ins = [(r[isrc], int(r[iex] or 0)) for r in rows[2:] if len(r) > iex]
